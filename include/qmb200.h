@@ -1,0 +1,131 @@
+/* qmb200 — C ABI of the B200-native batched MPC+WBC solver (drop-in for qm_control's per-tick numerical path).
+ *
+ * Every entry point replaces one reference interface; the thin C++ subclasses a maintainer adds on the
+ * reference side (B200Wbc : qm::WbcBase, B200Mpc : ocs2::MPC_BASE) are shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; return 0 on success, negative on error (never throws);
+ * qmb200_last_error() describes the last failure; the caller owns every buffer it passes; `_dev` variants
+ * take device pointers and a cudaStream_t (as void*) and do not synchronise; one handle per GPU, calls on
+ * one handle are serialised on its stream; batch = 1 works (plugin use).  All arithmetic is fp64
+ * (ocs2::scalar_t).  Layouts are robot-major, fixed stride:
+ *   state x[30]  = [h_lin/m(3), h_ang/m(3), base pos(3), base euler ZYX(3), joints(18: LF,LH,RF,RH,arm)]   task.info:150-189
+ *   input u[30]  = [contact forces(12: LF,RF,LH,RH), joint velocities(18)]                                  task.info:252-286
+ *   rbd[55]      = [euler ZYX(3), pos(3), joints(18), w_world(3), v_lin(3), joint vel(18), ee pos(3), ee quat xyzw(4)]
+ *                                                                                  qm_estimation/src/StateEstimateBase.cpp:41-103
+ *   cmd[54]      = [vdot(24), F(12), tau(18)]                                      qm_wbc/src/WbcBase.cpp:548-563
+ *   mode         = 4-bit stance code LF=8 RF=4 LH=2 RH=1 (ocs2_legged_robot MotionPhaseDefinition)
+ */
+#ifndef QMB200_H
+#define QMB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMB200_NX 30
+#define QMB200_NU 30
+#define QMB200_RBD 55
+#define QMB200_CMD 54
+#define QMB200_TARGET 37   /* 30-dim state + end-effector pose [pos(3), quat xyzw(4)] (QMController.cpp:106-112) */
+#define QMB200_EMAX 32     /* max events of one robot's mode schedule window */
+#define QMB200_KMAX 4      /* max knots of one robot's target trajectory */
+
+#define QMB200_WBC_HIERARCHICAL 0      /* qm::HierarchicalWbc      (qm_wbc/src/HierarchicalWbc.cpp:18-44)    */
+#define QMB200_WBC_HIERARCHICAL_MPC 1  /* qm::HierarchicalMpcWbc   (qm_wbc/src/HierarchicalMpcWbc.cpp:18-34) */
+
+/* per-robot status bits (the reference ignores solver status, HoQp.cpp:143; here it is reported) */
+#define QMB200_ST_ITER_CAP 1
+#define QMB200_ST_OVERFLOW 2
+#define QMB200_ST_NAN 4
+#define QMB200_ST_NOT_PD 8
+#define QMB200_ST_NO_STEP 16      /* line search rejected every step size (solution = initial guess, as in SqpSolver::takeStep) */
+
+typedef struct qmb200_handle qmb200_handle;
+
+/* Replaces the constructor chain QMController::setupInterface/setupMpc/setupWbc
+ * (qm_controllers/src/QMController.cpp:272-306,336-340) → QMInterface(taskFile, urdfFile, referenceFile)
+ * (qm_interface/include/qm_interface/QMInterface.h:31-35). */
+typedef struct {
+  const char* task_file;        /* task.info */
+  const char* urdf_file;        /* robot.urdf */
+  const char* reference_file;   /* reference.info */
+  const char* wbc_gains_file;   /* optional INFO file with a wbcGains{} block; NULL → defaults of qm_wbc/cfg/wbcWigeht.cfg:7-47 */
+  int32_t batch;                /* robots per call on this GPU */
+  int32_t device;               /* CUDA device ordinal */
+  double time_horizon;          /* <= 0 → mpc.timeHorizon (task.info:140) */
+  double dt;                    /* <= 0 → sqp.dt (task.info:78) */
+  int32_t max_nodes;            /* <= 0 → ceil(horizon/dt) + 1 + 2*10 (room for 10 events inside the horizon) */
+  int32_t wbc_variant;          /* QMB200_WBC_* */
+} qmb200_config;
+
+int qmb200_create(const qmb200_config* cfg, qmb200_handle** out);
+void qmb200_destroy(qmb200_handle* h);
+const char* qmb200_last_error(const qmb200_handle* h);   /* h may be NULL (error of a failed create) */
+
+/* dimensions of this handle: batch, node capacity NMAX, event capacity, target-knot capacity */
+int qmb200_get_dims(const qmb200_handle* h, int32_t* batch, int32_t* nmax, int32_t* emax, int32_t* kmax);
+/* CentroidalModelInfo / settings as the reference exposes them (QMInterface.h:37-54): robotMass, initialState[30] (task.info:150-189),
+ * defaultJointState[18] (reference.info:6-26), time horizon, dt */
+int qmb200_get_model_info(const qmb200_handle* h, double* robot_mass, double* initial_state30, double* default_joint_state18, double* time_horizon, double* dt);
+int qmb200_get_joint_name(const qmb200_handle* h, int32_t joint, char* out, int32_t capacity);
+
+/* ---- WBC seam: qm::WbcBase::update(stateDesired, inputDesired, rbdStateMeasured, mode, period, time) → vector_t
+ *      (qm_wbc/include/qm_wbc/WbcBase.h:31-32), batched.  Host-pointer version copies in/out on the handle's stream
+ *      and returns after the result is in cmd/status. */
+int qmb200_wbc_update(qmb200_handle* h, const double* x_des /*[B][30]*/, const double* u_des /*[B][30]*/, const double* rbd /*[B][55]*/,
+                      const int32_t* mode /*[B]*/, const double* period /*[B]*/, const double* time /*[B]*/, double* cmd /*[B][54]*/, int32_t* status /*[B]*/);
+int qmb200_wbc_update_dev(qmb200_handle* h, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period,
+                          const double* time, double* cmd, int32_t* status, void* cuda_stream);
+/* WbcBase::inputLast_ (WbcBase.cpp:42,212-213): set for all robots (NULL → zeros, the constructor state) / read back */
+int qmb200_wbc_set_input_last(qmb200_handle* h, const double* input_last /*[B][30] or NULL*/);
+int qmb200_wbc_get_input_last(qmb200_handle* h, double* input_last /*[B][30]*/);
+
+/* ---- MPC seam: ocs2::MPC_BASE::run → SqpSolver::run(t0, x0, t0+T), one SQP iteration (QMController.cpp:287-288,315-332),
+ *      with the inputs the reference manager holds: mode schedule (SwitchedModelReferenceManager) and TargetTrajectories.
+ *      The previous PrimalSolution (warm start, mpc.coldStart=false) lives in the handle. */
+int qmb200_mpc_solve(qmb200_handle* h, const double* t0 /*[B]*/, const double* x0 /*[B][30]*/,
+                     const int32_t* n_events /*[B]*/, const double* event_times /*[B][EMAX]*/, const int32_t* mode_sequence /*[B][EMAX+1]*/,
+                     const int32_t* n_target /*[B]*/, const double* target_times /*[B][KMAX]*/, const double* target_states /*[B][KMAX][37]*/,
+                     int32_t* n_nodes /*[B]*/, double* node_times /*[B][NMAX]*/, int32_t* node_events /*[B][NMAX]*/,
+                     double* x_traj /*[B][NMAX][30]*/, double* u_traj /*[B][NMAX][30]*/, int32_t* status /*[B]*/, double* step_info /*[B][4] or NULL: alpha, cost, dyn SSE, eq SSE after the step*/);
+int qmb200_mpc_solve_dev(qmb200_handle* h, const double* t0, const double* x0, const int32_t* n_events, const double* event_times, const int32_t* mode_sequence,
+                         const int32_t* n_target, const double* target_times, const double* target_states, void* cuda_stream);
+/* drop the stored PrimalSolution: next solve starts from QMInitializer (qm_interface/src/initialization/QMInitializer.cpp:33-41) */
+int qmb200_mpc_reset(qmb200_handle* h);
+/* load a PrimalSolution as warm start (n_nodes[b] < 2 → cold start for robot b) */
+int qmb200_mpc_set_solution(qmb200_handle* h, const int32_t* n_nodes, const double* node_times, const int32_t* node_events, const double* x_traj, const double* u_traj);
+/* read the stored solution (device → host) */
+int qmb200_mpc_get_solution(qmb200_handle* h, int32_t* n_nodes, double* node_times, int32_t* node_events, double* x_traj, double* u_traj, int32_t* status, double* step_info);
+
+/* ---- MPC→WBC hand-off: MPC_MRT_Interface::evaluatePolicy(t, x, → optimizedState, optimizedInput, plannedMode) (QMController.cpp:141)
+ *      on the stored solution and the mode schedule of the last solve. */
+int qmb200_policy_eval(qmb200_handle* h, const double* t /*[B]*/, double* x_des /*[B][30]*/, double* u_des /*[B][30]*/, int32_t* mode /*[B]*/);
+int qmb200_policy_eval_dev(qmb200_handle* h, const double* t, double* x_des, double* u_des, int32_t* mode, void* cuda_stream);
+
+/* ---- one controller tick on the device: mpc_solve → policy_eval(t_eval) → wbc_update, torque buffer out.
+ *      Host-pointer version: observation in, cmd out (the e2e path bench.py times). */
+int qmb200_tick(qmb200_handle* h, const double* t0, const double* x0, const int32_t* n_events, const double* event_times, const int32_t* mode_sequence,
+                const int32_t* n_target, const double* target_times, const double* target_states, const double* t_eval, const double* rbd,
+                const double* period, double* cmd /*[B][54]*/, int32_t* status /*[B]*/);
+int qmb200_tick_dev(qmb200_handle* h, const double* t0, const double* x0, const int32_t* n_events, const double* event_times, const int32_t* mode_sequence,
+                    const int32_t* n_target, const double* target_times, const double* target_states, const double* t_eval, const double* rbd,
+                    const double* period, double* cmd, int32_t* status, void* cuda_stream);
+
+/* ---- observation: CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel (QMController.cpp:238-241), host utility */
+int qmb200_centroidal_state_from_rbd(const qmb200_handle* h, int32_t n, const double* rbd /*[n][55]*/, double* x /*[n][30]*/);
+
+/* ---- gait front-end: GaitSchedule::getModeSchedule tiling of a ModeSequenceTemplate (QMInterface.cpp:455-480, gait.info) for one robot:
+ *      STANCE until t_start, then the template repeated; window [lo, hi]; returns the number of events written (<= EMAX) or negative. */
+int qmb200_gait_schedule(const char* gait_file, const char* gait_name, double t_start, double lo, double hi,
+                         double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
+
+/* number of kernels this library launched since create (bench.py's gpu_launches) */
+int64_t qmb200_launch_count(const qmb200_handle* h);
+/* stream the handle launches on (cudaStream_t as void*) */
+void* qmb200_stream(const qmb200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMB200_H */

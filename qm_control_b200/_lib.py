@@ -1,0 +1,59 @@
+"""ctypes binding of libqmb200.so (C ABI: include/qmb200.h).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libqmb200.so")
+ASSETS = os.path.join(ROOT, "assets")
+
+NX, NU, RBD, CMD, TARGET, EMAX, KMAX = 30, 30, 55, 54, 37, 32, 4
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+
+class QmbError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("task_file", C.c_char_p), ("urdf_file", C.c_char_p), ("reference_file", C.c_char_p), ("wbc_gains_file", C.c_char_p),
+                ("batch", C.c_int32), ("device", C.c_int32), ("time_horizon", C.c_double), ("dt", C.c_double), ("max_nodes", C.c_int32), ("wbc_variant", C.c_int32)]
+
+
+# every symbol include/qmb200.h declares (checked by the CPU test-suite)
+SYMBOLS = ["qmb200_create", "qmb200_destroy", "qmb200_last_error", "qmb200_get_dims", "qmb200_get_model_info", "qmb200_get_joint_name",
+           "qmb200_wbc_update", "qmb200_wbc_update_dev", "qmb200_wbc_set_input_last", "qmb200_wbc_get_input_last",
+           "qmb200_mpc_solve", "qmb200_mpc_solve_dev", "qmb200_mpc_reset", "qmb200_mpc_set_solution", "qmb200_mpc_get_solution",
+           "qmb200_policy_eval", "qmb200_policy_eval_dev", "qmb200_tick", "qmb200_tick_dev", "qmb200_centroidal_state_from_rbd",
+           "qmb200_gait_schedule", "qmb200_launch_count", "qmb200_stream"]
+
+_lib = None
+
+
+def load_library():
+    """Load libqmb200.so; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QmbError("libqmb200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` — there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.qmb200_last_error.restype = C.c_char_p
+    lib.qmb200_last_error.argtypes = [C.c_void_p]
+    lib.qmb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.qmb200_destroy.argtypes = [C.c_void_p]
+    lib.qmb200_destroy.restype = None
+    lib.qmb200_launch_count.restype = C.c_int64
+    lib.qmb200_launch_count.argtypes = [C.c_void_p]
+    lib.qmb200_stream.restype = C.c_void_p
+    lib.qmb200_stream.argtypes = [C.c_void_p]
+    for name in SYMBOLS:
+        getattr(lib, name)
+    _lib = lib
+    return lib
+
+
+def asset(name):
+    return os.path.join(ASSETS, name)

@@ -1,0 +1,137 @@
+// C-ABI of libqmb200 (include/qmb200.h).  Host logic only: argument checks, device buffers, stream ordering,
+// kernel launches.  No CPU fallback: every compute entry point launches the sm_100a kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qmb200.h"
+#include "host/qm_config.h"
+#include "kernels/mpc_api.cuh"
+
+namespace qmb {
+void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
+                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream);
+}
+
+using namespace qmb;
+
+static thread_local std::string g_create_error;
+
+struct qmb200_handle {
+  HostModel hm;
+  DevModel* d_model = nullptr;
+  int B = 0, nmax = 0, variant = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // staging for the host-pointer API
+  double *d_xdes = nullptr, *d_udes = nullptr, *d_rbd = nullptr, *d_period = nullptr, *d_time = nullptr, *d_cmd = nullptr, *d_input_last = nullptr, *d_teval = nullptr;
+  int32_t *d_mode = nullptr, *d_status = nullptr;
+  MpcBuffers mpc;   // device buffers of the MPC path (kernels/mpc_api.cuh)
+  std::vector<void*> allocs;
+};
+
+namespace {
+template <class T> bool dalloc(qmb200_handle* h, T** p, size_t count) {
+  void* q = nullptr; cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) { h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); return false; }
+  cudaMemset(q, 0, count * sizeof(T)); h->allocs.push_back(q); *p = static_cast<T*>(q); return true;
+}
+int fail(qmb200_handle* h, const std::string& msg) { if (h) h->err = msg; else g_create_error = msg; return -1; }
+#define QMB_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+}  // namespace
+
+extern "C" {
+
+int qmb200_create(const qmb200_config* cfg, qmb200_handle** out) {
+  if (!cfg || !out) return fail(nullptr, "qmb200_create: null argument");
+  if (!cfg->task_file || !cfg->urdf_file || !cfg->reference_file) return fail(nullptr, "qmb200_create: task/urdf/reference file required");
+  if (cfg->batch < 1) return fail(nullptr, "qmb200_create: batch must be >= 1");
+  qmb200_handle* h = new qmb200_handle();
+  try {
+    h->hm = build_host_model(cfg->task_file, cfg->urdf_file, cfg->reference_file, cfg->wbc_gains_file ? cfg->wbc_gains_file : "");
+  } catch (const std::exception& e) { g_create_error = e.what(); delete h; return -2; }
+  if (cfg->time_horizon > 0) h->hm.dev.time_horizon = cfg->time_horizon;
+  if (cfg->dt > 0) h->hm.dev.dt = cfg->dt;
+  h->B = cfg->batch; h->variant = cfg->wbc_variant; h->device = cfg->device;
+  const int nint = (int)std::ceil(h->hm.dev.time_horizon / h->hm.dev.dt - 1e-9);
+  h->nmax = cfg->max_nodes > 0 ? cfg->max_nodes : nint + 1 + 20;
+  int ndev = 0; cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("qmb200_create: no CUDA device (") + cudaGetErrorString(e) + ") — this library has no CPU fallback"; delete h; return -3; }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { g_create_error = "qmb200_create: cudaSetDevice failed"; delete h; return -3; }
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  const size_t B = (size_t)h->B;
+  bool ok = dalloc(h, &h->d_model, 1) && dalloc(h, &h->d_xdes, B * NX) && dalloc(h, &h->d_udes, B * NU) && dalloc(h, &h->d_rbd, B * QMB200_RBD) && dalloc(h, &h->d_period, B) &&
+            dalloc(h, &h->d_time, B) && dalloc(h, &h->d_cmd, B * QMB200_CMD) && dalloc(h, &h->d_input_last, B * NU) && dalloc(h, &h->d_mode, B) && dalloc(h, &h->d_status, B) && dalloc(h, &h->d_teval, B);
+  if (ok) { std::string merr; ok = mpc_alloc(h->mpc, h->B, h->nmax, merr, h->allocs); if (!ok) h->err = merr; }
+  if (!ok) { g_create_error = h->err; qmb200_destroy(h); return -4; }
+  cudaMemcpy(h->d_model, &h->hm.dev, sizeof(DevModel), cudaMemcpyHostToDevice);
+  *out = h; return 0;
+}
+
+void qmb200_destroy(qmb200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+const char* qmb200_last_error(const qmb200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int qmb200_get_dims(const qmb200_handle* h, int32_t* batch, int32_t* nmax, int32_t* emax, int32_t* kmax) {
+  if (!h) return -1; if (batch) *batch = h->B; if (nmax) *nmax = h->nmax; if (emax) *emax = QMB200_EMAX; if (kmax) *kmax = QMB200_KMAX; return 0;
+}
+int qmb200_get_model_info(const qmb200_handle* h, double* robot_mass, double* initial_state30, double* default_joint_state18, double* time_horizon, double* dt) {
+  if (!h) return -1;
+  if (robot_mass) *robot_mass = h->hm.dev.total_mass;
+  if (initial_state30) std::memcpy(initial_state30, h->hm.initial_state, sizeof(double) * NX);
+  if (default_joint_state18) std::memcpy(default_joint_state18, h->hm.default_joint_state, sizeof(double) * NJ);
+  if (time_horizon) *time_horizon = h->hm.dev.time_horizon; if (dt) *dt = h->hm.dev.dt; return 0;
+}
+int qmb200_get_joint_name(const qmb200_handle* h, int32_t joint, char* out, int32_t capacity) {
+  if (!h || joint < 0 || joint >= NJ || !out || capacity < 1) return -1; std::snprintf(out, capacity, "%s", h->hm.joint_names[joint].c_str()); return 0;
+}
+int64_t qmb200_launch_count(const qmb200_handle* h) { return h ? h->launches : 0; }
+void* qmb200_stream(const qmb200_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+// ------------------------------------------------------------------ WBC
+int qmb200_wbc_update_dev(qmb200_handle* h, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
+                          double* cmd, int32_t* status, void* cuda_stream) {
+  if (!h) return -1; if (!x_des || !u_des || !rbd || !mode || !period || !time || !cmd || !status) return fail(h, "qmb200_wbc_update_dev: null buffer");
+  QMB_CUDA(h, cudaSetDevice(h->device));
+  launch_wbc_update(h->d_model, h->B, x_des, u_des, rbd, mode, period, time, h->d_input_last, h->variant, cmd, status, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
+  h->launches += 1;
+  QMB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int qmb200_wbc_update(qmb200_handle* h, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time, double* cmd, int32_t* status) {
+  if (!h) return -1; if (!x_des || !u_des || !rbd || !mode || !period || !time || !cmd || !status) return fail(h, "qmb200_wbc_update: null buffer");
+  QMB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = (size_t)h->B; cudaStream_t s = h->stream;
+  QMB_CUDA(h, cudaMemcpyAsync(h->d_xdes, x_des, B * NX * 8, cudaMemcpyHostToDevice, s)); QMB_CUDA(h, cudaMemcpyAsync(h->d_udes, u_des, B * NU * 8, cudaMemcpyHostToDevice, s));
+  QMB_CUDA(h, cudaMemcpyAsync(h->d_rbd, rbd, B * QMB200_RBD * 8, cudaMemcpyHostToDevice, s)); QMB_CUDA(h, cudaMemcpyAsync(h->d_mode, mode, B * 4, cudaMemcpyHostToDevice, s));
+  QMB_CUDA(h, cudaMemcpyAsync(h->d_period, period, B * 8, cudaMemcpyHostToDevice, s)); QMB_CUDA(h, cudaMemcpyAsync(h->d_time, time, B * 8, cudaMemcpyHostToDevice, s));
+  int rc = qmb200_wbc_update_dev(h, h->d_xdes, h->d_udes, h->d_rbd, h->d_mode, h->d_period, h->d_time, h->d_cmd, h->d_status, s); if (rc) return rc;
+  QMB_CUDA(h, cudaMemcpyAsync(cmd, h->d_cmd, B * QMB200_CMD * 8, cudaMemcpyDeviceToHost, s)); QMB_CUDA(h, cudaMemcpyAsync(status, h->d_status, B * 4, cudaMemcpyDeviceToHost, s));
+  QMB_CUDA(h, cudaStreamSynchronize(s));
+  return 0;
+}
+int qmb200_wbc_set_input_last(qmb200_handle* h, const double* input_last) {
+  if (!h) return -1; QMB_CUDA(h, cudaSetDevice(h->device));
+  if (input_last) QMB_CUDA(h, cudaMemcpyAsync(h->d_input_last, input_last, (size_t)h->B * NU * 8, cudaMemcpyHostToDevice, h->stream)); else QMB_CUDA(h, cudaMemsetAsync(h->d_input_last, 0, (size_t)h->B * NU * 8, h->stream));
+  QMB_CUDA(h, cudaStreamSynchronize(h->stream)); return 0;
+}
+int qmb200_wbc_get_input_last(qmb200_handle* h, double* input_last) {
+  if (!h || !input_last) return -1; QMB_CUDA(h, cudaSetDevice(h->device));
+  QMB_CUDA(h, cudaMemcpyAsync(input_last, h->d_input_last, (size_t)h->B * NU * 8, cudaMemcpyDeviceToHost, h->stream)); QMB_CUDA(h, cudaStreamSynchronize(h->stream)); return 0;
+}
+
+}  // extern "C"
+
+#include "capi_mpc.inc"

@@ -1,0 +1,150 @@
+// Device-side common definitions for the batched MPC+WBC kernels (sm_100a, fp64).
+// One warp owns one robot; lanes cooperate over bodies / matrix rows; all per-robot state lives in
+// shared memory or registers, HBM is touched only for the batch I/O buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qmb {
+
+constexpr int NQ = 24;   // generalized coordinates (WbcBase.cpp:36, task.info:150-189)
+constexpr int NJ = 18;   // actuated joints
+constexpr int NB = 19;   // bodies (base + one per joint)
+constexpr int NX = 30;   // centroidal state
+constexpr int NU = 30;   // input: 12 contact forces (LF,RF,LH,RH) + 18 joint velocities
+constexpr int NDEC = 36; // WBC decision vector [vdot(24); F(12)]
+constexpr unsigned FULL = 0xffffffffu;
+
+// Model + settings constants, replicated per GPU (read-only, L1/L2 resident).
+struct DevModel {
+  // kinematic tree: joint j moves body j+1
+  int parent[NJ];          // parent body index
+  int axis[NJ];            // 0/1/2 = x/y/z in the joint frame
+  int depth[NB];           // base 0
+  int chain_start[NJ];     // first joint of the serial chain joint j belongs to
+  double Rj[NJ][9];        // joint frame in parent body frame (row-major)
+  double pj[NJ][3];
+  double mass[NB];
+  double com[NB][3];       // body frame
+  double Ib[NB][9];        // about com, body frame
+  int foot_body[4];        // contact order LF, RF, LH, RH
+  int foot_leg[4];         // index of the leg's first joint (joint order LF, LH, RF, RH)
+  double foot_p[4][3];
+  int ee_body; double ee_R[9]; double ee_p[3];
+  double total_mass;
+  double I_nom[9], I_nom_inv[9], c_nom[3];   // SRBD centroidalInertiaNominal, its inverse, comToBasePositionNominal
+  double effort[NJ];
+  double arm_pos_lower[6], arm_pos_upper[6];
+  // WBC gains (wbcWigeht.cfg:7-47) and friction (task.info:346-349)
+  double kp_swing, kd_swing, base_height_kp, base_height_kd, base_linear_kp, base_linear_kd, base_angular_kp, base_angular_kd;
+  double arm_joint_kp[6], arm_joint_kd[6], ee_linear_kp[3], ee_linear_kd[3], ee_angular_kp[3], ee_angular_kd[3];
+  double wbc_friction;
+  // MPC settings (task.info:75-92,138-147,192-343)
+  double Q[NX * NX], R[NU * NU];
+  double mu_ee_pos, mu_ee_ori, mu_final_ee_pos, mu_final_ee_ori;
+  double friction_mu, friction_barrier_mu, friction_barrier_delta, friction_reg, friction_hess_shift;
+  double pos_limit_mu, pos_limit_delta, vel_limit_mu, vel_limit_delta;
+  double arm_vel_lower[6], arm_vel_upper[6];
+  double lift_off_velocity, touch_down_velocity, swing_height, swing_time_scale, position_error_gain;
+  double dt, time_horizon, delta_tol, g_max, g_min, alpha_decay, alpha_min, gamma_c, armijo_factor;
+  double rk_c, rk_w1, rk_w2;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+// argmax over lanes: returns (value, index) of the maximum; ties → lowest index
+__device__ __forceinline__ void warp_argmax(double& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(FULL, v, o); int oi = __shfl_xor_sync(FULL, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+__device__ __forceinline__ void warp_argmin(double& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(FULL, v, o); int oi = __shfl_xor_sync(FULL, idx, o);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+// ---- tiny 3-vector / 3x3 helpers on plain arrays ----
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void cross3_add(const double* a, const double* b, double* c) {
+  c[0] += a[1] * b[2] - a[2] * b[1]; c[1] += a[2] * b[0] - a[0] * b[2]; c[2] += a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void matvec3(const double* M, const double* v, double* o) {
+  o[0] = M[0] * v[0] + M[1] * v[1] + M[2] * v[2]; o[1] = M[3] * v[0] + M[4] * v[1] + M[5] * v[2]; o[2] = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+}
+__device__ __forceinline__ void matTvec3(const double* M, const double* v, double* o) {
+  o[0] = M[0] * v[0] + M[3] * v[1] + M[6] * v[2]; o[1] = M[1] * v[0] + M[4] * v[1] + M[7] * v[2]; o[2] = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+}
+__device__ __forceinline__ void matmul3(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+// C = A * B^T
+__device__ __forceinline__ void matmul3_nt(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+// R = Rz(z) Ry(y) Rx(x)   (ocs2 getRotationMatrixFromZyxEulerAngles)
+__device__ __forceinline__ void rot_zyx(double z, double y, double x, double* R) {
+  double sz, cz, sy, cy, sx, cx; sincos(z, &sz, &cz); sincos(y, &sy, &cy); sincos(x, &sx, &cx);
+  R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
+  R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
+  R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
+}
+// T: euler-ZYX rates → world angular velocity (ocs2 getMappingFromEulerAnglesZyxDerivativeToGlobalAngularVelocity)
+__device__ __forceinline__ void euler_rate_map(double z, double y, double* T) {
+  double sz, cz, sy, cy; sincos(z, &sz, &cz); sincos(y, &sy, &cy);
+  T[0] = 0; T[1] = -sz; T[2] = cy * cz; T[3] = 0; T[4] = cz; T[5] = cy * sz; T[6] = 1; T[7] = 0; T[8] = -sy;
+}
+// Tdot * ed  (time derivative of T along euler rates ed=(zd,yd,xd), applied to ed)
+__device__ __forceinline__ void euler_rate_map_dot_times(double z, double y, const double* ed, double* o) {
+  double sz, cz, sy, cy; sincos(z, &sz, &cz); sincos(y, &sy, &cy);
+  const double zd = ed[0], yd = ed[1];
+  // d/dt of columns: col1 = (-sz, cz, 0) → (-cz zd, -sz zd, 0); col2 = (cy cz, cy sz, -sy) → (-sy yd cz - cy sz zd, -sy yd sz + cy cz zd, -cy yd)
+  o[0] = (-cz * zd) * ed[1] + (-sy * yd * cz - cy * sz * zd) * ed[2];
+  o[1] = (-sz * zd) * ed[1] + (-sy * yd * sz + cy * cz * zd) * ed[2];
+  o[2] = (-cy * yd) * ed[2];
+}
+__device__ __forceinline__ void inv3(const double* m, double* o) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double id = 1.0 / (m[0] * c00 + m[1] * c01 + m[2] * c02);
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+// rotation vector of E = L * R^T  (ocs2 rotationErrorInWorld)
+__device__ __forceinline__ void rotation_error_world(const double* L, const double* Rr, double* e) {
+  double E[9]; matmul3_nt(L, Rr, E);
+  const double w[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
+  const double c = 0.5 * (E[0] + E[4] + E[8] - 1.0), s = 0.5 * sqrt(dot3(w, w));
+  if (s < 1e-12) { e[0] = 0.5 * w[0]; e[1] = 0.5 * w[1]; e[2] = 0.5 * w[2]; return; }
+  const double k = atan2(s, c) / (2.0 * s); e[0] = k * w[0]; e[1] = k * w[1]; e[2] = k * w[2];
+}
+// modeNumber2StanceLeg: bit3 LF, bit2 RF, bit1 LH, bit0 RH (contact order LF,RF,LH,RH)
+__device__ __forceinline__ bool contact_flag(int mode, int foot) { return (mode >> (3 - foot)) & 1; }
+
+}  // namespace qmb

@@ -1,0 +1,430 @@
+// Batched whole-body controller: one warp per robot.
+//
+// Path replaced (reference, CPU, one robot per call):
+//   WbcBase::update            qm_wbc/src/WbcBase.cpp:118-132   (mode → contact flags)
+//   WbcBase::updateMeasured    WbcBase.cpp:134-191               (Pinocchio FK/Jacobians/crba/nle)
+//   WbcBase::updateDesired     WbcBase.cpp:193-226               (centroidal desired base acceleration, incl. the
+//                                                                 SRBD/full-model evaluation-order quirk)
+//   formulate*Task             WbcBase.cpp:228-546
+//   HierarchicalWbc::update    qm_wbc/src/HierarchicalWbc.cpp:18-44, HierarchicalMpcWbc.cpp:18-34
+//   HoQp (3 levels)            qm_wbc/src/HoQp.cpp:12-159        (qpOASES dense active set per level)
+//   WbcBase::updateCmd         WbcBase.cpp:548-563
+//
+// B200-first restatement of HoQp: the cascade "min ||A_p x - b_p||^2 + ||v_p||^2 over the optimal set of the
+// higher levels, D x <= f + v" is solved directly in the 36-dim decision space with an ORTHONORMAL null-space
+// basis Z (Householder complete orthogonal decomposition) instead of Eigen's fullPivLu kernel + a 92-variable
+// QP with explicit slack variables: level 0's slack is eliminated analytically (v = max(0, D x - f)), the torque
+// and friction rows are never materialised (they are read out of M and J), and inequalities are handled by a
+// primal active set on the step.  The cascade optimum is basis independent, so the result equals the
+// reference's wherever that optimum is unique.
+#include "dev_common.cuh"
+#include "rbd.cuh"
+#include "wlinalg.cuh"
+
+namespace qmb {
+
+constexpr int LDM = 25;   // leading dimension of 24-column matrices (odd → conflict-free column walks)
+constexpr int LDZ = 37;   // leading dimension of 36-column / 36-row matrices
+constexpr int MAXR = 32;  // max rows of one level's equality task (+ violated rows at level 0)
+constexpr int MAXW = 20;  // max size of the inequality working set
+constexpr int WBC_WARPS = 3;
+
+enum { ST_OK = 0, ST_ITER_CAP = 1, ST_TOO_MANY_ROWS = 2, ST_NAN = 4 };
+
+struct QpWs {
+  double Ap[MAXR * LDZ];       // current level's task rows (r x 36)
+  double Z[36 * LDZ];          // orthonormal basis; active window = columns [off, 36)
+  double W[LDZ * MAXR];        // COD workspace (n_z x r, column-major)
+  double Wc[LDZ * MAXW];       // working-set constraint COD workspace (n_z x nw)
+  double tau[MAXR], tauc[MAXW];
+  double xbar[36], dx[36], g[36], y[36], s[36], rhs[MAXR], bp[MAXR], lam[MAXW], G[MAXR * (MAXR + 1)], t18[MAXR];
+  int perm[MAXR], permc[MAXW], wset[MAXW];
+};
+
+struct WbcSmem {
+  double q[NQ], v[NQ], qd[NQ], vd[NQ];
+  double M[NQ * LDM], nle[NQ];
+  double Jf[12 * LDM], djv_f[12], fpos_m[12], fvel_m[12], fpos_d[12], fvel_d[12];
+  double Jee[6 * LDM], djv_ee[6], ee_m_pos[3], ee_m_vel[3], ee_m_rot[9], ee_m_w[3], ee_d_pos[3], ee_d_vel[3], ee_d_rot[9];
+  double Tm[9], wdot_base[3], base_acc[6], xdes[NX], udes[NU], lim[NJ], vstar[64];
+  union U { RbdWs rbd; QpWs qp; __device__ U() {} } u;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Inequality rows of task0 (never stored): i in [0,18): +tau_i <= lim_i ; [18,36): -tau_i <= lim_i ;
+// [36, 36+5*nc): friction pyramid of the stance feet (WbcBase.cpp:360-383, 407-437).  The trailing all-zero
+// rows the reference appends (WbcBase.cpp:426-427) can never be active and are skipped.
+// value(i, x) = D_i x - f_i
+struct IneqCtx { const WbcSmem* sm; int mode; int nc; double mu; };
+
+__device__ __forceinline__ int stance_foot_by_rank(int mode, int rank) { int k = 0; for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { if (k == rank) return f; ++k; } return -1; }
+
+__device__ __forceinline__ double ineq_row_dot(const IneqCtx& c, int i, const double* x) {  // D_i . x
+  if (i < 36) {
+    const int jn = i < 18 ? i : i - 18; const double* Mr = c.sm->M + (6 + jn) * LDM; double s = 0.0;
+    for (int k = 0; k < NQ; ++k) s += Mr[k] * x[k];
+    for (int k = 0; k < 12; ++k) s -= c.sm->Jf[k * LDM + 6 + jn] * x[NQ + k];
+    return i < 18 ? s : -s;
+  }
+  const int r = i - 36; const int foot = stance_foot_by_rank(c.mode, r / 5); const int t = r % 5; const double* F = x + NQ + 3 * foot;
+  if (t == 0) return -F[2];
+  if (t == 1) return F[0] - c.mu * F[2];
+  if (t == 2) return -F[0] - c.mu * F[2];
+  if (t == 3) return F[1] - c.mu * F[2];
+  return -F[1] - c.mu * F[2];
+}
+__device__ __forceinline__ double ineq_rhs(const IneqCtx& c, int i) {   // f_i + v*_i
+  double f = 0.0;
+  if (i < 18) f = c.sm->lim[i] - c.sm->nle[6 + i]; else if (i < 36) f = c.sm->lim[i - 18] + c.sm->nle[6 + i - 18];
+  return f + c.sm->vstar[i];
+}
+__device__ __forceinline__ double ineq_row_elem(const IneqCtx& c, int i, int k) {   // D_i[k]
+  if (i < 36) { const int jn = i < 18 ? i : i - 18; const double sgn = i < 18 ? 1.0 : -1.0; return sgn * (k < NQ ? c.sm->M[(6 + jn) * LDM + k] : -c.sm->Jf[(k - NQ) * LDM + 6 + jn]); }
+  const int r = i - 36; const int foot = stance_foot_by_rank(c.mode, r / 5); const int t = r % 5; const int kk = k - NQ - 3 * foot;
+  if (kk < 0 || kk > 2) return 0.0;
+  if (kk == 2) return t == 0 ? -1.0 : -c.mu;
+  if (kk == 0) return t == 1 ? 1.0 : (t == 2 ? -1.0 : 0.0);
+  return t == 3 ? 1.0 : (t == 4 ? -1.0 : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Minimum-norm least squares  min || Abar y - rhs ||  with Abar^T stored column-wise in W (n x r): COD.
+// On exit y[0..n) holds the solution in the coordinates of W's rows; returns rank.  Uses qp.tau/perm/G/t18.
+__device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, const double* rhs, double* y, int lane) {
+  const int k = w_qrcp(W, n, r, LDZ, qp.tau, qp.perm, 1e-11, lane);
+  // Abar = P R^T Q^T  →  residual_c = sum_{i<=min(c,k-1)} R[i][c] y_i - rhs[perm[c]]
+  for (int i = lane; i < n; i += 32) y[i] = 0.0;
+  __syncwarp();
+  if (k == 0) return 0;
+  if (k == r) {   // square lower-triangular system R11^T y1 = P^T rhs
+    for (int c = 0; c < k; ++c) {
+      double part = 0.0; if (lane < c) part = W[lane + c * LDZ] * y[lane];
+      const double s = warp_sum(part);
+      if (lane == 0) y[c] = (rhs[qp.perm[c]] - s) / W[c + c * LDZ];
+      __syncwarp();
+    }
+  } else {        // overdetermined / rank deficient: normal equations on the k x k triangular factor
+    for (int e = lane; e < k * k; e += 32) { const int a = e / k, b = e % k; double s = 0.0; for (int c = (a > b ? a : b); c < r; ++c) s += W[a + c * LDZ] * W[b + c * LDZ]; qp.G[a * (MAXR + 1) + b] = s; }
+    if (lane < k) { double s = 0.0; for (int c = lane; c < r; ++c) s += W[lane + c * LDZ] * rhs[qp.perm[c]]; qp.t18[lane] = s; }
+    __syncwarp();
+    w_cholesky(qp.G, k, MAXR + 1, lane);
+    w_chol_solve(qp.G, k, MAXR + 1, qp.t18, lane);
+    if (lane < k) y[lane] = qp.t18[lane];
+    __syncwarp();
+  }
+  w_apply_q(W, n, k, LDZ, qp.tau, y, lane);
+  return k;
+}
+
+// Build the task rows of one hierarchy level into qp.Ap / qp.bp.  Returns the row count.
+//   level 0: floating-base EoM + no-contact-motion + swing zero-force           (WbcBase.cpp:338-356, 386-401, 407-415)
+//   level 1: HierarchicalWbc: height, base angular, EE linear, EE angular, 100*swing (t>=10) | arm joint tracking (t<10)
+//            HierarchicalMpcWbc: height, base angular, base linear, 100*swing
+//   level 2: contact force + base linear | contact force
+__device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int level, int mode, int variant, bool init_phase, int lane) {
+  QpWs& qp = sm.u.qp; int nc = 0; for (int f = 0; f < 4; ++f) nc += contact_flag(mode, f);
+  int rows = 0;
+  if (level == 0) rows = 18;
+  else if (level == 1) rows = (variant == 0) ? (init_phase ? 6 : 10 + 3 * (4 - nc)) : (6 + 3 * (4 - nc));
+  else rows = (variant == 0) ? 14 : 12;
+  for (int e = lane; e < rows * LDZ; e += 32) qp.Ap[e] = 0.0;
+  __syncwarp();
+  if (level == 0) {
+    for (int e = lane; e < 6 * 36; e += 32) { const int r = e / 36, k = e % 36; qp.Ap[r * LDZ + k] = (k < NQ) ? sm.M[r * LDM + k] : -sm.Jf[(k - NQ) * LDM + r]; }
+    if (lane < 6) qp.bp[lane] = -sm.nle[lane];
+    int row = 6;
+    for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; qp.Ap[(row + a) * LDZ + k] = sm.Jf[(3 * f + a) * LDM + k]; } if (lane < 3) qp.bp[row + lane] = -sm.djv_f[3 * f + lane]; row += 3; }
+    for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) { if (lane < 3) { qp.Ap[(row + lane) * LDZ + NQ + 3 * f + lane] = 1.0; qp.bp[row + lane] = 0.0; } row += 3; }
+  } else if (level == 1) {
+    int row = 0;
+    if (variant == 0 && init_phase) {   // formulateArmJointNomalTrackingTask (WbcBase.cpp:439-465)
+      if (lane < 6) { const int k = NQ - 6 + lane; qp.Ap[lane * LDZ + k] = 1.0; qp.bp[lane] = mdl->arm_joint_kp[lane] * (sm.qd[k] - sm.q[k]) + mdl->arm_joint_kd[lane] * (sm.vd[k] - sm.v[k]); }
+      row = 6;
+    } else {
+      // formulateBaseHeightMotionTask (WbcBase.cpp:296-308)
+      if (lane == 0) { qp.Ap[2] = 1.0; qp.bp[0] = sm.base_acc[2] + mdl->base_height_kp * (sm.qd[2] - sm.q[2]) + mdl->base_height_kd * (sm.vd[2] - sm.v[2]); }
+      // formulateBaseAngularMotionTask (WbcBase.cpp:258-293): base_j angular rows are [0 | T | 0]
+      if (lane < 3) {
+        const int r = lane; for (int k = 0; k < 3; ++k) qp.Ap[(1 + r) * LDZ + 3 + k] = sm.Tm[3 * r + k];
+        double wM[3], wD[3]; matvec3(sm.Tm, sm.v + 3, wM); matvec3(sm.Tm, sm.vd + 3, wD);
+        double Rm[9], Rr[9], err[3]; rot_zyx(sm.q[3], sm.q[4], sm.q[5], Rm); rot_zyx(sm.qd[3], sm.qd[4], sm.qd[5], Rr); rotation_error_world(Rr, Rm, err);
+        // getGlobalAngularAccelerationFromEulerAnglesZyxDerivatives(eulerMeasured, eulerRatesDesired, eulerAccDesired) = T edd + Tdot(ed) ed
+        double tdd[3], tde[3]; matvec3(sm.Tm, sm.base_acc + 3, tdd); euler_rate_map_dot_times(sm.q[3], sm.q[4], sm.vd + 3, tde);
+        qp.bp[1 + r] = tdd[r] + tde[r] + mdl->base_angular_kp * err[r] + mdl->base_angular_kd * (wD[r] - wM[r]) - sm.wdot_base[r];
+      }
+      row = 4;
+      if (variant == 0) {
+        // formulateEeLinearMotionTrackingTask (WbcBase.cpp:467-492) and formulateEeAngularMotionTrackingTask (:494-531)
+        for (int e = lane; e < 6 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; const bool zero = (a >= 3 && k >= 3 && k < 6); qp.Ap[(row + a) * LDZ + k] = zero ? 0.0 : sm.Jee[a * LDM + k]; }
+        if (lane < 3) qp.bp[row + lane] = mdl->ee_linear_kp[lane] * (sm.ee_d_pos[lane] - sm.ee_m_pos[lane]) + mdl->ee_linear_kd[lane] * (sm.ee_d_vel[lane] - sm.ee_m_vel[lane]) - sm.djv_ee[lane];
+        if (lane == 3) { double err[3]; rotation_error_world(sm.ee_d_rot, sm.ee_m_rot, err);
+          // arm_dj_tmp zeroes columns 3:6 of the angular rows: Jdot_w v minus the base euler part (= Tdot ed = base angular bias acc)
+          for (int a = 0; a < 3; ++a) qp.bp[row + 3 + a] = mdl->ee_angular_kp[a] * err[a] - mdl->ee_angular_kd[a] * sm.ee_m_w[a] - (sm.djv_ee[3 + a] - sm.wdot_base[a]); }
+        row += 6;
+      } else {
+        // formulateBaseLinearMotionTask (WbcBase.cpp:228-240)
+        if (lane < 2) { qp.Ap[(row + lane) * LDZ + lane] = 1.0; qp.bp[row + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
+        row += 2;
+      }
+      // formulateSwingLegTask * 100 (WbcBase.cpp:311-334, HierarchicalWbc.cpp:29)
+      for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) {
+        for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; qp.Ap[(row + a) * LDZ + k] = 100.0 * sm.Jf[(3 * f + a) * LDM + k]; }
+        if (lane < 3) { const int i = 3 * f + lane; qp.bp[row + lane] = 100.0 * (mdl->kp_swing * (sm.fpos_d[i] - sm.fpos_m[i]) + mdl->kd_swing * (sm.fvel_d[i] - sm.fvel_m[i]) - sm.djv_f[i]); }
+        row += 3;
+      }
+    }
+  } else {
+    // formulateContactForceTask (WbcBase.cpp:534-546)
+    if (lane < 12) { qp.Ap[lane * LDZ + NQ + lane] = 1.0; qp.bp[lane] = sm.udes[lane]; }
+    if (variant == 0 && lane < 2) { qp.Ap[(12 + lane) * LDZ + lane] = 1.0; qp.bp[12 + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
+  }
+  __syncwarp();
+  return rows;
+}
+
+// W[c + i*LDZ] = sum_k Ap[i][k] Z[k][off+c]   (n_z x rows)
+__device__ __forceinline__ void project_task(QpWs& qp, int rows, int off, int nz, int lane) {
+  for (int e = lane; e < rows * nz; e += 32) { const int i = e / nz, c = e % nz; const double* a = qp.Ap + i * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.Z[k * LDZ + off + c]; qp.W[c + i * LDZ] = s; }
+  __syncwarp();
+}
+
+// One hierarchy level >= 1: primal active set over the hard inequalities, equality residual minimised in the window.
+__device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, int& nw, int lane, int& iters_out) {
+  QpWs& qp = sm.u.qp; const int nz = 36 - off; const int nineq = 36 + 5 * ic.nc; int status = 0;
+  if (nz <= 0) return 0;
+  bool converged = false;
+  for (int iter = 0; iter < 80; ++iter) {
+    iters_out = iter + 1;
+    // (1) working-set constraints in window coordinates: Wc[c + k*LDZ] = G_{w_k} . Z[:, off+c]
+    int kc = 0;
+    if (nw > 0) {
+      for (int e = lane; e < nw * nz; e += 32) { const int k = e / nz, c = e % nz; double s = 0.0; for (int j = 0; j < 36; ++j) s += ineq_row_elem(ic, qp.wset[k], j) * qp.Z[j * LDZ + off + c]; qp.Wc[c + k * LDZ] = s; }
+      __syncwarp();
+      kc = w_qrcp(qp.Wc, nz, nw, LDZ, qp.tauc, qp.permc, 1e-10, lane);
+      if (kc < nw) {   // dependent rows in this window: keep an independent subset and refactor
+        int keep = (lane < kc) ? qp.wset[qp.permc[lane]] : -1; __syncwarp(); if (lane < kc) qp.wset[lane] = keep; nw = kc; __syncwarp(); continue;
+      }
+    }
+    // (2) least squares for the step in the free directions
+    project_task(qp, rows, off, nz, lane);
+    if (lane < rows) { const double* a = qp.Ap + lane * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.xbar[k]; qp.rhs[lane] = qp.bp[lane] - s; }
+    __syncwarp();
+    if (kc > 0) { for (int i = 0; i < rows; ++i) w_apply_qt(qp.Wc, nz, kc, LDZ, qp.tauc, qp.W + i * LDZ, lane); }
+    const int nfree = nz - kc;
+    for (int i = lane; i < nz; i += 32) qp.s[i] = 0.0;
+    __syncwarp();
+    if (nfree > 0) cod_lstsq(qp, qp.W + kc, nfree, rows, qp.rhs, qp.s + kc, lane);
+    if (kc > 0) w_apply_q(qp.Wc, nz, kc, LDZ, qp.tauc, qp.s, lane);
+    for (int i = lane; i < 36; i += 32) { double d = 0.0; for (int c = 0; c < nz; ++c) d += qp.Z[i * LDZ + off + c] * qp.s[c]; qp.dx[i] = d; }
+    __syncwarp();
+    double dmax = 0.0, xmax = 0.0; for (int i = lane; i < 36; i += 32) { dmax = fmax(dmax, fabs(qp.dx[i])); xmax = fmax(xmax, fabs(qp.xbar[i])); }
+    dmax = warp_max(dmax); xmax = warp_max(xmax);
+    bool full_step = true;
+    if (dmax > 1e-12 * (1.0 + xmax)) {
+      // (3) ratio test over the inequalities outside the working set
+      double alpha = 1.0; int blk = -1;
+      for (int i = lane; i < nineq; i += 32) {
+        bool inw = false; for (int k = 0; k < nw; ++k) inw |= (qp.wset[k] == i);
+        if (inw) continue;
+        const double ad = ineq_row_dot(ic, i, qp.dx);
+        if (ad > 1e-12 * (1.0 + dmax)) { double r = (ineq_rhs(ic, i) - ineq_row_dot(ic, i, qp.xbar)) / ad; if (r < 0.0) r = 0.0; if (r < alpha) { alpha = r; blk = i; } }
+      }
+      { double a = alpha; int b = (blk < 0) ? 0x7fffffff : blk; warp_argmin(a, b); alpha = a; blk = (alpha < 1.0) ? b : -1; }
+      for (int i = lane; i < 36; i += 32) qp.xbar[i] += alpha * qp.dx[i];
+      __syncwarp();
+      if (blk >= 0) { if (nw >= MAXW) { status |= ST_TOO_MANY_ROWS; break; } if (lane == 0) qp.wset[nw] = blk; nw += 1; __syncwarp(); full_step = false; }
+    }
+    if (!full_step) continue;
+    if (nw == 0) { converged = true; break; }
+    // (4) multipliers of the working set at the face minimiser:  C^T lam = -g,  g = Zw^T Ap^T (Ap xbar - bp)
+    if (lane < rows) { const double* a = qp.Ap + lane * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.xbar[k]; qp.rhs[lane] = s - qp.bp[lane]; }
+    __syncwarp();
+    for (int i = lane; i < 36; i += 32) { double s = 0.0; for (int r = 0; r < rows; ++r) s += qp.Ap[r * LDZ + i] * qp.rhs[r]; qp.y[i] = s; }
+    __syncwarp();
+    for (int c = lane; c < nz; c += 32) { double s = 0.0; for (int j = 0; j < 36; ++j) s += qp.Z[j * LDZ + off + c] * qp.y[j]; qp.g[c] = s; }
+    __syncwarp();
+    w_apply_qt(qp.Wc, nz, kc, LDZ, qp.tauc, qp.g, lane);
+    double gmax = 0.0; for (int i = lane; i < nz; i += 32) gmax = fmax(gmax, fabs(qp.g[i])); gmax = warp_max(gmax);
+    for (int c = kc - 1; c >= 0; --c) {   // back substitution R lam_p = -g[0:kc]
+      double part = 0.0; if (lane > c && lane < kc) part = qp.Wc[c + lane * LDZ] * qp.lam[lane];
+      const double s = warp_sum(part);
+      if (lane == 0) qp.lam[c] = (-qp.g[c] - s) / qp.Wc[c + c * LDZ];
+      __syncwarp();
+    }
+    double lmin = (lane < kc) ? qp.lam[lane] : 1e300; int li = lane; warp_argmin(lmin, li);
+    if (lmin >= -1e-9 * (1.0 + gmax)) { converged = true; break; }
+    // drop the constraint with the most negative multiplier (position li in pivoted order)
+    { const int drop = qp.permc[li]; int keep = -1; if (lane < nw) { int src = lane < drop ? lane : lane + 1; keep = (src < nw) ? qp.wset[src] : -1; } __syncwarp(); if (lane < nw - 1) qp.wset[lane] = keep; nw -= 1; __syncwarp(); }
+  }
+  if (!converged) status |= ST_ITER_CAP;
+  return status;
+}
+
+__global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevModel* __restrict__ mdl, int B, const double* __restrict__ x_des, const double* __restrict__ u_des,
+                                                                   const double* __restrict__ rbd_meas, const int32_t* __restrict__ mode_in, const double* __restrict__ period_in,
+                                                                   const double* __restrict__ time_in, double* __restrict__ input_last, int variant,
+                                                                   double* __restrict__ cmd_out, int32_t* __restrict__ status_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WBC_WARPS + warp;
+  if (b >= B) return;
+  WbcSmem& sm = reinterpret_cast<WbcSmem*>(smem_raw)[warp];
+  const int mode = mode_in[b]; const double period = period_in[b]; const double time = time_in[b];
+  int nc = 0; for (int f = 0; f < 4; ++f) nc += contact_flag(mode, f);
+
+  // ---- load the robot's inputs (coalesced, one 240-B / 440-B record each) ----
+  if (lane < NX) { sm.xdes[lane] = x_des[(size_t)b * NX + lane]; sm.udes[lane] = u_des[(size_t)b * NU + lane]; }
+  const double* rb = rbd_meas + (size_t)b * 55;
+  // updateMeasured (WbcBase.cpp:138-144): rbd = [zyx(3), pos(3), joints(18), w_world(3), v_lin(3), joint vel(18), ...]
+  if (lane < 3) { sm.q[lane] = rb[3 + lane]; sm.q[3 + lane] = rb[lane]; sm.v[lane] = rb[NQ + 3 + lane]; }
+  if (lane < NJ) { sm.q[6 + lane] = rb[6 + lane]; sm.v[6 + lane] = rb[NQ + 6 + lane]; sm.lim[lane] = (lane < 12) ? mdl->effort[lane % 3] : mdl->effort[lane]; }
+  for (int i = lane; i < 64; i += 32) sm.vstar[i] = 0.0;
+  __syncwarp();
+  if (lane == 0) { euler_rate_map(sm.q[3], sm.q[4], sm.Tm); double Ti[9]; inv3(sm.Tm, Ti); const double w[3] = {rb[NQ], rb[NQ + 1], rb[NQ + 2]}; matvec3(Ti, w, sm.v + 3); }
+  if (lane < NQ) sm.qd[lane] = sm.xdes[6 + lane];
+  __syncwarp();
+
+  // ---- measured side: M, nle, foot/EE Jacobians and bias accelerations ----
+  RbdWs* ws = &sm.u.rbd;
+  rbd_kinematics(mdl, sm.q, sm.v, ws, lane, true);
+  rbd_inertias(mdl, ws, lane, 1);
+  rbd_accumulate(mdl, ws, lane, true);
+  rbd_mass_matrix_nle(mdl, ws, sm.M, LDM, sm.nle, lane);
+  for (int f = 0; f < 4; ++f) {
+    const int body = mdl->foot_body[f]; double pl[3] = {mdl->foot_p[f][0], mdl->foot_p[f][1], mdl->foot_p[f][2]}, pw[3]; matvec3(ws->R[body], pl, pw);
+    pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
+    const int first = mdl->foot_leg[f]; point_jacobian(ws, pw, first, first + 2, sm.Jf + 3 * f * LDM, LDM, lane);
+    if (lane == 0) { double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.fpos_m[3 * f + a] = pw[a]; sm.fvel_m[3 * f + a] = vel[a]; sm.djv_f[3 * f + a] = acc[a]; } }
+  }
+  {
+    const int body = mdl->ee_body; double pl[3] = {mdl->ee_p[0], mdl->ee_p[1], mdl->ee_p[2]}, pw[3]; matvec3(ws->R[body], pl, pw);
+    pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
+    point_jacobian(ws, pw, 12, 17, sm.Jee, LDM, lane);
+    if (lane < NQ) { const bool on = (lane < 6) || (lane >= 18); for (int a = 0; a < 3; ++a) sm.Jee[(3 + a) * LDM + lane] = on ? ws->S[lane][a] : 0.0; }
+    if (lane == 0) { double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.ee_m_pos[a] = pw[a]; sm.ee_m_vel[a] = vel[a]; sm.djv_ee[a] = acc[a]; sm.djv_ee[3 + a] = ws->A[body][a]; sm.ee_m_w[a] = ws->V[body][a]; sm.wdot_base[a] = ws->A[0][a]; }
+      matmul3(ws->R[body], mdl->ee_R, sm.ee_m_rot); }
+  }
+  __syncwarp();
+
+  // ---- desired side (WbcBase.cpp:193-226) ----
+  // vDesired = [A_b^{-1}(qD) m h ; u joints]  (SRBD mapping); jointAccel = (u - inputLast)/period; inputLast <- u
+  double jacc = 0.0;
+  if (lane < NJ) { jacc = (sm.udes[12 + lane] - input_last[(size_t)b * NU + 12 + lane]) / period; sm.vd[6 + lane] = sm.udes[12 + lane]; }
+  __syncwarp();
+  if (lane < NU) input_last[(size_t)b * NU + lane] = sm.udes[lane];
+  double A22inv[9], A12[9];   // SRBD blocks at qDesired (kept in lane 0's registers; bound BEFORE dccrba in the reference)
+  if (lane == 0) {
+    double R[9], T[9]; rot_zyx(sm.qd[3], sm.qd[4], sm.qd[5], R); euler_rate_map(sm.qd[3], sm.qd[4], T);
+    double c[3]; matvec3(R, mdl->c_nom, c);
+    double RI[9], RIRt[9], A22[9]; matmul3(R, mdl->I_nom, RI); matmul3_nt(RI, R, RIRt); matmul3(RIRt, T, A22); inv3(A22, A22inv);
+    const double Sx[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0}; double ST[9]; matmul3(Sx, T, ST); for (int i = 0; i < 9; ++i) A12[i] = mdl->total_mass * ST[i];
+    double ha[3] = {mdl->total_mass * sm.xdes[3], mdl->total_mass * sm.xdes[4], mdl->total_mass * sm.xdes[5]}, ed[3]; matvec3(A22inv, ha, ed);
+    double t[3]; matvec3(A12, ed, t);
+    for (int a = 0; a < 3; ++a) { sm.vd[a] = sm.xdes[a] - t[a] / mdl->total_mass; sm.vd[3 + a] = ed[a]; }
+  }
+  __syncwarp();
+  rbd_kinematics(mdl, sm.qd, sm.vd, ws, lane, true);
+  rbd_inertias(mdl, ws, lane, 2);            // bias forces WITHOUT gravity: sum = dAg * v about the origin
+  rbd_accumulate(mdl, ws, lane, true);
+  // Aj * jointAccel: sum_j (Ic_{j+1} S_j) qdd_j  (full-model centroidal momentum matrix columns, after dccrba)
+  double Phi[6] = {0, 0, 0, 0, 0, 0};
+  if (lane < NJ) { inertia_apply(ws->Ic[lane + 1], ws->S[6 + lane], Phi); for (int i = 0; i < 6; ++i) Phi[i] *= jacc; }
+  for (int i = 0; i < 6; ++i) Phi[i] = warp_sum(Phi[i]);
+  for (int f = 0; f < 4; ++f) {
+    const int body = mdl->foot_body[f]; double pl[3] = {mdl->foot_p[f][0], mdl->foot_p[f][1], mdl->foot_p[f][2]}, pw[3]; matvec3(ws->R[body], pl, pw);
+    pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
+    if (lane == 0) { double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.fpos_d[3 * f + a] = pw[a]; sm.fvel_d[3 * f + a] = vel[a]; } }
+  }
+  if (lane == 0) {
+    const int body = mdl->ee_body; double pl[3] = {mdl->ee_p[0], mdl->ee_p[1], mdl->ee_p[2]}, pw[3]; matvec3(ws->R[body], pl, pw);
+    pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
+    double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.ee_d_pos[a] = pw[a]; sm.ee_d_vel[a] = vel[a]; }
+    matmul3(ws->R[body], mdl->ee_R, sm.ee_d_rot);
+    // centroidalMomentumRate = m*getNormalizedCentroidalMomentumRate(u) [true COM] - dAg v - Aj qdd_j ; baseAcc = AbInv(SRBD) * that
+    const double mt = ws->Ic[0][0]; const double com[3] = {ws->Ic[0][1] / mt, ws->Ic[0][2] / mt, ws->Ic[0][3] / mt};
+    double lin[3] = {0, 0, -9.81 * mdl->total_mass}, ang[3] = {0, 0, 0};
+    for (int f = 0; f < 4; ++f) { const double* F = sm.udes + 3 * f; const double r[3] = {sm.fpos_d[3 * f] - com[0], sm.fpos_d[3 * f + 1] - com[1], sm.fpos_d[3 * f + 2] - com[2]}; lin[0] += F[0]; lin[1] += F[1]; lin[2] += F[2]; cross3_add(r, F, ang); }
+    // spatial force about the origin → about the COM: n_com = nO - com x f
+    const double* Fb = ws->F[0]; double cf[3]; cross3(com, Fb + 3, cf);
+    double cp[3]; cross3(com, Phi + 3, cp);
+    for (int a = 0; a < 3; ++a) { lin[a] -= Fb[3 + a] + Phi[3 + a]; ang[a] -= (Fb[a] - cf[a]) + (Phi[a] - cp[a]); }
+    double ed[3]; matvec3(A22inv, ang, ed); double t[3]; matvec3(A12, ed, t);
+    for (int a = 0; a < 3; ++a) { sm.base_acc[a] = (lin[a] - t[a]) / mdl->total_mass; sm.base_acc[3 + a] = ed[a]; }
+  }
+  __syncwarp();
+
+  // ---- hierarchy ----
+  QpWs& qp = sm.u.qp; IneqCtx ic{&sm, mode, nc, mdl->wbc_friction}; int status = 0;
+  const bool init_phase = time < 10.0;   // HierarchicalWbc.cpp:32
+  for (int e = lane; e < 36 * LDZ; e += 32) qp.Z[e] = ((e / LDZ) == (e % LDZ)) ? 1.0 : 0.0;
+  for (int i = lane; i < 36; i += 32) qp.xbar[i] = 0.0;
+  __syncwarp();
+  // level 0: min ||A0 x - b0||^2 + ||(D0 x - f0)_+||^2  — semismooth iteration on the violated set V
+  int rows0 = build_level(sm, mdl, 0, mode, variant, init_phase, lane);
+  const int nineq = 36 + 5 * nc;
+  unsigned vmask0 = 0, vmask1 = 0;   // violated set, bit per inequality (lane-uniform)
+  for (int it = 0; it < 30; ++it) {
+    int r = rows0;
+    // append violated rows
+    for (int i = 0; i < nineq; ++i) { const bool in = (i < 32) ? ((vmask0 >> i) & 1u) : ((vmask1 >> (i - 32)) & 1u); if (in) { if (r >= MAXR) { status |= ST_TOO_MANY_ROWS; break; }
+        for (int k = lane; k < 36; k += 32) qp.Ap[r * LDZ + k] = ineq_row_elem(ic, i, k); if (lane == 0) qp.bp[r] = ineq_rhs(ic, i); ++r; } }
+    __syncwarp();
+    for (int e = lane; e < r * 36; e += 32) { const int i = e / 36, c = e % 36; qp.W[c + i * LDZ] = qp.Ap[i * LDZ + c]; }
+    __syncwarp();
+    cod_lstsq(qp, qp.W, 36, r, qp.bp, qp.xbar, lane);
+    __syncwarp();
+    unsigned n0 = 0, n1 = 0;   // next violated set: strictly violated rows, plus rows of V sitting on their boundary
+    for (int i = lane; i < nineq; i += 32) { const double val = ineq_row_dot(ic, i, qp.xbar) - ineq_rhs(ic, i); const double sc = 1e-9 * (1.0 + fabs(ineq_rhs(ic, i)));
+      const bool inV = (i < 32) ? ((vmask0 >> i) & 1u) : ((vmask1 >> (i - 32)) & 1u);
+      if (val > sc || (inV && val >= -sc)) { if (i < 32) n0 |= 1u << i; else n1 |= 1u << (i - 32); } }
+    for (int o = 16; o > 0; o >>= 1) { n0 |= __shfl_xor_sync(FULL, n0, o); n1 |= __shfl_xor_sync(FULL, n1, o); }
+    if (n0 == vmask0 && n1 == vmask1) break;
+    vmask0 = n0; vmask1 = n1;
+    if (it == 29) status |= ST_ITER_CAP;
+  }
+  // optimal slack of level 0 and the null space of A0 (HoQp::buildZMatrix, HoQp.cpp:126-133)
+  for (int i = lane; i < nineq; i += 32) { const double val = ineq_row_dot(ic, i, qp.xbar) - ineq_rhs(ic, i); sm.vstar[i] = val > 0.0 ? val : 0.0; }
+  __syncwarp();
+  int off = 0, nw = 0, it1 = 0, it2 = 0;
+  {
+    for (int e = lane; e < rows0 * 36; e += 32) { const int i = e / 36, c = e % 36; qp.W[c + i * LDZ] = qp.Ap[i * LDZ + c]; }
+    __syncwarp();
+    const int k = w_qrcp(qp.W, 36, rows0, LDZ, qp.tau, qp.perm, 1e-11, lane);
+    w_apply_q_right(qp.W, 36, k, LDZ, qp.tau, qp.Z, 36, LDZ, 0, lane);
+    off = k;
+  }
+  // levels 1 and 2
+  for (int level = 1; level <= 2; ++level) {
+    const int rows = build_level(sm, mdl, level, mode, variant, init_phase, lane);
+    const int nz = 36 - off;
+    if (nz <= 0) break;                                   // trivial kernel (the reference keeps one zero column, HoQp.cpp:129)
+    status |= solve_level(sm, ic, rows, off, nw, lane, level == 1 ? it1 : it2);
+    if (level == 1) {                                    // Z <- Z * kernel(A_1 Z)
+      project_task(qp, rows, off, nz, lane);
+      const int k = w_qrcp(qp.W, nz, rows, LDZ, qp.tau, qp.perm, 1e-11, lane);
+      w_apply_q_right(qp.W, nz, k, LDZ, qp.tau, qp.Z, 36, LDZ, off, lane);
+      off += k;
+    }
+  }
+  // ---- updateCmd (WbcBase.cpp:548-563): tau = [M_j, -J_j^T] x + h_j ; cmd = [x; tau] ----
+  double* out = cmd_out + (size_t)b * 54;
+  for (int i = lane; i < 36; i += 32) out[i] = qp.xbar[i];
+  bool bad = false;
+  if (lane < NJ) { const double* Mr = sm.M + (6 + lane) * LDM; double s = sm.nle[6 + lane]; for (int k = 0; k < NQ; ++k) s += Mr[k] * qp.xbar[k]; for (int k = 0; k < 12; ++k) s -= sm.Jf[k * LDM + 6 + lane] * qp.xbar[NQ + k]; out[36 + lane] = s; bad = !isfinite(s); }
+  if (__any_sync(FULL, bad)) status |= ST_NAN;
+  if (status) status |= (it1 << 8) | (it2 << 16) | (nw << 24);   // diagnostics ride in the high bits of a failed robot's status
+  if (lane == 0) status_out[b] = status;
+}
+
+size_t wbc_smem_bytes() { return sizeof(WbcSmem) * WBC_WARPS; }
+
+void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
+                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = wbc_smem_bytes();
+  if (!configured) { cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  const int grid = (B + WBC_WARPS - 1) / WBC_WARPS;
+  wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, B, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status);
+}
+
+}  // namespace qmb

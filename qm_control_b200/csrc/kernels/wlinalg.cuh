@@ -1,0 +1,111 @@
+// Warp-level dense linear algebra on small shared-memory matrices (n <= 36): Householder QR with column
+// pivoting (rank revealing), application of Q / Q^T, triangular solves, Cholesky.  These replace the Eigen
+// calls on the reference WBC path (fullPivLu().kernel() at qm_wbc/src/HoQp.cpp:129, the dense products in
+// HoQp::buildHMatrix/buildCVector HoQp.cpp:60-90) and qpOASES' internal factorizations.
+#pragma once
+#include "dev_common.cuh"
+
+namespace qmb {
+
+// QR with column pivoting of W (n x r, column-major, leading dimension ld, r <= 32).
+// On exit: R in the upper triangle, Householder vectors below the diagonal (unit leading entry implied),
+// tau[0..k), perm[c] = original index of the column now at position c.  Returns the numerical rank k
+// (columns whose remaining norm is <= tol_rel * largest initial column norm are treated as zero).
+__device__ __forceinline__ int w_qrcp(double* W, int n, int r, int ld, double* tau, int* perm, double tol_rel, int lane) {
+  if (lane < r) perm[lane] = lane;
+  double n0 = 0.0;
+  if (lane < r) for (int i = 0; i < n; ++i) { const double x = W[i + lane * ld]; n0 += x * x; }
+  const double thresh = tol_rel * tol_rel * warp_max(n0);
+  const int kmax = n < r ? n : r; int rank = kmax;
+  __syncwarp();
+  for (int j = 0; j < kmax; ++j) {
+    double nr = -1.0; int pc = lane;
+    if (lane >= j && lane < r) { nr = 0.0; for (int i = j; i < n; ++i) { const double x = W[i + lane * ld]; nr += x * x; } }
+    warp_argmax(nr, pc);
+    if (!(nr > thresh)) { rank = j; break; }
+    if (pc != j) {
+      for (int i = lane; i < n; i += 32) { const double t = W[i + j * ld]; W[i + j * ld] = W[i + pc * ld]; W[i + pc * ld] = t; }
+      if (lane == 0) { const int t = perm[j]; perm[j] = perm[pc]; perm[pc] = t; }
+    }
+    __syncwarp();
+    const double x0 = W[j + j * ld]; const double beta = (x0 >= 0.0) ? -sqrt(nr) : sqrt(nr);
+    const double tj = (beta - x0) / beta; const double scal = 1.0 / (x0 - beta);
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) W[i + j * ld] *= scal;
+    if (lane == 0) { W[j + j * ld] = beta; tau[j] = tj; }
+    __syncwarp();
+    if (lane > j && lane < r) {
+      double* col = W + lane * ld; const double* v = W + j * ld;
+      double w = col[j]; for (int i = j + 1; i < n; ++i) w += v[i] * col[i];
+      w *= tj; col[j] -= w; for (int i = j + 1; i < n; ++i) col[i] -= w * v[i];
+    }
+    __syncwarp();
+  }
+  return rank;
+}
+
+// g <- Q^T g  (g has n entries in shared memory)
+__device__ __forceinline__ void w_apply_qt(const double* W, int n, int k, int ld, const double* tau, double* g, int lane) {
+  for (int j = 0; j < k; ++j) {
+    const double* v = W + j * ld; double part = 0.0;
+    for (int i = j + lane; i < n; i += 32) part += (i == j ? 1.0 : v[i]) * g[i];
+    const double w = tau[j] * warp_sum(part);
+    for (int i = j + lane; i < n; i += 32) g[i] -= w * (i == j ? 1.0 : v[i]);
+    __syncwarp();
+  }
+}
+// g <- Q g
+__device__ __forceinline__ void w_apply_q(const double* W, int n, int k, int ld, const double* tau, double* g, int lane) {
+  for (int j = k - 1; j >= 0; --j) {
+    const double* v = W + j * ld; double part = 0.0;
+    for (int i = j + lane; i < n; i += 32) part += (i == j ? 1.0 : v[i]) * g[i];
+    const double w = tau[j] * warp_sum(part);
+    for (int i = j + lane; i < n; i += 32) g[i] -= w * (i == j ? 1.0 : v[i]);
+    __syncwarp();
+  }
+}
+// Z[:, off:off+n] <- Z[:, off:off+n] * Q   (Z has `rows` rows, row-major, leading dimension ldz); lanes over rows
+__device__ __forceinline__ void w_apply_q_right(const double* W, int n, int k, int ld, const double* tau, double* Z, int rows, int ldz, int off, int lane) {
+  for (int j = 0; j < k; ++j) {
+    const double* v = W + j * ld; const double tj = tau[j];
+    for (int i = lane; i < rows; i += 32) {
+      double* zr = Z + i * ldz + off; double d = zr[j]; for (int c = j + 1; c < n; ++c) d += zr[c] * v[c];
+      d *= tj; zr[j] -= d; for (int c = j + 1; c < n; ++c) zr[c] -= d * v[c];
+    }
+    __syncwarp();
+  }
+}
+
+// In-place Cholesky (lower) of the n x n symmetric matrix A (row-major, ld), n <= 32.  Returns false when a pivot <= 0.
+__device__ __forceinline__ bool w_cholesky(double* A, int n, int ld, int lane) {
+  bool ok = true;
+  for (int j = 0; j < n; ++j) {
+    const double d = A[j * ld + j];
+    if (!(d > 0.0)) { ok = false; break; }
+    const double s = sqrt(d);
+    __syncwarp();
+    if (lane == j) A[j * ld + j] = s;
+    if (lane > j && lane < n) A[lane * ld + j] /= s;
+    __syncwarp();
+    if (lane > j && lane < n) { const double lij = A[lane * ld + j]; for (int c = j + 1; c <= lane; ++c) A[lane * ld + c] -= lij * A[c * ld + j]; }
+    __syncwarp();
+  }
+  return ok;
+}
+// Solve L L^T x = b in place (b in shared memory, n <= 32); L lower from w_cholesky.
+__device__ __forceinline__ void w_chol_solve(const double* L, int n, int ld, double* b, int lane) {
+  for (int j = 0; j < n; ++j) {   // forward
+    if (lane == j) b[j] /= L[j * ld + j];
+    __syncwarp();
+    if (lane > j && lane < n) b[lane] -= L[lane * ld + j] * b[j];
+    __syncwarp();
+  }
+  for (int j = n - 1; j >= 0; --j) {   // backward with L^T
+    if (lane == j) b[j] /= L[j * ld + j];
+    __syncwarp();
+    if (lane < j) b[lane] -= L[j * ld + lane] * b[j];
+    __syncwarp();
+  }
+}
+
+}  // namespace qmb

@@ -1,0 +1,176 @@
+"""Python mirror of qm::QMInterface (qm_interface/include/qm_interface/QMInterface.h:31-54) and the solver handle.
+
+QMInterface only records the three files the reference constructor takes and raises the same way on missing files
+(QMInterface.cpp:45,53,61); ``Solver`` owns one ``qmb200_handle`` (one per GPU) and exposes the C-ABI calls on numpy
+(host) or torch-cuda (device) buffers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import NX, NU, RBD, CMD, TARGET, EMAX, KMAX, Config, QmbError, dp, ip
+
+
+class QMInterface:
+    def __init__(self, taskFile=None, urdfFile=None, referenceFile=None, wbcGainsFile=None):
+        self.taskFile = taskFile or _lib.asset("qm_task.info")
+        self.urdfFile = urdfFile or _lib.asset("qm_robot.urdf")
+        self.referenceFile = referenceFile or _lib.asset("qm_reference.info")
+        self.gaitFile = _lib.asset("qm_gait.info")
+        self.wbcGainsFile = wbcGainsFile
+        for what, path in (("Task file", self.taskFile), ("URDF file", self.urdfFile), ("targetCommand file", self.referenceFile)):
+            if not os.path.exists(path):
+                raise ValueError("[QMInterface] %s not found: %s" % (what, path))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (shape, a.shape))
+    return a
+
+
+def _i32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (shape, a.shape))
+    return a
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())   # torch tensor (device pointer)
+
+
+class Solver:
+    """One qmb200_handle: batched MPC + WBC for `batch` robots on CUDA device `device`."""
+
+    def __init__(self, interface=None, batch=1, device=0, time_horizon=0.0, dt=0.0, max_nodes=0, wbc_variant=0):
+        self.lib = _lib.load_library()
+        self.interface = interface or QMInterface()
+        cfg = Config(self.interface.taskFile.encode(), self.interface.urdfFile.encode(), self.interface.referenceFile.encode(),
+                     self.interface.wbcGainsFile.encode() if self.interface.wbcGainsFile else None, batch, device, time_horizon, dt, max_nodes, wbc_variant)
+        self._cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.qmb200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise QmbError("qmb200_create failed (%d): %s" % (rc, self.lib.qmb200_last_error(None).decode()))
+        self.h = h
+        b, n, e, k = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self.lib.qmb200_get_dims(self.h, C.byref(b), C.byref(n), C.byref(e), C.byref(k))
+        self.batch, self.nmax, self.emax, self.kmax = b.value, n.value, e.value, k.value
+        mass, hor, dtt = C.c_double(), C.c_double(), C.c_double()
+        self.initial_state = np.zeros(NX); self.default_joint_state = np.zeros(18)
+        self.lib.qmb200_get_model_info(self.h, C.byref(mass), _p(self.initial_state), _p(self.default_joint_state), C.byref(hor), C.byref(dtt))
+        self.robot_mass, self.time_horizon, self.dt = mass.value, hor.value, dtt.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qmb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise QmbError("%s failed (%d): %s" % (what, rc, self.lib.qmb200_last_error(self.h).decode()))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.qmb200_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.qmb200_stream(self.h)
+
+    def joint_names(self):
+        out = []
+        for j in range(18):
+            buf = C.create_string_buffer(64); self.lib.qmb200_get_joint_name(self.h, j, buf, 64); out.append(buf.value.decode())
+        return out
+
+    # ---------------- WBC ----------------
+    def wbc_update(self, x_des, u_des, rbd, mode, period, time):
+        B = self.batch
+        x_des = _f64(x_des, (B, NX)); u_des = _f64(u_des, (B, NU)); rbd = _f64(rbd, (B, RBD)); mode = _i32(mode, (B,)); period = _f64(period, (B,)); time = _f64(time, (B,))
+        cmd = np.empty((B, CMD)); status = np.empty(B, dtype=np.int32)
+        self._chk(self.lib.qmb200_wbc_update(self.h, _p(x_des), _p(u_des), _p(rbd), _p(mode), _p(period), _p(time), _p(cmd), _p(status)), "qmb200_wbc_update")
+        return cmd, status
+
+    def wbc_update_dev(self, x_des, u_des, rbd, mode, period, time, cmd, status, stream=None):
+        self._chk(self.lib.qmb200_wbc_update_dev(self.h, _p(x_des), _p(u_des), _p(rbd), _p(mode), _p(period), _p(time), _p(cmd), _p(status), C.c_void_p(stream) if stream else None), "qmb200_wbc_update_dev")
+
+    def wbc_set_input_last(self, input_last=None):
+        self._chk(self.lib.qmb200_wbc_set_input_last(self.h, _p(_f64(input_last, (self.batch, NU))) if input_last is not None else None), "qmb200_wbc_set_input_last")
+
+    def wbc_get_input_last(self):
+        out = np.empty((self.batch, NU)); self._chk(self.lib.qmb200_wbc_get_input_last(self.h, _p(out)), "qmb200_wbc_get_input_last"); return out
+
+    # ---------------- MPC ----------------
+    def _prob(self, prob):
+        B = self.batch
+        return [_f64(prob["t0"], (B,)), _f64(prob["x0"], (B, NX)), _i32(prob["n_events"], (B,)), _f64(prob["event_times"], (B, EMAX)), _i32(prob["modes"], (B, EMAX + 1)),
+                _i32(prob["n_target"], (B,)), _f64(prob["target_times"], (B, KMAX)), _f64(prob["target_states"], (B, KMAX, TARGET))]
+
+    def mpc_solve(self, prob):
+        B, N = self.batch, self.nmax; a = self._prob(prob)
+        out = dict(n_nodes=np.zeros(B, dtype=np.int32), t=np.zeros((B, N)), event=np.zeros((B, N), dtype=np.int32), x=np.zeros((B, N, NX)), u=np.zeros((B, N, NU)),
+                   status=np.zeros(B, dtype=np.int32), step_info=np.zeros((B, 4)))
+        self._chk(self.lib.qmb200_mpc_solve(self.h, *[_p(v) for v in a], _p(out["n_nodes"]), _p(out["t"]), _p(out["event"]), _p(out["x"]), _p(out["u"]), _p(out["status"]), _p(out["step_info"])), "qmb200_mpc_solve")
+        return out
+
+    def mpc_solve_dev(self, prob_dev, stream=None):
+        keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
+        self._chk(self.lib.qmb200_mpc_solve_dev(self.h, *[_p(prob_dev[k]) for k in keys], C.c_void_p(stream) if stream else None), "qmb200_mpc_solve_dev")
+
+    def mpc_reset(self):
+        self._chk(self.lib.qmb200_mpc_reset(self.h), "qmb200_mpc_reset")
+
+    def mpc_set_solution(self, sol):
+        B, N = self.batch, self.nmax
+        self._chk(self.lib.qmb200_mpc_set_solution(self.h, _p(_i32(sol["n_nodes"], (B,))), _p(_f64(sol["t"], (B, N))), _p(_i32(sol["event"], (B, N))), _p(_f64(sol["x"], (B, N, NX))), _p(_f64(sol["u"], (B, N, NU)))), "qmb200_mpc_set_solution")
+
+    def mpc_get_solution(self):
+        B, N = self.batch, self.nmax
+        out = dict(n_nodes=np.zeros(B, dtype=np.int32), t=np.zeros((B, N)), event=np.zeros((B, N), dtype=np.int32), x=np.zeros((B, N, NX)), u=np.zeros((B, N, NU)),
+                   status=np.zeros(B, dtype=np.int32), step_info=np.zeros((B, 4)))
+        self._chk(self.lib.qmb200_mpc_get_solution(self.h, _p(out["n_nodes"]), _p(out["t"]), _p(out["event"]), _p(out["x"]), _p(out["u"]), _p(out["status"]), _p(out["step_info"])), "qmb200_mpc_get_solution")
+        return out
+
+    def policy_eval(self, t):
+        B = self.batch; t = _f64(t, (B,)); xd = np.empty((B, NX)); ud = np.empty((B, NU)); mode = np.empty(B, dtype=np.int32)
+        self._chk(self.lib.qmb200_policy_eval(self.h, _p(t), _p(xd), _p(ud), _p(mode)), "qmb200_policy_eval")
+        return xd, ud, mode
+
+    def tick(self, prob, t_eval, rbd, period):
+        B = self.batch; a = self._prob(prob); t_eval = _f64(t_eval, (B,)); rbd = _f64(rbd, (B, RBD)); period = _f64(period, (B,))
+        cmd = np.empty((B, CMD)); status = np.empty(B, dtype=np.int32)
+        self._chk(self.lib.qmb200_tick(self.h, *[_p(v) for v in a], _p(t_eval), _p(rbd), _p(period), _p(cmd), _p(status)), "qmb200_tick")
+        return cmd, status
+
+    def tick_dev(self, prob_dev, t_eval, rbd, period, cmd, status, stream=None):
+        keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
+        self._chk(self.lib.qmb200_tick_dev(self.h, *[_p(prob_dev[k]) for k in keys], _p(t_eval), _p(rbd), _p(period), _p(cmd), _p(status), C.c_void_p(stream) if stream else None), "qmb200_tick_dev")
+
+    # ---------------- utilities ----------------
+    def centroidal_state_from_rbd(self, rbd):
+        rbd = _f64(rbd); n = rbd.shape[0]; x = np.empty((n, NX))
+        self._chk(self.lib.qmb200_centroidal_state_from_rbd(self.h, n, _p(rbd), _p(x)), "qmb200_centroidal_state_from_rbd"); return x
+
+
+def gait_schedule(gait_name, t_start, lo, hi, gait_file=None):
+    """GaitSchedule tiling of a gait.info template → (event_times[EMAX], mode_sequence[EMAX+1], n_events)."""
+    lib = _lib.load_library(); ev = np.zeros(EMAX); md = np.full(EMAX + 1, 15, dtype=np.int32)
+    n = lib.qmb200_gait_schedule((gait_file or _lib.asset("qm_gait.info")).encode(), gait_name.encode(), C.c_double(t_start), C.c_double(lo), C.c_double(hi), _p(ev), _p(md))
+    if n < 0:
+        raise QmbError("qmb200_gait_schedule failed: " + lib.qmb200_last_error(None).decode())
+    return ev, md, n

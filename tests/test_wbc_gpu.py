@@ -1,0 +1,90 @@
+"""Parity of the CUDA WBC path (through the C-ABI) against the CPU oracle — the reference's WbcBase::update →
+HierarchicalWbc::update → HoQp → updateCmd chain (qm_wbc/src/*.cpp).  Tolerance: 1e-5 relative (BASELINE.json north_star),
+measured per robot as max|cuda - oracle| / max(1, max|oracle|) over the 54-vector."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _rel_err(a, b):
+    return np.max(np.abs(a - b), axis=1) / np.maximum(1.0, np.max(np.abs(b), axis=1))
+
+
+def _run(oracle, config, B, variant, time, gait=None, perturb_u=True):
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    solver = q.Solver(batch=B, wbc_variant=variant)
+    prob, wbc = synthetic.make_batch(np.arange(B), config=config, gait=gait)
+    x_des, u_des, mode = synthetic.nominal_wbc_inputs(prob, solver.robot_mass)
+    if perturb_u:   # desired forces / joint velocities away from the nominal so every task row is exercised
+        u_des = u_des + synthetic.uniform(77, np.arange(B), 1, 30, -1.0, 1.0) * np.r_[np.full(12, 5.0), np.full(18, 0.2)]
+        for b in range(B):
+            for f in range(4):
+                if not (mode[b] >> (3 - f)) & 1:
+                    u_des[b, 3 * f:3 * f + 3] = 0.0
+    il = synthetic.uniform(78, np.arange(B), 2, 30, -0.1, 0.1)
+    tarr = np.full(B, time)
+    solver.wbc_set_input_last(il)
+    cmd, status = solver.wbc_update(x_des, u_des, wbc["rbd"], mode, wbc["period"], tarr)
+    ref, il_ref = oracle.wbc_update_batch(x_des, u_des, wbc["rbd"], mode, wbc["period"], tarr, il, variant=variant, nthreads=8)
+    assert np.all(status == 0), "status flags: %s" % np.unique(status)
+    np.testing.assert_array_equal(solver.wbc_get_input_last(), u_des)   # WbcBase::inputLast_ update (WbcBase.cpp:213)
+    err = _rel_err(cmd, ref)
+    assert err.max() < RTOL, "max rel err %.3e at robot %d (mode %d)" % (err.max(), err.argmax(), mode[err.argmax()])
+    return cmd, ref, mode
+
+
+def test_wbc_stance_matches_oracle(oracle):
+    _run(oracle, config=3, B=256, variant=0, time=12.0)
+
+
+def test_wbc_init_branch_matches_oracle(oracle):
+    """time < 10 → task0 → taskInit → task2 (HierarchicalWbc.cpp:32-37)."""
+    _run(oracle, config=3, B=64, variant=0, time=3.0)
+
+
+def test_wbc_trot_matches_oracle(oracle):
+    cmd, ref, mode = _run(oracle, config=4, B=256, variant=0, time=12.0)
+    assert set(np.unique(mode)) <= {6, 9, 15}
+
+
+def test_wbc_mixed_gaits_match_oracle(oracle):
+    """stance / trot / flying trot incl. zero-contact modes (n_c in {4,2,0})."""
+    cmd, ref, mode = _run(oracle, config=5, B=384, variant=0, time=12.0)
+    assert 0 in mode and 15 in mode
+
+
+def test_wbc_mpc_variant_matches_oracle(oracle):
+    _run(oracle, config=5, B=192, variant=1, time=12.0)
+
+
+def test_wbc_equation_of_motion_and_limits(oracle):
+    """Solver-independent properties: floating-base EoM residual, contact constraint, friction pyramid, torque limits."""
+    cmd, ref, mode = _run(oracle, config=4, B=128, variant=0, time=12.0)
+    from qm_control_b200 import synthetic
+    prob, wbc = synthetic.make_batch(np.arange(128), config=4)
+    eff = oracle.model_info()["effort"]; lim = np.r_[np.tile(eff[:3], 4), eff[12:]]
+    for b in range(0, 128, 8):
+        rbd = wbc["rbd"][b]; q = np.r_[rbd[3:6], rbd[0:3], rbd[6:24]]
+        z, y = q[3], q[4]; T = np.array([[0, -np.sin(z), np.cos(y) * np.cos(z)], [0, np.cos(z), np.cos(y) * np.sin(z)], [1, 0, -np.sin(y)]])
+        v = np.r_[rbd[27:30], np.linalg.solve(T, rbd[24:27]), rbd[30:48]]
+        r = oracle.rbd(q, v); x = cmd[b, :36]; tau = cmd[b, 36:]
+        res = r["M"] @ x[:24] + r["nle"] - r["Jfoot"].T @ x[24:] - np.r_[np.zeros(6), tau]
+        assert np.max(np.abs(res)) < 1e-6
+        assert np.all(np.abs(tau) <= lim + 1e-6)
+        for f in range(4):
+            F = x[24 + 3 * f:27 + 3 * f]
+            if (mode[b] >> (3 - f)) & 1:
+                assert F[2] >= -1e-7 and abs(F[0]) <= 0.3 * F[2] + 1e-6 and abs(F[1]) <= 0.3 * F[2] + 1e-6
+                acc = r["Jfoot"][3 * f:3 * f + 3] @ x[:24] + r["dJfoot"][3 * f:3 * f + 3] @ v
+                assert np.max(np.abs(acc)) < 1e-6
+            else:
+                assert np.max(np.abs(F)) < 1e-9
+
+
+def test_wbc_batch_one(oracle):
+    """B = 1 must work (plugin use, config 1)."""
+    _run(oracle, config=1, B=1, variant=0, time=12.0)
