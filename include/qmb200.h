@@ -120,6 +120,9 @@ int qmb200_centroidal_state_from_rbd(const qmb200_handle* h, int32_t n, const do
 int qmb200_gait_schedule(const char* gait_file, const char* gait_name, double t_start, double lo, double hi,
                          double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
 
+/* diagnostics: the QP step (dx, du) of the last solve and per-robot scalars [armijo, baseline cost, dyn SSE, eq SSE, |dx|, |du|, -, -] */
+int qmb200_debug_get_step(qmb200_handle* h, double* dx /*[B][NMAX][30]*/, double* du /*[B][NMAX][30]*/, double* robot /*[B][8]*/);
+
 /* number of kernels this library launched since create (bench.py's gpu_launches) */
 int64_t qmb200_launch_count(const qmb200_handle* h);
 /* stream the handle launches on (cudaStream_t as void*) */

@@ -1,0 +1,285 @@
+// Per-node device functions of the MPC path (one warp per node): centroidal flow map with ANALYTIC Jacobians,
+// cost terms and equality-constraint linearisation.  They restate, for the SRBD quadruped-manipulator,
+//   PinocchioCentroidalDynamicsAD behind QMDynamicsAD (qm_interface/src/dynamics/QMDynamicsAD.cpp:22-33),
+//   LeggedRobotStateInputQuadraticCost (include/qm_interface/cost/LeggedRobotQuadraticTrackingCost.h:34-40),
+//   EndEffectorConstraint soft cost (src/constraint/EndEffectorConstraint.cpp:36-113, QMInterface.cpp:147-172),
+//   arm joint soft box (QMInterface.cpp:177-259), friction-cone soft constraint (QMInterface.cpp:344-358),
+//   ZeroForce / ZeroVelocity / NormalVelocity equality constraints (QMInterface.cpp:116-131,
+//   NormalVelocityConstraintCppAd.cpp:37-66, QMPreComputation.cpp:50-71).
+// The reference differentiates these with CppAD tapes; here the derivatives are written out by hand
+// (the sparsity of the SRBD model is what makes the per-node work small enough for one warp).
+#pragma once
+#include "dev_common.cuh"
+#include "rbd.cuh"
+
+namespace qmb {
+
+constexpr int MU = 18;      // max projected input dimension (30 - 12 equality rows in stance)
+constexpr int MAXDEP = 16;  // max dependent inputs (fly: 4 x (3 forces + 1 joint))
+constexpr double WEAK_EPS = 1e-6;   // ocs2 numeric_traits::weakEpsilon: interval start/end shift at event nodes [upstream]
+
+struct PointWs {
+  KinWs kin;
+  double x[NX], u[NU], f[NX];
+  double Ar[9 * NX];          // rows 3:12 of df/dx
+  double Bh[3 * 12];          // rows 3:6, cols 0:12 of df/du
+  double T[9], Tinv[9], W[9], c[3], rcom[3], omega[3], thd[3], dom[3][3];
+  double Mpc[9], Mtw[9], vp[3][3], vt[3][3], hth[3][3];
+  double pf[4][3], d[4][3], Jl[4][9], al[4][9];   // Jl[i][3*j + a]: component a of leg-Jacobian column j of foot i
+};
+
+__device__ __forceinline__ int foot_of_leg_joint(const DevModel* __restrict__ mdl, int j) { const int first = 3 * (j / 3); for (int i = 0; i < 4; ++i) if (mdl->foot_leg[i] == first) return i; return -1; }
+
+// Evaluate the flow map (and its Jacobian rows if with_jac) at (ws->x, ws->u).
+template <bool with_jac>
+__device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, PointWs* ws, int lane) {
+  rbd_kinematics<false>(mdl, ws->x + 6, (const double*)nullptr, &ws->kin, lane);
+  const double m = mdl->total_mass;
+  if (lane == 0) {
+    const double* R = ws->kin.R[0]; const double z = ws->x[9], y = ws->x[10];
+    euler_rate_map(z, y, ws->T); inv3(ws->T, ws->Tinv);
+    double RIi[9]; matmul3(R, mdl->I_nom_inv, RIi); matmul3_nt(RIi, R, ws->W); for (int i = 0; i < 9; ++i) ws->W[i] *= m;
+    matvec3(R, mdl->c_nom, ws->c); for (int a = 0; a < 3; ++a) ws->rcom[a] = ws->x[6 + a] - ws->c[a];
+    const double* ha = ws->x + 3; matvec3(ws->W, ha, ws->omega); matvec3(ws->Tinv, ws->omega, ws->thd);
+    if (with_jac) {
+      double sz, cz, sy, cy; sincos(z, &sz, &cz); sincos(y, &sy, &cy);
+      const double* om = ws->omega; const double* th = ws->thd;
+      const double dT[3][3] = {{-cz * th[1] - cy * sz * th[2], -sz * th[1] + cy * cz * th[2], 0.0}, {-sy * cz * th[2], -sy * sz * th[2], -cy * th[2]}, {0.0, 0.0, 0.0}};
+      for (int k = 0; k < 3; ++k) {
+        const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double t1[3], t2[3], t3[3];
+        cross3(Tk, om, t1); cross3(Tk, ha, t2); matvec3(ws->W, t2, t3);
+        for (int a = 0; a < 3; ++a) ws->dom[k][a] = t1[a] - t3[a];                       // d omega / d theta_k
+        double tc[3]; cross3(Tk, ws->c, tc); cross3(ws->dom[k], ws->c, ws->vp[k]); cross3_add(om, tc, ws->vp[k]);   // d(omega x c)/d theta_k
+        const double tmp[3] = {ws->dom[k][0] - dT[k][0], ws->dom[k][1] - dT[k][1], ws->dom[k][2] - dT[k][2]}; matvec3(ws->Tinv, tmp, ws->vt[k]);
+      }
+      const double* c = ws->c; const double Sc[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+      matmul3(Sc, ws->W, ws->Mpc); for (int i = 0; i < 9; ++i) ws->Mpc[i] = -ws->Mpc[i];
+      matmul3(ws->Tinv, ws->W, ws->Mtw);
+    }
+  }
+  __syncwarp();
+  if (lane < 4) {
+    const int i = lane; const int body = mdl->foot_body[i]; double pl[3] = {mdl->foot_p[i][0], mdl->foot_p[i][1], mdl->foot_p[i][2]}, pw[3];
+    matvec3(ws->kin.R[body], pl, pw); for (int a = 0; a < 3; ++a) { pw[a] += ws->kin.p[body][a]; ws->pf[i][a] = pw[a]; ws->d[i][a] = pw[a] - ws->rcom[a]; }
+    const int first = mdl->foot_leg[i];
+    for (int j = 0; j < 3; ++j) { const double* S = ws->kin.S[6 + first + j]; const double* o = ws->kin.p[first + j + 1]; const double r[3] = {pw[0] - o[0], pw[1] - o[1], pw[2] - o[2]}; double col[3]; cross3(S, r, col);
+      for (int a = 0; a < 3; ++a) { ws->Jl[i][3 * j + a] = col[a]; ws->al[i][3 * j + a] = S[a]; } }
+    if (with_jac) { for (int a = 0; a < 3; ++a) { const double ea[3] = {a == 0 ? 1.0 : 0.0, a == 1 ? 1.0 : 0.0, a == 2 ? 1.0 : 0.0}; double col[3]; cross3(ws->d[i], ea, col); for (int r = 0; r < 3; ++r) ws->Bh[r * 12 + 3 * i + a] = col[r] / m; } }
+  }
+  __syncwarp();
+  if (with_jac && lane < 3) {   // sum_i (T_k x d_i) x F_i / m
+    const int k = lane; const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double acc[3] = {0, 0, 0};
+    for (int i = 0; i < 4; ++i) { double t[3]; cross3(Tk, ws->d[i], t); cross3_add(t, ws->u + 3 * i, acc); }
+    for (int a = 0; a < 3; ++a) ws->hth[k][a] = acc[a] / m;
+  }
+  if (lane < NX) {
+    double val;
+    if (lane < 3) { val = (ws->u[lane] + ws->u[3 + lane] + ws->u[6 + lane] + ws->u[9 + lane]) / m + (lane == 2 ? -9.81 : 0.0); }
+    else if (lane < 6) { const int a = lane - 3; double acc = 0.0; for (int i = 0; i < 4; ++i) { const double* d = ws->d[i]; const double* F = ws->u + 3 * i; acc += (a == 0) ? d[1] * F[2] - d[2] * F[1] : (a == 1 ? d[2] * F[0] - d[0] * F[2] : d[0] * F[1] - d[1] * F[0]); } val = acc / m; }
+    else if (lane < 9) { const int a = lane - 6; const double* o = ws->omega; const double* c = ws->c; const double oc = (a == 0) ? o[1] * c[2] - o[2] * c[1] : (a == 1 ? o[2] * c[0] - o[0] * c[2] : o[0] * c[1] - o[1] * c[0]); val = ws->x[a] + oc; }
+    else if (lane < 12) val = ws->thd[lane - 9];
+    else val = ws->u[lane];
+    ws->f[lane] = val;
+  }
+  __syncwarp();
+  if (with_jac) {
+    for (int e = lane; e < 9 * NX; e += 32) {
+      const int r = e / NX, col = e % NX; double v = 0.0;
+      if (r < 3) {
+        if (col >= 9 && col < 12) v = ws->hth[col - 9][r];
+        else if (col >= 12 && col < 24) { const int j = col - 12; const int i = foot_of_leg_joint(mdl, j); const double* J = ws->Jl[i] + 3 * (j % 3); const double* F = ws->u + 3 * i;
+          v = ((r == 0) ? J[1] * F[2] - J[2] * F[1] : (r == 1 ? J[2] * F[0] - J[0] * F[2] : J[0] * F[1] - J[1] * F[0])) / m; }
+      } else if (r < 6) {
+        const int a = r - 3; if (col < 3) v = (a == col) ? 1.0 : 0.0; else if (col < 6) v = ws->Mpc[3 * a + col - 3]; else if (col >= 9 && col < 12) v = ws->vp[col - 9][a];
+      } else {
+        const int a = r - 6; if (col >= 3 && col < 6) v = ws->Mtw[3 * a + col - 3]; else if (col >= 9 && col < 12) v = ws->vt[col - 9][a];
+      }
+      ws->Ar[e] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- reference signals -------------------------------------------------------------------------------
+// ocs2::lookup::findIndexInTimeArray (std::lower_bound)
+__device__ __forceinline__ int lower_bound_idx(const double* a, int n, double t) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < t) lo = mid + 1; else hi = mid; } return lo; }
+__device__ __forceinline__ int mode_at_time(const double* ev, const int32_t* modes, int ne, double t) { return modes[lower_bound_idx(ev, ne, t)]; }
+// ocs2::LinearInterpolation::timeSegment
+__device__ __forceinline__ void time_segment(const double* times, int n, double t, int& index, double& alpha) {
+  if (n <= 1) { index = 0; alpha = 1.0; return; }
+  const int part = lower_bound_idx(times, n, t); int idx = (part != 0 || t != times[0]) ? part - 1 : 0; const int last = n - 1;
+  if (idx >= 0) {
+    if (idx < last) { const double len = times[idx + 1] - times[idx], till = times[idx + 1] - t; index = idx; alpha = (len > 2.0 * 2.220446049250313e-16) ? till / len : (till > 0.5 * len ? 1.0 : 0.0); return; }
+    index = (last - 1 > 0) ? last - 1 : 0; alpha = 0.0; return;
+  }
+  index = 0; alpha = 1.0;
+}
+// SwingTrajectoryPlanner::getZvelocityConstraint / getZpositionConstraint [upstream]: status=false when the swing phase is not enclosed
+__device__ __forceinline__ bool swing_reference(const DevModel* __restrict__ mdl, const double* ev, const int32_t* modes, int ne, int leg, double t, double& zp, double& zv) {
+  const int np = ne + 1; const int p = lower_bound_idx(ev, ne, t); zp = 0.0; zv = 0.0;
+  if (contact_flag(modes[p], leg)) return true;
+  int start = -1; for (int ip = p - 1; ip >= 0; --ip) if (contact_flag(modes[ip], leg)) { start = ip; break; }
+  int fin = np - 1; for (int ip = p + 1; ip < np; ++ip) if (contact_flag(modes[ip], leg)) { fin = ip - 1; break; }
+  if (start < 0 || fin >= np - 1) return false;
+  const double t0 = ev[start], t1 = ev[fin]; const double scaling = fmin(1.0, (t1 - t0) / mdl->swing_time_scale); const double tm = 0.5 * (t0 + t1), zm = scaling * mdl->swing_height;
+  double ta, pa, va, tb, pb, vb;
+  if (t < tm) { ta = t0; pa = 0.0; va = scaling * mdl->lift_off_velocity; tb = tm; pb = zm; vb = 0.0; } else { ta = tm; pa = zm; va = 0.0; tb = t1; pb = 0.0; vb = scaling * mdl->touch_down_velocity; }
+  const double dtt = tb - ta, dp = pb - pa, dv = vb - va; const double c0 = pa, c1 = va * dtt, c2 = -(3.0 * va + dv) * dtt + 3.0 * dp, c3 = (2.0 * va + dv) * dtt - 2.0 * dp; const double tn = (t - ta) / dtt;
+  zp = ((c3 * tn + c2) * tn + c1) * tn + c0; zv = ((3.0 * c3 * tn + 2.0 * c2) * tn + c1) / dtt; return true;
+}
+// ocs2 RelaxedBarrierPenalty [upstream]
+__device__ __forceinline__ void relaxed_barrier(double mu, double delta, double h, double& p0, double& p1, double& p2) {
+  if (h > delta) { p0 = -mu * log(h); p1 = -mu / h; p2 = mu / (h * h); }
+  else { const double t = (h - 2.0 * delta) / delta; p0 = mu * (-log(delta) + 0.5 * t * t - 0.5); p1 = mu * (h - 2.0 * delta) / (delta * delta); p2 = mu / (delta * delta); }
+}
+
+// Target trajectory references at time t: xnom[30] (TargetTrajectories::getDesiredState().head(30)), EE pose reference
+// (EndEffectorConstraint::interpolateEndEffectorPose, EndEffectorConstraint.cpp:82-113; Eigen slerp semantics).  All lanes compute the same
+// scalars; lane < 30 returns its own xnom component.
+struct TargetRef { double xnom; double pref[3]; double qref[4]; };
+__device__ __forceinline__ TargetRef target_reference(const double* tt, const double* ts /*[K][37]*/, int nk, double t, int lane) {
+  TargetRef r; int idx; double a; time_segment(tt, nk, t, idx, a);
+  const double* l = ts + (size_t)idx * 37; const double* rr = ts + (size_t)((nk > 1) ? idx + 1 : idx) * 37;
+  if (nk <= 1) a = 1.0;
+  r.xnom = (lane < NX) ? a * l[lane] + (1.0 - a) * rr[lane] : 0.0;
+  for (int i = 0; i < 3; ++i) r.pref[i] = a * l[30 + i] + (1.0 - a) * rr[30 + i];
+  if (nk > 1) {
+    const double* ql = l + 33; const double* qr = rr + 33; const double tq = 1.0 - a; double d = 0.0; for (int i = 0; i < 4; ++i) d += ql[i] * qr[i];
+    const double ad = fabs(d); double s0, s1;
+    if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - tq; s1 = tq; } else { const double th = acos(ad), st = sin(th); s0 = sin((1.0 - tq) * th) / st; s1 = sin(tq * th) / st; }
+    if (d < 0.0) s1 = -s1; for (int i = 0; i < 4; ++i) r.qref[i] = s0 * ql[i] + s1 * qr[i];
+  } else { for (int i = 0; i < 4; ++i) r.qref[i] = l[33 + i]; }
+  return r;
+}
+
+// ---- cost --------------------------------------------------------------------------------------------
+struct QuadWs { double Qf[NX * 31], Rf[NU * 31], qf[NX], rf[NU]; };   // quadratic model (unscaled by dt), leading dimension 31
+struct CostWs { double Je[6 * 12], e[6], quat[4], pee[3]; };
+__device__ __forceinline__ int ee_col(int i) { return i < 6 ? 6 + i : 18 + i; }   // 12 state columns the EE pose depends on: p(6:9), theta(9:12), arm(24:30)
+
+// End-effector error e = [p_ee - p_ref; quaternionDistance(q_ee, q_ref)] and (optionally) its Jacobian columns.  ws must hold the kinematics at x.
+template <bool with_jac>
+__device__ __forceinline__ void ee_error(const DevModel* __restrict__ mdl, const PointWs* ws, CostWs* cw, const TargetRef& ref, int lane) {
+  const int body = mdl->ee_body;
+  if (lane == 0) {
+    double R[9]; matmul3(ws->kin.R[body], mdl->ee_R, R); double pl[3] = {mdl->ee_p[0], mdl->ee_p[1], mdl->ee_p[2]}, pw[3]; matvec3(ws->kin.R[body], pl, pw);
+    for (int a = 0; a < 3; ++a) { pw[a] += ws->kin.p[body][a]; cw->pee[a] = pw[a]; cw->e[a] = pw[a] - ref.pref[a]; }
+    // rotation → quaternion (w,x,y,z); sign free (quadratic penalty), same q used for e and its Jacobian
+    double q[4]; const double tr = R[0] + R[4] + R[8];
+    if (tr > 0.0) { const double s = sqrt(tr + 1.0) * 2.0; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+    else if (R[0] > R[4] && R[0] > R[8]) { const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+    else if (R[4] > R[8]) { const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+    else { const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+    for (int i = 0; i < 4; ++i) cw->quat[i] = q[i];
+    const double* rv = ref.qref; const double rw = ref.qref[3]; const double* qv = q + 1; double cr[3]; cross3(qv, rv, cr);
+    for (int a = 0; a < 3; ++a) cw->e[3 + a] = q[0] * rv[a] - rw * qv[a] + cr[a];   // ocs2 quaternionDistance(q, qRef) [upstream]
+  }
+  __syncwarp();
+  if (with_jac && lane < 12) {
+    // column lane: angular direction n and linear velocity of the EE point for a unit rate of the coordinate
+    double n[3] = {0, 0, 0}, lin[3] = {0, 0, 0};
+    if (lane < 3) { lin[lane] = 1.0; }
+    else if (lane < 6) { const int k = lane - 3; n[0] = ws->T[k]; n[1] = ws->T[3 + k]; n[2] = ws->T[6 + k]; const double r[3] = {cw->pee[0] - ws->x[6], cw->pee[1] - ws->x[7], cw->pee[2] - ws->x[8]}; cross3(n, r, lin); }
+    else { const int j = 12 + lane - 6; const double* S = ws->kin.S[6 + j]; const double* o = ws->kin.p[j + 1]; n[0] = S[0]; n[1] = S[1]; n[2] = S[2]; const double r[3] = {cw->pee[0] - o[0], cw->pee[1] - o[1], cw->pee[2] - o[2]}; cross3(n, r, lin); }
+    const double* q = cw->quat; const double* qv = q + 1; const double* rv = ref.qref; const double rw = ref.qref[3];
+    // qdot_w = -1/2 n.qv ; qdot_v = 1/2 (qw n + n x qv) ; de = qdot_w rv - rw qdot_v + qdot_v x rv
+    const double dw = -0.5 * dot3(n, qv); double dv[3]; cross3(n, qv, dv); for (int a = 0; a < 3; ++a) dv[a] = 0.5 * (q[0] * n[a] + dv[a]);
+    double cr[3]; cross3(dv, rv, cr);
+    for (int a = 0; a < 3; ++a) { cw->Je[a * 12 + lane] = lin[a]; cw->Je[(3 + a) * 12 + lane] = dw * rv[a] - rw * dv[a] + cr[a]; }
+  }
+  __syncwarp();
+}
+
+// Intermediate (or terminal) cost value; when with_quad also the quadratic model in cw (NOT scaled by dt).  `flags` = contact flags bitmask (bit i = foot i).
+// Returns the cost value (lane-uniform).
+template <bool with_quad>
+__device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, const PointWs* ws, CostWs* cw, QuadWs* qw, const TargetRef& ref, int flagmask, bool terminal, int lane) {
+  double value = 0.0;
+  if (with_quad) { for (int e = lane; e < NX * 31; e += 32) { qw->Qf[e] = 0.0; qw->Rf[e] = 0.0; } if (lane < NX) { qw->qf[lane] = 0.0; qw->rf[lane] = 0.0; } __syncwarp(); }
+  int nst = 0; for (int i = 0; i < 4; ++i) nst += (flagmask >> i) & 1;
+  if (!terminal) {
+    // tracking cost: 1/2 dx'Q dx + 1/2 du'R du, u_nom = weightCompensatingInput(contact flags)
+    double dx = 0.0, du = 0.0;
+    if (lane < NX) { dx = ws->x[lane] - ref.xnom; double un = 0.0; if (lane < 12 && (lane % 3) == 2 && ((flagmask >> (lane / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du = ws->u[lane] - un; }
+    double qd = 0.0, rd = 0.0;
+    for (int j = 0; j < NX; ++j) { const double dxj = __shfl_sync(FULL, dx, j), duj = __shfl_sync(FULL, du, j);
+      if (lane < NX) { const double qij = mdl->Q[lane * NX + j], rij = mdl->R[lane * NU + j]; qd += qij * dxj; rd += rij * duj; if (with_quad) { qw->Qf[lane * 31 + j] = qij; qw->Rf[lane * 31 + j] = rij; } } }
+    value += 0.5 * warp_sum(lane < NX ? dx * qd + du * rd : 0.0);
+    if (with_quad && lane < NX) { qw->qf[lane] = qd; qw->rf[lane] = rd; }
+    __syncwarp();
+  }
+  // end-effector soft constraint (quadratic penalty, Gauss-Newton)
+  ee_error<with_quad>(mdl, ws, cw, ref, lane);
+  {
+    const double mup = terminal ? mdl->mu_final_ee_pos : mdl->mu_ee_pos, muo = terminal ? mdl->mu_final_ee_ori : mdl->mu_ee_ori;
+    double v = 0.0; for (int r = 0; r < 6; ++r) v += 0.5 * (r < 3 ? mup : muo) * cw->e[r] * cw->e[r]; value += v;
+    if (with_quad) {
+      for (int e = lane; e < 144; e += 32) { const int i = e / 12, j = e % 12; double s = 0.0; for (int r = 0; r < 6; ++r) s += (r < 3 ? mup : muo) * cw->Je[r * 12 + i] * cw->Je[r * 12 + j]; qw->Qf[ee_col(i) * 31 + ee_col(j)] += s; }
+      if (lane < 12) { double s = 0.0; for (int r = 0; r < 6; ++r) s += (r < 3 ? mup : muo) * cw->e[r] * cw->Je[r * 12 + lane]; qw->qf[ee_col(lane)] += s; }
+      __syncwarp();
+    }
+  }
+  if (!terminal) {
+    // arm joint position (state 24:30) and velocity (input 24:30) soft box, relaxed log barrier
+    double bv = 0.0;
+    if (lane < 12) {
+      const int i = lane % 6; const bool pos = lane < 6; const double val = pos ? ws->x[24 + i] : ws->u[24 + i];
+      const double lo = pos ? mdl->arm_pos_lower[i] : mdl->arm_vel_lower[i], hi = pos ? mdl->arm_pos_upper[i] : mdl->arm_vel_upper[i];
+      const double mu = pos ? mdl->pos_limit_mu : mdl->vel_limit_mu, de = pos ? mdl->pos_limit_delta : mdl->vel_limit_delta;
+      double a0, a1, a2, b0, b1, b2; relaxed_barrier(mu, de, val - lo, a0, a1, a2); relaxed_barrier(mu, de, hi - val, b0, b1, b2);
+      bv = a0 + b0;
+      if (with_quad) { if (pos) { qw->qf[24 + i] += a1 - b1; qw->Qf[(24 + i) * 31 + 24 + i] += a2 + b2; } else { qw->rf[24 + i] += a1 - b1; qw->Rf[(24 + i) * 31 + 24 + i] += a2 + b2; } }
+    }
+    // friction cone soft constraints of the stance feet; hessianDiagonalShift acts on every state and input diagonal [upstream FrictionConeConstraint]
+    double shift = 0.0;
+    if (lane >= 12 && lane < 16) {
+      const int i = lane - 12;
+      if ((flagmask >> i) & 1) {
+        const double Fx = ws->u[3 * i], Fy = ws->u[3 * i + 1], Fz = ws->u[3 * i + 2]; const double n2 = Fx * Fx + Fy * Fy + mdl->friction_reg, n = sqrt(n2), n32 = n * n2;
+        const double h = mdl->friction_mu * Fz - n; double p0, p1, p2; relaxed_barrier(mdl->friction_barrier_mu, mdl->friction_barrier_delta, h, p0, p1, p2); bv = p0;
+        if (with_quad) {
+          const double g[3] = {-Fx / n, -Fy / n, mdl->friction_mu}; const double H2[9] = {-(Fy * Fy + mdl->friction_reg) / n32, Fx * Fy / n32, 0, Fx * Fy / n32, -(Fx * Fx + mdl->friction_reg) / n32, 0, 0, 0, 0};
+          for (int a = 0; a < 3; ++a) { qw->rf[3 * i + a] += p1 * g[a]; for (int b = 0; b < 3; ++b) qw->Rf[(3 * i + a) * 31 + 3 * i + b] += p2 * g[a] * g[b] + p1 * H2[3 * a + b]; }
+          shift = -p1 * mdl->friction_hess_shift;
+        }
+      }
+    }
+    value += warp_sum(bv);
+    if (with_quad) { shift = warp_sum(shift); __syncwarp(); if (lane < NX) { qw->Qf[lane * 31 + lane] += shift; qw->Rf[lane * 31 + lane] += shift; } }
+  }
+  __syncwarp();
+  return value;
+}
+
+// ---- equality constraints ---------------------------------------------------------------------------
+struct ConWs {
+  double C[4][3][NX];   // dg/dx rows of foot i (stance: 3 rows; swing: row 2 only)
+  double e[4][3];       // constraint values (stance: foot velocity; swing: e[i][2] = v_z - zdot_ref)
+};
+// foot velocity v = h_lin + omega x d + sum_j Jl_j qd_j and (optionally) its state Jacobian; lanes 0..3 (one per foot)
+template <bool with_jac>
+__device__ __forceinline__ void foot_velocity(const DevModel* __restrict__ mdl, const PointWs* ws, ConWs* cn, int lane) {
+  if (lane < 4) {
+    const int i = lane; const int first = mdl->foot_leg[i]; const double* d = ws->d[i]; const double* om = ws->omega;
+    double qd[3] = {ws->u[12 + first], ws->u[12 + first + 1], ws->u[12 + first + 2]};
+    double w[3] = {0, 0, 0}; for (int j = 0; j < 3; ++j) for (int a = 0; a < 3; ++a) w[a] += ws->Jl[i][3 * j + a] * qd[j];
+    double v[3]; cross3(om, d, v); for (int a = 0; a < 3; ++a) { v[a] += ws->x[a] + w[a]; cn->e[i][a] = v[a]; }
+    if (with_jac) {
+      for (int a = 0; a < 3; ++a) for (int c = 0; c < NX; ++c) cn->C[i][a][c] = 0.0;
+      for (int a = 0; a < 3; ++a) cn->C[i][a][a] = 1.0;
+      const double Sd[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0}; double SW[9]; matmul3(Sd, ws->W, SW);
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cn->C[i][a][3 + b] = -SW[3 * a + b];
+      for (int k = 0; k < 3; ++k) { const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double t[3], col[3]; cross3(ws->dom[k], d, col); cross3(Tk, d, t); cross3_add(om, t, col); cross3_add(Tk, w, col); for (int a = 0; a < 3; ++a) cn->C[i][a][9 + k] = col[a]; }
+      for (int j = 0; j < 3; ++j) {
+        const double* Jj = ws->Jl[i] + 3 * j; const double* aj = ws->al[i] + 3 * j; double above[3] = {0, 0, 0}, below[3] = {0, 0, 0};
+        for (int l = j + 1; l < 3; ++l) for (int a = 0; a < 3; ++a) above[a] += ws->Jl[i][3 * l + a] * qd[l];
+        for (int l = 0; l <= j; ++l) for (int a = 0; a < 3; ++a) below[a] += ws->al[i][3 * l + a] * qd[l];
+        double col[3]; cross3(om, Jj, col); cross3_add(aj, above, col); cross3_add(below, Jj, col);
+        for (int a = 0; a < 3; ++a) cn->C[i][a][12 + first + j] = col[a];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace qmb

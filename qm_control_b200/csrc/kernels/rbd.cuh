@@ -37,7 +37,8 @@ __device__ __forceinline__ double dot6(const double* a, const double* b) { retur
 
 // Pass 1: kinematics (+ optional velocities / bias accelerations).  q,v are in shared memory (24 each).
 // Lane L < 19 owns body L.  with_vel: 0 = positions only, 1 = V and A as well.
-__device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl, const double* q, const double* v, RbdWs* ws, int lane, bool with_vel) {
+template <bool with_vel, class WS>
+__device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl, const double* q, const double* v, WS* ws, int lane) {
   // base (lane 0) and the 6 base columns of S
   if (lane == 0) {
     double R[9]; rot_zyx(q[3], q[4], q[5], R);
@@ -52,7 +53,7 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
       const double w[3] = {T[k], T[3 + k], T[6 + k]}; double vo[3]; cross3(pb, w, vo);   // euler-rate columns: w = T[:,k], vO = p x w
       ws->S[3 + k][0] = w[0]; ws->S[3 + k][1] = w[1]; ws->S[3 + k][2] = w[2]; ws->S[3 + k][3] = vo[0]; ws->S[3 + k][4] = vo[1]; ws->S[3 + k][5] = vo[2];
     }
-    if (with_vel) {
+    if constexpr (with_vel) {
       const double ed[3] = {v[3], v[4], v[5]}; double w[3]; matvec3(T, ed, w);
       double wd[3]; euler_rate_map_dot_times(q[3], q[4], ed, wd);
       const double pd[3] = {v[0], v[1], v[2]};
@@ -83,7 +84,7 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
       ws->p[body][0] = pw[0]; ws->p[body][1] = pw[1]; ws->p[body][2] = pw[2];
       const double a[3] = {Rw[ax], Rw[3 + ax], Rw[6 + ax]}; double vo[3]; cross3(pw, a, vo);
       double* Sc = ws->S[6 + j]; Sc[0] = a[0]; Sc[1] = a[1]; Sc[2] = a[2]; Sc[3] = vo[0]; Sc[4] = vo[1]; Sc[5] = vo[2];
-      if (with_vel) {
+      if constexpr (with_vel) {
         const double qd = v[6 + j]; const double* Vp = ws->V[pb]; const double* Ap = ws->A[pb];
         // V = Vp + S qd ;  A = Ap + (Vp x S) qd   with motion cross [w;v]x[a;b] = [w x a; w x b + v x a]
         double c1[3], c2[3]; cross3(Vp, a, c1); cross3(Vp, vo, c2); cross3_add(Vp + 3, a, c2);
@@ -95,6 +96,9 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
     __syncwarp();
   }
 }
+
+// positions-only workspace (MPC kernels)
+struct KinWs { double R[NB][9]; double p[NB][3]; double S[NQ][6]; };
 
 // Pass 2: per-body world inertias; optionally RNEA body forces (gravity: +9.81 z base acceleration trick).
 // with_force: 0 none, 1 = F = I (A + Ag) + V x* I V with gravity, 2 = same without gravity (centroidal momentum rate bias)

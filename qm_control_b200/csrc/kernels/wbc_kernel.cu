@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
 
   // ---- measured side: M, nle, foot/EE Jacobians and bias accelerations ----
   RbdWs* ws = &sm.u.rbd;
-  rbd_kinematics(mdl, sm.q, sm.v, ws, lane, true);
+  rbd_kinematics<true>(mdl, sm.q, sm.v, ws, lane);
   rbd_inertias(mdl, ws, lane, 1);
   rbd_accumulate(mdl, ws, lane, true);
   rbd_mass_matrix_nle(mdl, ws, sm.M, LDM, sm.nle, lane);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
     for (int a = 0; a < 3; ++a) { sm.vd[a] = sm.xdes[a] - t[a] / mdl->total_mass; sm.vd[3 + a] = ed[a]; }
   }
   __syncwarp();
-  rbd_kinematics(mdl, sm.qd, sm.vd, ws, lane, true);
+  rbd_kinematics<true>(mdl, sm.qd, sm.vd, ws, lane);
   rbd_inertias(mdl, ws, lane, 2);            // bias forces WITHOUT gravity: sum = dAg * v about the origin
   rbd_accumulate(mdl, ws, lane, true);
   // Aj * jointAccel: sum_j (Ic_{j+1} S_j) qdd_j  (full-model centroidal momentum matrix columns, after dccrba)

@@ -1,0 +1,109 @@
+"""Parity of the CUDA MPC tick (through the C-ABI) against the CPU oracle: one multiple-shooting SQP iteration
+(QMController.cpp:287-288 → SqpSolver::runImpl) on the OCP of qm_interface.  Tolerance 1e-5 relative on the optimal
+state / input trajectories (BASELINE.json north_star), measured per robot as max|cuda - oracle| / max(1, max|oracle|)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _traj_err(out, ref):
+    errs = []
+    for b in range(len(ref["n_nodes"])):
+        n = int(ref["n_nodes"][b]); assert int(out["n_nodes"][b]) == n
+        np.testing.assert_allclose(out["t"][b, :n], ref["t"][b, :n], rtol=0, atol=1e-12); np.testing.assert_array_equal(out["event"][b, :n], ref["event"][b, :n])
+        ex = np.max(np.abs(out["x"][b, :n] - ref["x"][b, :n])) / max(1.0, np.max(np.abs(ref["x"][b, :n])))
+        k = np.nonzero(ref["event"][b, :n - 1] != 1)[0]
+        eu = np.max(np.abs(out["u"][b, k] - ref["u"][b, k])) / max(1.0, np.max(np.abs(ref["u"][b, k])))
+        errs.append(max(ex, eu))
+    return np.array(errs)
+
+
+def _solve_both(oracle, config, B, dt, ticks=2, gait=None, horizon=1.0):
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    solver = q.Solver(batch=B, dt=dt, time_horizon=horizon)
+    oracle.mpc_set(dt=dt, horizon=horizon)
+    prob, wbc = synthetic.make_batch(np.arange(B), config=config, gait=gait, horizon=horizon)
+    prev = None; results = []
+    for tick in range(ticks):
+        if tick > 0:   # advance 10 ms along the oracle's own policy (same x0 for both)
+            prob["t0"] = prob["t0"] + 0.01
+            x0 = np.zeros((B, 30))
+            for b in range(B):
+                n = prev["n_nodes"][b]; ne = prob["n_events"][b]
+                x0[b], _, _ = oracle.evaluate_policy(prev["t"][b, :n], prev["event"][b, :n], prev["x"][b, :n], prev["u"][b, :n], prob["event_times"][b, :ne], prob["modes"][b, :ne + 1], prob["t0"][b])
+            prob["x0"] = x0
+        out = solver.mpc_solve(prob)
+        ref = oracle.mpc_solve_batch(prob, solver.nmax, prev=prev, nthreads=8)
+        results.append((out, ref))
+        prev = ref
+        # hand the oracle's solution to the CUDA path as warm start so both ticks start from identical data
+        ref_fixed = dict(ref); solver.mpc_set_solution(ref_fixed)
+    return solver, prob, results
+
+
+def _check(results):
+    for tick, (out, ref) in enumerate(results):
+        assert np.all((out["status"] & ~16) == 0), "tick %d status %s" % (tick, np.unique(out["status"]))
+        np.testing.assert_allclose(out["step_info"][:, 0], ref["dbg"][:, 0], rtol=0, atol=0, err_msg="line-search step size differs (tick %d)" % tick)
+        err = _traj_err(out, ref)
+        assert err.max() < RTOL, "tick %d: max rel err %.3e at robot %d" % (tick, err.max(), err.argmax())
+        acc = ref["dbg"][:, 0] > 0
+        np.testing.assert_allclose(out["step_info"][acc, 1], ref["dbg"][acc, 4], rtol=1e-6, atol=1e-8)   # cost after the step
+
+
+def test_mpc_stance_reference_grid(oracle):
+    """config 1/2: stance, reference default grid (dt = 0.015 → 67 intervals + stance-template event nodes)."""
+    _, _, results = _solve_both(oracle, config=2, B=8, dt=0.015)
+    _check(results)
+
+
+def test_mpc_stance_n100(oracle):
+    """config 2: horizon 100 nodes (dt = 0.01)."""
+    _, _, results = _solve_both(oracle, config=2, B=8, dt=0.01, ticks=2)
+    _check(results)
+
+
+def test_mpc_trot_contact_switches(oracle):
+    """config 4: trot — swing legs (zero force + normal velocity rows), event nodes inside the horizon."""
+    _, prob, results = _solve_both(oracle, config=4, B=8, dt=0.015)
+    assert results[0][1]["event"].max() == 2
+    _check(results)
+
+
+def test_mpc_mixed_gaits(oracle):
+    """config 5: stance / trot / flying trot (n_c in {4,2,0})."""
+    _, _, results = _solve_both(oracle, config=5, B=12, dt=0.015)
+    _check(results)
+
+
+def test_policy_eval_matches_oracle(oracle):
+    solver, prob, results = _solve_both(oracle, config=4, B=6, dt=0.015, ticks=1)
+    out, ref = results[0]
+    solver.mpc_set_solution(ref)
+    tq = prob["t0"] + 0.0123
+    xd, ud, mode = solver.policy_eval(tq)
+    for b in range(6):
+        n = ref["n_nodes"][b]; ne = prob["n_events"][b]
+        x, u, m = oracle.evaluate_policy(ref["t"][b, :n], ref["event"][b, :n], ref["x"][b, :n], ref["u"][b, :n], prob["event_times"][b, :ne], prob["modes"][b, :ne + 1], tq[b])
+        np.testing.assert_allclose(xd[b], x, rtol=0, atol=1e-12); np.testing.assert_allclose(ud[b], u, rtol=0, atol=1e-10); assert mode[b] == m
+
+
+def test_full_tick_matches_oracle(oracle):
+    """config 4 loop: mpc_solve → evaluatePolicy → wbc update through qmb200_tick vs the same chain on the oracle."""
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    B = 8; solver = q.Solver(batch=B, dt=0.015); oracle.mpc_set(dt=0.015, horizon=1.0)
+    prob, wbc = synthetic.make_batch(np.arange(B), config=4)
+    t_eval = prob["t0"] + 0.002
+    cmd, status = solver.tick(prob, t_eval, wbc["rbd"], wbc["period"])
+    assert np.all((status & ~(16 << 8)) == 0), np.unique(status)
+    ref = oracle.mpc_solve_batch(prob, solver.nmax, nthreads=8)
+    for b in range(B):
+        n = ref["n_nodes"][b]; ne = prob["n_events"][b]
+        x, u, m = oracle.evaluate_policy(ref["t"][b, :n], ref["event"][b, :n], ref["x"][b, :n], ref["u"][b, :n], prob["event_times"][b, :ne], prob["modes"][b, :ne + 1], t_eval[b])
+        c, _, _ = oracle.wbc_update(x, u, wbc["rbd"][b], m, wbc["period"][b], t_eval[b], input_last=np.zeros(30))
+        err = np.max(np.abs(cmd[b] - c)) / max(1.0, np.max(np.abs(c)))
+        assert err < 1e-4, "robot %d rel err %.2e" % (b, err)   # WBC amplifies the 1e-5 MPC tolerance (kp gains up to 6000)
