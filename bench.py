@@ -1,0 +1,262 @@
+#!/usr/bin/env python3
+"""bench.py — MPC+WBC iterations/s of the batched solver on B200 (BASELINE.json metric).
+
+One "step" = one controller tick for every robot of the batch: MPC solve (one multiple-shooting SQP iteration over the
+horizon: LQ approximation + projection + Riccati + filter line search), policy evaluation, WBC update (3-level HoQp) →
+54-vector; with N>1 GPUs one all-gather of the torque buffer.  Workload = BASELINE.json configs[3] shape on ONE GPU:
+trot gait schedule, horizon 1.0 s / dt 0.01 (100 intervals + event nodes), batch 8192 robots PER GPU (weak scaling),
+synthetic 24-DoF states, fp64.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+`value`   device-resident: inputs already in HBM, CUDA events on the launch stream, max over ranks.
+`e2e`     the same tick through the C-ABI host call qmb200_tick with pinned HOST buffers (H2D of the observation,
+          schedule and targets, D2H of the 54-vector inside the timed region).
+`--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+UNIT_BATCH = 8192           # one "iteration" of the metric = one tick of an 8192-robot batch
+DT, HORIZON, CONFIG = 0.01, 1.0, 4
+METRIC = "mpc_wbc_iters_per_s"
+UNIT = "iter/s (one iter = MPC+WBC tick of an 8192-robot batch, horizon 100)"
+
+
+def algorithmic_bytes(n_intervals):
+    """Per robot-iteration: warm start + solution, feedback hand-off, observation/targets/WBC I/O; split per kernel."""
+    N = n_intervals
+    return dict(lq=8 * (60 * N + 30) + 1352, riccati=2 * 8 * N * (30 * 30 + 30) + 8 * (60 * N + 30), linesearch=3 * 8 * (60 * N + 30), wbc=1856, setup=8 * (60 * N + 30) + 496, policy_eval=480,
+                total=15840 * N + 4184)
+
+
+def riccati_flops(n_intervals, m=16.0):
+    fma = 2 * 27000 + 3 * 900 * m + 30 * m * m + 31 * m * m + (900 + 60 * m)   # backward blocks + forward rollout, per node
+    return 2.0 * fma * n_intervals
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True); self.index = index; self.rows = []; self.stop_flag = False; self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        try:
+            if self.proc:
+                self.proc.terminate()
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(prob, wbc, nmax, cores, seconds_target=15.0):
+    """CPU restatement of the reference path (oracle/), one robot per task on a std::thread pool over all host cores, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import Oracle
+    o = Oracle(); o.mpc_set(dt=DT, horizon=HORIZON)
+    n = min(prob["t0"].shape[0], max(cores, 8)); sub = {k: v[:n] for k, v in prob.items()}
+    t_eval = sub["t0"] + 0.002; il = np.zeros((n, 30))
+    t = time.perf_counter(); out = o.tick_batch(sub, nmax, t_eval, wbc["rbd"][:n], wbc["period"][:n], il, nthreads=cores); cold = time.perf_counter() - t
+    # warm-started ticks (the steady state the GPU loop is in) until ~seconds_target of CPU work
+    reps = max(1, int(seconds_target / max(cold, 1e-3))); done = 0; t = time.perf_counter(); prev = out
+    for r in range(min(reps, 8)):
+        sub = dict(sub); sub["t0"] = sub["t0"] + DT
+        prev = o.tick_batch(sub, nmax, sub["t0"] + 0.002, wbc["rbd"][:n], wbc["period"][:n], prev["input_last"], prev=prev, nthreads=cores); done += 1
+    el = time.perf_counter() - t
+    robots_per_s = n * done / el
+    return robots_per_s / UNIT_BATCH, "%d robots x %d warm-started ticks (trot, N=100), %.1f s of CPU work" % (n, done, el)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from qm_control_b200 import synthetic
+    cores = os.cpu_count() or 1
+    prob, wbc = synthetic.make_batch(np.arange(max(cores, 8)), config=CONFIG, horizon=HORIZON)
+    nmax = int(round(HORIZON / DT)) + 21
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import Oracle
+    o = Oracle(); o.mpc_set(dt=DT, horizon=HORIZON); n = prob["t0"].shape[0]; il = np.zeros((n, 30)); prev = None; times = []
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        prev = o.tick_batch(prob, nmax, prob["t0"] + 0.002, wbc["rbd"], wbc["period"], il if prev is None else prev["input_last"], prev=prev, nthreads=cores)
+        el = time.perf_counter() - t; prob = dict(prob); prob["t0"] = prob["t0"] + DT
+        if s >= args.warmup:
+            times.append(el)
+    ms = 1e3 * float(np.mean(times)); value = (n / UNIT_BATCH) / (ms * 1e-3)
+    sample = "%d robots per step (bounded sample of the 8192-robot batch), trot, N=100, %d host threads" % (n, cores)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "MPC+WBC tick, trot gait, horizon 1.0 s / dt 0.01, CPU restatement of the reference path (OCS2/Pinocchio/qpOASES cannot be built offline)"},
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=UNIT_BATCH); ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world); return
+    import torch
+    import qm_control_b200 as q
+    from qm_control_b200 import parallel, synthetic
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    rank, world, local = parallel.init_distributed()
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    B = args.batch; n_int = int(round(HORIZON / DT))
+    solver = q.Solver(batch=B, device=local, dt=DT, time_horizon=HORIZON)
+    ids = np.arange(rank * B, (rank + 1) * B)
+    prob, wbc = synthetic.make_batch(ids, config=CONFIG, horizon=HORIZON)
+    t_eval0 = prob["t0"] + 0.002
+    keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
+    pdev = {k: torch.from_numpy(np.ascontiguousarray(prob[k])).to(dev) for k in keys}
+    rbd_d = torch.from_numpy(wbc["rbd"]).to(dev); per_d = torch.from_numpy(wbc["period"]).to(dev); te_d = torch.from_numpy(t_eval0).to(dev)
+    cmd_d = torch.zeros((B, 54), dtype=torch.float64, device=dev); st_d = torch.zeros(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step_dev():
+        solver.tick_dev(pdev, te_d, rbd_d, per_d, cmd_d, st_d, stream=stream)
+        if world > 1:
+            parallel.allgather_torque(cmd_d[:, 36:].contiguous(), B * world, rank, world)
+        pdev["t0"] += DT; te_d.add_(DT)   # the observation time advances one MPC period per tick
+
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.15)
+    l0 = solver.launch_count; e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev); e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(); torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    ms_local = e0.elapsed_time(e1) / args.steps; launches = solver.launch_count - l0
+    clocks = sampler.finish()
+    ms = parallel.max_over_ranks(ms_local, dev)
+    value = (B * world / UNIT_BATCH) / (ms * 1e-3)
+    status = st_d.cpu().numpy(); bad = int(np.count_nonzero(status & ~(16 << 8)))
+
+    # per-kernel device times (separate profiled ticks; CUDA events inside the library on the same stream)
+    ktimes = {}
+    try:
+        solver.set_profiling(True)
+        for _ in range(3):
+            step_dev(); torch.cuda.synchronize(dev); solver.collect_kernel_times()
+        ktimes = solver.kernel_times(); solver.set_profiling(False)
+    except Exception as e:   # measurement support only
+        ktimes = {"error": str(e)}
+    peaks, peak_src = measured_peaks(); ab = algorithmic_bytes(n_int)
+    roof = None
+    if ktimes and "error" not in ktimes:
+        dom = max(("lq", "riccati", "linesearch", "wbc"), key=lambda k: ktimes[k])
+        achieved = ab[dom] * B / (ktimes[dom] * 1e-3) / 1e9
+        fp64_peak = None
+        try:
+            fp64_peak = solver.measure_fp64_peak()
+        except Exception:
+            pass
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dom)
+            except Exception:
+                pass
+        roof = {"bound": "hbm", "kernel": "mpc_%s_kernel" % dom if dom != "wbc" else "wbc_update_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                "peak_source": peak_src, "kernel_ms": ktimes, "algorithmic_bytes_per_robot": ab[dom],
+                "whole_tick": {"achieved": ab["total"] * B / (ms_local * 1e-3) / 1e9, "frac": ab["total"] * B / (ms_local * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_robot": ab["total"]},
+                "fp64": {"kernel": "mpc_riccati_kernel", "achieved_tflops": riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 if ktimes.get("riccati") else None, "peak_tflops": fp64_peak, "peak_source": "measured in-process (FMA microbenchmark)",
+                         "frac": (riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and ktimes.get("riccati")) else None,
+                         "note": "the path is fp64 compute/latency bound (~48 FLOP/B vs a ~6 FLOP/B fp64 ridge, SURVEY §8d); the HBM fraction is reported because BASELINE.json asks for it"}}
+
+    # end-to-end through the host C-ABI call with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        solver.mpc_reset(); solver.wbc_set_input_last(None)
+        pin = {k: torch.from_numpy(np.ascontiguousarray(prob[k])).pin_memory() for k in keys}
+        hp = {k: v.numpy() for k, v in pin.items()}
+        te_h = torch.from_numpy(t_eval0.copy()).pin_memory().numpy(); rbd_h = torch.from_numpy(wbc["rbd"]).pin_memory().numpy(); per_h = torch.from_numpy(wbc["period"]).pin_memory().numpy()
+        h2d = sum(v.nbytes for v in hp.values()) + te_h.nbytes + rbd_h.nbytes + per_h.nbytes; d2h = B * 54 * 8 + B * 4
+        for s in range(args.warmup):
+            solver.tick(hp, te_h, rbd_h, per_h); hp["t0"] += DT; te_h += DT
+        if world > 1:
+            torch.distributed.barrier()
+        t = time.perf_counter()
+        for s in range(args.steps):
+            cmd_h, st_h = solver.tick(hp, te_h, rbd_h, per_h); hp["t0"] += DT; te_h += DT
+            if world > 1:
+                parallel.allgather_torque(torch.from_numpy(cmd_h[:, 36:].copy()).to(dev), B * world, rank, world)
+        el = (time.perf_counter() - t) / args.steps
+        el = parallel.max_over_ranks(el, dev)
+        e2e = {"value": (B * world / UNIT_BATCH) / el, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": el * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1; v, sample = cpu_baseline(prob, wbc, solver.nmax, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                   "note": "CPU restatement of the reference path (oracle/): the reference's OCS2+Pinocchio+qpOASES stack cannot be built offline; Jacobians by forward-mode AD"}
+        except Exception as e:
+            cpu = {"error": str(e)}
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "full MPC+WBC tick (BASELINE configs[3] shape): trot gait schedule, horizon 1.0 s / dt 0.01 (100 intervals + event nodes), 24-DoF quadruped-manipulator, one SQP iteration + 3-level HoQp",
+                          "batch_per_gpu": B, "global_batch": B * world, "robot_ticks_per_s": B * world / (ms * 1e-3), "parallelism": "dp%d (robots sharded, one all-gather of the torque buffer)" % world,
+                          "l2": "per-tick working set (LQ stage buffer %.1f GB) >> 126 MB L2; no flush needed" % (B * solver.nmax * 4072 * 8 / 1e9), "robots_with_error_status": bad},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

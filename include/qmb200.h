@@ -120,6 +120,13 @@ int qmb200_centroidal_state_from_rbd(const qmb200_handle* h, int32_t n, const do
 int qmb200_gait_schedule(const char* gait_file, const char* gait_name, double t_start, double lo, double hi,
                          double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
 
+/* measurement support (bench.py): per-kernel device times of the tick [setup, lq, riccati, linesearch, policy_eval, wbc] in ms (mean per call),
+ * and the measured fp64 FMA throughput of this GPU */
+int qmb200_set_profiling(qmb200_handle* h, int on);
+int qmb200_collect_kernel_times(qmb200_handle* h);
+int qmb200_get_kernel_times(qmb200_handle* h, double* ms6);
+int qmb200_measure_fp64_peak(qmb200_handle* h, double* tflops);
+
 /* diagnostics: the QP step (dx, du) of the last solve and per-robot scalars [armijo, baseline cost, dyn SSE, eq SSE, |dx|, |du|, -, -] */
 int qmb200_debug_get_step(qmb200_handle* h, double* dx /*[B][NMAX][30]*/, double* du /*[B][NMAX][30]*/, double* robot /*[B][8]*/);
 

@@ -202,7 +202,7 @@ void centroidal_state_from_rbd(const Model& m, const double* rbd, double* x) {
 int mode_at_time(const ModeSchedule& s, double t) { return s.mode_sequence[find_index(s.event_times, t)]; }
 
 std::vector<NodeInfo> time_discretization_with_events(double t0, double tf, double dt, const std::vector<double>& ev) {
-  const double dt_min = 10.0 * std::numeric_limits<double>::epsilon();
+  const double dt_min = 10.0 * 1e-9;   // 10 * ocs2 numeric_traits::limitEpsilon (1e-9) [upstream, recalled]
   std::vector<NodeInfo> g; g.push_back({t0, 0}); size_t next_ev = (size_t)find_index(ev, t0);
   while (g.back().t < tf) {
     NodeInfo nn{g.back().t + dt, 0}; bool is_event = false;

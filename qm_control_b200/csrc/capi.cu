@@ -33,6 +33,8 @@ struct qmb200_handle {
   int32_t *d_mode = nullptr, *d_status = nullptr;
   MpcBuffers mpc;   // device buffers of the MPC path (kernels/mpc_api.cuh)
   std::vector<void*> allocs;
+  bool profiling = false; cudaEvent_t ev[8] = {nullptr};   // [0..4] MPC kernels, [5..7] policy / wbc brackets
+  double kernel_ms[6] = {0, 0, 0, 0, 0, 0}; int64_t kernel_calls = 0; bool ev_pending = false;
 };
 
 namespace {

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevMo
   // ---- timeDiscretizationWithEvents [upstream ocs2_oc/oc_data/TimeDiscretization.cpp] ----
   int n = 0;
   if (lane == 0) {
-    const double dt_min = 10.0 * 2.220446049250313e-16; gt[0] = t0; ge[0] = 0; n = 1; int next_ev = lower_bound_idx(ev, ne, t0);
+    const double dt_min = 10.0 * 1e-9; /* 10 * ocs2 numeric_traits::limitEpsilon [upstream] */ gt[0] = t0; ge[0] = 0; n = 1; int next_ev = lower_bound_idx(ev, ne, t0);
     while (gt[n - 1] < tf) {
       double nt = gt[n - 1] + dt; int nev = 0; bool is_event = false;
       if (next_ev < ne && nt >= ev[next_ev]) { nt = ev[next_ev]; is_event = true; nev = 1; ++next_ev; }
@@ -511,7 +511,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
   return ok;
 }
 
-int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, const MpcProblemDev& p, cudaStream_t stream) {
+int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, const MpcProblemDev& p, cudaStream_t stream, cudaEvent_t* ev) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
@@ -521,11 +521,16 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   }
   (void)hm;
   const int B = m.B, nmax = m.nmax; MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];
+  if (ev) cudaEventRecord(ev[0], stream);
   mpc_setup_kernel<<<(B + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, 0, stream>>>(mdl, B, nmax, p, prev, next, m.status);
+  if (ev) cudaEventRecord(ev[1], stream);
   const long long nodes = (long long)B * nmax;
   mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.status);
+  if (ev) cudaEventRecord(ev[2], stream);
   mpc_riccati_kernel<<<(B + RIC_WARPS - 1) / RIC_WARPS, 32 * RIC_WARPS, sizeof(RicSmem) * RIC_WARPS, stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
+  if (ev) cudaEventRecord(ev[3], stream);
   mpc_linesearch_kernel<<<B, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, B, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info);
+  if (ev) cudaEventRecord(ev[4], stream);
   m.cur = 1 - m.cur;
   return 4;
 }
@@ -535,5 +540,23 @@ int mpc_policy_eval_launch(const MpcBuffers& m, const double* t, double* x_des, 
   return 1;
 }
 int mpc_fixup_launch(const MpcBuffers& m, cudaStream_t stream) { mpc_fixup_kernel<<<m.B, 32, 0, stream>>>(m.B, m.nmax, m.sol[m.cur]); return 1; }
+
+// ---- fp64 FMA throughput probe: 8 independent chains per thread, enough CTAs to fill every SM ----
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) { x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b); x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b); }
+  if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 12345.678) out[0] = x0;
+}
+double measure_fp64_peak(cudaStream_t stream) {
+  double* d = nullptr; cudaMalloc(&d, 8); cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, iters = 1 << 15; double best = 0.0;
+  fp64_peak_kernel<<<blocks, 256, 0, stream>>>(d, 1024, 0.999999, 1e-9);
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, stream); fp64_peak_kernel<<<blocks, 256, 0, stream>>>(d, iters, 0.999999, 1e-9); cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12; if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); return best;
+}
 
 }  // namespace qmb

@@ -161,6 +161,19 @@ class Solver:
         keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
         self._chk(self.lib.qmb200_tick_dev(self.h, *[_p(prob_dev[k]) for k in keys], _p(t_eval), _p(rbd), _p(period), _p(cmd), _p(status), C.c_void_p(stream) if stream else None), "qmb200_tick_dev")
 
+    def set_profiling(self, on=True):
+        self._chk(self.lib.qmb200_set_profiling(self.h, 1 if on else 0), "qmb200_set_profiling")
+
+    def collect_kernel_times(self):
+        self.lib.qmb200_collect_kernel_times(self.h)
+
+    def kernel_times(self):
+        ms = np.zeros(6); self._chk(self.lib.qmb200_get_kernel_times(self.h, _p(ms)), "qmb200_get_kernel_times")
+        return dict(zip(("setup", "lq", "riccati", "linesearch", "policy_eval", "wbc"), ms.tolist()))
+
+    def measure_fp64_peak(self):
+        v = C.c_double(); self._chk(self.lib.qmb200_measure_fp64_peak(self.h, C.byref(v)), "qmb200_measure_fp64_peak"); return v.value
+
     def debug_get_step(self):
         B, N = self.batch, self.nmax; dx = np.zeros((B, N, NX)); du = np.zeros((B, N, NU)); robot = np.zeros((B, 8))
         self._chk(self.lib.qmb200_debug_get_step(self.h, _p(dx), _p(du), _p(robot)), "qmb200_debug_get_step"); return dx, du, robot

@@ -140,6 +140,18 @@ class Oracle:
             out["dbg"] = dbg
         return out
 
+    def tick_batch(self, prob, nmax, t_eval, rbd, period, input_last, prev=None, variant=0, nthreads=1):
+        """mpc_solve → evaluatePolicy(t_eval) → wbc update per robot (thread pool) — the CPU baseline of bench.py."""
+        B = prob["t0"].shape[0]
+        out = dict(n_nodes=np.zeros(B, dtype=np.int32), t=np.zeros((B, nmax)), event=np.zeros((B, nmax), dtype=np.int32), x=np.zeros((B, nmax, 30)), u=np.zeros((B, nmax, 30)), cmd=np.zeros((B, 54)))
+        pa = [None] * 5 if prev is None else [_i(i32(prev["n_nodes"])), _d(f64(prev["t"])), _i(i32(prev["event"])), _d(f64(prev["x"])), _d(f64(prev["u"]))]
+        keep = [f64(prob["t0"]), f64(prob["x0"]), i32(prob["n_events"]), f64(prob["event_times"]), i32(prob["modes"]), i32(prob["n_target"]), f64(prob["target_times"]), f64(prob["target_states"])]
+        te = f64(t_eval); rb = f64(rbd); pe = f64(period); il = f64(input_last).copy(); emax = keep[3].shape[1]; kmax = keep[6].shape[1]
+        self._chk(self.lib.orc_tick_batch(self.h, C.c_int(B), C.c_int(emax), C.c_int(kmax), C.c_int(nmax), _d(keep[0]), _d(keep[1]), _i(keep[2]), _d(keep[3]), _i(keep[4]), _i(keep[5]), _d(keep[6]), _d(keep[7]),
+                                          *pa, _d(te), _d(rb), _d(pe), _d(il), C.c_int(variant), _i(out["n_nodes"]), _d(out["t"]), _i(out["event"]), _d(out["x"]), _d(out["u"]), _d(out["cmd"]), C.c_int(nthreads)))
+        out["input_last"] = il
+        return out
+
     def mpc_debug(self, prob, nmax, prev=None, max_k=200):
         keep = [f64(prob["t0"][:1]), f64(prob["x0"][:1]), i32(prob["n_events"][:1]), f64(prob["event_times"][:1]), i32(prob["modes"][:1]), i32(prob["n_target"][:1]), f64(prob["target_times"][:1]), f64(prob["target_states"][:1])]
         emax = keep[3].shape[1]; kmax = keep[6].shape[1]

@@ -1,0 +1,71 @@
+"""CPU checks of the product's host side: the C-ABI library loads and exports every symbol include/qmb200.h declares,
+fails loudly without a GPU (no CPU fallback), host utilities (gait tiling, observation conversion inputs) and the
+synthetic-batch generator."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qm_control_b200 as q
+from qm_control_b200 import _lib, synthetic
+from qm_control_b200.interface import gait_schedule
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qmb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(qmb200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 24
+    lib = q.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(set(_lib.SYMBOLS)) == declared   # the python binding tracks the header
+
+
+def test_create_fails_loudly_without_gpu_or_files():
+    import torch
+    lib = q.load_library()
+    with pytest.raises(ValueError):
+        q.QMInterface(taskFile="/nonexistent/task.info")   # QMInterface.cpp:45: invalid_argument on a missing file
+    if not torch.cuda.is_available():
+        with pytest.raises(q.QmbError) as e:
+            q.Solver(batch=2)
+        assert "no CPU fallback" in str(e.value)
+    cfg = _lib.Config(b"/nonexistent/task.info", _lib.asset("qm_robot.urdf").encode(), _lib.asset("qm_reference.info").encode(), None, 1, 0, 0.0, 0.0, 0, 0)
+    h = C.c_void_p()
+    assert lib.qmb200_create(C.byref(cfg), C.byref(h)) == -2 and b"not found" in lib.qmb200_last_error(None)
+    assert lib.qmb200_create(None, C.byref(h)) == -1
+
+
+def test_gait_schedule_tiling_matches_python_twin():
+    """GaitSchedule::getModeSchedule tiling: C++ host helper vs the numpy generator used for the synthetic batches."""
+    for gait in ("stance", "trot", "flying_trot"):
+        times, modes = synthetic._gait_template(_lib.asset("qm_gait.info"), gait)
+        ev, md, n = gait_schedule(gait, 10.3, 11.0, 14.0)
+        e2, m2 = synthetic.tile_schedule(times, modes, 10.3, 11.0, 14.0)
+        assert n == len(e2) and md[0] == 15 and md[n] == 15
+        np.testing.assert_allclose(ev[:n], e2, atol=1e-12); np.testing.assert_array_equal(md[:n + 1], m2)
+    ev, md, n = gait_schedule("trot", 0.0, -1.0, 1.0)
+    np.testing.assert_allclose(np.diff(ev[:n]), 0.35); assert list(md[1:3]) == [9, 6]   # LF_RH then RF_LH (gait.info:30-43)
+
+
+def test_synthetic_batches_are_shard_invariant_and_deterministic():
+    full, wf = synthetic.make_batch(np.arange(24), config=5)
+    part, wp = synthetic.make_batch(np.arange(8, 16), config=5)
+    for k in full:
+        np.testing.assert_array_equal(full[k][8:16], part[k])
+    np.testing.assert_array_equal(wf["rbd"][8:16], wp["rbd"])
+    again, _ = synthetic.make_batch(np.arange(24), config=5)
+    np.testing.assert_array_equal(full["x0"], again["x0"])
+    assert set(np.unique(full["modes"])) <= {0, 6, 9, 15}
+    u = synthetic.uniform(1, np.arange(4000), 3, 8, -1.0, 1.0); assert abs(u.mean()) < 0.02 and abs(u.std() - 1 / np.sqrt(3)) < 0.02
+
+
+def test_shard_ranges_cover_the_batch():
+    from qm_control_b200.parallel import shard_range
+    for total, world in ((8192, 8), (10, 4), (7, 8), (1, 1)):
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
