@@ -157,7 +157,8 @@ def main():
     pdev = {k: torch.from_numpy(np.ascontiguousarray(prob[k])).to(dev) for k in keys}
     rbd_d = torch.from_numpy(wbc["rbd"]).to(dev); per_d = torch.from_numpy(wbc["period"]).to(dev); te_d = torch.from_numpy(t_eval0).to(dev)
     cmd_d = torch.zeros((B, 54), dtype=torch.float64, device=dev); st_d = torch.zeros(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    side = torch.cuda.Stream(dev); torch.cuda.set_stream(side)   # a non-default stream: its handle is what the C-ABI launches on, and torch events bracket it
+    stream = side.cuda_stream
 
     def step_dev():
         solver.tick_dev(pdev, te_d, rbd_d, per_d, cmd_d, st_d, stream=stream)

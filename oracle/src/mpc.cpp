@@ -208,7 +208,7 @@ std::vector<NodeInfo> time_discretization_with_events(double t0, double tf, doub
     NodeInfo nn{g.back().t + dt, 0}; bool is_event = false;
     if (next_ev < ev.size() && nn.t >= ev[next_ev]) { nn.t = ev[next_ev]; is_event = true; nn.event = 1; ++next_ev; }
     if (nn.t >= tf) { is_event = false; nn.t = tf; nn.event = 0; }
-    if (nn.t > g.back().t + dt_min) g.push_back(nn); else if (g.back().event != 2) g.back() = nn;
+    if (nn.t > g.back().t + dt_min) g.push_back(nn); else if (g.back().event != 2) g.back() = nn; else if (nn.t >= tf) break;
     if (is_event) { nn.event = 2; g.push_back(nn); }
   }
   return g;

@@ -153,7 +153,15 @@ __device__ __forceinline__ TargetRef target_reference(const double* tt, const do
 }
 
 // ---- cost --------------------------------------------------------------------------------------------
-struct QuadWs { double Qf[NX * 31], Rf[NU * 31], qf[NX], rf[NU]; };   // quadratic model (unscaled by dt), leading dimension 31
+// Quadratic model of the intermediate cost (unscaled by dt) in COMPACT form: the constant weights stay in DevModel (L1/L2 resident),
+// only what depends on (x,u) is stored:  Qf = Q + diag(qdiag) + scatter(E on the 12 end-effector columns),
+// Rf = R + diag(rdiag) + blockdiag(fric[foot]) on the 12 force inputs.
+struct QuadWs { double E[144], fric[36], qdiag[NX], rdiag[NU], qf[NX], rf[NU]; };
+__device__ __forceinline__ int ee_pos(int c) { return (c >= 6 && c < 12) ? c - 6 : (c >= 24 ? c - 18 : -1); }
+__device__ __forceinline__ double quad_Q(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
+  double v = mdl->Q[i * NX + j]; if (i == j) v += q->qdiag[i]; const int a = ee_pos(i), b = ee_pos(j); if (a >= 0 && b >= 0) v += q->E[a * 12 + b]; return v; }
+__device__ __forceinline__ double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
+  double v = mdl->R[i * NU + j]; if (i == j) v += q->rdiag[i]; if (i < 12 && j < 12 && i / 3 == j / 3) v += q->fric[(i / 3) * 9 + (i % 3) * 3 + (j % 3)]; return v; }
 struct CostWs { double Je[6 * 12], e[6], quat[4], pee[3]; };
 __device__ __forceinline__ int ee_col(int i) { return i < 6 ? 6 + i : 18 + i; }   // 12 state columns the EE pose depends on: p(6:9), theta(9:12), arm(24:30)
 
@@ -195,15 +203,16 @@ __device__ __forceinline__ void ee_error(const DevModel* __restrict__ mdl, const
 template <bool with_quad>
 __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, const PointWs* ws, CostWs* cw, QuadWs* qw, const TargetRef& ref, int flagmask, bool terminal, int lane) {
   double value = 0.0;
-  if (with_quad) { for (int e = lane; e < NX * 31; e += 32) { qw->Qf[e] = 0.0; qw->Rf[e] = 0.0; } if (lane < NX) { qw->qf[lane] = 0.0; qw->rf[lane] = 0.0; } __syncwarp(); }
+  if (with_quad) { for (int e = lane; e < 144; e += 32) qw->E[e] = 0.0; for (int e = lane; e < 36; e += 32) qw->fric[e] = 0.0; if (lane < NX) { qw->qdiag[lane] = 0.0; qw->rdiag[lane] = 0.0; qw->qf[lane] = 0.0; qw->rf[lane] = 0.0; } __syncwarp(); }
   int nst = 0; for (int i = 0; i < 4; ++i) nst += (flagmask >> i) & 1;
   if (!terminal) {
     // tracking cost: 1/2 dx'Q dx + 1/2 du'R du, u_nom = weightCompensatingInput(contact flags)
     double dx = 0.0, du = 0.0;
     if (lane < NX) { dx = ws->x[lane] - ref.xnom; double un = 0.0; if (lane < 12 && (lane % 3) == 2 && ((flagmask >> (lane / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du = ws->u[lane] - un; }
     double qd = 0.0, rd = 0.0;
-    for (int j = 0; j < NX; ++j) { const double dxj = __shfl_sync(FULL, dx, j), duj = __shfl_sync(FULL, du, j);
-      if (lane < NX) { const double qij = mdl->Q[lane * NX + j], rij = mdl->R[lane * NU + j]; qd += qij * dxj; rd += rij * duj; if (with_quad) { qw->Qf[lane * 31 + j] = qij; qw->Rf[lane * 31 + j] = rij; } } }
+    const double* Qr = mdl->Q + (lane < NX ? lane : 0) * NX; const double* Rr = mdl->R + (lane < NU ? lane : 0) * NU;
+#pragma unroll 6
+    for (int j = 0; j < NX; ++j) { const double dxj = __shfl_sync(FULL, dx, j), duj = __shfl_sync(FULL, du, j); qd = fma(Qr[j], dxj, qd); rd = fma(Rr[j], duj, rd); }
     value += 0.5 * warp_sum(lane < NX ? dx * qd + du * rd : 0.0);
     if (with_quad && lane < NX) { qw->qf[lane] = qd; qw->rf[lane] = rd; }
     __syncwarp();
@@ -214,7 +223,7 @@ __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, c
     const double mup = terminal ? mdl->mu_final_ee_pos : mdl->mu_ee_pos, muo = terminal ? mdl->mu_final_ee_ori : mdl->mu_ee_ori;
     double v = 0.0; for (int r = 0; r < 6; ++r) v += 0.5 * (r < 3 ? mup : muo) * cw->e[r] * cw->e[r]; value += v;
     if (with_quad) {
-      for (int e = lane; e < 144; e += 32) { const int i = e / 12, j = e % 12; double s = 0.0; for (int r = 0; r < 6; ++r) s += (r < 3 ? mup : muo) * cw->Je[r * 12 + i] * cw->Je[r * 12 + j]; qw->Qf[ee_col(i) * 31 + ee_col(j)] += s; }
+      for (int e = lane; e < 144; e += 32) { const int i = e / 12, j = e % 12; double s = 0.0; for (int r = 0; r < 6; ++r) s += (r < 3 ? mup : muo) * cw->Je[r * 12 + i] * cw->Je[r * 12 + j]; qw->E[e] = s; }
       if (lane < 12) { double s = 0.0; for (int r = 0; r < 6; ++r) s += (r < 3 ? mup : muo) * cw->e[r] * cw->Je[r * 12 + lane]; qw->qf[ee_col(lane)] += s; }
       __syncwarp();
     }
@@ -228,7 +237,7 @@ __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, c
       const double mu = pos ? mdl->pos_limit_mu : mdl->vel_limit_mu, de = pos ? mdl->pos_limit_delta : mdl->vel_limit_delta;
       double a0, a1, a2, b0, b1, b2; relaxed_barrier(mu, de, val - lo, a0, a1, a2); relaxed_barrier(mu, de, hi - val, b0, b1, b2);
       bv = a0 + b0;
-      if (with_quad) { if (pos) { qw->qf[24 + i] += a1 - b1; qw->Qf[(24 + i) * 31 + 24 + i] += a2 + b2; } else { qw->rf[24 + i] += a1 - b1; qw->Rf[(24 + i) * 31 + 24 + i] += a2 + b2; } }
+      if (with_quad) { if (pos) { qw->qf[24 + i] += a1 - b1; qw->qdiag[24 + i] += a2 + b2; } else { qw->rf[24 + i] += a1 - b1; qw->rdiag[24 + i] += a2 + b2; } }
     }
     // friction cone soft constraints of the stance feet; hessianDiagonalShift acts on every state and input diagonal [upstream FrictionConeConstraint]
     double shift = 0.0;
@@ -239,23 +248,26 @@ __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, c
         const double h = mdl->friction_mu * Fz - n; double p0, p1, p2; relaxed_barrier(mdl->friction_barrier_mu, mdl->friction_barrier_delta, h, p0, p1, p2); bv = p0;
         if (with_quad) {
           const double g[3] = {-Fx / n, -Fy / n, mdl->friction_mu}; const double H2[9] = {-(Fy * Fy + mdl->friction_reg) / n32, Fx * Fy / n32, 0, Fx * Fy / n32, -(Fx * Fx + mdl->friction_reg) / n32, 0, 0, 0, 0};
-          for (int a = 0; a < 3; ++a) { qw->rf[3 * i + a] += p1 * g[a]; for (int b = 0; b < 3; ++b) qw->Rf[(3 * i + a) * 31 + 3 * i + b] += p2 * g[a] * g[b] + p1 * H2[3 * a + b]; }
+          for (int a = 0; a < 3; ++a) { qw->rf[3 * i + a] += p1 * g[a]; for (int b = 0; b < 3; ++b) qw->fric[i * 9 + 3 * a + b] = p2 * g[a] * g[b] + p1 * H2[3 * a + b]; }
           shift = -p1 * mdl->friction_hess_shift;
         }
       }
     }
     value += warp_sum(bv);
-    if (with_quad) { shift = warp_sum(shift); __syncwarp(); if (lane < NX) { qw->Qf[lane * 31 + lane] += shift; qw->Rf[lane * 31 + lane] += shift; } }
+    if (with_quad) { shift = warp_sum(shift); __syncwarp(); if (lane < NX) { qw->qdiag[lane] += shift; qw->rdiag[lane] += shift; } }
   }
   __syncwarp();
   return value;
 }
 
 // ---- equality constraints ---------------------------------------------------------------------------
+// The foot-velocity rows depend on 12 state columns only: h (0:6), euler angles (9:12) and the 3 joints of the own leg → compact storage.
 struct ConWs {
-  double C[4][3][NX];   // dg/dx rows of foot i (stance: 3 rows; swing: row 2 only)
+  double C[4][3][12];   // dg/dx rows of foot i on its support columns (stance: 3 rows; swing: row 2 only)
   double e[4][3];       // constraint values (stance: foot velocity; swing: e[i][2] = v_z - zdot_ref)
 };
+// state column of support position `pos` (0..11) for the leg whose first joint is `first`
+__device__ __forceinline__ int sup_col(int pos, int first) { return pos < 6 ? pos : (pos < 9 ? pos + 3 : 12 + first + pos - 9); }
 // foot velocity v = h_lin + omega x d + sum_j Jl_j qd_j and (optionally) its state Jacobian; lanes 0..3 (one per foot)
 template <bool with_jac>
 __device__ __forceinline__ void foot_velocity(const DevModel* __restrict__ mdl, const PointWs* ws, ConWs* cn, int lane) {
@@ -265,17 +277,16 @@ __device__ __forceinline__ void foot_velocity(const DevModel* __restrict__ mdl, 
     double w[3] = {0, 0, 0}; for (int j = 0; j < 3; ++j) for (int a = 0; a < 3; ++a) w[a] += ws->Jl[i][3 * j + a] * qd[j];
     double v[3]; cross3(om, d, v); for (int a = 0; a < 3; ++a) { v[a] += ws->x[a] + w[a]; cn->e[i][a] = v[a]; }
     if (with_jac) {
-      for (int a = 0; a < 3; ++a) for (int c = 0; c < NX; ++c) cn->C[i][a][c] = 0.0;
-      for (int a = 0; a < 3; ++a) cn->C[i][a][a] = 1.0;
+      for (int a = 0; a < 3; ++a) for (int c = 0; c < 12; ++c) cn->C[i][a][c] = (c == a) ? 1.0 : 0.0;
       const double Sd[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0}; double SW[9]; matmul3(Sd, ws->W, SW);
       for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cn->C[i][a][3 + b] = -SW[3 * a + b];
-      for (int k = 0; k < 3; ++k) { const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double t[3], col[3]; cross3(ws->dom[k], d, col); cross3(Tk, d, t); cross3_add(om, t, col); cross3_add(Tk, w, col); for (int a = 0; a < 3; ++a) cn->C[i][a][9 + k] = col[a]; }
+      for (int k = 0; k < 3; ++k) { const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double t[3], col[3]; cross3(ws->dom[k], d, col); cross3(Tk, d, t); cross3_add(om, t, col); cross3_add(Tk, w, col); for (int a = 0; a < 3; ++a) cn->C[i][a][6 + k] = col[a]; }
       for (int j = 0; j < 3; ++j) {
         const double* Jj = ws->Jl[i] + 3 * j; const double* aj = ws->al[i] + 3 * j; double above[3] = {0, 0, 0}, below[3] = {0, 0, 0};
         for (int l = j + 1; l < 3; ++l) for (int a = 0; a < 3; ++a) above[a] += ws->Jl[i][3 * l + a] * qd[l];
         for (int l = 0; l <= j; ++l) for (int a = 0; a < 3; ++a) below[a] += ws->al[i][3 * l + a] * qd[l];
         double col[3]; cross3(om, Jj, col); cross3_add(aj, above, col); cross3_add(below, Jj, col);
-        for (int a = 0; a < 3; ++a) cn->C[i][a][12 + first + j] = col[a];
+        for (int a = 0; a < 3; ++a) cn->C[i][a][9 + j] = col[a];
       }
     }
   }

@@ -13,7 +13,7 @@
 
 namespace qmb {
 
-constexpr int LQ_WARPS = 4, RIC_WARPS = 4, LS_WARPS = 4, SETUP_WARPS = 4;
+constexpr int LQ_WARPS = 2, LS_WARPS = 4, SETUP_WARPS = 4;
 enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16 };
 
 __device__ __forceinline__ double interval_start(double t, int ev) { return ev == 2 ? t + WEAK_EPS : t; }
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevMo
       double nt = gt[n - 1] + dt; int nev = 0; bool is_event = false;
       if (next_ev < ne && nt >= ev[next_ev]) { nt = ev[next_ev]; is_event = true; nev = 1; ++next_ev; }
       if (nt >= tf) { is_event = false; nt = tf; nev = 0; }
-      if (nt > gt[n - 1] + dt_min) { if (n >= nmax) { st |= MST_OVERFLOW; break; } gt[n] = nt; ge[n] = nev; ++n; } else if (ge[n - 1] != 2) { gt[n - 1] = nt; ge[n - 1] = nev; }
+      if (nt > gt[n - 1] + dt_min) { if (n >= nmax) { st |= MST_OVERFLOW; break; } gt[n] = nt; ge[n] = nev; ++n; } else if (ge[n - 1] != 2) { gt[n - 1] = nt; ge[n - 1] = nev; } else if (nt >= tf) break;
       if (is_event) { if (n >= nmax) { st |= MST_OVERFLOW; break; } gt[n] = nt; ge[n] = 2; ++n; }
     }
     next.n_nodes[b] = n;
@@ -66,13 +66,25 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevMo
 }
 
 // =====================================================================================================
-// K2: linear-quadratic approximation + projection of one node
+// K2: linear-quadratic approximation + projection of one node (one warp per node).
+// Everything is kept in the model's natural sparsity: the continuous Jacobians have 9 non-trivial rows, the velocity
+// constraint of a foot touches 12 state columns (h, euler angles, own leg joints) and its own 3 joint-velocity inputs,
+// the input weight couples joint velocities only inside a leg.  The projection is therefore assembled per leg
+// (3x12 blocks) and written straight into the dense stage record the Riccati kernel consumes.
+struct LegWs {
+  double Px[3][12];     // rows of P_x of the dependent joint-velocity inputs of this leg on the support columns (stance: 3 rows; swing: pivot row only)
+  double U[3][12];      // R_leg * Px
+  double Rl[9];         // 3x3 input-weight block of the leg (incl. diagonal additions)
+  double Pe[3], rs[3];  // P_e of the dependent joints ; r + R P_e on the leg's joint inputs
+  double Pu2[2];        // swing: coupling of the pivot joint to the two free joints
+  int dep[3];           // is joint j of this leg dependent
+  int pivot, stance, first, free_col[3];   // projected-input column of each free joint (-1 if dependent)
+};
 struct LqSmem {
-  PointWs pt; QuadWs quad; CostWs cost; ConWs con;
+  PointWs pt; QuadWs quad; CostWs cost; ConWs con; LegWs leg[4];
   double xs[NX], us[NU], xnext[NX], f1[NX], A1r[9 * NX], B1h[36];
-  double Ard[9 * NX], Brd[9 * NX], bvec[NX];        // discrete: rows 3:12 of (A_d - I) and of B_d; defect
-  double Pxd[MAXDEP * NX], Pud[MAXDEP * MU], Ped[MAXDEP], Pe_full[NU], rs[NU], RPx[NU * 31];
-  int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU], piv_dep[4], piv_free[4][2];
+  double Ard[9 * NX], BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX], Pe_full[NU], rs[NU];
+  int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
 };
 
 __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
     point_eval<false>(mdl, &sm.pt, lane);
     TargetRef ref = target_reference(tt, ts, nk, t, lane);
     const double val = stage_cost<true>(mdl, &sm.pt, &sm.cost, &sm.quad, ref, 0, true, lane);
-    for (int e = lane; e < NX * NX; e += 32) sg[ST_Q + e] = sm.quad.Qf[(e / NX) * 31 + (e % NX)];
+    for (int e = lane; e < NX * NX; e += 32) { const int a = ee_pos(e / NX), c = ee_pos(e % NX); sg[ST_Q + e] = (a >= 0 && c >= 0) ? sm.quad.E[a * 12 + c] : 0.0; }
     if (lane < NX) sg[ST_q + lane] = sm.quad.qf[lane];
     if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; sg[ST_PERF] = val; sg[ST_PERF + 1] = 0.0; sg[ST_PERF + 2] = 0.0; }
     return;
@@ -114,26 +126,22 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   TargetRef ref = target_reference(tt, ts, nk, t, lane);
   const double cost_val = stage_cost<true>(mdl, &sm.pt, &sm.cost, &sm.quad, ref, fm, false, lane);
   foot_velocity<true>(mdl, &sm.pt, &sm.con, lane);
-  // swing references and the dependent-input bookkeeping (one lane per foot)
   int nd_before = 0; for (int i = 0; i < 4; ++i) if (i < lane) nd_before += ((fm >> i) & 1) ? 3 : 4;
   int ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
   const int m = NU - ndep;
-  for (int e = lane; e < MAXDEP * MU; e += 32) sm.Pud[e] = 0.0;
-  for (int e = lane; e < MAXDEP * NX; e += 32) sm.Pxd[e] = 0.0;
   if (lane < NU) sm.Pe_full[lane] = 0.0;
   double eq_ss = 0.0; bool swing_ok = true; int pivot = -1;
-  if (lane < 4) {
-    const int i = lane; const int first = mdl->foot_leg[i];
-    if ((fm >> i) & 1) { for (int j = 0; j < 3; ++j) sm.dep_idx[nd_before + j] = 12 + first + j; for (int a = 0; a < 3; ++a) eq_ss += sm.con.e[i][a] * sm.con.e[i][a]; }
+  if (lane < 4) {   // lane = foot (contact order); its leg's first joint = foot_leg
+    const int i = lane; const int first = mdl->foot_leg[i]; LegWs& L = sm.leg[i]; L.first = first; L.stance = (fm >> i) & 1;
+    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.con.e[i][a] * sm.con.e[i][a]; }
     else {
       double zp, zv; swing_ok = swing_reference(mdl, ev, modes, ne, i, t, zp, zv);
       double ez = sm.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp);
       sm.con.e[i][2] = ez;
       for (int a = 0; a < 3; ++a) { sm.dep_idx[nd_before + a] = 3 * i + a; eq_ss += sm.pt.u[3 * i + a] * sm.pt.u[3 * i + a]; }
       eq_ss += ez * ez;
-      // pivot joint of the normal-velocity row: largest |d v_z / d qdot_j|
-      double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.pt.Jl[i][3 * j + 2]); if (a > best) { best = a; pivot = j; } }
-      sm.dep_idx[nd_before + 3] = 12 + first + pivot;
+      double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.pt.Jl[i][3 * j + 2]); if (a > best) { best = a; pivot = j; } }   // pivot: largest |d v_z / d qdot_j|
+      sm.dep_idx[nd_before + 3] = 12 + first + pivot; L.pivot = pivot; for (int j = 0; j < 3; ++j) L.dep[j] = (j == pivot);
     }
   }
   eq_ss = warp_sum(eq_ss);
@@ -144,24 +152,35 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   const unsigned free_mask = __ballot_sync(FULL, lane < NU && !is_dep);
   if (lane < NU) { const int rank = __popc(free_mask & ((1u << lane) - 1u)); sm.col_of_input[lane] = is_dep ? -1 : rank; if (!is_dep) sm.free_idx[rank] = lane; }
   __syncwarp();
-  // projection rows (structured elimination; the projected optimum does not depend on the null-space basis)
+  // ---- per-leg projection blocks (structured elimination; the projected optimum does not depend on the null-space basis) ----
   if (lane < 4) {
-    const int i = lane; const int first = mdl->foot_leg[i];
-    if ((fm >> i) & 1) {   // zero velocity: Jl dqd = -(C dx + e)  →  dqd = -Jl^{-1} (C dx + e)
+    const int i = lane; LegWs& L = sm.leg[i]; const int first = L.first;
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) L.Rl[3 * a + c] = quad_R(mdl, &sm.quad, 12 + first + a, 12 + first + c);
+    for (int j = 0; j < 3; ++j) { L.free_col[j] = sm.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) { L.Px[j][c] = 0.0; L.U[j][c] = 0.0; } }
+    L.Pu2[0] = L.Pu2[1] = 0.0;
+    if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  →  dqd = -Jl^{-1} (C dx + e)
       double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.pt.Jl[i][3 * j + a]; inv3(Jm, Ji);
-      for (int j = 0; j < 3; ++j) { const int d = nd_before + j; double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.con.e[i][a]; sm.Ped[d] = pe;
-        for (int c = 0; c < NX; ++c) { double s = 0.0; for (int a = 0; a < 3; ++a) s -= Ji[3 * j + a] * sm.con.C[i][a][c]; sm.Pxd[d * NX + c] = s; } }
-      sm.piv_dep[i] = -1;
-    } else {               // zero force: dF = -F ; normal velocity: pivot joint eliminated
-      for (int a = 0; a < 3; ++a) { sm.Ped[nd_before + a] = -sm.pt.u[3 * i + a]; }
-      const int d = nd_before + 3; const double piv = sm.pt.Jl[i][3 * pivot + 2];
-      sm.Ped[d] = -sm.con.e[i][2] / piv; for (int c = 0; c < NX; ++c) sm.Pxd[d * NX + c] = -sm.con.C[i][2][c] / piv;
-      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) { const int col = sm.col_of_input[12 + first + j]; sm.Pud[d * MU + col] = -sm.pt.Jl[i][3 * j + 2] / piv; sm.piv_free[i][nf++] = col; }
-      sm.piv_dep[i] = d;
+      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.con.e[i][a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
+        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.con.C[i][a][c]; L.Px[j][c] = sv; } }
+    } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
+      for (int a = 0; a < 3; ++a) sm.Pe_full[3 * i + a] = -sm.pt.u[3 * i + a];
+      const double piv = sm.pt.Jl[i][3 * pivot + 2];
+      L.Pe[pivot] = -sm.con.e[i][2] / piv; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
+      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = -sm.con.C[i][2][c] / piv;
+      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = -sm.pt.Jl[i][3 * j + 2] / piv;
     }
+    // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
+    for (int a = 0; a < 3; ++a) { double sv = sm.quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Px[j][c]; L.U[a][c] = sv; }
   }
   __syncwarp();
-  if (lane < ndep) sm.Pe_full[sm.dep_idx[lane]] = sm.Ped[lane];
+  // rs of every input: r + R Pe (R couples joint velocities only inside a leg; forces and arm inputs only with themselves)
+  if (lane < NU) {
+    double sv = sm.quad.rf[lane];
+    if (lane < 12) { const int f = lane / 3; for (int a = 0; a < 3; ++a) sv += quad_R(mdl, &sm.quad, lane, 3 * f + a) * sm.Pe_full[3 * f + a]; }
+    else if (lane < 24) { const int i = foot_of_leg_joint(mdl, lane - 12); sv = sm.leg[i].rs[(lane - 12) % 3]; }
+    sm.rs[lane] = sv;
+  }
   // keep k1 data, then second flow evaluation at x + c dt k1
   if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
   for (int e = lane; e < 9 * NX; e += 32) sm.A1r[e] = sm.pt.Ar[e];
@@ -171,238 +190,342 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   __syncwarp();
   point_eval<true>(mdl, &sm.pt, lane);
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2);
-  // defect b = x + dt (w1 k1 + w2 k2) - x_{k+1}
-  double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.bvec[lane] = bb; }
+  double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.bvec[lane] = bb; }   // defect
   const double dyn_ss = warp_sum(bb * bb);
-  // A_d - I (rows 3:12) = dt (w1 A1 + w2 (A2 + c dt A2 A1)) ; B_d rows 3:12 = dt (w1 B1 + w2 (B2 + c dt A2 B1))
+  // A_d - I (rows 3:12) = dt (w1 A1 + w2 (A2 + c dt A2 A1)) ; B_d rows 3:12 = dt (w1 B1 + w2 (B2 + c dt A2 B1)): force columns (9x12), joint columns only in the h_ang rows (3x18)
   for (int e = lane; e < 9 * NX; e += 32) {
     const int r = e / NX, c = e % NX; const double* a2 = sm.pt.Ar + r * NX;
-    double aa = 0.0; for (int q = 0; q < 9; ++q) aa += a2[3 + q] * sm.A1r[q * NX + c];
+    double aa = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) aa = fma(a2[3 + q], sm.A1r[q * NX + c], aa);
     sm.Ard[e] = dt * (w1 * sm.A1r[e] + w2 * (a2[c] + cdt * aa));
-    double b1 = 0.0, b2 = 0.0, ab = 0.0;
-    if (c < 12) { if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } ab = a2[c % 3] / mass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; }
-    else ab = a2[c];
-    sm.Brd[e] = dt * (w1 * b1 + w2 * (b2 + cdt * ab));
+    if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } double ab = a2[c % 3] / mass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; sm.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
+    else if (r < 3) sm.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c];
   }
   __syncwarp();
-  // ---- projected dynamics: A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
-  // rows 0:3 and 12:30 of B_d are dtw/m selectors (forces) and dtw identity (joint velocities)
+  // ---- projected dynamics rows (lane = state row): A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
   if (lane < NX) {
-    const int i = lane; double* Arow = sg + ST_A + (size_t)i * NX; double* Brow = sg + ST_B + (size_t)i * MU;
-    double bt = sm.bvec[i];
-    if (i < 3) {
-      for (int c = 0; c < NX; ++c) Arow[c] = (c == i) ? 1.0 : 0.0;
-      for (int a = 0; a < m; ++a) { const int fa = sm.free_idx[a]; Brow[a] = (fa < 12 && fa % 3 == i) ? dtw / mass : 0.0; }
-      for (int f = 0; f < 4; ++f) bt += (dtw / mass) * sm.Pe_full[3 * f + i];
-    } else if (i < 12) {
-      const int r = i - 3; const double* br = sm.Brd + r * NX;
-      for (int c = 0; c < NX; ++c) { double s = sm.Ard[r * NX + c] + ((c == i) ? 1.0 : 0.0); for (int d = 0; d < ndep; ++d) s += br[sm.dep_idx[d]] * sm.Pxd[d * NX + c]; Arow[c] = s; }
-      for (int a = 0; a < m; ++a) { double s = br[sm.free_idx[a]]; for (int f = 0; f < 4; ++f) { const int d = sm.piv_dep[f]; if (d >= 0) s += br[sm.dep_idx[d]] * sm.Pud[d * MU + a]; } Brow[a] = s; }
-      for (int d = 0; d < ndep; ++d) bt += br[sm.dep_idx[d]] * sm.Ped[d];
+    const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; double* Brow = sg + ST_B + (size_t)r * MU; double bt = sm.bvec[r];
+    if (r >= 3 && r < 12) {
+#pragma unroll 6
+      for (int c = 0; c < NX; ++c) Arow[c] = sm.Ard[(r - 3) * NX + c] + ((c == r) ? 1.0 : 0.0);
     } else {
-      const int col = sm.col_of_input[i];   // input i (joint velocity) is free (col >= 0) or dependent
-      int dd = -1; if (col < 0) for (int d = 0; d < ndep; ++d) if (sm.dep_idx[d] == i) dd = d;
-      for (int c = 0; c < NX; ++c) Arow[c] = ((c == i) ? 1.0 : 0.0) + (dd >= 0 ? dtw * sm.Pxd[dd * NX + c] : 0.0);
-      for (int a = 0; a < m; ++a) Brow[a] = (col == a) ? dtw : (dd >= 0 ? dtw * sm.Pud[dd * MU + a] : 0.0);
-      if (dd >= 0) bt += dtw * sm.Ped[dd];
+#pragma unroll 6
+      for (int c = 0; c < NX; ++c) Arow[c] = (c == r) ? 1.0 : 0.0;
     }
-    for (int a = m; a < MU; ++a) Brow[a] = 0.0;
-    sg[ST_b + i] = bt;
+    if (r >= 3 && r < 6) {       // h_ang rows pick up the dependent joint velocities: + sum_legs BrdJ[r][joint] * Px_joint
+      double acc[12]; 
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const LegWs& L = sm.leg[i];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) acc[c] = 0.0;
+        for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double coef = sm.BrdJ[(r - 3) * NJ + L.first + j]; bt += coef * L.Pe[j];
+#pragma unroll
+          for (int c = 0; c < 12; ++c) acc[c] = fma(coef, L.Px[j][c], acc[c]); }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) Arow[sup_col(c, L.first)] += acc[c];      // common columns accumulate over the legs (own row, own thread: ordered)
+#pragma unroll
+        for (int c = 9; c < 12; ++c) Arow[sup_col(c, L.first)] += acc[c];
+      }
+    }
+    if (r >= 12 && r < 24) {     // dependent joint-velocity rows: I + dtw * Px
+      const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3;
+      if (L.dep[j]) { bt += dtw * L.Pe[j]; for (int c = 0; c < 12; ++c) { const int col = sup_col(c, L.first); Arow[col] = ((col == r) ? 1.0 : 0.0) + dtw * L.Px[j][c]; } }
+    }
+    if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw / mass) * sm.Pe_full[3 * f + r];
+    if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
+    // B~ row
+    for (int a = 0; a < MU; ++a) {
+      double v = 0.0;
+      if (a < m) { const int fa = sm.free_idx[a];
+        if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw / mass : 0.0;
+        else if (r < 12) { if (fa < 12) v = sm.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(mdl, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.BrdJ[(r - 3) * NJ + fa - 12]; }
+        else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
+      }
+      Brow[a] = v;
+    }
+    sg[ST_b + r] = bt;
   }
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
-  // rs = r + R Pe ; RPx = R Px
-  if (lane < NU) { double s = sm.quad.rf[lane]; for (int d = 0; d < ndep; ++d) s += sm.quad.Rf[lane * 31 + sm.dep_idx[d]] * sm.Ped[d]; sm.rs[lane] = s; }
-  for (int e = lane; e < NU * NX; e += 32) { const int i = e / NX, c = e % NX; double s = 0.0; for (int d = 0; d < ndep; ++d) s += sm.quad.Rf[i * 31 + sm.dep_idx[d]] * sm.Pxd[d * NX + c]; sm.RPx[i * 31 + c] = s; }
-  __syncwarp();
-  if (lane < NX) {   // q~ = q + Px' rs ; Q~ = Q + Px' R Px   (the cost has no state-input cross term before projection)
-    double s = sm.quad.qf[lane]; for (int d = 0; d < ndep; ++d) s += sm.Pxd[d * NX + lane] * sm.rs[sm.dep_idx[d]]; sg[ST_q + lane] = dt * s;
-    double* Qrow = sg + ST_Q + (size_t)lane * NX;
-    for (int c = 0; c < NX; ++c) { double q = sm.quad.Qf[lane * 31 + c]; for (int d = 0; d < ndep; ++d) q += sm.Pxd[d * NX + lane] * sm.RPx[sm.dep_idx[d] * 31 + c]; Qrow[c] = dt * q; }
+  if (lane < NX) {   // q~ = q + Px' rs ; Q~ = Q + Px' R Px : per leg a 12x12 block on its support columns
+    const int r = lane; double acc[NX];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) acc[c] = mdl->Q[r * NX + c];
+    acc[0] += 0.0; double qv = sm.quad.qf[r];
+    const int ea = ee_pos(r);
+    if (ea >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { acc[6 + c] += sm.quad.E[ea * 12 + c]; acc[24 + c] += sm.quad.E[ea * 12 + 6 + c]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const LegWs& L = sm.leg[i]; const int first = L.first;   // first is 0,3,6,9 in some foot order: resolve the static column block by comparing
+      const int pr = (r < 6) ? r : ((r >= 9 && r < 12) ? r - 3 : ((r >= 12 + first && r < 15 + first) ? 9 + r - 12 - first : -1));
+      if (pr >= 0) {
+        double blk[12];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) blk[c] = 0.0;
+        for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double pj = L.Px[j][pr]; qv = fma(pj, L.rs[j], qv);
+#pragma unroll
+          for (int c = 0; c < 12; ++c) blk[c] = fma(pj, L.U[j][c], blk[c]); }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[c] += blk[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[9 + c] += blk[6 + c];
+        // leg-specific columns 12+first+c: first ∈ {0,3,6,9}
+#pragma unroll
+        for (int l = 0; l < 4; ++l) if (first == 3 * l) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[12 + 3 * l + c] += blk[9 + c]; }
+      }
+    }
+    double* Qrow = sg + ST_Q + (size_t)r * NX; const double dq = sm.quad.qdiag[r];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) Qrow[c] = dt * (acc[c] + ((c == r) ? dq : 0.0));
+    sg[ST_q + r] = dt * qv;
   }
   if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu
     const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rrow = sg + ST_R + (size_t)a * MU;
+#pragma unroll 6
+    for (int c = 0; c < NX; ++c) Srow[c] = 0.0;
     if (a < m) {
-      const int fa = sm.free_idx[a]; double r = sm.rs[fa];
-      for (int f = 0; f < 4; ++f) { const int d = sm.piv_dep[f]; if (d >= 0) r += sm.Pud[d * MU + a] * sm.rs[sm.dep_idx[d]]; }
-      sg[ST_r + a] = dt * r;
-      for (int c = 0; c < NX; ++c) { double s = sm.RPx[fa * 31 + c]; for (int f = 0; f < 4; ++f) { const int d = sm.piv_dep[f]; if (d >= 0) s += sm.Pud[d * MU + a] * sm.RPx[sm.dep_idx[d] * 31 + c]; } Srow[c] = dt * s; }
-      for (int c = 0; c < m; ++c) {
-        const int fc = sm.free_idx[c]; double s = sm.quad.Rf[fa * 31 + fc];
-        for (int f = 0; f < 4; ++f) { const int d = sm.piv_dep[f]; if (d < 0) continue; const int di = sm.dep_idx[d];
-          s += sm.Pud[d * MU + a] * sm.quad.Rf[di * 31 + fc] + sm.quad.Rf[fa * 31 + di] * sm.Pud[d * MU + c];
-          for (int g = 0; g < 4; ++g) { const int d2 = sm.piv_dep[g]; if (d2 >= 0) s += sm.Pud[d * MU + a] * sm.quad.Rf[di * 31 + sm.dep_idx[d2]] * sm.Pud[d2 * MU + c]; } }
-        Rrow[c] = dt * s;
+      const int fa = sm.free_idx[a]; double rv = sm.rs[fa]; int li = -1, jf = -1;
+      if (fa >= 12 && fa < 24) { li = foot_of_leg_joint(mdl, fa - 12); jf = (fa - 12) % 3; }
+      const bool swing_joint = li >= 0 && !sm.leg[li].stance;
+      if (swing_joint) {   // free joint of a swing leg: coupled to the pivot through R_leg and Pu
+        const LegWs& L = sm.leg[li]; const int pv = L.pivot; const double pu = L.Pu2[jf > pv ? jf - 1 : jf];
+        rv += pu * L.rs[pv];
+        const double coef = L.Rl[3 * jf + pv];
+        for (int c = 0; c < 12; ++c) Srow[sup_col(c, L.first)] = dt * (coef * L.Px[pv][c] + pu * L.U[pv][c]);
       }
-      for (int c = m; c < MU; ++c) Rrow[c] = 0.0;
-    } else { sg[ST_r + a] = 0.0; for (int c = 0; c < NX; ++c) Srow[c] = 0.0; for (int c = 0; c < MU; ++c) Rrow[c] = (c == a) ? 1.0 : 0.0; }
+      sg[ST_r + a] = dt * rv;
+      for (int c = 0; c < MU; ++c) {
+        double v = 0.0;
+        if (c < m) { const int fc = sm.free_idx[c]; v = quad_R(mdl, &sm.quad, fa, fc);
+          if (swing_joint && fc >= 12 + sm.leg[li].first && fc < 15 + sm.leg[li].first) { const LegWs& L = sm.leg[li]; const int pv = L.pivot; const int jc = fc - 12 - L.first; const double pa = L.Pu2[jf > pv ? jf - 1 : jf], pc = L.Pu2[jc > pv ? jc - 1 : jc];
+            v += pa * L.Rl[3 * pv + jc] + L.Rl[3 * jf + pv] * pc + pa * L.Rl[3 * pv + pv] * pc; } }
+        Rrow[c] = dt * v;
+      }
+    } else { sg[ST_r + a] = 0.0; for (int c = 0; c < MU; ++c) Rrow[c] = (c == a) ? 1.0 : 0.0; }
   }
-  // projection data for the forward pass
-  for (int e = lane; e < MAXDEP * NX; e += 32) sg[ST_PXD + e] = sm.Pxd[e];
-  for (int e = lane; e < MAXDEP * MU; e += 32) sg[ST_PUD + e] = sm.Pud[e];
-  if (lane < MAXDEP) { sg[ST_PED + lane] = (lane < ndep) ? sm.Ped[lane] : 0.0; si[SI_DEP + lane] = (lane < ndep) ? sm.dep_idx[lane] : -1; }
+  // projection data for the forward pass: dense rows of Px / Pu / Pe of the dependent inputs
+  for (int e = lane; e < MAXDEP * NX; e += 32) sg[ST_PXD + e] = 0.0;
+  for (int e = lane; e < MAXDEP * MU; e += 32) sg[ST_PUD + e] = 0.0;
+  __syncwarp();
+  if (lane < MAXDEP) {
+    const int d = lane; double pe = 0.0; int di = -1;
+    if (d < ndep) { di = sm.dep_idx[d]; pe = sm.Pe_full[di];
+      if (di >= 12) { const int i = foot_of_leg_joint(mdl, di - 12); const LegWs& L = sm.leg[i]; const int j = (di - 12) % 3;
+        for (int c = 0; c < 12; ++c) sg[ST_PXD + (size_t)d * NX + sup_col(c, L.first)] = L.Px[j][c];
+        if (!L.stance) { int nf = 0; for (int jj = 0; jj < 3; ++jj) if (jj != L.pivot) { sg[ST_PUD + (size_t)d * MU + L.free_col[jj]] = L.Pu2[nf++]; } } } }
+    sg[ST_PED + d] = pe; si[SI_DEP + d] = di;
+  }
   if (lane < MU) si[SI_FREE + lane] = (lane < m) ? sm.free_idx[lane] : -1;
   if (lane == 0) { si[SI_TYPE] = 0; si[SI_M] = m; si[SI_NDEP] = ndep; sg[ST_PERF] = dt * cost_val; sg[ST_PERF + 1] = dt * dyn_ss; sg[ST_PERF + 2] = dt * eq_ss; }
 }
 
 // =====================================================================================================
-// K3: Riccati backward sweep + forward rollout of the projected LQ problem (one warp per robot)
-constexpr int LDX = 31, LDU = MU + 1;
+// K3: Riccati backward sweep + forward rollout of the projected LQ problem.
+// One CTA (4 warps) per robot.  Every 30x30 product is tiled 1x8 over 120 threads (thread t: row t/4, columns 8*(t%4)..+7),
+// operands in shared memory (row operand walked with an odd leading dimension, column-block operand read as 16-byte
+// broadcasts), stage records prefetched with cp.async while the previous phases compute, Cholesky + triangular solves
+// warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
+// LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
+constexpr int RIC_THREADS = 128;
+constexpr int LDP = 33, LDA = 32, LDB = 24;
 struct RicSmem {
-  double P[NX * LDX], A[NX * LDX], W[NX * LDX];       // value Hessian, stage A~, P A~
-  double Bm[NX * LDU], PB[NX * LDU], G[MU * LDX], H[MU * LDU];
-  double p[NX], b[NX], q[NX], r[MU], pPb[NX], h[MU], dx[NX], dut[MU], tmp[NX];
+  double P[NX * LDP];                       // value-function Hessian (row operand)
+  double A[NX * LDA], W[NX * LDA], Qb[NX * LDA];
+  double Bm[NX * LDB], PB[NX * LDB];
+  double G[MU * LDA];                       // S~, then G, then Y = L^{-1} G
+  double H[MU * LDB];                       // R~, then H, then its Cholesky factor
+  double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32];
+  double red[RIC_THREADS / 32][4];
+  int flag;
 };
-// copy a rows x cols matrix from global (row stride gs) into shared (row stride ls)
-__device__ __forceinline__ void load_mat(const double* __restrict__ g, int rows, int cols, int gs, double* s, int ls, int lane) {
-  for (int e = lane; e < rows * cols; e += 32) { const int i = e / cols, j = e % cols; s[i * ls + j] = g[(size_t)i * gs + j]; }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+// rows x cols doubles (cols even, 16-B aligned rows on both sides) global → shared, all threads
+__device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, int cols, int gs, double* s, int ls, int tid) {
+  const int cpr = cols >> 1;
+  for (int e = tid; e < rows * cpr; e += RIC_THREADS) { const int i = e / cpr, c = e - i * cpr; cp_async16(s + i * ls + 2 * c, g + (size_t)i * gs + 2 * c); }
+}
+// acc[v] += sum_k X[k*xs] * Y[k*ldy + v], v = 0..7   (Y rows 16-B aligned)
+__device__ __forceinline__ void tile_mac(const double* __restrict__ X, int xs, const double* __restrict__ Y, int ldy, int K, double (&acc)[8]) {
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const double a = X[k * xs]; const double2* y = reinterpret_cast<const double2*>(Y + k * ldy);
+    const double2 y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+    acc[0] = fma(a, y0.x, acc[0]); acc[1] = fma(a, y0.y, acc[1]); acc[2] = fma(a, y1.x, acc[2]); acc[3] = fma(a, y1.y, acc[3]);
+    acc[4] = fma(a, y2.x, acc[4]); acc[5] = fma(a, y2.y, acc[5]); acc[6] = fma(a, y3.x, acc[6]); acc[7] = fma(a, y3.y, acc[7]);
+  }
 }
 
-__global__ void __launch_bounds__(32 * RIC_WARPS) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const int32_t* __restrict__ stage_i,
-                                                                   double* __restrict__ gains, double* __restrict__ dxo, double* __restrict__ duo, double* __restrict__ robot, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const int32_t* __restrict__ stage_i,
+                                                                  double* __restrict__ gains, double* __restrict__ dxo, double* __restrict__ duo, double* __restrict__ robot, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = blockIdx.x * RIC_WARPS + warp; if (b >= B) return;
-  RicSmem& sm = reinterpret_cast<RicSmem*>(smem_raw)[warp];
-  const int n = sol.n_nodes[b]; const int N = n - 1; int st = 0;
+  RicSmem& sm = *reinterpret_cast<RicSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ti = tid >> 2, jb = tid & 3; const int b = blockIdx.x;
+  const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
+  for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
+  __syncthreads();
+  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid); if (tid < 15) cp_async16(sm.b + 2 * tid, sg + ST_b + 2 * tid); cp_async_commit(); };
+  auto issue_srq = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_S, MU, NX, NX, sm.G, LDA, tid); cp_rows(sg + ST_R, MU, MU, MU, sm.H, LDB, tid); cp_rows(sg + ST_Q, NX, NX, NX, sm.Qb, LDA, tid);
+    if (tid < 15) cp_async16(sm.q + 2 * tid, sg + ST_q + 2 * tid); else if (tid < 24) cp_async16(sm.r + 2 * (tid - 15), sg + ST_r + 2 * (tid - 15)); cp_async_commit(); };
   // terminal value function and baseline performance
-  load_mat(sgb + (size_t)N * STAGE_DBL + ST_Q, NX, NX, NX, sm.P, LDX, lane);
-  if (lane < NX) sm.p[lane] = sgb[(size_t)N * STAGE_DBL + ST_q + lane];
-  double perf[3] = {0, 0, 0};
-  for (int k = lane; k < n; k += 32) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_PERF; perf[0] += pf[0]; perf[1] += pf[1]; perf[2] += pf[2]; }
-  for (int i = 0; i < 3; ++i) perf[i] = warp_sum(perf[i]);
-  { double d = 0.0; if (lane < NX) { d = p.x0[(size_t)b * NX + lane] - sol.x[(size_t)b * nmax * NX + lane]; sm.dx[lane] = d; } perf[1] += warp_sum(d * d); }
-  __syncwarp();
+  for (int e = tid; e < NX * NX; e += RIC_THREADS) sm.P[(e / NX) * LDP + (e % NX)] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
+  if (tid < NX) sm.p[tid] = sgb[(size_t)N * STAGE_DBL + ST_q + tid];
+  double perf0 = 0, perf1 = 0, perf2 = 0;
+  for (int k = tid; k < n; k += RIC_THREADS) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_PERF; perf0 += pf[0]; perf1 += pf[1]; perf2 += pf[2]; }
+  if (tid < NX) { const double d = p.x0[(size_t)b * NX + tid] - sol.x[(size_t)b * nmax * NX + tid]; sm.dx[tid] = d; perf1 += d * d; }
+  perf0 = warp_sum(perf0); perf1 = warp_sum(perf1); perf2 = warp_sum(perf2);
+  if (lane == 0) { sm.red[warp][0] = perf0; sm.red[warp][1] = perf1; sm.red[warp][2] = perf2; }
+  if (N >= 1) { issue_ab(N - 1); issue_srq(N - 1); }
+  __syncthreads();
+  double perf[3]; for (int i = 0; i < 3; ++i) perf[i] = sm.red[0][i] + sm.red[1][i] + sm.red[2][i] + sm.red[3][i];
+  int st = 0;
   for (int k = N - 1; k >= 0; --k) {
-    const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sib + (size_t)k * STAGE_INT; const int type = si[SI_TYPE], m = si[SI_M];
-    if (lane < NX) sm.b[lane] = sg[ST_b + lane];
-    __syncwarp();
-    if (lane < NX) { double s = sm.p[lane]; for (int j = 0; j < NX; ++j) s += sm.P[lane * LDX + j] * sm.b[j]; sm.pPb[lane] = s; }   // p + P b
-    __syncwarp();
-    if (type == 1) { if (lane < NX) sm.p[lane] = sm.pPb[lane]; __syncwarp(); continue; }   // event: A = I, no input
-    load_mat(sg + ST_A, NX, NX, NX, sm.A, LDX, lane); load_mat(sg + ST_B, NX, m, MU, sm.Bm, LDU, lane);
-    load_mat(sg + ST_S, m, NX, NX, sm.G, LDX, lane); load_mat(sg + ST_R, m, m, MU, sm.H, LDU, lane);
-    if (lane < NX) sm.q[lane] = sg[ST_q + lane]; if (lane < m) sm.r[lane] = sg[ST_r + lane];
-    __syncwarp();
-    // W = P A ; PB = P B        (lane = row; P[i][:] walks shared memory conflict-free, A rows are broadcast)
-    if (lane < NX) {
-      double acc[NX];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) acc[j] = 0.0;
-      for (int kk = 0; kk < NX; ++kk) { const double pik = sm.P[lane * LDX + kk]; const double* ar = sm.A + kk * LDX;
-#pragma unroll
-        for (int j = 0; j < NX; ++j) acc[j] = fma(pik, ar[j], acc[j]); }
-#pragma unroll
-      for (int j = 0; j < NX; ++j) sm.W[lane * LDX + j] = acc[j];
-      double accb[MU];
-#pragma unroll
-      for (int j = 0; j < MU; ++j) accb[j] = 0.0;
-      for (int kk = 0; kk < NX; ++kk) { const double pik = sm.P[lane * LDX + kk]; const double* br = sm.Bm + kk * LDU;
-#pragma unroll
-        for (int j = 0; j < MU; ++j) accb[j] = fma(pik, br[j], accb[j]); }
-#pragma unroll
-      for (int j = 0; j < MU; ++j) sm.PB[lane * LDU + j] = accb[j];
+    const int type = sib[(size_t)k * STAGE_INT + SI_TYPE];
+    cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed
+    // ---- phase 1: pPb = p + P b ; W = P A ; PB = P B ----
+    if (type == 1) {                                // event node: A = I, no input
+      if (tid < NX) { double s = sm.p[tid]; for (int j = 0; j < NX; ++j) s = fma(sm.P[tid * LDP + j], sm.b[j], s); sm.tmp[tid] = s; }
+      cp_async_wait<0>(); __syncthreads();
+      if (tid < NX) sm.p[tid] = sm.tmp[tid];
+      __syncthreads();
+      if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }
+      continue;
     }
-    __syncwarp();
-    // G = S + B'W ; H = R + B'PB ; h = r + B'(p + P b)      (lane = projected input)
-    if (lane < m) {
-      double acc[NX];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) acc[j] = sm.G[lane * LDX + j];
-      double hh = sm.r[lane];
-      for (int kk = 0; kk < NX; ++kk) { const double bka = sm.Bm[kk * LDU + lane]; const double* wr = sm.W + kk * LDX; hh = fma(bka, sm.pPb[kk], hh);
-#pragma unroll
-        for (int j = 0; j < NX; ++j) acc[j] = fma(bka, wr[j], acc[j]); }
-#pragma unroll
-      for (int j = 0; j < NX; ++j) sm.G[lane * LDX + j] = acc[j];
-      sm.h[lane] = hh;
-      double acch[MU];
-#pragma unroll
-      for (int j = 0; j < MU; ++j) acch[j] = sm.H[lane * LDU + j];
-      for (int kk = 0; kk < NX; ++kk) { const double bka = sm.Bm[kk * LDU + lane]; const double* pr = sm.PB + kk * LDU;
-#pragma unroll
-        for (int j = 0; j < MU; ++j) acch[j] = fma(bka, pr[j], acch[j]); }
-#pragma unroll
-      for (int j = 0; j < MU; ++j) sm.H[lane * LDU + j] = acch[j];
+    if (ti < NX) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + ti * LDP, 1, sm.A + jb * 8, LDA, NX, acc);
+      double2* w = reinterpret_cast<double2*>(sm.W + ti * LDA + jb * 8); w[0] = make_double2(acc[0], acc[1]); w[1] = make_double2(acc[2], acc[3]); w[2] = make_double2(acc[4], acc[5]); w[3] = make_double2(acc[6], acc[7]);
+      if (jb < 3) { double ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + ti * LDP, 1, sm.Bm + jb * 8, LDB, NX, ab);
+        double2* pb = reinterpret_cast<double2*>(sm.PB + ti * LDB + jb * 8); pb[0] = make_double2(ab[0], ab[1]); pb[1] = make_double2(ab[2], ab[3]); pb[2] = make_double2(ab[4], ab[5]); pb[3] = make_double2(ab[6], ab[7]); }
+      else { double s = sm.p[ti]; for (int j = 0; j < NX; ++j) s = fma(sm.P[ti * LDP + j], sm.b[j], s); sm.pPb[ti] = s; }
     }
-    __syncwarp();
-    // P <- Q + A'W ; p <- q + A'(p + P b)
-    if (lane < NX) {
-      double acc[NX]; const double* qrow = sg + ST_Q + (size_t)lane * NX;
+    cp_async_wait<0>(); __syncthreads();           // S~, R~, Q~, q~, r~ have landed; W, PB, pPb visible
+    // ---- phase 2: P <- Q + A'W ; G = S + B'W ; H = R + B'PB ; h = r + B'(p + P b) ; p <- q + A'(p + P b) ----
+    if (ti < NX) {
+      double acc[8]; { const double2* qv = reinterpret_cast<const double2*>(sm.Qb + ti * LDA + jb * 8); const double2 q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3]; acc[0] = q0.x; acc[1] = q0.y; acc[2] = q1.x; acc[3] = q1.y; acc[4] = q2.x; acc[5] = q2.y; acc[6] = q3.x; acc[7] = q3.y; }
+      tile_mac(sm.A + ti, LDA, sm.W + jb * 8, LDA, NX, acc);
+      double* pr = sm.P + ti * LDP + jb * 8;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) acc[j] = qrow[j];
-      double pp = sm.q[lane];
-      for (int kk = 0; kk < NX; ++kk) { const double aki = sm.A[kk * LDX + lane]; const double* wr = sm.W + kk * LDX; pp = fma(aki, sm.pPb[kk], pp);
-#pragma unroll
-        for (int j = 0; j < NX; ++j) acc[j] = fma(aki, wr[j], acc[j]); }
-#pragma unroll
-      for (int j = 0; j < NX; ++j) sm.P[lane * LDX + j] = acc[j];
-      sm.p[lane] = pp;
+      for (int v = 0; v < 8; ++v) if (jb * 8 + v < NX) pr[v] = acc[v];
+      if (jb == 0) { double s = sm.q[ti]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.A[kk * LDA + ti], sm.pPb[kk], s); sm.tmp[ti] = s; }
     }
-    __syncwarp();
-    // symmetrise H, factor, Y = L^{-1} [G | h]
-    if (lane < m) for (int j = 0; j < lane; ++j) { const double a = 0.5 * (sm.H[lane * LDU + j] + sm.H[j * LDU + lane]); sm.H[lane * LDU + j] = a; }
-    __syncwarp();
-    if (!w_cholesky(sm.H, m, LDU, lane)) { st |= MST_NOT_PD; break; }
-    if (lane <= NX) {   // columns 0..29 of G and column 30 = h
-      for (int a = 0; a < m; ++a) { double s = (lane < NX) ? sm.G[a * LDX + lane] : sm.h[a]; for (int c = 0; c < a; ++c) s -= sm.H[a * LDU + c] * ((lane < NX) ? sm.G[c * LDX + lane] : sm.h[c]); s /= sm.H[a * LDU + a]; if (lane < NX) sm.G[a * LDX + lane] = s; else sm.h[a] = s; }
+    if (ti < MU) {
+      double acc[8]; { const double2* gv = reinterpret_cast<const double2*>(sm.G + ti * LDA + jb * 8); const double2 g0 = gv[0], g1 = gv[1], g2 = gv[2], g3 = gv[3]; acc[0] = g0.x; acc[1] = g0.y; acc[2] = g1.x; acc[3] = g1.y; acc[4] = g2.x; acc[5] = g2.y; acc[6] = g3.x; acc[7] = g3.y; }
+      tile_mac(sm.Bm + ti, LDB, sm.W + jb * 8, LDA, NX, acc);
+      double2* gw = reinterpret_cast<double2*>(sm.G + ti * LDA + jb * 8); gw[0] = make_double2(acc[0], acc[1]); gw[1] = make_double2(acc[2], acc[3]); gw[2] = make_double2(acc[4], acc[5]); gw[3] = make_double2(acc[6], acc[7]);
+      if (jb < 3) { double ah[8]; { const double2* hv = reinterpret_cast<const double2*>(sm.H + ti * LDB + jb * 8); const double2 h0 = hv[0], h1 = hv[1], h2 = hv[2], h3 = hv[3]; ah[0] = h0.x; ah[1] = h0.y; ah[2] = h1.x; ah[3] = h1.y; ah[4] = h2.x; ah[5] = h2.y; ah[6] = h3.x; ah[7] = h3.y; }
+        tile_mac(sm.Bm + ti, LDB, sm.PB + jb * 8, LDB, NX, ah);
+        double2* hw = reinterpret_cast<double2*>(sm.H + ti * LDB + jb * 8); hw[0] = make_double2(ah[0], ah[1]); hw[1] = make_double2(ah[2], ah[3]); hw[2] = make_double2(ah[4], ah[5]); hw[3] = make_double2(ah[6], ah[7]); }
+      else { double s = sm.r[ti]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.Bm[kk * LDB + ti], sm.pPb[kk], s); sm.G[ti * LDA + NX] = s; }   // h rides in column 30 of G
     }
-    __syncwarp();
-    // P -= Y'Y ; p -= Y' yh ; symmetrise
-    if (lane < NX) {
-      double acc[NX];
+    __syncthreads();
+    if (tid < NX) sm.p[tid] = sm.tmp[tid];
+    if (k > 0) issue_ab(k - 1);                    // A~/B~ buffers are free: prefetch the next node under phases 3-4
+    // ---- phase 3 (warp 0): H = L L', Y = L^{-1}[G | h], K = -L^{-T} Y → global ----
+    if (warp == 0) {
+      double hr[MU];
 #pragma unroll
-      for (int j = 0; j < NX; ++j) acc[j] = sm.P[lane * LDX + j];
-      double pp = sm.p[lane];
-      for (int a = 0; a < m; ++a) { const double yai = sm.G[a * LDX + lane]; const double* yr = sm.G + a * LDX; pp = fma(-yai, sm.h[a], pp);
+      for (int c = 0; c < MU; ++c) hr[c] = (lane < MU) ? 0.5 * (sm.H[lane * LDB + c] + sm.H[c * LDB + lane]) : 0.0;
+      bool ok = true;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) acc[j] = fma(-yai, yr[j], acc[j]); }
+      for (int j = 0; j < MU; ++j) {
+        const double djj = __shfl_sync(FULL, hr[j], j); if (!(djj > 0.0)) ok = false;
+        const double d = sqrt(djj); const double lij = hr[j] / d;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) sm.P[lane * LDX + j] = acc[j];
-      sm.p[lane] = pp;
+        for (int c = j + 1; c < MU; ++c) { const double lcj = __shfl_sync(FULL, lij, c); if (lane >= c) hr[c] = fma(-lij, lcj, hr[c]); }
+        hr[j] = (lane == j) ? d : lij;
+      }
+      __syncwarp();
+      if (lane < MU) {
+#pragma unroll
+        for (int c = 0; c < MU; ++c) sm.H[lane * LDB + c] = hr[c];
+      }
+      __syncwarp();
+      if (!ok && lane == 0) sm.flag = 1;
+      if (lane <= NX) {   // lane j < 30: column j of G ; lane 30: column 30 of G = h (kept there by phase 2)
+        double* col = sm.G + lane; double* kc = sm.W + lane;   // W is free after phase 2: scratch for the gain columns
+#pragma unroll 1
+        for (int a = 0; a < MU; ++a) { double s = col[a * LDA];
+#pragma unroll 4
+          for (int c = 0; c < a; ++c) s = fma(-sm.H[a * LDB + c], col[c * LDA], s);
+          col[a * LDA] = s / sm.H[a * LDB + a]; }
+        double* gk = gb + (size_t)k * GAIN_DBL;
+#pragma unroll 1
+        for (int a = MU - 1; a >= 0; --a) { double s = col[a * LDA];
+#pragma unroll 4
+          for (int c = a + 1; c < MU; ++c) s = fma(-sm.H[c * LDB + a], kc[c * LDA], s);
+          s /= sm.H[a * LDB + a]; kc[a * LDA] = s; if (lane < NX) gk[a * NX + lane] = -s; else gk[MU * NX + a] = -s; }
+      }
     }
-    __syncwarp();
-    if (lane < NX) for (int j = 0; j < lane; ++j) { const double a = 0.5 * (sm.P[lane * LDX + j] + sm.P[j * LDX + lane]); sm.P[lane * LDX + j] = a; }
-    __syncwarp();
-    if (lane < NX) for (int j = lane + 1; j < NX; ++j) sm.P[lane * LDX + j] = sm.P[j * LDX + lane];
-    // K = -L^{-T} Y ; k = -L^{-T} yh     → global
-    if (lane <= NX) {
-      for (int a = m - 1; a >= 0; --a) { double s = (lane < NX) ? sm.G[a * LDX + lane] : sm.h[a]; for (int c = a + 1; c < m; ++c) s -= sm.H[c * LDU + a] * ((lane < NX) ? sm.G[c * LDX + lane] : sm.h[c]); s /= sm.H[a * LDU + a]; if (lane < NX) sm.G[a * LDX + lane] = s; else sm.h[a] = s; }
+    __syncthreads();
+    if (sm.flag) { st |= MST_NOT_PD; break; }
+    // ---- phase 4: P -= Y'Y ; p -= Y' yh ----
+    if (ti < NX) {
+      double* pr = sm.P + ti * LDP + jb * 8; double acc[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) acc[v] = pr[v];
+      double neg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.G + ti, LDA, sm.G + jb * 8, LDA, MU, neg);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) if (jb * 8 + v < NX) pr[v] = acc[v] - neg[v];
+      if (jb == 0) { double s = sm.p[ti]; for (int a = 0; a < MU; ++a) s = fma(-sm.G[a * LDA + ti], sm.G[a * LDA + NX], s); sm.tmp[ti] = s; }
     }
-    __syncwarp();
-    double* gk = gb + (size_t)k * GAIN_DBL;
-    for (int e = lane; e < m * NX; e += 32) gk[e] = -sm.G[(e / NX) * LDX + (e % NX)];
-    if (lane < m) gk[MU * NX + lane] = -sm.h[lane];
-    __syncwarp();
+    __syncthreads();
+    if (tid < NX) sm.p[tid] = sm.tmp[tid];
+    if (k > 0) issue_srq(k - 1);                   // G/H/Qb buffers are free now
   }
-  // ---- forward rollout: dx_{k+1} = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~ ----
+  cp_async_wait<0>(); __syncthreads();
+  // ---- forward rollout: du~ = K dx + k ; dx+ = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~ ----
   double armijo = 0.0, dxn2 = 0.0, dun2 = 0.0;
   if (!(st & MST_NOT_PD)) {
     for (int k = 0; k < N; ++k) {
-      const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sib + (size_t)k * STAGE_INT; const int type = si[SI_TYPE], m = si[SI_M], ndep = si[SI_NDEP];
+      const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sib + (size_t)k * STAGE_INT; const int type = si[SI_TYPE], ndep = si[SI_NDEP];
       double* dxk = dxo + ((size_t)b * nmax + k) * NX; double* duk = duo + ((size_t)b * nmax + k) * NU;
-      const double dxi = (lane < NX) ? sm.dx[lane] : 0.0; if (lane < NX) dxk[lane] = dxi; dxn2 += dxi * dxi;
-      if (type == 1) { if (lane < NX) { duk[lane] = 0.0; sm.tmp[lane] = dxi + sg[ST_b + lane]; } __syncwarp(); if (lane < NX) sm.dx[lane] = sm.tmp[lane]; __syncwarp(); continue; }
+      if (tid < NX) { const double dxi = sm.dx[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
+      if (type == 1) { if (tid < NX) { duk[tid] = 0.0; sm.tmp[tid] = sm.dx[tid] + sg[ST_b + tid]; } __syncthreads(); if (tid < NX) sm.dx[tid] = sm.tmp[tid]; __syncthreads(); continue; }
       const double* gk = gb + (size_t)k * GAIN_DBL;
-      load_mat(gk, m, NX, NX, sm.G, LDX, lane); load_mat(sg + ST_A, NX, NX, NX, sm.A, LDX, lane); load_mat(sg + ST_B, NX, m, MU, sm.Bm, LDU, lane);
-      __syncwarp();
-      double dut = 0.0; if (lane < m) { dut = gk[MU * NX + lane]; for (int j = 0; j < NX; ++j) dut += sm.G[lane * LDX + j] * sm.dx[j]; sm.dut[lane] = dut; }
-      armijo += ((lane < NX) ? sg[ST_q + lane] * dxi : 0.0) + ((lane < m) ? sg[ST_r + lane] * dut : 0.0);
-      __syncwarp();
-      if (lane < NX) { double s = sg[ST_b + lane]; for (int j = 0; j < NX; ++j) s += sm.A[lane * LDX + j] * sm.dx[j]; for (int a = 0; a < m; ++a) s += sm.Bm[lane * LDU + a] * sm.dut[a]; sm.tmp[lane] = s; }
-      // full-space input step
-      if (lane < m) duk[si[SI_FREE + lane]] = dut;
-      double dud = 0.0;
-      if (lane < ndep) { dud = sg[ST_PED + lane]; const double* px = sg + ST_PXD + (size_t)lane * NX; const double* pu = sg + ST_PUD + (size_t)lane * MU; for (int j = 0; j < NX; ++j) dud += px[j] * sm.dx[j]; for (int a = 0; a < m; ++a) dud += pu[a] * sm.dut[a]; duk[si[SI_DEP + lane]] = dud; }
-      dun2 += ((lane < m) ? dut * dut : 0.0) + dud * dud;
-      __syncwarp();
-      if (lane < NX) sm.dx[lane] = sm.tmp[lane];
-      __syncwarp();
+      cp_rows(gk, MU, NX, NX, sm.G, LDA, tid); cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
+      if (tid < 15) cp_async16(sm.b + 2 * tid, sg + ST_b + 2 * tid); else if (tid < 30) cp_async16(sm.q + 2 * (tid - 15), sg + ST_q + 2 * (tid - 15)); else if (tid < 39) cp_async16(sm.r + 2 * (tid - 30), sg + ST_r + 2 * (tid - 30)); else if (tid < 48) cp_async16(sm.kff + 2 * (tid - 39), gk + MU * NX + 2 * (tid - 39));
+      cp_async_commit(); cp_async_wait<0>(); __syncthreads();
+      { double s = 0.0;   // all lanes take part in the quad reduction (shfl_sync needs the full mask)
+        if (ti < MU) { const double* kr = sm.G + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) s = fma(kr[v], dx[v], s); }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + sm.kff[ti]; }
+      __syncthreads();
+      { double s = 0.0;
+        if (ti < NX) { const double* ar = sm.A + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) s = fma(ar[v], dx[v], s);
+          if (jb < 3) { const double* br = sm.Bm + ti * LDB + jb * 8; const double* du = sm.dut + jb * 8;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) s = fma(br[v], du[v], s); } }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) sm.tmp[ti] = s + sm.b[ti]; }
+      if (tid < NX) armijo += sm.q[tid] * sm.dx[tid];
+      if (tid < MU) { const double dut = sm.dut[tid]; armijo += sm.r[tid] * dut; const int fi = si[SI_FREE + tid]; if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; } }
+      if (tid >= 64 && tid < 64 + MAXDEP) { const int d = tid - 64; if (d < ndep) { double s = sg[ST_PED + d]; const double* px = sg + ST_PXD + (size_t)d * NX; const double* pu = sg + ST_PUD + (size_t)d * MU;
+          for (int j = 0; j < NX; ++j) s = fma(px[j], sm.dx[j], s); for (int a = 0; a < MU; ++a) s = fma(pu[a], sm.dut[a], s); duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
+      __syncthreads();
+      if (tid < NX) sm.dx[tid] = sm.tmp[tid];
+      __syncthreads();
     }
-    { const double dxi = (lane < NX) ? sm.dx[lane] : 0.0; if (lane < NX) { dxo[((size_t)b * nmax + N) * NX + lane] = dxi; duo[((size_t)b * nmax + N) * NU + lane] = 0.0; } dxn2 += dxi * dxi;
-      armijo += (lane < NX) ? sgb[(size_t)N * STAGE_DBL + ST_q + lane] * dxi : 0.0; }
+    if (tid < NX) { const double dxi = sm.dx[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_q + tid] * dxi; }
   }
   armijo = warp_sum(armijo); dxn2 = warp_sum(dxn2); dun2 = warp_sum(dun2);
-  if (lane == 0) { double* rb = robot + (size_t)b * ROBOT_DBL; rb[0] = armijo; rb[1] = perf[0]; rb[2] = perf[1]; rb[3] = perf[2]; rb[4] = sqrt(dxn2); rb[5] = sqrt(dun2); if (st) atomicOr(&status[b], st); }
+  __syncthreads();
+  if (lane == 0) { sm.red[warp][0] = armijo; sm.red[warp][1] = dxn2; sm.red[warp][2] = dun2; }
+  __syncthreads();
+  if (tid == 0) { double a = 0, x2 = 0, u2 = 0; for (int w = 0; w < RIC_THREADS / 32; ++w) { a += sm.red[w][0]; x2 += sm.red[w][1]; u2 += sm.red[w][2]; }
+    double* rb = robot + (size_t)b * ROBOT_DBL; rb[0] = a; rb[1] = perf[0]; rb[2] = perf[1]; rb[3] = perf[2]; rb[4] = sqrt(x2); rb[5] = sqrt(u2); if (st) atomicOr(&status[b], st); }
 }
 
 // =====================================================================================================
@@ -515,7 +638,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
-    cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RicSmem) * RIC_WARPS));
+    cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
     cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
     configured = true;
   }
@@ -527,7 +650,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   const long long nodes = (long long)B * nmax;
   mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.status);
   if (ev) cudaEventRecord(ev[2], stream);
-  mpc_riccati_kernel<<<(B + RIC_WARPS - 1) / RIC_WARPS, 32 * RIC_WARPS, sizeof(RicSmem) * RIC_WARPS, stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
+  mpc_riccati_kernel<<<B, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
   if (ev) cudaEventRecord(ev[3], stream);
   mpc_linesearch_kernel<<<B, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, B, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info);
   if (ev) cudaEventRecord(ev[4], stream);

@@ -25,9 +25,9 @@ namespace qmb {
 
 constexpr int LDM = 25;   // leading dimension of 24-column matrices (odd → conflict-free column walks)
 constexpr int LDZ = 37;   // leading dimension of 36-column / 36-row matrices
-constexpr int MAXR = 32;  // max rows of one level's equality task (+ violated rows at level 0)
-constexpr int MAXW = 20;  // max size of the inequality working set
-constexpr int WBC_WARPS = 3;
+constexpr int MAXR = 24;  // max rows of one level's equality task (22 in flight mode) or 18 + violated rows at level 0
+constexpr int MAXW = 16;  // max size of the inequality working set
+constexpr int WBC_WARPS = 4;
 
 enum { ST_OK = 0, ST_ITER_CAP = 1, ST_TOO_MANY_ROWS = 2, ST_NAN = 4 };
 
