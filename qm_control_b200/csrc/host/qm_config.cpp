@@ -214,7 +214,7 @@ HostModel build_host_model(const std::string& task_file, const std::string& urdf
   for (int b = 0; b < NB; ++b) { d.mass[b] = lumps[b].m; std::memcpy(d.com[b], lumps[b].c, sizeof(lumps[b].c)); std::memcpy(d.Ib[b], lumps[b].I, sizeof(lumps[b].I)); d.total_mass += lumps[b].m; }
   auto frame = [&](const std::string& n) -> const HostFrame& { for (auto& f : hm.frames) if (f.name == n) return f; throw std::runtime_error("URDF: frame not found: " + n); };
   const char* feet[4] = {"LF_FOOT", "RF_FOOT", "LH_FOOT", "RH_FOOT"};   // ModelSettings.h:38
-  for (int i = 0; i < 4; ++i) { const HostFrame& f = frame(feet[i]); d.foot_body[i] = f.body; std::memcpy(d.foot_p[i], f.p, sizeof(f.p)); d.foot_leg[i] = d.chain_start[f.body - 1]; }
+  for (int i = 0; i < 4; ++i) { const HostFrame& f = frame(feet[i]); d.foot_body[i] = f.body; std::memcpy(d.foot_p[i], f.p, sizeof(f.p)); d.foot_leg[i] = d.chain_start[f.body - 1]; d.leg_foot[d.foot_leg[i] / 3] = i; }
   { const HostFrame& f = frame(task.text("model_settings.eeFrame")); d.ee_body = f.body; std::memcpy(d.ee_R, f.R, sizeof(f.R)); std::memcpy(d.ee_p, f.p, sizeof(f.p)); }
 
   // --- CentroidalModelInfo, SRBD (createCentroidalModelInfo [upstream]) ---

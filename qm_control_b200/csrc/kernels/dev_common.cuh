@@ -29,6 +29,7 @@ struct DevModel {
   double Ib[NB][9];        // about com, body frame
   int foot_body[4];        // contact order LF, RF, LH, RH
   int foot_leg[4];         // index of the leg's first joint (joint order LF, LH, RF, RH)
+  int leg_foot[4];         // inverse map: leg (first joint / 3) → foot index
   double foot_p[4][3];
   int ee_body; double ee_R[9]; double ee_p[3];
   double total_mass;

@@ -28,7 +28,7 @@ struct PointWs {
   double pf[4][3], d[4][3], Jl[4][9], al[4][9];   // Jl[i][3*j + a]: component a of leg-Jacobian column j of foot i
 };
 
-__device__ __forceinline__ int foot_of_leg_joint(const DevModel* __restrict__ mdl, int j) { const int first = 3 * (j / 3); for (int i = 0; i < 4; ++i) if (mdl->foot_leg[i] == first) return i; return -1; }
+__device__ __forceinline__ int foot_of_leg_joint(const DevModel* __restrict__ mdl, int j) { return mdl->leg_foot[j / 3]; }
 
 // Evaluate the flow map (and its Jacobian rows if with_jac) at (ws->x, ws->u).
 template <bool with_jac>

@@ -332,13 +332,14 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
 // warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
 // LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
 constexpr int RIC_THREADS = 128;
-constexpr int LDP = 33, LDA = 32, LDB = 24;
+constexpr int LDP = 33, LDA = 32, LDB = 24, LDL = 19;
 struct RicSmem {
   double P[NX * LDP];                       // value-function Hessian (row operand)
   double A[NX * LDA], W[NX * LDA], Qb[NX * LDA];
   double Bm[NX * LDB], PB[NX * LDB];
   double G[MU * LDA];                       // S~, then G, then Y = L^{-1} G
   double H[MU * LDB];                       // R~, then H, then its Cholesky factor
+  double Li[MU * LDL];                      // L^{-1} (lower triangular; upper part stays zero)
   double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32];
   double red[RIC_THREADS / 32][4];
   int flag;
@@ -390,10 +391,10 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   __syncthreads();
   double perf[3]; for (int i = 0; i < 3; ++i) perf[i] = sm.red[0][i] + sm.red[1][i] + sm.red[2][i] + sm.red[3][i];
   int st = 0;
+  const int cb = warp * 8;                          // backward sweep mapping: lane = row, warp = 8-column block (operand rows are pure broadcasts)
   for (int k = N - 1; k >= 0; --k) {
     const int type = sib[(size_t)k * STAGE_INT + SI_TYPE];
     cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed
-    // ---- phase 1: pPb = p + P b ; W = P A ; PB = P B ----
     if (type == 1) {                                // event node: A = I, no input
       if (tid < NX) { double s = sm.p[tid]; for (int j = 0; j < NX; ++j) s = fma(sm.P[tid * LDP + j], sm.b[j], s); sm.tmp[tid] = s; }
       cp_async_wait<0>(); __syncthreads();
@@ -402,85 +403,84 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }
       continue;
     }
-    if (ti < NX) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + ti * LDP, 1, sm.A + jb * 8, LDA, NX, acc);
-      double2* w = reinterpret_cast<double2*>(sm.W + ti * LDA + jb * 8); w[0] = make_double2(acc[0], acc[1]); w[1] = make_double2(acc[2], acc[3]); w[2] = make_double2(acc[4], acc[5]); w[3] = make_double2(acc[6], acc[7]);
-      if (jb < 3) { double ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + ti * LDP, 1, sm.Bm + jb * 8, LDB, NX, ab);
-        double2* pb = reinterpret_cast<double2*>(sm.PB + ti * LDB + jb * 8); pb[0] = make_double2(ab[0], ab[1]); pb[1] = make_double2(ab[2], ab[3]); pb[2] = make_double2(ab[4], ab[5]); pb[3] = make_double2(ab[6], ab[7]); }
-      else { double s = sm.p[ti]; for (int j = 0; j < NX; ++j) s = fma(sm.P[ti * LDP + j], sm.b[j], s); sm.pPb[ti] = s; }
+    // ---- phase 1: W = P A (4 warps) ; PB = P B (warps 0-2) ; pPb = p + P b (warp 3) ----
+    if (lane < NX) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + lane * LDP, 1, sm.A + cb, LDA, NX, acc);
+      double2* w = reinterpret_cast<double2*>(sm.W + lane * LDA + cb); w[0] = make_double2(acc[0], acc[1]); w[1] = make_double2(acc[2], acc[3]); w[2] = make_double2(acc[4], acc[5]); w[3] = make_double2(acc[6], acc[7]);
+      if (warp < 3) { double ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + lane * LDP, 1, sm.Bm + cb, LDB, NX, ab);
+        double2* pb = reinterpret_cast<double2*>(sm.PB + lane * LDB + cb); pb[0] = make_double2(ab[0], ab[1]); pb[1] = make_double2(ab[2], ab[3]); pb[2] = make_double2(ab[4], ab[5]); pb[3] = make_double2(ab[6], ab[7]); }
+      else { double s = sm.p[lane]; for (int j = 0; j < NX; ++j) s = fma(sm.P[lane * LDP + j], sm.b[j], s); sm.pPb[lane] = s; }
     }
     cp_async_wait<0>(); __syncthreads();           // S~, R~, Q~, q~, r~ have landed; W, PB, pPb visible
-    // ---- phase 2: P <- Q + A'W ; G = S + B'W ; H = R + B'PB ; h = r + B'(p + P b) ; p <- q + A'(p + P b) ----
-    if (ti < NX) {
-      double acc[8]; { const double2* qv = reinterpret_cast<const double2*>(sm.Qb + ti * LDA + jb * 8); const double2 q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3]; acc[0] = q0.x; acc[1] = q0.y; acc[2] = q1.x; acc[3] = q1.y; acc[4] = q2.x; acc[5] = q2.y; acc[6] = q3.x; acc[7] = q3.y; }
-      tile_mac(sm.A + ti, LDA, sm.W + jb * 8, LDA, NX, acc);
-      double* pr = sm.P + ti * LDP + jb * 8;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) if (jb * 8 + v < NX) pr[v] = acc[v];
-      if (jb == 0) { double s = sm.q[ti]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.A[kk * LDA + ti], sm.pPb[kk], s); sm.tmp[ti] = s; }
-    }
-    if (ti < MU) {
-      double acc[8]; { const double2* gv = reinterpret_cast<const double2*>(sm.G + ti * LDA + jb * 8); const double2 g0 = gv[0], g1 = gv[1], g2 = gv[2], g3 = gv[3]; acc[0] = g0.x; acc[1] = g0.y; acc[2] = g1.x; acc[3] = g1.y; acc[4] = g2.x; acc[5] = g2.y; acc[6] = g3.x; acc[7] = g3.y; }
-      tile_mac(sm.Bm + ti, LDB, sm.W + jb * 8, LDA, NX, acc);
-      double2* gw = reinterpret_cast<double2*>(sm.G + ti * LDA + jb * 8); gw[0] = make_double2(acc[0], acc[1]); gw[1] = make_double2(acc[2], acc[3]); gw[2] = make_double2(acc[4], acc[5]); gw[3] = make_double2(acc[6], acc[7]);
-      if (jb < 3) { double ah[8]; { const double2* hv = reinterpret_cast<const double2*>(sm.H + ti * LDB + jb * 8); const double2 h0 = hv[0], h1 = hv[1], h2 = hv[2], h3 = hv[3]; ah[0] = h0.x; ah[1] = h0.y; ah[2] = h1.x; ah[3] = h1.y; ah[4] = h2.x; ah[5] = h2.y; ah[6] = h3.x; ah[7] = h3.y; }
-        tile_mac(sm.Bm + ti, LDB, sm.PB + jb * 8, LDB, NX, ah);
-        double2* hw = reinterpret_cast<double2*>(sm.H + ti * LDB + jb * 8); hw[0] = make_double2(ah[0], ah[1]); hw[1] = make_double2(ah[2], ah[3]); hw[2] = make_double2(ah[4], ah[5]); hw[3] = make_double2(ah[6], ah[7]); }
-      else { double s = sm.r[ti]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.Bm[kk * LDB + ti], sm.pPb[kk], s); sm.G[ti * LDA + NX] = s; }   // h rides in column 30 of G
+    // ---- phase 2: G = S + B'W (4 warps) ; H = R + B'PB (warps 0-2) ; h = r + B'(p + P b) (warp 3, kept in column 30 of G) ----
+    if (lane < MU) {
+      double acc[8]; { const double2* gv = reinterpret_cast<const double2*>(sm.G + lane * LDA + cb); const double2 g0 = gv[0], g1 = gv[1], g2 = gv[2], g3 = gv[3]; acc[0] = g0.x; acc[1] = g0.y; acc[2] = g1.x; acc[3] = g1.y; acc[4] = g2.x; acc[5] = g2.y; acc[6] = g3.x; acc[7] = g3.y; }
+      tile_mac(sm.Bm + lane, LDB, sm.W + cb, LDA, NX, acc);
+      if (warp == 3) { double s = sm.r[lane]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.Bm[kk * LDB + lane], sm.pPb[kk], s); acc[6] = s; }   // column 30 := h
+      double2* gw = reinterpret_cast<double2*>(sm.G + lane * LDA + cb); gw[0] = make_double2(acc[0], acc[1]); gw[1] = make_double2(acc[2], acc[3]); gw[2] = make_double2(acc[4], acc[5]); gw[3] = make_double2(acc[6], acc[7]);
+      if (warp < 3) { double ah[8]; { const double2* hv = reinterpret_cast<const double2*>(sm.H + lane * LDB + cb); const double2 h0 = hv[0], h1 = hv[1], h2 = hv[2], h3 = hv[3]; ah[0] = h0.x; ah[1] = h0.y; ah[2] = h1.x; ah[3] = h1.y; ah[4] = h2.x; ah[5] = h2.y; ah[6] = h3.x; ah[7] = h3.y; }
+        tile_mac(sm.Bm + lane, LDB, sm.PB + cb, LDB, NX, ah);
+        double2* hw = reinterpret_cast<double2*>(sm.H + lane * LDB + cb); hw[0] = make_double2(ah[0], ah[1]); hw[1] = make_double2(ah[2], ah[3]); hw[2] = make_double2(ah[4], ah[5]); hw[3] = make_double2(ah[6], ah[7]); }
     }
     __syncthreads();
-    if (tid < NX) sm.p[tid] = sm.tmp[tid];
-    if (k > 0) issue_ab(k - 1);                    // A~/B~ buffers are free: prefetch the next node under phases 3-4
-    // ---- phase 3 (warp 0): H = L L', Y = L^{-1}[G | h], K = -L^{-T} Y → global ----
-    if (warp == 0) {
-      double hr[MU];
-#pragma unroll
-      for (int c = 0; c < MU; ++c) hr[c] = (lane < MU) ? 0.5 * (sm.H[lane * LDB + c] + sm.H[c * LDB + lane]) : 0.0;
+    // ---- phase 3: one warp factors H and inverts the factor ; the other three compute P <- Q + A'W and p <- q + A'(p + P b) meanwhile.
+    // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
+    const int sw = (k + b) & 3, rel = (warp - sw - 1) & 3;
+    if (warp == sw) {
+      if (lane < MU) for (int c = 0; c < lane; ++c) sm.H[lane * LDB + c] = 0.5 * (sm.H[lane * LDB + c] + sm.H[c * LDB + lane]);
+      __syncwarp();
+      // in-place lower Cholesky, lane = row; reciprocal pivots kept in sm.dut so that the solves multiply instead of divide
       bool ok = true;
-#pragma unroll
       for (int j = 0; j < MU; ++j) {
-        const double djj = __shfl_sync(FULL, hr[j], j); if (!(djj > 0.0)) ok = false;
-        const double d = sqrt(djj); const double lij = hr[j] / d;
-#pragma unroll
-        for (int c = j + 1; c < MU; ++c) { const double lcj = __shfl_sync(FULL, lij, c); if (lane >= c) hr[c] = fma(-lij, lcj, hr[c]); }
-        hr[j] = (lane == j) ? d : lij;
+        const double djj = sm.H[j * LDB + j]; if (!(djj > 0.0)) ok = false;
+        const double inv = rsqrt(djj);
+        __syncwarp();
+        if (lane == j) { sm.H[j * LDB + j] = djj * inv; sm.dut[j] = inv; }
+        if (lane > j && lane < MU) sm.H[lane * LDB + j] *= inv;
+        __syncwarp();
+        if (lane > j && lane < MU) { const double lij = sm.H[lane * LDB + j]; for (int c = j + 1; c <= lane; ++c) sm.H[lane * LDB + c] = fma(-lij, sm.H[c * LDB + j], sm.H[lane * LDB + c]); }
+        __syncwarp();
       }
-      __syncwarp();
-      if (lane < MU) {
-#pragma unroll
-        for (int c = 0; c < MU; ++c) sm.H[lane * LDB + c] = hr[c];
-      }
-      __syncwarp();
       if (!ok && lane == 0) sm.flag = 1;
-      if (lane <= NX) {   // lane j < 30: column j of G ; lane 30: column 30 of G = h (kept there by phase 2)
-        double* col = sm.G + lane; double* kc = sm.W + lane;   // W is free after phase 2: scratch for the gain columns
-#pragma unroll 1
-        for (int a = 0; a < MU; ++a) { double s = col[a * LDA];
-#pragma unroll 4
-          for (int c = 0; c < a; ++c) s = fma(-sm.H[a * LDB + c], col[c * LDA], s);
-          col[a * LDA] = s / sm.H[a * LDB + a]; }
-        double* gk = gb + (size_t)k * GAIN_DBL;
-#pragma unroll 1
-        for (int a = MU - 1; a >= 0; --a) { double s = col[a * LDA];
-#pragma unroll 4
-          for (int c = a + 1; c < MU; ++c) s = fma(-sm.H[c * LDB + a], kc[c * LDA], s);
-          s /= sm.H[a * LDB + a]; kc[a * LDA] = s; if (lane < NX) gk[a * NX + lane] = -s; else gk[MU * NX + a] = -s; }
+      if (lane < MU) {   // column `lane` of L^{-1} by forward substitution
+        const int j = lane;
+        for (int a = j; a < MU; ++a) { double s = (a == j) ? 1.0 : 0.0; for (int c = j; c < a; ++c) s = fma(-sm.H[a * LDB + c], sm.Li[c * LDL + j], s); sm.Li[a * LDL + j] = s * sm.dut[a]; }
+      }
+    } else {
+      if (lane < NX) {
+        for (int blk = rel; blk < 4; blk += 3) {   // column blocks 0..3 over the three helper warps (the first also takes block 3)
+          const int c0 = blk * 8; double acc[8]; { const double2* qv = reinterpret_cast<const double2*>(sm.Qb + lane * LDA + c0); const double2 q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3]; acc[0] = q0.x; acc[1] = q0.y; acc[2] = q1.x; acc[3] = q1.y; acc[4] = q2.x; acc[5] = q2.y; acc[6] = q3.x; acc[7] = q3.y; }
+          tile_mac(sm.A + lane, LDA, sm.W + c0, LDA, NX, acc);
+          double* pr = sm.P + lane * LDP + c0;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) if (c0 + v < NX) pr[v] = acc[v];
+        }
+        if (rel == 2) { double s = sm.q[lane]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.A[kk * LDA + lane], sm.pPb[kk], s); sm.tmp[lane] = s; }
       }
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; break; }
-    // ---- phase 4: P -= Y'Y ; p -= Y' yh ----
-    if (ti < NX) {
-      double* pr = sm.P + ti * LDP + jb * 8; double acc[8];
-#pragma unroll
-      for (int v = 0; v < 8; ++v) acc[v] = pr[v];
-      double neg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.G + ti, LDA, sm.G + jb * 8, LDA, MU, neg);
-#pragma unroll
-      for (int v = 0; v < 8; ++v) if (jb * 8 + v < NX) pr[v] = acc[v] - neg[v];
-      if (jb == 0) { double s = sm.p[ti]; for (int a = 0; a < MU; ++a) s = fma(-sm.G[a * LDA + ti], sm.G[a * LDA + NX], s); sm.tmp[ti] = s; }
+    if (k > 0) issue_ab(k - 1);                    // A~/B~ buffers are free: prefetch the next node under phases 4-5
+    // ---- phase 4: Y = L^{-1} [G | h] → W buffer (rows 0..17) ----
+    if (lane < MU) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.Li + lane * LDL, 1, sm.G + cb, LDA, MU, acc);
+      double2* yw = reinterpret_cast<double2*>(sm.W + lane * LDA + cb); yw[0] = make_double2(acc[0], acc[1]); yw[1] = make_double2(acc[2], acc[3]); yw[2] = make_double2(acc[4], acc[5]); yw[3] = make_double2(acc[6], acc[7]);
     }
     __syncthreads();
-    if (tid < NX) sm.p[tid] = sm.tmp[tid];
+    // ---- phase 5: K = -L^{-T} Y → global ; P -= Y'Y ; p -= Y' yh ----
+    if (lane < MU) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.Li + lane, LDL, sm.W + cb, LDA, MU, acc);
+      double* gk = gb + (size_t)k * GAIN_DBL;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) { const int col = cb + v; if (col < NX) gk[lane * NX + col] = -acc[v]; else if (col == NX) gk[MU * NX + lane] = -acc[v]; }
+    }
+    if (lane < NX) {
+      double* pr = sm.P + lane * LDP + cb; double neg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.W + lane, LDA, sm.W + cb, LDA, MU, neg);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) if (cb + v < NX) pr[v] -= neg[v];
+      if (warp == 3) { double s = sm.tmp[lane]; for (int a = 0; a < MU; ++a) s = fma(-sm.W[a * LDA + lane], sm.W[a * LDA + NX], s); sm.p[lane] = s; }
+    }
+    __syncthreads();
     if (k > 0) issue_srq(k - 1);                   // G/H/Qb buffers are free now
   }
   cp_async_wait<0>(); __syncthreads();

@@ -26,7 +26,7 @@ namespace qmb {
 constexpr int LDM = 25;   // leading dimension of 24-column matrices (odd → conflict-free column walks)
 constexpr int LDZ = 37;   // leading dimension of 36-column / 36-row matrices
 constexpr int MAXR = 24;  // max rows of one level's equality task (22 in flight mode) or 18 + violated rows at level 0
-constexpr int MAXW = 16;  // max size of the inequality working set
+constexpr int MAXW = 20;  // max size of the inequality working set
 constexpr int WBC_WARPS = 4;
 
 enum { ST_OK = 0, ST_ITER_CAP = 1, ST_TOO_MANY_ROWS = 2, ST_NAN = 4 };
@@ -36,6 +36,7 @@ struct QpWs {
   double Z[36 * LDZ];          // orthonormal basis; active window = columns [off, 36)
   double W[LDZ * MAXR];        // COD workspace (n_z x r, column-major)
   double Wc[LDZ * MAXW];       // working-set constraint COD workspace (n_z x nw)
+  double Gw[MAXW * LDZ];       // explicit rows of the working-set constraints (filled when a row enters the set)
   double tau[MAXR], tauc[MAXW];
   double xbar[36], dx[36], g[36], y[36], s[36], rhs[MAXR], bp[MAXR], lam[MAXW], G[MAXR * (MAXR + 1)], t18[MAXR];
   int perm[MAXR], permc[MAXW], wset[MAXW];
@@ -198,18 +199,23 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
     // (1) working-set constraints in window coordinates: Wc[c + k*LDZ] = G_{w_k} . Z[:, off+c]
     int kc = 0;
     if (nw > 0) {
-      for (int e = lane; e < nw * nz; e += 32) { const int k = e / nz, c = e % nz; double s = 0.0; for (int j = 0; j < 36; ++j) s += ineq_row_elem(ic, qp.wset[k], j) * qp.Z[j * LDZ + off + c]; qp.Wc[c + k * LDZ] = s; }
+      for (int e = lane; e < nw * nz; e += 32) { const int k = e / nz, c = e % nz; const double* gr = qp.Gw + k * LDZ; double s = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < 36; ++j) s = fma(gr[j], qp.Z[j * LDZ + off + c], s);
+        qp.Wc[c + k * LDZ] = s; }
       __syncwarp();
       kc = w_qrcp(qp.Wc, nz, nw, LDZ, qp.tauc, qp.permc, 1e-10, lane);
       if (kc < nw) {   // dependent rows in this window: keep an independent subset and refactor
-        int keep = (lane < kc) ? qp.wset[qp.permc[lane]] : -1; __syncwarp(); if (lane < kc) qp.wset[lane] = keep; nw = kc; __syncwarp(); continue;
+        int keep = (lane < kc) ? qp.wset[qp.permc[lane]] : -1; __syncwarp(); if (lane < kc) qp.wset[lane] = keep; nw = kc; __syncwarp();
+        for (int k2 = 0; k2 < nw; ++k2) for (int j = lane; j < 36; j += 32) qp.Gw[k2 * LDZ + j] = ineq_row_elem(ic, qp.wset[k2], j);
+        __syncwarp(); continue;
       }
     }
     // (2) least squares for the step in the free directions
     project_task(qp, rows, off, nz, lane);
     if (lane < rows) { const double* a = qp.Ap + lane * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.xbar[k]; qp.rhs[lane] = qp.bp[lane] - s; }
     __syncwarp();
-    if (kc > 0) { for (int i = 0; i < rows; ++i) w_apply_qt(qp.Wc, nz, kc, LDZ, qp.tauc, qp.W + i * LDZ, lane); }
+    if (kc > 0) w_apply_qt_cols(qp.Wc, nz, kc, LDZ, qp.tauc, qp.W, rows, LDZ, lane);
     const int nfree = nz - kc;
     for (int i = lane; i < nz; i += 32) qp.s[i] = 0.0;
     __syncwarp();
@@ -232,7 +238,7 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
       { double a = alpha; int b = (blk < 0) ? 0x7fffffff : blk; warp_argmin(a, b); alpha = a; blk = (alpha < 1.0) ? b : -1; }
       for (int i = lane; i < 36; i += 32) qp.xbar[i] += alpha * qp.dx[i];
       __syncwarp();
-      if (blk >= 0) { if (nw >= MAXW) { status |= ST_TOO_MANY_ROWS; break; } if (lane == 0) qp.wset[nw] = blk; nw += 1; __syncwarp(); full_step = false; }
+      if (blk >= 0) { if (nw >= MAXW) { status |= ST_TOO_MANY_ROWS; break; } if (lane == 0) qp.wset[nw] = blk; for (int j = lane; j < 36; j += 32) qp.Gw[nw * LDZ + j] = ineq_row_elem(ic, blk, j); nw += 1; __syncwarp(); full_step = false; }
     }
     if (!full_step) continue;
     if (nw == 0) { converged = true; break; }
@@ -254,7 +260,9 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
     double lmin = (lane < kc) ? qp.lam[lane] : 1e300; int li = lane; warp_argmin(lmin, li);
     if (lmin >= -1e-9 * (1.0 + gmax)) { converged = true; break; }
     // drop the constraint with the most negative multiplier (position li in pivoted order)
-    { const int drop = qp.permc[li]; int keep = -1; if (lane < nw) { int src = lane < drop ? lane : lane + 1; keep = (src < nw) ? qp.wset[src] : -1; } __syncwarp(); if (lane < nw - 1) qp.wset[lane] = keep; nw -= 1; __syncwarp(); }
+    { const int drop = qp.permc[li]; int keep = -1; if (lane < nw) { int src = lane < drop ? lane : lane + 1; keep = (src < nw) ? qp.wset[src] : -1; } __syncwarp(); if (lane < nw - 1) qp.wset[lane] = keep;
+      for (int k2 = drop; k2 < nw - 1; ++k2) { double v0 = 0.0, v1 = 0.0; if (lane < 36) v0 = qp.Gw[(k2 + 1) * LDZ + lane]; if (lane < 4) v1 = qp.Gw[(k2 + 1) * LDZ + 32 + lane]; __syncwarp(); if (lane < 36) qp.Gw[k2 * LDZ + lane] = v0; if (lane < 4) qp.Gw[k2 * LDZ + 32 + lane] = v1; __syncwarp(); }
+      nw -= 1; __syncwarp(); }
   }
   if (!converged) status |= ST_ITER_CAP;
   return status;
@@ -416,6 +424,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   if (lane == 0) status_out[b] = status;
 }
 
+static_assert(sizeof(WbcSmem) * WBC_WARPS <= 227 * 1024, "WBC shared-memory budget exceeded");
 size_t wbc_smem_bytes() { return sizeof(WbcSmem) * WBC_WARPS; }
 
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,

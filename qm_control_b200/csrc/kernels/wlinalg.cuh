@@ -64,6 +64,17 @@ __device__ __forceinline__ void w_apply_q(const double* W, int n, int k, int ld,
     __syncwarp();
   }
 }
+// C[:, c] <- Q^T C[:, c] for `ncols` columns stored column-major (leading dimension ldc): one lane per column, no reductions
+__device__ __forceinline__ void w_apply_qt_cols(const double* W, int n, int k, int ld, const double* tau, double* C, int ncols, int ldc, int lane) {
+  if (lane < ncols) {
+    double* col = C + lane * ldc;
+    for (int j = 0; j < k; ++j) {
+      const double* v = W + j * ld; double w = col[j]; for (int i = j + 1; i < n; ++i) w = fma(v[i], col[i], w);
+      w *= tau[j]; col[j] -= w; for (int i = j + 1; i < n; ++i) col[i] = fma(-w, v[i], col[i]);
+    }
+  }
+  __syncwarp();
+}
 // Z[:, off:off+n] <- Z[:, off:off+n] * Q   (Z has `rows` rows, row-major, leading dimension ldz); lanes over rows
 __device__ __forceinline__ void w_apply_q_right(const double* W, int n, int k, int ld, const double* tau, double* Z, int rows, int ldz, int off, int lane) {
   for (int j = 0; j < k; ++j) {
