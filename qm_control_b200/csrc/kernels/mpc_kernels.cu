@@ -80,10 +80,13 @@ struct LegWs {
   int dep[3];           // is joint j of this leg dependent
   int pivot, stance, first, free_col[3];   // projected-input column of each free joint (-1 if dependent)
 };
+struct LqEarly { CostWs cost; ConWs con; };                                   // live until the per-leg projection blocks are built
+struct LqLate { double BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX]; };                // produced after the second flow evaluation
 struct LqSmem {
-  PointWs pt; QuadWs quad; CostWs cost; ConWs con; LegWs leg[4];
-  double xs[NX], us[NU], xnext[NX], f1[NX], A1r[9 * NX], B1h[36];
-  double Ard[9 * NX], BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX], Pe_full[NU], rs[NU];
+  PointWs pt; QuadWs quad; LegWs leg[4];
+  union EL { LqEarly e; LqLate l; __device__ EL() {} } el;
+  double xs[NX], xnext[NX], f1[NX], A1r[9 * NX], B1h[36];             // A1r becomes A_d - I (rows 3:12) in place
+  double Pe_full[NU], rs[NU];
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
 };
 
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
   const bool terminal = (k == n - 1);
-  if (lane < NX) { sm.xs[lane] = xk[lane]; sm.us[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
+  if (lane < NX) { sm.xs[lane] = xk[lane]; sm.pt.u[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
   __syncwarp();
   if (!terminal && ge[k] == 1) {   // event node: identity jump map, no input, no cost (setupEventNode)
     double d = 0.0; if (lane < NX) { d = sm.xs[lane] - sm.xnext[lane]; sg[ST_b + lane] = d; }
@@ -108,12 +111,12 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
     return;
   }
   const double t = interval_start(gt[k], ge[k]);
-  if (lane < NX) { sm.pt.x[lane] = sm.xs[lane]; sm.pt.u[lane] = sm.us[lane]; }
+  if (lane < NX) sm.pt.x[lane] = sm.xs[lane];
   __syncwarp();
   if (terminal) {   // setupTerminalNode: finalEndEffector soft constraint only (QMInterface.cpp:104)
     point_eval<false>(mdl, &sm.pt, lane);
     TargetRef ref = target_reference(tt, ts, nk, t, lane);
-    const double val = stage_cost<true>(mdl, &sm.pt, &sm.cost, &sm.quad, ref, 0, true, lane);
+    const double val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, 0, true, lane);
     for (int e = lane; e < NX * NX; e += 32) { const int a = ee_pos(e / NX), c = ee_pos(e % NX); sg[ST_Q + e] = (a >= 0 && c >= 0) ? sm.quad.E[a * 12 + c] : 0.0; }
     if (lane < NX) sg[ST_q + lane] = sm.quad.qf[lane];
     if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; sg[ST_PERF] = val; sg[ST_PERF + 1] = 0.0; sg[ST_PERF + 2] = 0.0; }
@@ -124,8 +127,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
   point_eval<true>(mdl, &sm.pt, lane);
   TargetRef ref = target_reference(tt, ts, nk, t, lane);
-  const double cost_val = stage_cost<true>(mdl, &sm.pt, &sm.cost, &sm.quad, ref, fm, false, lane);
-  foot_velocity<true>(mdl, &sm.pt, &sm.con, lane);
+  const double cost_val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, fm, false, lane);
+  foot_velocity<true>(mdl, &sm.pt, &sm.el.e.con, lane);
   int nd_before = 0; for (int i = 0; i < 4; ++i) if (i < lane) nd_before += ((fm >> i) & 1) ? 3 : 4;
   int ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
   const int m = NU - ndep;
@@ -133,11 +136,11 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   double eq_ss = 0.0; bool swing_ok = true; int pivot = -1;
   if (lane < 4) {   // lane = foot (contact order); its leg's first joint = foot_leg
     const int i = lane; const int first = mdl->foot_leg[i]; LegWs& L = sm.leg[i]; L.first = first; L.stance = (fm >> i) & 1;
-    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.con.e[i][a] * sm.con.e[i][a]; }
+    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.el.e.con.e[i][a] * sm.el.e.con.e[i][a]; }
     else {
       double zp, zv; swing_ok = swing_reference(mdl, ev, modes, ne, i, t, zp, zv);
-      double ez = sm.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp);
-      sm.con.e[i][2] = ez;
+      double ez = sm.el.e.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp);
+      sm.el.e.con.e[i][2] = ez;
       for (int a = 0; a < 3; ++a) { sm.dep_idx[nd_before + a] = 3 * i + a; eq_ss += sm.pt.u[3 * i + a] * sm.pt.u[3 * i + a]; }
       eq_ss += ez * ez;
       double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.pt.Jl[i][3 * j + 2]); if (a > best) { best = a; pivot = j; } }   // pivot: largest |d v_z / d qdot_j|
@@ -160,13 +163,13 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
     L.Pu2[0] = L.Pu2[1] = 0.0;
     if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  →  dqd = -Jl^{-1} (C dx + e)
       double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.pt.Jl[i][3 * j + a]; inv3(Jm, Ji);
-      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.con.e[i][a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
-        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.con.C[i][a][c]; L.Px[j][c] = sv; } }
+      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.el.e.con.e[i][a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
+        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.el.e.con.C[i][a][c]; L.Px[j][c] = sv; } }
     } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
       for (int a = 0; a < 3; ++a) sm.Pe_full[3 * i + a] = -sm.pt.u[3 * i + a];
       const double piv = sm.pt.Jl[i][3 * pivot + 2];
-      L.Pe[pivot] = -sm.con.e[i][2] / piv; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
-      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = -sm.con.C[i][2][c] / piv;
+      L.Pe[pivot] = -sm.el.e.con.e[i][2] / piv; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
+      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = -sm.el.e.con.C[i][2][c] / piv;
       int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = -sm.pt.Jl[i][3 * j + 2] / piv;
     }
     // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
@@ -190,25 +193,30 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   __syncwarp();
   point_eval<true>(mdl, &sm.pt, lane);
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2);
-  double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.bvec[lane] = bb; }   // defect
+  double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.el.l.bvec[lane] = bb; }   // defect
   const double dyn_ss = warp_sum(bb * bb);
   // A_d - I (rows 3:12) = dt (w1 A1 + w2 (A2 + c dt A2 A1)) ; B_d rows 3:12 = dt (w1 B1 + w2 (B2 + c dt A2 B1)): force columns (9x12), joint columns only in the h_ang rows (3x18)
-  for (int e = lane; e < 9 * NX; e += 32) {
-    const int r = e / NX, c = e % NX; const double* a2 = sm.pt.Ar + r * NX;
-    double aa = 0.0;
+  if (lane < NX) {   // lane = column c: needs column c of A1 only, so A1r can be overwritten in place
+    const int c = lane; double a1[9], out[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) aa = fma(a2[3 + q], sm.A1r[q * NX + c], aa);
-    sm.Ard[e] = dt * (w1 * sm.A1r[e] + w2 * (a2[c] + cdt * aa));
-    if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } double ab = a2[c % 3] / mass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; sm.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
-    else if (r < 3) sm.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c];
+    for (int q = 0; q < 9; ++q) a1[q] = sm.A1r[q * NX + c];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) { const double* a2 = sm.pt.Ar + r * NX; double aa = 0.0;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) aa = fma(a2[3 + q], a1[q], aa);
+      out[r] = dt * (w1 * a1[r] + w2 * (a2[c] + cdt * aa));
+      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } double ab = a2[c % 3] / mass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; sm.el.l.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
+      else if (r < 3) sm.el.l.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c]; }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) sm.A1r[r * NX + c] = out[r];
   }
   __syncwarp();
   // ---- projected dynamics rows (lane = state row): A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
   if (lane < NX) {
-    const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; double* Brow = sg + ST_B + (size_t)r * MU; double bt = sm.bvec[r];
+    const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; double* Brow = sg + ST_B + (size_t)r * MU; double bt = sm.el.l.bvec[r];
     if (r >= 3 && r < 12) {
 #pragma unroll 6
-      for (int c = 0; c < NX; ++c) Arow[c] = sm.Ard[(r - 3) * NX + c] + ((c == r) ? 1.0 : 0.0);
+      for (int c = 0; c < NX; ++c) Arow[c] = sm.A1r[(r - 3) * NX + c] + ((c == r) ? 1.0 : 0.0);
     } else {
 #pragma unroll 6
       for (int c = 0; c < NX; ++c) Arow[c] = (c == r) ? 1.0 : 0.0;
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
       for (int i = 0; i < 4; ++i) { const LegWs& L = sm.leg[i];
 #pragma unroll
         for (int c = 0; c < 12; ++c) acc[c] = 0.0;
-        for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double coef = sm.BrdJ[(r - 3) * NJ + L.first + j]; bt += coef * L.Pe[j];
+        for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double coef = sm.el.l.BrdJ[(r - 3) * NJ + L.first + j]; bt += coef * L.Pe[j];
 #pragma unroll
           for (int c = 0; c < 12; ++c) acc[c] = fma(coef, L.Px[j][c], acc[c]); }
 #pragma unroll
@@ -233,13 +241,13 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
       if (L.dep[j]) { bt += dtw * L.Pe[j]; for (int c = 0; c < 12; ++c) { const int col = sup_col(c, L.first); Arow[col] = ((col == r) ? 1.0 : 0.0) + dtw * L.Px[j][c]; } }
     }
     if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw / mass) * sm.Pe_full[3 * f + r];
-    if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
+    if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.el.l.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
     // B~ row
     for (int a = 0; a < MU; ++a) {
       double v = 0.0;
       if (a < m) { const int fa = sm.free_idx[a];
         if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw / mass : 0.0;
-        else if (r < 12) { if (fa < 12) v = sm.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(mdl, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.BrdJ[(r - 3) * NJ + fa - 12]; }
+        else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(mdl, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
         else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
       }
       Brow[a] = v;
@@ -332,15 +340,15 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
 // warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
 // LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
 constexpr int RIC_THREADS = 128;
-constexpr int LDP = 33, LDA = 32, LDB = 24, LDL = 19;
+constexpr int LDP = 33, LDA = 32, LDB = 24;
 struct RicSmem {
   double P[NX * LDP];                       // value-function Hessian (row operand)
   double A[NX * LDA], W[NX * LDA], Qb[NX * LDA];
   double Bm[NX * LDB], PB[NX * LDB];
   double G[MU * LDA];                       // S~, then G, then Y = L^{-1} G
   double H[MU * LDB];                       // R~, then H, then its Cholesky factor
-  double Li[MU * LDL];                      // L^{-1} (lower triangular; upper part stays zero)
-  double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32];
+  double Lt[MU * MU];                       // Cholesky factor of H, transposed: Lt[c][a] = L[a][c] (strict lower part; pivots live as reciprocals in dut)
+  double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32], kff2[32];
   double red[RIC_THREADS / 32][4];
   int flag;
 };
@@ -356,8 +364,8 @@ __device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, 
   const int cpr = cols >> 1;
   for (int e = tid; e < rows * cpr; e += RIC_THREADS) { const int i = e / cpr, c = e - i * cpr; cp_async16(s + i * ls + 2 * c, g + (size_t)i * gs + 2 * c); }
 }
-// acc[v] += sum_k X[k*xs] * Y[k*ldy + v], v = 0..7   (Y rows 16-B aligned)
-__device__ __forceinline__ void tile_mac(const double* __restrict__ X, int xs, const double* __restrict__ Y, int ldy, int K, double (&acc)[8]) {
+// acc[v] += sum_k X[k*xs] * Y[k*ldy + v], v = 0..7   (Y rows 16-B aligned; K is a compile-time trip count)
+template <int K> __device__ __forceinline__ void tile_mac(const double* __restrict__ X, int xs, const double* __restrict__ Y, int ldy, double (&acc)[8]) {
 #pragma unroll 2
   for (int k = 0; k < K; ++k) {
     const double a = X[k * xs]; const double2* y = reinterpret_cast<const double2*>(Y + k * ldy);
@@ -405,9 +413,9 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
     }
     // ---- phase 1: W = P A (4 warps) ; PB = P B (warps 0-2) ; pPb = p + P b (warp 3) ----
     if (lane < NX) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + lane * LDP, 1, sm.A + cb, LDA, NX, acc);
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac<NX>(sm.P + lane * LDP, 1, sm.A + cb, LDA, acc);
       double2* w = reinterpret_cast<double2*>(sm.W + lane * LDA + cb); w[0] = make_double2(acc[0], acc[1]); w[1] = make_double2(acc[2], acc[3]); w[2] = make_double2(acc[4], acc[5]); w[3] = make_double2(acc[6], acc[7]);
-      if (warp < 3) { double ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.P + lane * LDP, 1, sm.Bm + cb, LDB, NX, ab);
+      if (warp < 3) { double ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac<NX>(sm.P + lane * LDP, 1, sm.Bm + cb, LDB, ab);
         double2* pb = reinterpret_cast<double2*>(sm.PB + lane * LDB + cb); pb[0] = make_double2(ab[0], ab[1]); pb[1] = make_double2(ab[2], ab[3]); pb[2] = make_double2(ab[4], ab[5]); pb[3] = make_double2(ab[6], ab[7]); }
       else { double s = sm.p[lane]; for (int j = 0; j < NX; ++j) s = fma(sm.P[lane * LDP + j], sm.b[j], s); sm.pPb[lane] = s; }
     }
@@ -415,42 +423,61 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
     // ---- phase 2: G = S + B'W (4 warps) ; H = R + B'PB (warps 0-2) ; h = r + B'(p + P b) (warp 3, kept in column 30 of G) ----
     if (lane < MU) {
       double acc[8]; { const double2* gv = reinterpret_cast<const double2*>(sm.G + lane * LDA + cb); const double2 g0 = gv[0], g1 = gv[1], g2 = gv[2], g3 = gv[3]; acc[0] = g0.x; acc[1] = g0.y; acc[2] = g1.x; acc[3] = g1.y; acc[4] = g2.x; acc[5] = g2.y; acc[6] = g3.x; acc[7] = g3.y; }
-      tile_mac(sm.Bm + lane, LDB, sm.W + cb, LDA, NX, acc);
+      tile_mac<NX>(sm.Bm + lane, LDB, sm.W + cb, LDA, acc);
       if (warp == 3) { double s = sm.r[lane]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.Bm[kk * LDB + lane], sm.pPb[kk], s); acc[6] = s; }   // column 30 := h
       double2* gw = reinterpret_cast<double2*>(sm.G + lane * LDA + cb); gw[0] = make_double2(acc[0], acc[1]); gw[1] = make_double2(acc[2], acc[3]); gw[2] = make_double2(acc[4], acc[5]); gw[3] = make_double2(acc[6], acc[7]);
       if (warp < 3) { double ah[8]; { const double2* hv = reinterpret_cast<const double2*>(sm.H + lane * LDB + cb); const double2 h0 = hv[0], h1 = hv[1], h2 = hv[2], h3 = hv[3]; ah[0] = h0.x; ah[1] = h0.y; ah[2] = h1.x; ah[3] = h1.y; ah[4] = h2.x; ah[5] = h2.y; ah[6] = h3.x; ah[7] = h3.y; }
-        tile_mac(sm.Bm + lane, LDB, sm.PB + cb, LDB, NX, ah);
+        tile_mac<NX>(sm.Bm + lane, LDB, sm.PB + cb, LDB, ah);
         double2* hw = reinterpret_cast<double2*>(sm.H + lane * LDB + cb); hw[0] = make_double2(ah[0], ah[1]); hw[1] = make_double2(ah[2], ah[3]); hw[2] = make_double2(ah[4], ah[5]); hw[3] = make_double2(ah[6], ah[7]); }
     }
     __syncthreads();
-    // ---- phase 3: one warp factors H and inverts the factor ; the other three compute P <- Q + A'W and p <- q + A'(p + P b) meanwhile.
+    // ---- phase 3: one warp factors H and solves for Y and the gains ; the other three compute P <- Q + A'W and p <- q + A'(p + P b) meanwhile.
     // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
     const int sw = (k + b) & 3, rel = (warp - sw - 1) & 3;
     if (warp == sw) {
-      if (lane < MU) for (int c = 0; c < lane; ++c) sm.H[lane * LDB + c] = 0.5 * (sm.H[lane * LDB + c] + sm.H[c * LDB + lane]);
-      __syncwarp();
-      // in-place lower Cholesky, lane = row; reciprocal pivots kept in sm.dut so that the solves multiply instead of divide
-      bool ok = true;
+      // (a) Cholesky of H with the factor in registers: lane = row (read from the upper triangle: column access is bank-conflict free),
+      //     pivot and column broadcasts by shuffle; every lane runs the same unrolled code (lanes >= MU carry zeros).
+      double hr[MU]; double dinv = 0.0; bool ok = true;
+#pragma unroll
+      for (int c = 0; c < MU; ++c) hr[c] = (lane < MU) ? sm.H[c * LDB + lane] : 0.0;
+#pragma unroll
       for (int j = 0; j < MU; ++j) {
-        const double djj = sm.H[j * LDB + j]; if (!(djj > 0.0)) ok = false;
-        const double inv = rsqrt(djj);
-        __syncwarp();
-        if (lane == j) { sm.H[j * LDB + j] = djj * inv; sm.dut[j] = inv; }
-        if (lane > j && lane < MU) sm.H[lane * LDB + j] *= inv;
-        __syncwarp();
-        if (lane > j && lane < MU) { const double lij = sm.H[lane * LDB + j]; for (int c = j + 1; c <= lane; ++c) sm.H[lane * LDB + c] = fma(-lij, sm.H[c * LDB + j], sm.H[lane * LDB + c]); }
-        __syncwarp();
+        const double djj = __shfl_sync(FULL, hr[j], j); if (!(djj > 0.0)) ok = false;
+        const double inv = rsqrt(djj); const double lij = hr[j] * inv;
+        if (lane == j) dinv = inv;
+        if (lane < MU) sm.Lt[j * MU + lane] = lij;
+#pragma unroll
+        for (int c = j + 1; c < MU; ++c) hr[c] = fma(-lij, __shfl_sync(FULL, lij, c), hr[c]);
       }
+      if (lane < MU) sm.dut[lane] = dinv;
       if (!ok && lane == 0) sm.flag = 1;
-      if (lane < MU) {   // column `lane` of L^{-1} by forward substitution
-        const int j = lane;
-        for (int a = j; a < MU; ++a) { double s = (a == j) ? 1.0 : 0.0; for (int c = j; c < a; ++c) s = fma(-sm.H[a * LDB + c], sm.Li[c * LDL + j], s); sm.Li[a * LDL + j] = s * sm.dut[a]; }
+      __syncwarp();
+      // (b) lane = column of [G | h]: forward substitution Y = L^{-1}[G|h] (kept for P -= Y'Y), then back substitution K = -L^{-T} Y.
+      //     Factor entries are warp-uniform broadcasts, the running column lives in registers.
+      double y[MU]; double* Yb = sm.PB;   // PB is free after phase 2; Y uses leading dimension LDA
+#pragma unroll
+      for (int a = 0; a < MU; ++a) y[a] = sm.G[a * LDA + lane];
+#pragma unroll
+      for (int a = 0; a < MU; ++a) {       // right-looking: finish y[a], then subtract column a of L from the rows below
+        asm volatile("" ::: "memory");   // keep the factor loads of later columns from being hoisted (register pressure)
+        y[a] *= sm.dut[a]; Yb[a * LDA + lane] = y[a];
+#pragma unroll
+        for (int c = a + 1; c < MU; ++c) y[c] = fma(-sm.Lt[a * MU + c], y[a], y[c]);
+      }
+      double* gk = gb + (size_t)k * GAIN_DBL;
+#pragma unroll
+      for (int a = MU - 1; a >= 0; --a) {  // L' z = y, right-looking over row a of L'
+        asm volatile("" ::: "memory");
+        y[a] *= sm.dut[a];
+        if (lane < NX) gk[a * NX + lane] = -y[a]; else if (lane == NX) gk[MU * NX + a] = -y[a];
+#pragma unroll
+        for (int c = 0; c < a; ++c) y[c] = fma(-sm.Lt[c * MU + a], y[a], y[c]);
       }
     } else {
       if (lane < NX) {
         for (int blk = rel; blk < 4; blk += 3) {   // column blocks 0..3 over the three helper warps (the first also takes block 3)
           const int c0 = blk * 8; double acc[8]; { const double2* qv = reinterpret_cast<const double2*>(sm.Qb + lane * LDA + c0); const double2 q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3]; acc[0] = q0.x; acc[1] = q0.y; acc[2] = q1.x; acc[3] = q1.y; acc[4] = q2.x; acc[5] = q2.y; acc[6] = q3.x; acc[7] = q3.y; }
-          tile_mac(sm.A + lane, LDA, sm.W + c0, LDA, NX, acc);
+          tile_mac<NX>(sm.A + lane, LDA, sm.W + c0, LDA, acc);
           double* pr = sm.P + lane * LDP + c0;
 #pragma unroll
           for (int v = 0; v < 8; ++v) if (c0 + v < NX) pr[v] = acc[v];
@@ -460,58 +487,55 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; break; }
-    if (k > 0) issue_ab(k - 1);                    // A~/B~ buffers are free: prefetch the next node under phases 4-5
-    // ---- phase 4: Y = L^{-1} [G | h] → W buffer (rows 0..17) ----
-    if (lane < MU) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.Li + lane * LDL, 1, sm.G + cb, LDA, MU, acc);
-      double2* yw = reinterpret_cast<double2*>(sm.W + lane * LDA + cb); yw[0] = make_double2(acc[0], acc[1]); yw[1] = make_double2(acc[2], acc[3]); yw[2] = make_double2(acc[4], acc[5]); yw[3] = make_double2(acc[6], acc[7]);
-    }
-    __syncthreads();
-    // ---- phase 5: K = -L^{-T} Y → global ; P -= Y'Y ; p -= Y' yh ----
-    if (lane < MU) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.Li + lane, LDL, sm.W + cb, LDA, MU, acc);
-      double* gk = gb + (size_t)k * GAIN_DBL;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) { const int col = cb + v; if (col < NX) gk[lane * NX + col] = -acc[v]; else if (col == NX) gk[MU * NX + lane] = -acc[v]; }
-    }
+    if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }   // A~/B~ and S~/R~/Q~ buffers are all free: prefetch the next node
+    // ---- phase 4: P -= Y'Y ; p -= Y' yh  (the top-of-loop barrier closes this phase) ----
     if (lane < NX) {
-      double* pr = sm.P + lane * LDP + cb; double neg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac(sm.W + lane, LDA, sm.W + cb, LDA, MU, neg);
+      const double* Yb = sm.PB;
+      double* pr = sm.P + lane * LDP + cb; double neg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac<MU>(Yb + lane, LDA, Yb + cb, LDA, neg);
 #pragma unroll
       for (int v = 0; v < 8; ++v) if (cb + v < NX) pr[v] -= neg[v];
-      if (warp == 3) { double s = sm.tmp[lane]; for (int a = 0; a < MU; ++a) s = fma(-sm.W[a * LDA + lane], sm.W[a * LDA + NX], s); sm.p[lane] = s; }
+      if (warp == 3) { double s = sm.tmp[lane]; for (int a = 0; a < MU; ++a) s = fma(-Yb[a * LDA + lane], Yb[a * LDA + NX], s); sm.p[lane] = s; }
     }
-    __syncthreads();
-    if (k > 0) issue_srq(k - 1);                   // G/H/Qb buffers are free now
   }
   cp_async_wait<0>(); __syncthreads();
   // ---- forward rollout: du~ = K dx + k ; dx+ = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~ ----
   double armijo = 0.0, dxn2 = 0.0, dun2 = 0.0;
   if (!(st & MST_NOT_PD)) {
+    // two buffer sets (k & 1): {G, A, Bm, b, q, r, kff} and {W, Qb, PB, pPb, p, h, kff2}; node k+1 streams in while node k is applied
+    auto issue_fwd = [&](int k) {
+      if (k < N && sib[(size_t)k * STAGE_INT + SI_TYPE] != 1) {
+        const double* sg = sgb + (size_t)k * STAGE_DBL; const double* gk = gb + (size_t)k * GAIN_DBL; const bool o = k & 1;
+        cp_rows(gk, MU, NX, NX, o ? sm.W : sm.G, LDA, tid); cp_rows(sg + ST_A, NX, NX, NX, o ? sm.Qb : sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, o ? sm.PB : sm.Bm, LDB, tid);
+        if (tid < 15) cp_async16((o ? sm.pPb : sm.b) + 2 * tid, sg + ST_b + 2 * tid); else if (tid < 30) cp_async16((o ? sm.p : sm.q) + 2 * (tid - 15), sg + ST_q + 2 * (tid - 15));
+        else if (tid < 39) cp_async16((o ? sm.h : sm.r) + 2 * (tid - 30), sg + ST_r + 2 * (tid - 30)); else if (tid < 48) cp_async16((o ? sm.kff2 : sm.kff) + 2 * (tid - 39), gk + MU * NX + 2 * (tid - 39));
+      }
+      cp_async_commit(); };
+    issue_fwd(0);
     for (int k = 0; k < N; ++k) {
       const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sib + (size_t)k * STAGE_INT; const int type = si[SI_TYPE], ndep = si[SI_NDEP];
       double* dxk = dxo + ((size_t)b * nmax + k) * NX; double* duk = duo + ((size_t)b * nmax + k) * NU;
+      issue_fwd(k + 1);
       if (tid < NX) { const double dxi = sm.dx[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
       if (type == 1) { if (tid < NX) { duk[tid] = 0.0; sm.tmp[tid] = sm.dx[tid] + sg[ST_b + tid]; } __syncthreads(); if (tid < NX) sm.dx[tid] = sm.tmp[tid]; __syncthreads(); continue; }
-      const double* gk = gb + (size_t)k * GAIN_DBL;
-      cp_rows(gk, MU, NX, NX, sm.G, LDA, tid); cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
-      if (tid < 15) cp_async16(sm.b + 2 * tid, sg + ST_b + 2 * tid); else if (tid < 30) cp_async16(sm.q + 2 * (tid - 15), sg + ST_q + 2 * (tid - 15)); else if (tid < 39) cp_async16(sm.r + 2 * (tid - 30), sg + ST_r + 2 * (tid - 30)); else if (tid < 48) cp_async16(sm.kff + 2 * (tid - 39), gk + MU * NX + 2 * (tid - 39));
-      cp_async_commit(); cp_async_wait<0>(); __syncthreads();
+      const bool o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* Ab = o ? sm.Qb : sm.A; const double* Bb = o ? sm.PB : sm.Bm;
+      const double* bv = o ? sm.pPb : sm.b; const double* qv = o ? sm.p : sm.q; const double* rv = o ? sm.h : sm.r; const double* kv = o ? sm.kff2 : sm.kff;
+      cp_async_wait<1>(); __syncthreads();
       { double s = 0.0;   // all lanes take part in the quad reduction (shfl_sync needs the full mask)
-        if (ti < MU) { const double* kr = sm.G + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
+        if (ti < MU) { const double* kr = Kb + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(kr[v], dx[v], s); }
-        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + sm.kff[ti]; }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + kv[ti]; }
       __syncthreads();
       { double s = 0.0;
-        if (ti < NX) { const double* ar = sm.A + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
+        if (ti < NX) { const double* ar = Ab + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(ar[v], dx[v], s);
-          if (jb < 3) { const double* br = sm.Bm + ti * LDB + jb * 8; const double* du = sm.dut + jb * 8;
+          if (jb < 3) { const double* br = Bb + ti * LDB + jb * 8; const double* du = sm.dut + jb * 8;
 #pragma unroll
             for (int v = 0; v < 8; ++v) s = fma(br[v], du[v], s); } }
-        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) sm.tmp[ti] = s + sm.b[ti]; }
-      if (tid < NX) armijo += sm.q[tid] * sm.dx[tid];
-      if (tid < MU) { const double dut = sm.dut[tid]; armijo += sm.r[tid] * dut; const int fi = si[SI_FREE + tid]; if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; } }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) sm.tmp[ti] = s + bv[ti]; }
+      if (tid < NX) armijo += qv[tid] * sm.dx[tid];
+      if (tid < MU) { const double dut = sm.dut[tid]; armijo += rv[tid] * dut; const int fi = si[SI_FREE + tid]; if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; } }
       if (tid >= 64 && tid < 64 + MAXDEP) { const int d = tid - 64; if (d < ndep) { double s = sg[ST_PED + d]; const double* px = sg + ST_PXD + (size_t)d * NX; const double* pu = sg + ST_PUD + (size_t)d * MU;
           for (int j = 0; j < NX; ++j) s = fma(px[j], sm.dx[j], s); for (int a = 0; a < MU; ++a) s = fma(pu[a], sm.dut[a], s); duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
       __syncthreads();
