@@ -90,7 +90,7 @@ struct LqSmem {
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
 };
 
-__global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
   const int b = (int)(gid / nmax), k = (int)(gid % nmax); if (b >= B) return;
@@ -113,27 +113,30 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   const double t = interval_start(gt[k], ge[k]);
   if (lane < NX) sm.pt.x[lane] = sm.xs[lane];
   __syncwarp();
+  const double dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
+  const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
+  double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0;
+  // One inlined copy of the flow-map evaluation serves both RK2 stages (and the terminal node): the kernel is
+  // instruction-fetch sensitive (straight-line code of several hundred KB), so the pass loop is deliberately not unrolled.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  point_eval<true>(mdl, &sm.pt, lane);
+  if (pass == 1) break;
+  // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
+  TargetRef ref = target_reference(tt, ts, nk, t, lane);
+  cost_val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, fm, terminal, lane);
   if (terminal) {   // setupTerminalNode: finalEndEffector soft constraint only (QMInterface.cpp:104)
-    point_eval<false>(mdl, &sm.pt, lane);
-    TargetRef ref = target_reference(tt, ts, nk, t, lane);
-    const double val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, 0, true, lane);
     for (int e = lane; e < NX * NX; e += 32) { const int a = ee_pos(e / NX), c = ee_pos(e % NX); sg[ST_Q + e] = (a >= 0 && c >= 0) ? sm.quad.E[a * 12 + c] : 0.0; }
     if (lane < NX) sg[ST_q + lane] = sm.quad.qf[lane];
-    if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; sg[ST_PERF] = val; sg[ST_PERF + 1] = 0.0; sg[ST_PERF + 2] = 0.0; }
+    if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; sg[ST_PERF] = cost_val; sg[ST_PERF + 1] = 0.0; sg[ST_PERF + 2] = 0.0; }
     return;
   }
-  const double dt = interval_end(gt[k + 1], ge[k + 1]) - t;
-  const int mode = mode_at_time(ev, modes, ne, t); const int fm = flag_mask(mode);
-  // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
-  point_eval<true>(mdl, &sm.pt, lane);
-  TargetRef ref = target_reference(tt, ts, nk, t, lane);
-  const double cost_val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, fm, false, lane);
   foot_velocity<true>(mdl, &sm.pt, &sm.el.e.con, lane);
   int nd_before = 0; for (int i = 0; i < 4; ++i) if (i < lane) nd_before += ((fm >> i) & 1) ? 3 : 4;
-  int ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
-  const int m = NU - ndep;
+  ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
+  m = NU - ndep;
   if (lane < NU) sm.Pe_full[lane] = 0.0;
-  double eq_ss = 0.0; bool swing_ok = true; int pivot = -1;
+  bool swing_ok = true; int pivot = -1;
   if (lane < 4) {   // lane = foot (contact order); its leg's first joint = foot_leg
     const int i = lane; const int first = mdl->foot_leg[i]; LegWs& L = sm.leg[i]; L.first = first; L.stance = (fm >> i) & 1;
     if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.el.e.con.e[i][a] * sm.el.e.con.e[i][a]; }
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS) mpc_lq_kernel(const DevModel* _
   __syncwarp();
   if (lane < NX) sm.pt.x[lane] = sm.xs[lane] + mdl->rk_c * dt * sm.f1[lane];
   __syncwarp();
-  point_eval<true>(mdl, &sm.pt, lane);
+  }
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2);
   double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.el.l.bvec[lane] = bb; }   // defect
   const double dyn_ss = warp_sum(bb * bb);
@@ -587,13 +590,18 @@ __global__ void __launch_bounds__(32 * LS_WARPS) mpc_linesearch_kernel(const Dev
       const double t = interval_start(gt[k], ge[k]);
       if (lane < NX) { sm.pt.x[lane] = sm.xa[lane]; sm.pt.u[lane] = sm.ua[lane]; }
       __syncwarp();
-      point_eval<false>(mdl, &sm.pt, lane);
-      TargetRef ref = target_reference(tt, ts, nk, t, lane);
-      if (k == N) { cost += stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, 0, true, lane); __syncwarp(); continue; }
-      const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; const int mode = mode_at_time(ev, modes, ne, t); const int fm = flag_mask(mode);
-      cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, false, lane);
-      foot_velocity<false>(mdl, &sm.pt, &sm.con, lane);
-      double es = 0.0;
+      const bool terminal = (k == N);
+      const double dt = terminal ? 1.0 : interval_end(gt[k + 1], ge[k + 1]) - t; const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
+      bool done = false;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {   // one inlined copy of the flow map for both RK2 stages (instruction-fetch footprint)
+        point_eval<false>(mdl, &sm.pt, lane);
+        if (pass == 1) break;
+        TargetRef ref = target_reference(tt, ts, nk, t, lane);
+        cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, terminal, lane);
+        if (terminal) { done = true; break; }
+        foot_velocity<false>(mdl, &sm.pt, &sm.con, lane);
+        double es = 0.0;
       if (lane < 4) { const int i = lane; if ((fm >> i) & 1) { for (int a = 0; a < 3; ++a) es += sm.con.e[i][a] * sm.con.e[i][a]; }
         else { double zp, zv; swing_reference(mdl, ev, modes, ne, i, t, zp, zv); double ez = sm.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp); es += ez * ez; for (int a = 0; a < 3; ++a) es += sm.ua[3 * i + a] * sm.ua[3 * i + a]; } }
       eq += dt * warp_sum(es);
@@ -601,7 +609,8 @@ __global__ void __launch_bounds__(32 * LS_WARPS) mpc_linesearch_kernel(const Dev
       __syncwarp();
       if (lane < NX) sm.pt.x[lane] = sm.xa[lane] + mdl->rk_c * dt * sm.f1[lane];
       __syncwarp();
-      point_eval<false>(mdl, &sm.pt, lane);
+      }
+      if (done) { __syncwarp(); continue; }
       double d = (lane < NX) ? sm.xa[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xna[lane] : 0.0; dyn += dt * warp_sum(d * d);
       __syncwarp();
     }
