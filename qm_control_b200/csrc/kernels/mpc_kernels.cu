@@ -13,7 +13,10 @@
 
 namespace qmb {
 
-constexpr int LQ_WARPS = 2, LS_WARPS = 4, SETUP_WARPS = 4;
+#ifndef QMB_LQ_WARPS
+#define QMB_LQ_WARPS 6
+#endif
+constexpr int LQ_WARPS = QMB_LQ_WARPS, LS_WARPS = 4, SETUP_WARPS = 4;
 enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16 };
 
 __device__ __forceinline__ double interval_start(double t, int ev) { return ev == 2 ? t + WEAK_EPS : t; }
@@ -90,7 +93,10 @@ struct LqSmem {
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
 };
 
-__global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
+// The LQ kernel is ~220 KB of straight-line code executed once per node: warps of a CTA are re-aligned at a few phase
+// boundaries so that they share instruction-cache lines (exited warps - event / terminal / padding nodes - no longer take part).
+#define LQ_LOCKSTEP() __syncthreads()
+__global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
   const int b = (int)(gid / nmax), k = (int)(gid % nmax); if (b >= B) return;
@@ -121,6 +127,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
   point_eval<true>(mdl, &sm.pt, lane);
+  LQ_LOCKSTEP();
   if (pass == 1) break;
   // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
   TargetRef ref = target_reference(tt, ts, nk, t, lane);
@@ -132,6 +139,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel
     return;
   }
   foot_velocity<true>(mdl, &sm.pt, &sm.el.e.con, lane);
+  LQ_LOCKSTEP();
   int nd_before = 0; for (int i = 0; i < 4; ++i) if (i < lane) nd_before += ((fm >> i) & 1) ? 3 : 4;
   ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
   m = NU - ndep;
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel
     else if (lane < 24) { const int i = foot_of_leg_joint(mdl, lane - 12); sv = sm.leg[i].rs[(lane - 12) % 3]; }
     sm.rs[lane] = sv;
   }
+  LQ_LOCKSTEP();
   // keep k1 data, then second flow evaluation at x + c dt k1
   if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
   for (int e = lane; e < 9 * NX; e += 32) sm.A1r[e] = sm.pt.Ar[e];
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel
     for (int r = 0; r < 9; ++r) sm.A1r[r * NX + c] = out[r];
   }
   __syncwarp();
+  LQ_LOCKSTEP();
   // ---- projected dynamics rows (lane = state row): A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
   if (lane < NX) {
     const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; double* Brow = sg + ST_B + (size_t)r * MU; double bt = sm.el.l.bvec[r];
@@ -257,6 +267,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel
     }
     sg[ST_b + r] = bt;
   }
+  LQ_LOCKSTEP();
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
   if (lane < NX) {   // q~ = q + Px' rs ; Q~ = Q + Px' R Px : per leg a 12x12 block on its support columns
     const int r = lane; double acc[NX];
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 6) mpc_lq_kernel(const DevModel
     for (int c = 0; c < NX; ++c) Qrow[c] = dt * (acc[c] + ((c == r) ? dq : 0.0));
     sg[ST_q + r] = dt * qv;
   }
+  LQ_LOCKSTEP();
   if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu
     const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rrow = sg + ST_R + (size_t)a * MU;
 #pragma unroll 6
