@@ -26,6 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+PIPELINE_CHUNKS = 4         # qmb200_set_pipeline: ranges of the batch whose kernel chains overlap on the SMs
 UNIT_BATCH = 8192           # one "iteration" of the metric = one tick of an 8192-robot batch
 DT, HORIZON, CONFIG = 0.01, 1.0, 4
 METRIC = "mpc_wbc_iters_per_s"
@@ -137,6 +138,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=UNIT_BATCH); ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunks", type=int, default=PIPELINE_CHUNKS, help="robot ranges run as concurrent stream chains inside one tick")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
@@ -150,6 +152,7 @@ def main():
     torch.cuda.set_device(local); dev = torch.device("cuda", local)
     B = args.batch; n_int = int(round(HORIZON / DT))
     solver = q.Solver(batch=B, device=local, dt=DT, time_horizon=HORIZON)
+    solver.set_pipeline(args.chunks)
     ids = np.arange(rank * B, (rank + 1) * B)
     prob, wbc = synthetic.make_batch(ids, config=CONFIG, horizon=HORIZON)
     t_eval0 = prob["t0"] + 0.002
@@ -251,7 +254,7 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "full MPC+WBC tick (BASELINE configs[3] shape): trot gait schedule, horizon 1.0 s / dt 0.01 (100 intervals + event nodes), 24-DoF quadruped-manipulator, one SQP iteration + 3-level HoQp",
-                          "batch_per_gpu": B, "global_batch": B * world, "robot_ticks_per_s": B * world / (ms * 1e-3), "parallelism": "dp%d (robots sharded, one all-gather of the torque buffer)" % world,
+                          "batch_per_gpu": B, "pipeline_chunks": args.chunks, "global_batch": B * world, "robot_ticks_per_s": B * world / (ms * 1e-3), "parallelism": "dp%d (robots sharded, one all-gather of the torque buffer)" % world,
                           "l2": "per-tick working set (LQ stage buffer %.1f GB) >> 126 MB L2; no flush needed" % (B * solver.nmax * 4072 * 8 / 1e9), "robots_with_error_status": bad},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
         print(json.dumps(out))

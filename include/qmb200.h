@@ -120,6 +120,12 @@ int qmb200_centroidal_state_from_rbd(const qmb200_handle* h, int32_t n, const do
 int qmb200_gait_schedule(const char* gait_file, const char* gait_name, double t_start, double lo, double hi,
                          double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
 
+/* ---- tick pipeline: qmb200_tick / qmb200_tick_dev cut the batch into `chunks` (1..8) robot ranges and run each range's
+ *      MPC solve → evaluatePolicy → WbcBase::update chain on its own CUDA stream (forked from / joined into the caller's stream), so
+ *      kernels with different bottlenecks overlap on the SMs.  Robots are independent (the reference runs one controller per robot,
+ *      QMController.cpp:128-148), so results do not depend on the setting.  Default: 1. */
+int qmb200_set_pipeline(qmb200_handle* h, int chunks);
+
 /* measurement support (bench.py): per-kernel device times of the tick [setup, lq, riccati, linesearch, policy_eval, wbc] in ms (mean per call),
  * and the measured fp64 FMA throughput of this GPU */
 int qmb200_set_profiling(qmb200_handle* h, int on);

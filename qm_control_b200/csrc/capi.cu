@@ -14,7 +14,7 @@
 
 namespace qmb {
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
-                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream);
+                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0 = 0, int b1 = -1);
 }
 
 using namespace qmb;
@@ -35,6 +35,10 @@ struct qmb200_handle {
   std::vector<void*> allocs;
   bool profiling = false; cudaEvent_t ev[8] = {nullptr};   // [0..4] MPC kernels, [5..7] policy / wbc brackets
   double kernel_ms[6] = {0, 0, 0, 0, 0, 0}; int64_t kernel_calls = 0; bool ev_pending = false;
+  // tick pipeline: the batch is cut into `chunks` robot ranges, each running its MPC → policy → WBC chain on its own stream, so that
+  // kernels with different bottlenecks (LQ: instruction latency, Riccati: shared-memory bandwidth, WBC) share the SMs
+  static constexpr int MAX_CHUNKS = 8;
+  int chunks = 1; cudaStream_t cs[MAX_CHUNKS] = {nullptr}; cudaEvent_t fork_ev = nullptr, join_ev[MAX_CHUNKS] = {nullptr};
 };
 
 namespace {
@@ -79,6 +83,8 @@ void qmb200_destroy(qmb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  for (int c = 0; c < qmb200_handle::MAX_CHUNKS; ++c) { if (h->cs[c]) { cudaStreamSynchronize(h->cs[c]); cudaStreamDestroy(h->cs[c]); } if (h->join_ev[c]) cudaEventDestroy(h->join_ev[c]); }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }

@@ -33,13 +33,14 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
 
 struct MpcProblemDev { const double* t0; const double* x0; const int32_t* n_events; const double* event_times; const int32_t* modes; const int32_t* n_target; const double* target_times; const double* target_states; };
 
-// One SQP iteration for all robots (4 kernels on `stream`); flips m.cur.  Returns the number of kernels launched.
+// One SQP iteration for robots [b0, b1) (4 kernels on `stream`): reads m.sol[m.cur], writes m.sol[1 - m.cur]; the caller
+// flips m.cur after queueing every range.  Returns the number of kernels launched.
 // `ev` (optional, 5 events): recorded before K1 and after each of K1..K4 for per-kernel timing.
-int mpc_solve_launch(const DevModel* mdl, const DevModel& host_mdl, MpcBuffers& m, const MpcProblemDev& p, cudaStream_t stream, cudaEvent_t* ev = nullptr);
+int mpc_solve_launch(const DevModel* mdl, const DevModel& host_mdl, MpcBuffers& m, const MpcProblemDev& p, int b0, int b1, cudaStream_t stream, cudaEvent_t* ev = nullptr);
 // fp64 FMA throughput microbenchmark (roofline denominator for the compute-bound kernels); returns TFLOP/s
 double measure_fp64_peak(cudaStream_t stream);
 // evaluatePolicy on m.sol[m.cur]; returns kernels launched
-int mpc_policy_eval_launch(const MpcBuffers& m, const double* t, double* x_des, double* u_des, int32_t* mode, cudaStream_t stream);
+int mpc_policy_eval_launch(const MpcBuffers& m, const double* t, double* x_des, double* u_des, int32_t* mode, cudaStream_t stream, int b0 = 0, int b1 = -1);
 // input fix-up after loading a solution from the host (inputs at pre-event / last nodes)
 int mpc_fixup_launch(const MpcBuffers& m, cudaStream_t stream);
 

@@ -25,8 +25,8 @@ __device__ __forceinline__ int flag_mask(int mode) { int m = 0; for (int i = 0; 
 
 // =====================================================================================================
 // K1: time grid + initial guess
-__global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev prev, MpcSolutionDev next, int32_t* __restrict__ status) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = blockIdx.x * SETUP_WARPS + warp; if (b >= B) return;
+__global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev prev, MpcSolutionDev next, int32_t* __restrict__ status) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x * SETUP_WARPS + warp; if (b >= B) return;
   const double t0 = p.t0[b], tf = t0 + mdl->time_horizon, dt = mdl->dt; const int ne = p.n_events[b]; const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
   double* gt = next.t + (size_t)b * nmax; int32_t* ge = next.event + (size_t)b * nmax; int st = 0;
   // ---- timeDiscretizationWithEvents [upstream ocs2_oc/oc_data/TimeDiscretization.cpp] ----
@@ -96,10 +96,10 @@ struct LqSmem {
 // The LQ kernel is ~220 KB of straight-line code executed once per node: warps of a CTA are re-aligned at a few phase
 // boundaries so that they share instruction-cache lines (exited warps - event / terminal / padding nodes - no longer take part).
 #define LQ_LOCKSTEP() __syncthreads()
-__global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
-  const int b = (int)(gid / nmax), k = (int)(gid % nmax); if (b >= B) return;
+  const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax); if (b >= B) return;
   const int n = sol.n_nodes[b]; if (k >= n) return;
   LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp];
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
@@ -390,11 +390,11 @@ template <int K> __device__ __forceinline__ void tile_mac(const double* __restri
   }
 }
 
-__global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const int32_t* __restrict__ stage_i,
+__global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const int32_t* __restrict__ stage_i,
                                                                   double* __restrict__ gains, double* __restrict__ dxo, double* __restrict__ duo, double* __restrict__ robot, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RicSmem& sm = *reinterpret_cast<RicSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ti = tid >> 2, jb = tid & 3; const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ti = tid >> 2, jb = tid & 3; const int b = b0 + blockIdx.x;
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
   for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
@@ -577,11 +577,11 @@ __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax
   for (int k = 1; k < n; ++k) { const bool copy = (k == n - 1) || (ge[k] == 1); if (copy) { for (int i = tid; i < NU; i += nthreads) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i]; } __syncthreads(); }
 }
 
-__global__ void __launch_bounds__(32 * LS_WARPS) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
+__global__ void __launch_bounds__(32 * LS_WARPS) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
                                                                      const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[LS_WARPS][3]; __shared__ int decision;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = blockIdx.x; if (b >= B) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x; if (b >= B) return;
   LsSmem& sm = reinterpret_cast<LsSmem*>(smem_raw)[warp];
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
@@ -658,9 +658,9 @@ __global__ void mpc_fixup_kernel(int B, int nmax, MpcSolutionDev sol) { const in
 
 // =====================================================================================================
 // MPC_MRT_Interface::evaluatePolicy with a feed-forward policy (QMController.cpp:141): linear interpolation of the stored solution, modeAtTime
-__global__ void mpc_policy_eval_kernel(int B, int nmax, MpcSolutionDev sol, const int32_t* __restrict__ n_events, const double* __restrict__ event_times, const int32_t* __restrict__ modes,
+__global__ void mpc_policy_eval_kernel(int b0, int B, int nmax, MpcSolutionDev sol, const int32_t* __restrict__ n_events, const double* __restrict__ event_times, const int32_t* __restrict__ modes,
                                        const double* __restrict__ tq, double* __restrict__ x_des, double* __restrict__ u_des, int32_t* __restrict__ mode_out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = blockIdx.x * (blockDim.x >> 5) + warp; if (b >= B) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x * (blockDim.x >> 5) + warp; if (b >= B) return;
   const int n = sol.n_nodes[b]; const double* gt = sol.t + (size_t)b * nmax; const double t = tq[b];
   int idx; double a; time_segment(gt, n, t, idx, a); const int i2 = (idx + 1 < n) ? idx + 1 : idx;
   const double* gx = sol.x + (size_t)b * nmax * NX; const double* gu = sol.u + (size_t)b * nmax * NU;
@@ -679,7 +679,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
   return ok;
 }
 
-int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, const MpcProblemDev& p, cudaStream_t stream, cudaEvent_t* ev) {
+int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, const MpcProblemDev& p, int b0, int b1, cudaStream_t stream, cudaEvent_t* ev) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
@@ -688,23 +688,24 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     configured = true;
   }
   (void)hm;
-  const int B = m.B, nmax = m.nmax; MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];
+  const int nb = b1 - b0, nmax = m.nmax; if (nb <= 0) return 0;
+  MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];   // the caller flips m.cur once all ranges are queued
   if (ev) cudaEventRecord(ev[0], stream);
-  mpc_setup_kernel<<<(B + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, 0, stream>>>(mdl, B, nmax, p, prev, next, m.status);
+  mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
   if (ev) cudaEventRecord(ev[1], stream);
-  const long long nodes = (long long)B * nmax;
-  mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.status);
+  const long long nodes = (long long)nb * nmax;
+  mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.status);
   if (ev) cudaEventRecord(ev[2], stream);
-  mpc_riccati_kernel<<<B, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, B, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
+  mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
   if (ev) cudaEventRecord(ev[3], stream);
-  mpc_linesearch_kernel<<<B, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, B, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info);
+  mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info);
   if (ev) cudaEventRecord(ev[4], stream);
-  m.cur = 1 - m.cur;
   return 4;
 }
 
-int mpc_policy_eval_launch(const MpcBuffers& m, const double* t, double* x_des, double* u_des, int32_t* mode, cudaStream_t stream) {
-  mpc_policy_eval_kernel<<<(m.B + 3) / 4, 128, 0, stream>>>(m.B, m.nmax, m.sol[m.cur], m.n_events, m.event_times, m.modes, t, x_des, u_des, mode);
+int mpc_policy_eval_launch(const MpcBuffers& m, const double* t, double* x_des, double* u_des, int32_t* mode, cudaStream_t stream, int b0, int b1) {
+  if (b1 < 0) b1 = m.B; if (b1 <= b0) return 0;
+  mpc_policy_eval_kernel<<<(b1 - b0 + 3) / 4, 128, 0, stream>>>(b0, b1, m.nmax, m.sol[m.cur], m.n_events, m.event_times, m.modes, t, x_des, u_des, mode);
   return 1;
 }
 int mpc_fixup_launch(const MpcBuffers& m, cudaStream_t stream) { mpc_fixup_kernel<<<m.B, 32, 0, stream>>>(m.B, m.nmax, m.sol[m.cur]); return 1; }

@@ -268,13 +268,13 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
   return status;
 }
 
-__global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevModel* __restrict__ mdl, int B, const double* __restrict__ x_des, const double* __restrict__ u_des,
+__global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevModel* __restrict__ mdl, int b0, int B, const double* __restrict__ x_des, const double* __restrict__ u_des,
                                                                    const double* __restrict__ rbd_meas, const int32_t* __restrict__ mode_in, const double* __restrict__ period_in,
                                                                    const double* __restrict__ time_in, double* __restrict__ input_last, int variant,
                                                                    double* __restrict__ cmd_out, int32_t* __restrict__ status_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * WBC_WARPS + warp;
+  const int b = b0 + blockIdx.x * WBC_WARPS + warp;
   if (b >= B) return;
   WbcSmem& sm = reinterpret_cast<WbcSmem*>(smem_raw)[warp];
   const int mode = mode_in[b]; const double period = period_in[b]; const double time = time_in[b];
@@ -428,12 +428,13 @@ static_assert(sizeof(WbcSmem) * WBC_WARPS <= 227 * 1024, "WBC shared-memory budg
 size_t wbc_smem_bytes() { return sizeof(WbcSmem) * WBC_WARPS; }
 
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
-                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream) {
+                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0, int b1) {
   static bool configured = false;
   const size_t smem = wbc_smem_bytes();
   if (!configured) { cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-  const int grid = (B + WBC_WARPS - 1) / WBC_WARPS;
-  wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, B, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status);
+  if (b1 < 0) b1 = B; if (b1 <= b0) return;
+  const int grid = (b1 - b0 + WBC_WARPS - 1) / WBC_WARPS;
+  wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status);
 }
 
 }  // namespace qmb

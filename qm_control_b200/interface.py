@@ -161,6 +161,10 @@ class Solver:
         keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
         self._chk(self.lib.qmb200_tick_dev(self.h, *[_p(prob_dev[k]) for k in keys], _p(t_eval), _p(rbd), _p(period), _p(cmd), _p(status), C.c_void_p(stream) if stream else None), "qmb200_tick_dev")
 
+    def set_pipeline(self, chunks):
+        """Number of robot ranges the tick runs as concurrent stream chains (include/qmb200.h: qmb200_set_pipeline)."""
+        self._chk(self.lib.qmb200_set_pipeline(self.h, int(chunks)), "qmb200_set_pipeline")
+
     def set_profiling(self, on=True):
         self._chk(self.lib.qmb200_set_profiling(self.h, 1 if on else 0), "qmb200_set_profiling")
 

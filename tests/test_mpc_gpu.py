@@ -107,3 +107,25 @@ def test_full_tick_matches_oracle(oracle):
         c, _, _ = oracle.wbc_update(x, u, wbc["rbd"][b], m, wbc["period"][b], t_eval[b], input_last=np.zeros(30))
         err = np.max(np.abs(cmd[b] - c)) / max(1.0, np.max(np.abs(c)))
         assert err < 1e-4, "robot %d rel err %.2e" % (b, err)   # WBC amplifies the 1e-5 MPC tolerance (kp gains up to 6000)
+
+
+def test_pipelined_tick_is_bit_identical():
+    """qmb200_set_pipeline only changes how robot ranges are scheduled (streams): commands, status and the stored
+    solution must be bit-identical to the single-chain tick, over two consecutive ticks (warm start crosses the flip)."""
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    B = 37; prob, wbc = synthetic.make_batch(np.arange(B), config=4)
+    outs = []
+    for chunks in (1, 3, 8):
+        solver = q.Solver(batch=B, dt=0.015); solver.set_pipeline(chunks)
+        res = []
+        for tick in range(2):
+            p = dict(prob); p["t0"] = prob["t0"] + 0.01 * tick
+            cmd, status = solver.tick(p, p["t0"] + 0.002, wbc["rbd"], wbc["period"])
+            sol = solver.mpc_get_solution()
+            res.append((cmd.copy(), status.copy(), sol["x"].copy(), sol["u"].copy()))
+        outs.append(res)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            for xa, xb in zip(a, b):
+                assert np.array_equal(xa, xb)
