@@ -355,15 +355,17 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
 // warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
 // LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
 constexpr int RIC_THREADS = 128;
-constexpr int LDP = 33, LDA = 32, LDB = 24;
+constexpr int LDA = 34, LDB = 22;           // even (16-byte rows for LDS.128 / cp.async) and != 0 mod 32 banks across row pairs
 struct RicSmem {
-  double P[NX * LDP];                       // value-function Hessian (row operand)
-  double A[NX * LDA], W[NX * LDA], Qb[NX * LDA];
-  double Bm[NX * LDB], PB[NX * LDB];
-  double G[MU * LDA];                       // S~, then G, then Y = L^{-1} G
-  double H[MU * LDB];                       // R~, then H, then its Cholesky factor
+  double P[NX * LDA];                       // value function: Hessian in columns 0..29, gradient p in column 30
+  double A[NX * LDA];                       // A~ (column 30: b~)
+  double W[NX * LDA];                       // W = P'A (column 30: p + P b~)
+  double Qb[NX * LDA];                      // Q~ (column 30: q~)
+  double Bm[NX * LDB], PB[NX * LDB];        // B~ ; P'B~, later Y = L^{-1}[G | h] (18 x LDA)
+  double G[MU * LDA];                       // S~ (column 30: r~), then G = S~ + B~'W (column 30: h)
+  double H[MU * LDB];                       // R~, then H = R~ + B~'P B~
   double Lt[MU * MU];                       // Cholesky factor of H, transposed: Lt[c][a] = L[a][c] (strict lower part; pivots live as reciprocals in dut)
-  double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32], kff2[32];
+  double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32], kff2[32];   // rollout vectors (two buffer sets)
   double red[RIC_THREADS / 32][4];
   int flag;
 };
@@ -379,14 +381,48 @@ __device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, 
   const int cpr = cols >> 1;
   for (int e = tid; e < rows * cpr; e += RIC_THREADS) { const int i = e / cpr, c = e - i * cpr; cp_async16(s + i * ls + 2 * c, g + (size_t)i * gs + 2 * c); }
 }
-// acc[v] += sum_k X[k*xs] * Y[k*ldy + v], v = 0..7   (Y rows 16-B aligned; K is a compile-time trip count)
-template <int K> __device__ __forceinline__ void tile_mac(const double* __restrict__ X, int xs, const double* __restrict__ Y, int ldy, double (&acc)[8]) {
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+}
+// 4x4 register tile of C += X'Y over k: thread (rq, cq) owns rows {2rq, 2rq+1, RH+2rq, RH+2rq+1} x columns {2cq, 2cq+1, CH+2cq, CH+2cq+1}.
+// X[k][.] and Y[k][.] are rows of row-major shared-memory matrices, so every operand fetch is one LDS.128; within a half-warp the 8
+// rq values read 8 consecutive 16-byte chunks (one conflict-free wavefront) and the 2 cq values are broadcasts:
+// 4 LDS.128 feed 16 DFMA per k (the 1x8 broadcast tiling of the previous version was shared-memory-bandwidth bound at 80 %).
+template <int K, int RH, int CH>
+__device__ __forceinline__ void mm44(const double* __restrict__ X, int ldx, const double* __restrict__ Y, int ldy, int rq, int cq, double (&acc)[4][4]) {
+  const double* x0 = X + 2 * rq; const double* y0 = Y + 2 * cq;
 #pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    const double a = X[k * xs]; const double2* y = reinterpret_cast<const double2*>(Y + k * ldy);
-    const double2 y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
-    acc[0] = fma(a, y0.x, acc[0]); acc[1] = fma(a, y0.y, acc[1]); acc[2] = fma(a, y1.x, acc[2]); acc[3] = fma(a, y1.y, acc[3]);
-    acc[4] = fma(a, y2.x, acc[4]); acc[5] = fma(a, y2.y, acc[5]); acc[6] = fma(a, y3.x, acc[6]); acc[7] = fma(a, y3.y, acc[7]);
+    const double2 xa = *reinterpret_cast<const double2*>(x0 + k * ldx), xb = *reinterpret_cast<const double2*>(x0 + k * ldx + RH);
+    const double2 ya = *reinterpret_cast<const double2*>(y0 + k * ldy), yb = *reinterpret_cast<const double2*>(y0 + k * ldy + CH);
+    acc[0][0] = fma(xa.x, ya.x, acc[0][0]); acc[0][1] = fma(xa.x, ya.y, acc[0][1]); acc[0][2] = fma(xa.x, yb.x, acc[0][2]); acc[0][3] = fma(xa.x, yb.y, acc[0][3]);
+    acc[1][0] = fma(xa.y, ya.x, acc[1][0]); acc[1][1] = fma(xa.y, ya.y, acc[1][1]); acc[1][2] = fma(xa.y, yb.x, acc[1][2]); acc[1][3] = fma(xa.y, yb.y, acc[1][3]);
+    acc[2][0] = fma(xb.x, ya.x, acc[2][0]); acc[2][1] = fma(xb.x, ya.y, acc[2][1]); acc[2][2] = fma(xb.x, yb.x, acc[2][2]); acc[2][3] = fma(xb.x, yb.y, acc[2][3]);
+    acc[3][0] = fma(xb.y, ya.x, acc[3][0]); acc[3][1] = fma(xb.y, ya.y, acc[3][1]); acc[3][2] = fma(xb.y, yb.x, acc[3][2]); acc[3][3] = fma(xb.y, yb.y, acc[3][3]);
+  }
+}
+// 2x4 variant (rows {ro+2rq, ro+2rq+1}): lets both warp pairs share one short product
+template <int K, int CH>
+__device__ __forceinline__ void mm24(const double* __restrict__ X, int ldx, const double* __restrict__ Y, int ldy, int ro, int rq, int cq, double (&acc)[2][4]) {
+  const double* x0 = X + ro + 2 * rq; const double* y0 = Y + 2 * cq;
+#pragma unroll 3
+  for (int k = 0; k < K; ++k) {
+    const double2 xa = *reinterpret_cast<const double2*>(x0 + k * ldx);
+    const double2 ya = *reinterpret_cast<const double2*>(y0 + k * ldy), yb = *reinterpret_cast<const double2*>(y0 + k * ldy + CH);
+    acc[0][0] = fma(xa.x, ya.x, acc[0][0]); acc[0][1] = fma(xa.x, ya.y, acc[0][1]); acc[0][2] = fma(xa.x, yb.x, acc[0][2]); acc[0][3] = fma(xa.x, yb.y, acc[0][3]);
+    acc[1][0] = fma(xa.y, ya.x, acc[1][0]); acc[1][1] = fma(xa.y, ya.y, acc[1][1]); acc[1][2] = fma(xa.y, yb.x, acc[1][2]); acc[1][3] = fma(xa.y, yb.y, acc[1][3]);
+  }
+}
+// tile <-> shared memory: row r of the tile is matrix row (r < 2 ? 2rq + r : RH + 2rq + r - 2), guarded by `rows`
+template <int RH, int CH, bool LOAD>
+__device__ __forceinline__ void tile_io(double* M, int ld, int rows, int rq, int cq, double (&acc)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ri = (r < 2) ? 2 * rq + r : RH + 2 * rq + r - 2;
+    double2* m0 = reinterpret_cast<double2*>(M + ri * ld + 2 * cq); double2* m1 = reinterpret_cast<double2*>(M + ri * ld + CH + 2 * cq);
+    if (LOAD) { if (ri < rows) { const double2 v0 = *m0, v1 = *m1; acc[r][0] = v0.x; acc[r][1] = v0.y; acc[r][2] = v1.x; acc[r][3] = v1.y; } else { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; } }
+    else if (ri < rows) { *m0 = make_double2(acc[r][0], acc[r][1]); *m1 = make_double2(acc[r][2], acc[r][3]); }
   }
 }
 
@@ -399,12 +435,13 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
   for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
   __syncthreads();
-  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid); if (tid < 15) cp_async16(sm.b + 2 * tid, sg + ST_b + 2 * tid); cp_async_commit(); };
+  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
+    if (tid < NX) cp_async8(sm.A + tid * LDA + NX, sg + ST_b + tid); cp_async_commit(); };                                 // b~ rides in column 30 of A~
   auto issue_srq = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_S, MU, NX, NX, sm.G, LDA, tid); cp_rows(sg + ST_R, MU, MU, MU, sm.H, LDB, tid); cp_rows(sg + ST_Q, NX, NX, NX, sm.Qb, LDA, tid);
-    if (tid < 15) cp_async16(sm.q + 2 * tid, sg + ST_q + 2 * tid); else if (tid < 24) cp_async16(sm.r + 2 * (tid - 15), sg + ST_r + 2 * (tid - 15)); cp_async_commit(); };
+    if (tid < NX) cp_async8(sm.Qb + tid * LDA + NX, sg + ST_q + tid); else if (tid >= 32 && tid < 32 + MU) cp_async8(sm.G + (tid - 32) * LDA + NX, sg + ST_r + tid - 32); cp_async_commit(); };   // q~, r~ in column 30 of Q~, S~
   // terminal value function and baseline performance
-  for (int e = tid; e < NX * NX; e += RIC_THREADS) sm.P[(e / NX) * LDP + (e % NX)] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
-  if (tid < NX) sm.p[tid] = sgb[(size_t)N * STAGE_DBL + ST_q + tid];
+  for (int e = tid; e < NX * NX; e += RIC_THREADS) sm.P[(e / NX) * LDA + (e % NX)] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
+  if (tid < NX) sm.P[tid * LDA + NX] = sgb[(size_t)N * STAGE_DBL + ST_q + tid];
   double perf0 = 0, perf1 = 0, perf2 = 0;
   for (int k = tid; k < n; k += RIC_THREADS) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_PERF; perf0 += pf[0]; perf1 += pf[1]; perf2 += pf[2]; }
   if (tid < NX) { const double d = p.x0[(size_t)b * NX + tid] - sol.x[(size_t)b * nmax * NX + tid]; sm.dx[tid] = d; perf1 += d * d; }
@@ -414,41 +451,42 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   __syncthreads();
   double perf[3]; for (int i = 0; i < 3; ++i) perf[i] = sm.red[0][i] + sm.red[1][i] + sm.red[2][i] + sm.red[3][i];
   int st = 0;
-  const int cb = warp * 8;                          // backward sweep mapping: lane = row, warp = 8-column block (operand rows are pure broadcasts)
+  // backward sweep mapping: two warp pairs; inside a pair thread (rq, cq) owns a 4x4 tile (mm44).  The vector recursion rides in
+  // column 30 of the matrices (b~, p + P b~, h, q~, p), so no separate matrix-vector products are needed.
+  const int grp = warp >> 1, gt = tid & 63, rq = gt & 7, cq = gt >> 3;
   for (int k = N - 1; k >= 0; --k) {
     const int type = sib[(size_t)k * STAGE_INT + SI_TYPE];
-    cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed
-    if (type == 1) {                                // event node: A = I, no input
-      if (tid < NX) { double s = sm.p[tid]; for (int j = 0; j < NX; ++j) s = fma(sm.P[tid * LDP + j], sm.b[j], s); sm.tmp[tid] = s; }
+    cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed; P of node k+1 is complete
+    if (type == 1) {                                // event node: A = I, no input: p += P b
+      if (tid < NX) { double sv = sm.P[tid * LDA + NX]; for (int j = 0; j < NX; ++j) sv = fma(sm.P[tid * LDA + j], sm.A[j * LDA + NX], sv); sm.tmp[tid] = sv; }
       cp_async_wait<0>(); __syncthreads();
-      if (tid < NX) sm.p[tid] = sm.tmp[tid];
+      if (tid < NX) sm.P[tid * LDA + NX] = sm.tmp[tid];
       __syncthreads();
       if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }
       continue;
     }
-    // ---- phase 1: W = P A (4 warps) ; PB = P B (warps 0-2) ; pPb = p + P b (warp 3) ----
-    if (lane < NX) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac<NX>(sm.P + lane * LDP, 1, sm.A + cb, LDA, acc);
-      double2* w = reinterpret_cast<double2*>(sm.W + lane * LDA + cb); w[0] = make_double2(acc[0], acc[1]); w[1] = make_double2(acc[2], acc[3]); w[2] = make_double2(acc[4], acc[5]); w[3] = make_double2(acc[6], acc[7]);
-      if (warp < 3) { double ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac<NX>(sm.P + lane * LDP, 1, sm.Bm + cb, LDB, ab);
-        double2* pb = reinterpret_cast<double2*>(sm.PB + lane * LDB + cb); pb[0] = make_double2(ab[0], ab[1]); pb[1] = make_double2(ab[2], ab[3]); pb[2] = make_double2(ab[4], ab[5]); pb[3] = make_double2(ab[6], ab[7]); }
-      else { double s = sm.p[lane]; for (int j = 0; j < NX; ++j) s = fma(sm.P[lane * LDP + j], sm.b[j], s); sm.pPb[lane] = s; }
+    // ---- phase 1: pair 0: W = P'A (column 30: p + P b~) ; pair 1: PB = P'B~ ----
+    if (grp == 0) {
+      double acc[4][4] = {}; mm44<NX, 16, 16>(sm.P, LDA, sm.A, LDA, rq, cq, acc);
+      if (cq == 7) {   // this thread's third column is column 30
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const int ri = (r < 2) ? 2 * rq + r : 16 + 2 * rq + r - 2; if (ri < NX) acc[r][2] += sm.P[ri * LDA + NX]; } }
+      tile_io<16, 16, false>(sm.W, LDA, NX, rq, cq, acc);
+    } else if (cq < 5) {
+      double acc[4][4] = {}; mm44<NX, 16, 10>(sm.P, LDA, sm.Bm, LDB, rq, cq, acc);
+      tile_io<16, 10, false>(sm.PB, LDB, NX, rq, cq, acc);
     }
-    cp_async_wait<0>(); __syncthreads();           // S~, R~, Q~, q~, r~ have landed; W, PB, pPb visible
-    // ---- phase 2: G = S + B'W (4 warps) ; H = R + B'PB (warps 0-2) ; h = r + B'(p + P b) (warp 3, kept in column 30 of G) ----
-    if (lane < MU) {
-      double acc[8]; { const double2* gv = reinterpret_cast<const double2*>(sm.G + lane * LDA + cb); const double2 g0 = gv[0], g1 = gv[1], g2 = gv[2], g3 = gv[3]; acc[0] = g0.x; acc[1] = g0.y; acc[2] = g1.x; acc[3] = g1.y; acc[4] = g2.x; acc[5] = g2.y; acc[6] = g3.x; acc[7] = g3.y; }
-      tile_mac<NX>(sm.Bm + lane, LDB, sm.W + cb, LDA, acc);
-      if (warp == 3) { double s = sm.r[lane]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.Bm[kk * LDB + lane], sm.pPb[kk], s); acc[6] = s; }   // column 30 := h
-      double2* gw = reinterpret_cast<double2*>(sm.G + lane * LDA + cb); gw[0] = make_double2(acc[0], acc[1]); gw[1] = make_double2(acc[2], acc[3]); gw[2] = make_double2(acc[4], acc[5]); gw[3] = make_double2(acc[6], acc[7]);
-      if (warp < 3) { double ah[8]; { const double2* hv = reinterpret_cast<const double2*>(sm.H + lane * LDB + cb); const double2 h0 = hv[0], h1 = hv[1], h2 = hv[2], h3 = hv[3]; ah[0] = h0.x; ah[1] = h0.y; ah[2] = h1.x; ah[3] = h1.y; ah[4] = h2.x; ah[5] = h2.y; ah[6] = h3.x; ah[7] = h3.y; }
-        tile_mac<NX>(sm.Bm + lane, LDB, sm.PB + cb, LDB, ah);
-        double2* hw = reinterpret_cast<double2*>(sm.H + lane * LDB + cb); hw[0] = make_double2(ah[0], ah[1]); hw[1] = make_double2(ah[2], ah[3]); hw[2] = make_double2(ah[4], ah[5]); hw[3] = make_double2(ah[6], ah[7]); }
+    cp_async_wait<0>(); __syncthreads();           // S~, R~, Q~, q~, r~ have landed; W, PB visible
+    // ---- phase 2: pair 0: G = S~ + B~'W (column 30: h = r~ + B~'(p + P b~)) ; pair 1: H = R~ + B~'PB ----
+    if (grp == 0) {
+      if (rq < 5) { double acc[4][4]; tile_io<10, 16, true>(sm.G, LDA, MU, rq, cq, acc); mm44<NX, 10, 16>(sm.Bm, LDB, sm.W, LDA, rq, cq, acc); tile_io<10, 16, false>(sm.G, LDA, MU, rq, cq, acc); }
+    } else if (rq < 5 && cq < 5) {
+      double acc[4][4]; tile_io<10, 10, true>(sm.H, LDB, MU, rq, cq, acc); mm44<NX, 10, 10>(sm.Bm, LDB, sm.PB, LDB, rq, cq, acc); tile_io<10, 10, false>(sm.H, LDB, MU, rq, cq, acc);
     }
     __syncthreads();
-    // ---- phase 3: one warp factors H and solves for Y and the gains ; the other three compute P <- Q + A'W and p <- q + A'(p + P b) meanwhile.
+    // ---- phase 3: one warp factors H and solves for Y and the gains ; the other warp pair computes P <- Q~ + A~'W (column 30: q~ + A~'(p + P b~)).
     // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
-    const int sw = (k + b) & 3, rel = (warp - sw - 1) & 3;
+    const int sw = (k + b) & 3;
     if (warp == sw) {
       // (a) Cholesky of H with the factor in registers: lane = row (read from the upper triangle: column access is bank-conflict free),
       //     pivot and column broadcasts by shuffle; every lane runs the same unrolled code (lanes >= MU carry zeros).
@@ -488,29 +526,18 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
 #pragma unroll
         for (int c = 0; c < a; ++c) y[c] = fma(-sm.Lt[c * MU + a], y[a], y[c]);
       }
-    } else {
-      if (lane < NX) {
-        for (int blk = rel; blk < 4; blk += 3) {   // column blocks 0..3 over the three helper warps (the first also takes block 3)
-          const int c0 = blk * 8; double acc[8]; { const double2* qv = reinterpret_cast<const double2*>(sm.Qb + lane * LDA + c0); const double2 q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3]; acc[0] = q0.x; acc[1] = q0.y; acc[2] = q1.x; acc[3] = q1.y; acc[4] = q2.x; acc[5] = q2.y; acc[6] = q3.x; acc[7] = q3.y; }
-          tile_mac<NX>(sm.A + lane, LDA, sm.W + c0, LDA, acc);
-          double* pr = sm.P + lane * LDP + c0;
-#pragma unroll
-          for (int v = 0; v < 8; ++v) if (c0 + v < NX) pr[v] = acc[v];
-        }
-        if (rel == 2) { double s = sm.q[lane]; for (int kk = 0; kk < NX; ++kk) s = fma(sm.A[kk * LDA + lane], sm.pPb[kk], s); sm.tmp[lane] = s; }
-      }
+    } else if (grp != (sw >> 1)) {
+      double acc[4][4]; tile_io<16, 16, true>(sm.Qb, LDA, NX, rq, cq, acc); mm44<NX, 16, 16>(sm.A, LDA, sm.W, LDA, rq, cq, acc); tile_io<16, 16, false>(sm.P, LDA, NX, rq, cq, acc);
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; break; }
     if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }   // A~/B~ and S~/R~/Q~ buffers are all free: prefetch the next node
-    // ---- phase 4: P -= Y'Y ; p -= Y' yh  (the top-of-loop barrier closes this phase) ----
-    if (lane < NX) {
-      const double* Yb = sm.PB;
-      double* pr = sm.P + lane * LDP + cb; double neg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tile_mac<MU>(Yb + lane, LDA, Yb + cb, LDA, neg);
+    // ---- phase 4: P -= Y'Y, column 30: p -= Y' yh (both pairs, 2x4 tiles; the top-of-loop barrier closes this phase) ----
+    { const double* Yb = sm.PB; double neg[2][4] = {}; mm24<MU, 16>(Yb, LDA, Yb, LDA, 16 * grp, rq, cq, neg);
 #pragma unroll
-      for (int v = 0; v < 8; ++v) if (cb + v < NX) pr[v] -= neg[v];
-      if (warp == 3) { double s = sm.tmp[lane]; for (int a = 0; a < MU; ++a) s = fma(-Yb[a * LDA + lane], Yb[a * LDA + NX], s); sm.p[lane] = s; }
-    }
+      for (int r = 0; r < 2; ++r) { const int ri = 16 * grp + 2 * rq + r;
+        if (ri < NX) { double2* m0 = reinterpret_cast<double2*>(sm.P + ri * LDA + 2 * cq); double2* m1 = reinterpret_cast<double2*>(sm.P + ri * LDA + 16 + 2 * cq);
+          double2 v0 = *m0, v1 = *m1; v0.x -= neg[r][0]; v0.y -= neg[r][1]; v1.x -= neg[r][2]; v1.y -= neg[r][3]; *m0 = v0; *m1 = v1; } } }
   }
   cp_async_wait<0>(); __syncthreads();
   // ---- forward rollout: du~ = K dx + k ; dx+ = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~ ----
