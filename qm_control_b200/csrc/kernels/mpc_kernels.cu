@@ -355,15 +355,16 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
 // warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
 // LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
 constexpr int RIC_THREADS = 128;
-constexpr int LDA = 34, LDB = 22;           // even (16-byte rows for LDS.128 / cp.async) and != 0 mod 32 banks across row pairs
+// Leading dimensions.  MMA operands are fetched as X[(k0 + t) * ld + c0 + g] (t = lane % 4, g = lane / 4): 2 * ld = 8 (mod 32) or
+// 24 (mod 32) puts the four k-rows of a half-warp on disjoint bank octets, i.e. every fragment load is conflict free.
+constexpr int LDX = 36, LDB = 28, LDG = 34, LDH = 24;
 struct RicSmem {
-  double P[NX * LDA];                       // value function: Hessian in columns 0..29, gradient p in column 30
-  double A[NX * LDA];                       // A~ (column 30: b~)
-  double W[NX * LDA];                       // W = P'A (column 30: p + P b~)
-  double Qb[NX * LDA];                      // Q~ (column 30: q~)
-  double Bm[NX * LDB], PB[NX * LDB];        // B~ ; P'B~, later Y = L^{-1}[G | h] (18 x LDA)
-  double G[MU * LDA];                       // S~ (column 30: r~), then G = S~ + B~'W (column 30: h)
-  double H[MU * LDB];                       // R~, then H = R~ + B~'P B~
+  double P[NX * LDX];                       // value function: Hessian in columns 0..29, gradient p in column 30; receives Q~ (C operand of phase 3) in between
+  double A[NX * LDX];                       // A~ (column 30: b~)
+  double W[NX * LDX];                       // W = P'A (column 30: p + P b~)
+  double Bm[NX * LDB], PB[NX * LDB];        // B~ ; P'B~, later Y = L^{-1}[G | h] (18 x LDX)
+  double G[MU * LDG];                       // S~ (column 30: r~), then G = S~ + B~'W (column 30: h)
+  double H[MU * LDH];                       // R~, then H = R~ + B~'P B~
   double Lt[MU * MU];                       // Cholesky factor of H, transposed: Lt[c][a] = L[a][c] (strict lower part; pivots live as reciprocals in dut)
   double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32], kff2[32];   // rollout vectors (two buffer sets)
   double red[RIC_THREADS / 32][4];
@@ -376,54 +377,52 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-// rows x cols doubles (cols even, 16-B aligned rows on both sides) global → shared, all threads
-__device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, int cols, int gs, double* s, int ls, int tid) {
+// rows x cols doubles (cols even, 16-B aligned rows on both sides) global → shared, spread over threads tid = 0..nthr-1
+__device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, int cols, int gs, double* s, int ls, int tid, int nthr = RIC_THREADS) {
   const int cpr = cols >> 1;
-  for (int e = tid; e < rows * cpr; e += RIC_THREADS) { const int i = e / cpr, c = e - i * cpr; cp_async16(s + i * ls + 2 * c, g + (size_t)i * gs + 2 * c); }
+  for (int e = tid; e < rows * cpr; e += nthr) { const int i = e / cpr, c = e - i * cpr; cp_async16(s + i * ls + 2 * c, g + (size_t)i * gs + 2 * c); }
 }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
 }
-// 4x4 register tile of C += X'Y over k: thread (rq, cq) owns rows {2rq, 2rq+1, RH+2rq, RH+2rq+1} x columns {2cq, 2cq+1, CH+2cq, CH+2cq+1}.
-// X[k][.] and Y[k][.] are rows of row-major shared-memory matrices, so every operand fetch is one LDS.128; within a half-warp the 8
-// rq values read 8 consecutive 16-byte chunks (one conflict-free wavefront) and the 2 cq values are broadcasts:
-// 4 LDS.128 feed 16 DFMA per k (the 1x8 broadcast tiling of the previous version was shared-memory-bandwidth bound at 80 %).
-template <int K, int RH, int CH>
-__device__ __forceinline__ void mm44(const double* __restrict__ X, int ldx, const double* __restrict__ Y, int ldy, int rq, int cq, double (&acc)[4][4]) {
-  const double* x0 = X + 2 * rq; const double* y0 = Y + 2 * cq;
-#pragma unroll 2
-  for (int k = 0; k < K; ++k) {
-    const double2 xa = *reinterpret_cast<const double2*>(x0 + k * ldx), xb = *reinterpret_cast<const double2*>(x0 + k * ldx + RH);
-    const double2 ya = *reinterpret_cast<const double2*>(y0 + k * ldy), yb = *reinterpret_cast<const double2*>(y0 + k * ldy + CH);
-    acc[0][0] = fma(xa.x, ya.x, acc[0][0]); acc[0][1] = fma(xa.x, ya.y, acc[0][1]); acc[0][2] = fma(xa.x, yb.x, acc[0][2]); acc[0][3] = fma(xa.x, yb.y, acc[0][3]);
-    acc[1][0] = fma(xa.y, ya.x, acc[1][0]); acc[1][1] = fma(xa.y, ya.y, acc[1][1]); acc[1][2] = fma(xa.y, yb.x, acc[1][2]); acc[1][3] = fma(xa.y, yb.y, acc[1][3]);
-    acc[2][0] = fma(xb.x, ya.x, acc[2][0]); acc[2][1] = fma(xb.x, ya.y, acc[2][1]); acc[2][2] = fma(xb.x, yb.x, acc[2][2]); acc[2][3] = fma(xb.x, yb.y, acc[2][3]);
-    acc[3][0] = fma(xb.y, ya.x, acc[3][0]); acc[3][1] = fma(xb.y, ya.y, acc[3][1]); acc[3][2] = fma(xb.y, yb.x, acc[3][2]); acc[3][3] = fma(xb.y, yb.y, acc[3][3]);
-  }
+// ---- fp64 tensor-core tiles (DMMA.8x8x4, mma.sync m8n8k4 f64: measured 37 TFLOP/s on B200, the same rate as the DFMA pipe at 1/8 of
+// the issue slots and ~1/3 of the shared-memory operand traffic of a 4x4 register tile).  C(8x8) += A(8x4) B(4x8) with
+// A[i][k] = X[k][i0 + i], B[k][j] = Y[k][j0 + j]: lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g], C[g][2t], C[g][2t + 1].
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
-// 2x4 variant (rows {ro+2rq, ro+2rq+1}): lets both warp pairs share one short product
-template <int K, int CH>
-__device__ __forceinline__ void mm24(const double* __restrict__ X, int ldx, const double* __restrict__ Y, int ldy, int ro, int rq, int cq, double (&acc)[2][4]) {
-  const double* x0 = X + ro + 2 * rq; const double* y0 = Y + 2 * cq;
-#pragma unroll 3
-  for (int k = 0; k < K; ++k) {
-    const double2 xa = *reinterpret_cast<const double2*>(x0 + k * ldx);
-    const double2 ya = *reinterpret_cast<const double2*>(y0 + k * ldy), yb = *reinterpret_cast<const double2*>(y0 + k * ldy + CH);
-    acc[0][0] = fma(xa.x, ya.x, acc[0][0]); acc[0][1] = fma(xa.x, ya.y, acc[0][1]); acc[0][2] = fma(xa.x, yb.x, acc[0][2]); acc[0][3] = fma(xa.x, yb.y, acc[0][3]);
-    acc[1][0] = fma(xa.y, ya.x, acc[1][0]); acc[1][1] = fma(xa.y, ya.y, acc[1][1]); acc[1][2] = fma(xa.y, yb.x, acc[1][2]); acc[1][3] = fma(xa.y, yb.y, acc[1][3]);
-  }
-}
-// tile <-> shared memory: row r of the tile is matrix row (r < 2 ? 2rq + r : RH + 2rq + r - 2), guarded by `rows`
-template <int RH, int CH, bool LOAD>
-__device__ __forceinline__ void tile_io(double* M, int ld, int rows, int rq, int cq, double (&acc)[4][4]) {
+// c[m][n] += (+-) X[0:K, i0 + 8m ..]' Y[0:K, j0 + 8n ..] for an MT x NT block of 8x8 tiles; K need not be a multiple of 4 (tail lanes feed zeros)
+template <int K, int MT, int NT, bool NEG>
+__device__ __forceinline__ void warp_mma(const double* __restrict__ X, int ldx, int i0, const double* __restrict__ Y, int ldy, int j0, double (&c)[MT][NT][2], int g, int t) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int ri = (r < 2) ? 2 * rq + r : RH + 2 * rq + r - 2;
-    double2* m0 = reinterpret_cast<double2*>(M + ri * ld + 2 * cq); double2* m1 = reinterpret_cast<double2*>(M + ri * ld + CH + 2 * cq);
-    if (LOAD) { if (ri < rows) { const double2 v0 = *m0, v1 = *m1; acc[r][0] = v0.x; acc[r][1] = v0.y; acc[r][2] = v1.x; acc[r][3] = v1.y; } else { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; } }
-    else if (ri < rows) { *m0 = make_double2(acc[r][0], acc[r][1]); *m1 = make_double2(acc[r][2], acc[r][3]); }
+  for (int ks = 0; ks < (K + 3) / 4; ++ks) {
+    const int kr = 4 * ks + t; const bool ok = (4 * ks + 3 < K) || (kr < K);
+    double a[MT], bf[NT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { const double v = ok ? X[kr * ldx + i0 + 8 * m + g] : 0.0; a[m] = NEG ? -v : v; }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) bf[n] = ok ? Y[kr * ldy + j0 + 8 * n + g] : 0.0;
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) dmma884(c[m][n], a[m], bf[n]);
   }
+}
+template <int MT, int NT>
+__device__ __forceinline__ void cfrag_load(const double* M, int ld, int i0, int j0, int rows, double (&c)[MT][NT][2], int g, int t) {
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { const int ri = i0 + 8 * m + g;
+      if (ri < rows) { const double2 v = *reinterpret_cast<const double2*>(M + ri * ld + j0 + 8 * n + 2 * t); c[m][n][0] = v.x; c[m][n][1] = v.y; } else { c[m][n][0] = 0.0; c[m][n][1] = 0.0; } }
+}
+template <int MT, int NT>
+__device__ __forceinline__ void cfrag_store(double* M, int ld, int i0, int j0, int rows, const double (&c)[MT][NT][2], int g, int t) {
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { const int ri = i0 + 8 * m + g; if (ri < rows) *reinterpret_cast<double2*>(M + ri * ld + j0 + 8 * n + 2 * t) = make_double2(c[m][n][0], c[m][n][1]); }
 }
 
 __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const int32_t* __restrict__ stage_i,
@@ -435,56 +434,57 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
   for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
   __syncthreads();
-  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
-    if (tid < NX) cp_async8(sm.A + tid * LDA + NX, sg + ST_b + tid); cp_async_commit(); };                                 // b~ rides in column 30 of A~
-  auto issue_srq = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_S, MU, NX, NX, sm.G, LDA, tid); cp_rows(sg + ST_R, MU, MU, MU, sm.H, LDB, tid); cp_rows(sg + ST_Q, NX, NX, NX, sm.Qb, LDA, tid);
-    if (tid < NX) cp_async8(sm.Qb + tid * LDA + NX, sg + ST_q + tid); else if (tid >= 32 && tid < 32 + MU) cp_async8(sm.G + (tid - 32) * LDA + NX, sg + ST_r + tid - 32); cp_async_commit(); };   // q~, r~ in column 30 of Q~, S~
+  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDX, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
+    if (tid < NX) cp_async8(sm.A + tid * LDX + NX, sg + ST_b + tid); cp_async_commit(); };                                 // b~ rides in column 30 of A~
+  auto issue_sr = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_S, MU, NX, NX, sm.G, LDG, tid); cp_rows(sg + ST_R, MU, MU, MU, sm.H, LDH, tid);
+    if (tid < MU) cp_async8(sm.G + tid * LDG + NX, sg + ST_r + tid); cp_async_commit(); };                                 // r~ in column 30 of S~
+  // Q~, q~ land in the (dead) P buffer as the C operand of phase 3.  Only the three helper warps of node k issue (and later wait for) these
+  // copies, so the factorisation warp never waits on them; it still commits an empty group to keep the group count uniform.
+  auto issue_q = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; const int hw = (warp - ((k + b) & 3) - 1) & 3;
+    if (hw < 3) { const int ht = hw * 32 + lane; cp_rows(sg + ST_Q, NX, NX, NX, sm.P, LDX, ht, 96); if (ht < NX) cp_async8(sm.P + ht * LDX + NX, sg + ST_q + ht); }
+    cp_async_commit(); };
   // terminal value function and baseline performance
-  for (int e = tid; e < NX * NX; e += RIC_THREADS) sm.P[(e / NX) * LDA + (e % NX)] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
-  if (tid < NX) sm.P[tid * LDA + NX] = sgb[(size_t)N * STAGE_DBL + ST_q + tid];
+  for (int e = tid; e < NX * NX; e += RIC_THREADS) sm.P[(e / NX) * LDX + (e % NX)] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
+  if (tid < NX) sm.P[tid * LDX + NX] = sgb[(size_t)N * STAGE_DBL + ST_q + tid];
   double perf0 = 0, perf1 = 0, perf2 = 0;
   for (int k = tid; k < n; k += RIC_THREADS) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_PERF; perf0 += pf[0]; perf1 += pf[1]; perf2 += pf[2]; }
   if (tid < NX) { const double d = p.x0[(size_t)b * NX + tid] - sol.x[(size_t)b * nmax * NX + tid]; sm.dx[tid] = d; perf1 += d * d; }
   perf0 = warp_sum(perf0); perf1 = warp_sum(perf1); perf2 = warp_sum(perf2);
   if (lane == 0) { sm.red[warp][0] = perf0; sm.red[warp][1] = perf1; sm.red[warp][2] = perf2; }
-  if (N >= 1) { issue_ab(N - 1); issue_srq(N - 1); }
+  if (N >= 1) { issue_ab(N - 1); issue_sr(N - 1); }
   __syncthreads();
   double perf[3]; for (int i = 0; i < 3; ++i) perf[i] = sm.red[0][i] + sm.red[1][i] + sm.red[2][i] + sm.red[3][i];
   int st = 0;
-  // backward sweep mapping: two warp pairs; inside a pair thread (rq, cq) owns a 4x4 tile (mm44).  The vector recursion rides in
-  // column 30 of the matrices (b~, p + P b~, h, q~, p), so no separate matrix-vector products are needed.
-  const int grp = warp >> 1, gt = tid & 63, rq = gt & 7, cq = gt >> 3;
+  // backward sweep: every product is a set of 8x8 DMMA tiles spread over the four warps.  The vector recursion rides in column 30 of
+  // the matrices (b~, p + P b~, h, q~, p), so no separate matrix-vector products are needed.
+  const int g = lane >> 2, t = lane & 3;
   for (int k = N - 1; k >= 0; --k) {
     const int type = sib[(size_t)k * STAGE_INT + SI_TYPE];
     cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed; P of node k+1 is complete
     if (type == 1) {                                // event node: A = I, no input: p += P b
-      if (tid < NX) { double sv = sm.P[tid * LDA + NX]; for (int j = 0; j < NX; ++j) sv = fma(sm.P[tid * LDA + j], sm.A[j * LDA + NX], sv); sm.tmp[tid] = sv; }
+      if (tid < NX) { double sv = sm.P[tid * LDX + NX]; for (int j = 0; j < NX; ++j) sv = fma(sm.P[tid * LDX + j], sm.A[j * LDX + NX], sv); sm.tmp[tid] = sv; }
       cp_async_wait<0>(); __syncthreads();
-      if (tid < NX) sm.P[tid * LDA + NX] = sm.tmp[tid];
+      if (tid < NX) sm.P[tid * LDX + NX] = sm.tmp[tid];
       __syncthreads();
-      if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }
+      if (k > 0) { issue_ab(k - 1); issue_sr(k - 1); }
       continue;
     }
-    // ---- phase 1: pair 0: W = P'A (column 30: p + P b~) ; pair 1: PB = P'B~ ----
-    if (grp == 0) {
-      double acc[4][4] = {}; mm44<NX, 16, 16>(sm.P, LDA, sm.A, LDA, rq, cq, acc);
-      if (cq == 7) {   // this thread's third column is column 30
+    // ---- phase 1: W = P'A (32x32: warp = 16x16 block; column 30: p + P b~) ; PB = P'B~ (32x24: warp = row tile) ----
+    { const int i0 = 16 * (warp >> 1), j0 = 16 * (warp & 1);
+      double c[2][2][2] = {}; warp_mma<NX, 2, 2, false>(sm.P, LDX, i0, sm.A, LDX, j0, c, g, t);
+      if ((warp & 1) && t == 3) {   // C element (row, column 30) lives in n-tile 1 of the right-hand block, lane t = 3, slot 0
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { const int ri = (r < 2) ? 2 * rq + r : 16 + 2 * rq + r - 2; if (ri < NX) acc[r][2] += sm.P[ri * LDA + NX]; } }
-      tile_io<16, 16, false>(sm.W, LDA, NX, rq, cq, acc);
-    } else if (cq < 5) {
-      double acc[4][4] = {}; mm44<NX, 16, 10>(sm.P, LDA, sm.Bm, LDB, rq, cq, acc);
-      tile_io<16, 10, false>(sm.PB, LDB, NX, rq, cq, acc);
-    }
-    cp_async_wait<0>(); __syncthreads();           // S~, R~, Q~, q~, r~ have landed; W, PB visible
-    // ---- phase 2: pair 0: G = S~ + B~'W (column 30: h = r~ + B~'(p + P b~)) ; pair 1: H = R~ + B~'PB ----
-    if (grp == 0) {
-      if (rq < 5) { double acc[4][4]; tile_io<10, 16, true>(sm.G, LDA, MU, rq, cq, acc); mm44<NX, 10, 16>(sm.Bm, LDB, sm.W, LDA, rq, cq, acc); tile_io<10, 16, false>(sm.G, LDA, MU, rq, cq, acc); }
-    } else if (rq < 5 && cq < 5) {
-      double acc[4][4]; tile_io<10, 10, true>(sm.H, LDB, MU, rq, cq, acc); mm44<NX, 10, 10>(sm.Bm, LDB, sm.PB, LDB, rq, cq, acc); tile_io<10, 10, false>(sm.H, LDB, MU, rq, cq, acc);
-    }
+        for (int m = 0; m < 2; ++m) { const int ri = i0 + 8 * m + g; if (ri < NX) c[m][1][0] += sm.P[ri * LDX + NX]; } }
+      cfrag_store<2, 2>(sm.W, LDX, i0, j0, NX, c, g, t);
+      double d[1][3][2] = {}; warp_mma<NX, 1, 3, false>(sm.P, LDX, 8 * warp, sm.Bm, LDB, 0, d, g, t);
+      cfrag_store<1, 3>(sm.PB, LDB, 8 * warp, 0, NX, d, g, t); }
+    cp_async_wait<0>(); __syncthreads();           // S~, R~, r~ have landed; W, PB visible; P is dead until phase 3
+    issue_q(k);
+    // ---- phase 2: G = S~ + B~'W (24x32: warp = column tile; column 30: h = r~ + B~'(p + P b~)) ; H = R~ + B~'PB (24x24: warps 0-2) ----
+    { double c[3][1][2]; cfrag_load<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t); warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.W, LDX, 8 * warp, c, g, t); cfrag_store<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t);
+      if (warp < 3) { double d[3][1][2]; cfrag_load<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.PB, LDB, 8 * warp, d, g, t); cfrag_store<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); } }
     __syncthreads();
-    // ---- phase 3: one warp factors H and solves for Y and the gains ; the other warp pair computes P <- Q~ + A~'W (column 30: q~ + A~'(p + P b~)).
+    // ---- phase 3: one warp factors H and solves for Y and the gains ; the other three compute P <- Q~ + A~'W (column 30: q~ + A~'(p + P b~)).
     // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
     const int sw = (k + b) & 3;
     if (warp == sw) {
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       //     pivot and column broadcasts by shuffle; every lane runs the same unrolled code (lanes >= MU carry zeros).
       double hr[MU]; double dinv = 0.0; bool ok = true;
 #pragma unroll
-      for (int c = 0; c < MU; ++c) hr[c] = (lane < MU) ? sm.H[c * LDB + lane] : 0.0;
+      for (int c = 0; c < MU; ++c) hr[c] = (lane < MU) ? sm.H[c * LDH + lane] : 0.0;
 #pragma unroll
       for (int j = 0; j < MU; ++j) {
         const double djj = __shfl_sync(FULL, hr[j], j); if (!(djj > 0.0)) ok = false;
@@ -507,13 +507,13 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       __syncwarp();
       // (b) lane = column of [G | h]: forward substitution Y = L^{-1}[G|h] (kept for P -= Y'Y), then back substitution K = -L^{-T} Y.
       //     Factor entries are warp-uniform broadcasts, the running column lives in registers.
-      double y[MU]; double* Yb = sm.PB;   // PB is free after phase 2; Y uses leading dimension LDA
+      double y[MU]; double* Yb = sm.PB;   // PB is free after phase 2; Y uses leading dimension LDX
 #pragma unroll
-      for (int a = 0; a < MU; ++a) y[a] = sm.G[a * LDA + lane];
+      for (int a = 0; a < MU; ++a) y[a] = sm.G[a * LDG + lane];
 #pragma unroll
       for (int a = 0; a < MU; ++a) {       // right-looking: finish y[a], then subtract column a of L from the rows below
         asm volatile("" ::: "memory");   // keep the factor loads of later columns from being hoisted (register pressure)
-        y[a] *= sm.dut[a]; Yb[a * LDA + lane] = y[a];
+        y[a] *= sm.dut[a]; Yb[a * LDX + lane] = y[a];
 #pragma unroll
         for (int c = a + 1; c < MU; ++c) y[c] = fma(-sm.Lt[a * MU + c], y[a], y[c]);
       }
@@ -526,28 +526,28 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
 #pragma unroll
         for (int c = 0; c < a; ++c) y[c] = fma(-sm.Lt[c * MU + a], y[a], y[c]);
       }
-    } else if (grp != (sw >> 1)) {
-      double acc[4][4]; tile_io<16, 16, true>(sm.Qb, LDA, NX, rq, cq, acc); mm44<NX, 16, 16>(sm.A, LDA, sm.W, LDA, rq, cq, acc); tile_io<16, 16, false>(sm.P, LDA, NX, rq, cq, acc);
+    } else {
+      cp_async_wait<0>(); asm volatile("bar.sync 1, 96;\n" ::: "memory");   // Q~ (this thread's and the other helpers' copies) is in the P buffer
+      const int hi = (warp - sw - 1) & 3;                                      // helper index 0..2: 8x8 tiles hi, hi+3, ... of the 4x4 tile grid
+      for (int tile = hi; tile < 16; tile += 3) { const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3);
+        double c[1][1][2]; cfrag_load<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); warp_mma<NX, 1, 1, false>(sm.A, LDX, i0, sm.W, LDX, j0, c, g, t); cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); }
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; break; }
-    if (k > 0) { issue_ab(k - 1); issue_srq(k - 1); }   // A~/B~ and S~/R~/Q~ buffers are all free: prefetch the next node
-    // ---- phase 4: P -= Y'Y, column 30: p -= Y' yh (both pairs, 2x4 tiles; the top-of-loop barrier closes this phase) ----
-    { const double* Yb = sm.PB; double neg[2][4] = {}; mm24<MU, 16>(Yb, LDA, Yb, LDA, 16 * grp, rq, cq, neg);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) { const int ri = 16 * grp + 2 * rq + r;
-        if (ri < NX) { double2* m0 = reinterpret_cast<double2*>(sm.P + ri * LDA + 2 * cq); double2* m1 = reinterpret_cast<double2*>(sm.P + ri * LDA + 16 + 2 * cq);
-          double2 v0 = *m0, v1 = *m1; v0.x -= neg[r][0]; v0.y -= neg[r][1]; v1.x -= neg[r][2]; v1.y -= neg[r][3]; *m0 = v0; *m1 = v1; } } }
+    if (k > 0) { issue_ab(k - 1); issue_sr(k - 1); }   // A~/B~ and S~/R~ buffers are free: prefetch the next node
+    // ---- phase 4: P -= Y'Y, column 30: p -= Y' yh (warp = 16x16 block; the top-of-loop barrier closes this phase) ----
+    { const double* Yb = sm.PB; const int i0 = 16 * (warp >> 1), j0 = 16 * (warp & 1);
+      double c[2][2][2]; cfrag_load<2, 2>(sm.P, LDX, i0, j0, NX, c, g, t); warp_mma<MU, 2, 2, true>(Yb, LDX, i0, Yb, LDX, j0, c, g, t); cfrag_store<2, 2>(sm.P, LDX, i0, j0, NX, c, g, t); }
   }
   cp_async_wait<0>(); __syncthreads();
   // ---- forward rollout: du~ = K dx + k ; dx+ = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~ ----
   double armijo = 0.0, dxn2 = 0.0, dun2 = 0.0;
   if (!(st & MST_NOT_PD)) {
-    // two buffer sets (k & 1): {G, A, Bm, b, q, r, kff} and {W, Qb, PB, pPb, p, h, kff2}; node k+1 streams in while node k is applied
+    // two buffer sets (k & 1): {G, A, Bm, b, q, r, kff} and {W, P, PB, pPb, p, h, kff2}; node k+1 streams in while node k is applied
     auto issue_fwd = [&](int k) {
       if (k < N && sib[(size_t)k * STAGE_INT + SI_TYPE] != 1) {
         const double* sg = sgb + (size_t)k * STAGE_DBL; const double* gk = gb + (size_t)k * GAIN_DBL; const bool o = k & 1;
-        cp_rows(gk, MU, NX, NX, o ? sm.W : sm.G, LDA, tid); cp_rows(sg + ST_A, NX, NX, NX, o ? sm.Qb : sm.A, LDA, tid); cp_rows(sg + ST_B, NX, MU, MU, o ? sm.PB : sm.Bm, LDB, tid);
+        cp_rows(gk, MU, NX, NX, o ? sm.W : sm.G, LDG, tid); cp_rows(sg + ST_A, NX, NX, NX, o ? sm.P : sm.A, LDX, tid); cp_rows(sg + ST_B, NX, MU, MU, o ? sm.PB : sm.Bm, LDB, tid);
         if (tid < 15) cp_async16((o ? sm.pPb : sm.b) + 2 * tid, sg + ST_b + 2 * tid); else if (tid < 30) cp_async16((o ? sm.p : sm.q) + 2 * (tid - 15), sg + ST_q + 2 * (tid - 15));
         else if (tid < 39) cp_async16((o ? sm.h : sm.r) + 2 * (tid - 30), sg + ST_r + 2 * (tid - 30)); else if (tid < 48) cp_async16((o ? sm.kff2 : sm.kff) + 2 * (tid - 39), gk + MU * NX + 2 * (tid - 39));
       }
@@ -559,17 +559,17 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       issue_fwd(k + 1);
       if (tid < NX) { const double dxi = sm.dx[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
       if (type == 1) { if (tid < NX) { duk[tid] = 0.0; sm.tmp[tid] = sm.dx[tid] + sg[ST_b + tid]; } __syncthreads(); if (tid < NX) sm.dx[tid] = sm.tmp[tid]; __syncthreads(); continue; }
-      const bool o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* Ab = o ? sm.Qb : sm.A; const double* Bb = o ? sm.PB : sm.Bm;
+      const bool o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* Ab = o ? sm.P : sm.A; const double* Bb = o ? sm.PB : sm.Bm;
       const double* bv = o ? sm.pPb : sm.b; const double* qv = o ? sm.p : sm.q; const double* rv = o ? sm.h : sm.r; const double* kv = o ? sm.kff2 : sm.kff;
       cp_async_wait<1>(); __syncthreads();
       { double s = 0.0;   // all lanes take part in the quad reduction (shfl_sync needs the full mask)
-        if (ti < MU) { const double* kr = Kb + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
+        if (ti < MU) { const double* kr = Kb + ti * LDG + jb * 8; const double* dx = sm.dx + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(kr[v], dx[v], s); }
         s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + kv[ti]; }
       __syncthreads();
       { double s = 0.0;
-        if (ti < NX) { const double* ar = Ab + ti * LDA + jb * 8; const double* dx = sm.dx + jb * 8;
+        if (ti < NX) { const double* ar = Ab + ti * LDX + jb * 8; const double* dx = sm.dx + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(ar[v], dx[v], s);
           if (jb < 3) { const double* br = Bb + ti * LDB + jb * 8; const double* du = sm.dut + jb * 8;
