@@ -26,7 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-PIPELINE_CHUNKS = 4         # qmb200_set_pipeline: ranges of the batch whose kernel chains overlap on the SMs
+PIPELINE_CHUNKS = 1         # qmb200_set_pipeline: measured neutral on B200 (grids drain in launch order), so the bench runs one chain
 UNIT_BATCH = 8192           # one "iteration" of the metric = one tick of an 8192-robot batch
 DT, HORIZON, CONFIG = 0.01, 1.0, 4
 METRIC = "mpc_wbc_iters_per_s"

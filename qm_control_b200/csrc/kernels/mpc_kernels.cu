@@ -7,6 +7,7 @@
 //     K4 mpc_linesearch_kernel takeStep: filter line search, trajectory update
 // Parallelisation: K2 is node-parallel (one warp per (robot, node)); K3 is one warp per robot (the recursion is
 // sequential in time) with every 30x30 block in shared memory; K4 is one CTA per robot, warps striding over nodes.
+#include <cstdlib>
 #include "mpc_api.cuh"
 #include "mpc_device.cuh"
 #include "wlinalg.cuh"
@@ -712,6 +713,12 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
     cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
     cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
+    // one shared-memory carve-out for every kernel of the tick: CTAs of different kernels (chunk pipeline) can then share an SM
+    cudaFuncSetAttribute(mpc_setup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(mpc_policy_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   (void)hm;
