@@ -207,19 +207,27 @@ def main():
             fp64_peak = solver.measure_fp64_peak()
         except Exception:
             pass
-        traffic = None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per kernel (profiles/traffic_r01.json, bytes per robot at the
+        # captured batch; every kernel's traffic is linear in the batch), scaled to this launch
+        traffic = None; per_kernel = {}
         tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tj = {}
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(dom)
+                tj = json.load(open(tpath))
             except Exception:
-                pass
+                tj = {}
+        for kname in ("lq", "riccati", "linesearch", "wbc"):
+            tr = tj.get(kname, {}).get("dram_bytes_per_robot")
+            per_kernel[kname] = {"ms": ktimes[kname], "algorithmic_GBps": ab[kname] * B / (ktimes[kname] * 1e-3) / 1e9, "traffic_bytes_per_launch": (tr * B) if tr else None,
+                                 "dram_GBps": (tr * B / (ktimes[kname] * 1e-3) / 1e9) if tr else None}
+        traffic = per_kernel[dom]["traffic_bytes_per_launch"]
         roof = {"bound": "hbm", "kernel": "mpc_%s_kernel" % dom if dom != "wbc" else "wbc_update_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                "peak_source": peak_src, "kernel_ms": ktimes, "algorithmic_bytes_per_robot": ab[dom],
+                "peak_source": peak_src, "kernel_ms": ktimes, "per_kernel": per_kernel, "algorithmic_bytes_per_robot": ab[dom],
                 "whole_tick": {"achieved": ab["total"] * B / (ms_local * 1e-3) / 1e9, "frac": ab["total"] * B / (ms_local * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_robot": ab["total"]},
                 "fp64": {"kernel": "mpc_riccati_kernel", "achieved_tflops": riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 if ktimes.get("riccati") else None, "peak_tflops": fp64_peak, "peak_source": "measured in-process (FMA microbenchmark)",
                          "frac": (riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and ktimes.get("riccati")) else None,
-                         "note": "the path is fp64 compute/latency bound (~48 FLOP/B vs a ~6 FLOP/B fp64 ridge, SURVEY §8d); the HBM fraction is reported because BASELINE.json asks for it"}}
+                         "note": "the path is fp64 latency/issue bound, not HBM bound (SURVEY §8d: ~48 FLOP/B against a ~6 FLOP/B fp64 ridge); the Riccati products run on the fp64 tensor cores (DMMA.8x8x4, same 37 TFLOP/s peak as the DFMA pipe, tools/microbench/dmma_peak.cu); the HBM fraction is reported because BASELINE.json asks for it"}}
 
     # end-to-end through the host C-ABI call with pinned host buffers
     e2e = None

@@ -252,7 +252,13 @@ HostModel build_host_model(const std::string& task_file, const std::string& urdf
     for (int f = 0; f < 4; ++f) { const int body = d.foot_body[f]; double pf[3]; apply(Rw[body], d.foot_p[f], pf); for (int i = 0; i < 3; ++i) pf[i] += pw[body][i];
       for (int k = 0; k < 3; ++k) { const int j = d.foot_leg[f] + k; const int ax = d.axis[j]; const double a[3] = {Rw[j + 1].m[ax], Rw[j + 1].m[3 + ax], Rw[j + 1].m[6 + ax]}; const double r[3] = {pf[0] - pw[j + 1][0], pf[1] - pw[j + 1][1], pf[2] - pw[j + 1][2]};
         J[3 * f + 0][j] = a[1] * r[2] - a[2] * r[1]; J[3 * f + 1][j] = a[2] * r[0] - a[0] * r[2]; J[3 * f + 2][j] = a[0] * r[1] - a[1] * r[0]; } }
-    for (int a = 0; a < 12; ++a) for (int b = 0; b < 12; ++b) { double s = 0; for (int i = 0; i < 12; ++i) for (int k = 0; k < 12; ++k) s += J[i][a] * Rt[(size_t)(12 + i) * NU + 12 + k] * J[k][b]; d.R[(12 + a) * NU + 12 + b] = s; } }
+    for (int a = 0; a < 12; ++a) for (int b = 0; b < 12; ++b) { double s = 0; for (int i = 0; i < 12; ++i) for (int k = 0; k < 12; ++k) s += J[i][a] * Rt[(size_t)(12 + i) * NU + 12 + k] * J[k][b]; d.R[(12 + a) * NU + 12 + b] = s; }
+    // compact block form used by the kernels; anything outside the blocks is refused (the structured projection relies on it)
+    double rmax = 0.0; for (int i = 0; i < NU * NU; ++i) rmax = std::max(rmax, std::fabs(d.R[i]));
+    for (int i = 0; i < NU; ++i) for (int j = 0; j < NU; ++j) { const bool in_block = (i < 24 && j < 24) ? (i / 3 == j / 3) : (i == j);
+      if (!in_block && std::fabs(d.R[i * NU + j]) > 1e-12 * rmax) throw std::runtime_error("task.info R: entry (" + std::to_string(i) + "," + std::to_string(j) + ") couples different feet/legs; only the block structure of QMInterface::initializeInputCostWeight is supported"); }
+    for (int bq = 0; bq < 8; ++bq) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) d.Rblk[bq][3 * a + b] = d.R[(3 * bq + a) * NU + 3 * bq + b];
+    for (int i = 0; i < 6; ++i) d.Rarm[i] = d.R[(24 + i) * NU + 24 + i]; }
   d.mu_ee_pos = task.number("endEffector.muPosition", 1.0); d.mu_ee_ori = task.number("endEffector.muOrientation", 1.0);
   d.mu_final_ee_pos = task.number("finalEndEffector.muPosition", 1.0); d.mu_final_ee_ori = task.number("finalEndEffector.muOrientation", 1.0);
   d.friction_mu = task.number("frictionConeSoftConstraint.frictionCoefficient", 1.0); d.friction_barrier_mu = task.number("frictionConeSoftConstraint.mu", 0.1); d.friction_barrier_delta = task.number("frictionConeSoftConstraint.delta", 5.0);

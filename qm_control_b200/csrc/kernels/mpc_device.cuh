@@ -161,7 +161,9 @@ __device__ __forceinline__ int ee_pos(int c) { return (c >= 6 && c < 12) ? c - 6
 __device__ __forceinline__ double quad_Q(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
   double v = mdl->Q[i * NX + j]; if (i == j) v += q->qdiag[i]; const int a = ee_pos(i), b = ee_pos(j); if (a >= 0 && b >= 0) v += q->E[a * 12 + b]; return v; }
 __device__ __forceinline__ double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
-  double v = mdl->R[i * NU + j]; if (i == j) v += q->rdiag[i]; if (i < 12 && j < 12 && i / 3 == j / 3) v += q->fric[(i / 3) * 9 + (i % 3) * 3 + (j % 3)]; return v; }
+  if (i >= 24 || j >= 24) return (i == j) ? mdl->Rarm[i - 24] + q->rdiag[i] : 0.0;
+  const int bi = i / 3; if (bi != j / 3) return 0.0;
+  double v = mdl->Rblk[bi][(i - 3 * bi) * 3 + (j - 3 * bi)]; if (i == j) v += q->rdiag[i]; if (i < 12) v += q->fric[bi * 9 + (i - 3 * bi) * 3 + (j - 3 * bi)]; return v; }
 struct CostWs { double Je[6 * 12], e[6], quat[4], pee[3]; };
 __device__ __forceinline__ int ee_col(int i) { return i < 6 ? 6 + i : 18 + i; }   // 12 state columns the EE pose depends on: p(6:9), theta(9:12), arm(24:30)
 

@@ -228,15 +228,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   // ---- projected dynamics rows (lane = state row): A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
   if (lane < NX) {
     const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; double* Brow = sg + ST_B + (size_t)r * MU; double bt = sm.el.l.bvec[r];
-    if (r >= 3 && r < 12) {
-#pragma unroll 6
-      for (int c = 0; c < NX; ++c) Arow[c] = sm.A1r[(r - 3) * NX + c] + ((c == r) ? 1.0 : 0.0);
-    } else {
-#pragma unroll 6
-      for (int c = 0; c < NX; ++c) Arow[c] = (c == r) ? 1.0 : 0.0;
-    }
-    if (r >= 3 && r < 6) {       // h_ang rows pick up the dependent joint velocities: + sum_legs BrdJ[r][joint] * Px_joint
-      double acc[12]; 
+    if (r >= 3 && r < 6) {       // h_ang rows pick up the dependent joint velocities: + sum_legs BrdJ[r][joint] * Px_joint (accumulated in the shared-memory row, own thread)
+      double* arow = sm.A1r + (r - 3) * NX; double acc[12];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const LegWs& L = sm.leg[i];
 #pragma unroll
@@ -245,10 +238,15 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
 #pragma unroll
           for (int c = 0; c < 12; ++c) acc[c] = fma(coef, L.Px[j][c], acc[c]); }
 #pragma unroll
-        for (int c = 0; c < 9; ++c) Arow[sup_col(c, L.first)] += acc[c];      // common columns accumulate over the legs (own row, own thread: ordered)
-#pragma unroll
-        for (int c = 9; c < 12; ++c) Arow[sup_col(c, L.first)] += acc[c];
+        for (int c = 0; c < 12; ++c) arow[sup_col(c, L.first)] += acc[c];
       }
+    }
+    if (r >= 3 && r < 12) {
+#pragma unroll 6
+      for (int c = 0; c < NX; ++c) Arow[c] = sm.A1r[(r - 3) * NX + c] + ((c == r) ? 1.0 : 0.0);
+    } else {
+#pragma unroll 6
+      for (int c = 0; c < NX; ++c) Arow[c] = (c == r) ? 1.0 : 0.0;
     }
     if (r >= 12 && r < 24) {     // dependent joint-velocity rows: I + dtw * Px
       const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3;
@@ -713,12 +711,6 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
     cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
     cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
-    // one shared-memory carve-out for every kernel of the tick: CTAs of different kernels (chunk pipeline) can then share an SM
-    cudaFuncSetAttribute(mpc_setup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(mpc_policy_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   (void)hm;

@@ -431,7 +431,7 @@ void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const do
                        double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0, int b1) {
   static bool configured = false;
   const size_t smem = wbc_smem_bytes();
-  if (!configured) { cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); configured = true; }
+  if (!configured) { cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   if (b1 < 0) b1 = B; if (b1 <= b0) return;
   const int grid = (b1 - b0 + WBC_WARPS - 1) / WBC_WARPS;
   wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status);

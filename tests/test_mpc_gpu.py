@@ -129,3 +129,18 @@ def test_pipelined_tick_is_bit_identical():
         for a, b in zip(outs[0], other):
             for xa, xb in zip(a, b):
                 assert np.array_equal(xa, xb)
+
+
+def test_not_positive_definite_is_reported_like_the_oracle(oracle):
+    """Synthetic robot 1758 of the bench workload (dt 0.01, trot) has an indefinite projected input Hessian: the oracle raises
+    (HPIPM would fail in the reference), the CUDA path must flag MST_NOT_PD | MST_NO_STEP for that robot only and keep its warm start."""
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    ids = np.array([1758, 5]); solver = q.Solver(batch=2, dt=0.01); oracle.mpc_set(dt=0.01, horizon=1.0)
+    prob, _ = synthetic.make_batch(ids, config=4, horizon=1.0)
+    out = solver.mpc_solve(prob)
+    assert out["status"][0] & 8 and out["status"][0] & 16, hex(int(out["status"][0]))
+    assert out["status"][1] & ~16 == 0
+    with pytest.raises(RuntimeError, match="not positive definite"):
+        oracle.mpc_solve_batch({k: v[:1] for k, v in prob.items()}, solver.nmax, nthreads=1)
+    oracle.mpc_solve_batch({k: v[1:] for k, v in prob.items()}, solver.nmax, nthreads=1)
