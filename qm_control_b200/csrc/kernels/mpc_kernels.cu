@@ -487,35 +487,27 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
     // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
     const int sw = (k + b) & 3;
     if (warp == sw) {
-      // (a) Cholesky of H with the factor in registers: lane = row (read from the upper triangle: column access is bank-conflict free),
-      //     pivot and column broadcasts by shuffle; every lane runs the same unrolled code (lanes >= MU carry zeros).
-      double hr[MU]; double dinv = 0.0; bool ok = true;
+      // (a) Cholesky of H with the factor in registers (lane = row, read from the upper triangle: column access is bank-conflict free;
+      //     pivot and column broadcasts by shuffle) fused with the forward substitution Y = L^{-1}[G | h] (lane = column of [G | h]):
+      //     the broadcast L[c][j] that updates row c of the factor is exactly the multiplier of the right-looking substitution step,
+      //     so Y costs one more FMA per shuffle and no extra dependent chain.  Lanes >= MU carry zeros in the factor role.
+      double hr[MU], y[MU]; double dinv = 0.0; bool ok = true; double* Yb = sm.PB;   // PB is free after phase 2; Y uses leading dimension LDX
 #pragma unroll
-      for (int c = 0; c < MU; ++c) hr[c] = (lane < MU) ? sm.H[c * LDH + lane] : 0.0;
+      for (int c = 0; c < MU; ++c) { hr[c] = (lane < MU) ? sm.H[c * LDH + lane] : 0.0; y[c] = sm.G[c * LDG + lane]; }
 #pragma unroll
       for (int j = 0; j < MU; ++j) {
         const double djj = __shfl_sync(FULL, hr[j], j); if (!(djj > 0.0)) ok = false;
         const double inv = rsqrt(djj); const double lij = hr[j] * inv;
         if (lane == j) dinv = inv;
         if (lane < MU) sm.Lt[j * MU + lane] = lij;
+        y[j] *= inv; Yb[j * LDX + lane] = y[j];
 #pragma unroll
-        for (int c = j + 1; c < MU; ++c) hr[c] = fma(-lij, __shfl_sync(FULL, lij, c), hr[c]);
+        for (int c = j + 1; c < MU; ++c) { const double lcj = __shfl_sync(FULL, lij, c); hr[c] = fma(-lij, lcj, hr[c]); y[c] = fma(-lcj, y[j], y[c]); }
       }
       if (lane < MU) sm.dut[lane] = dinv;
       if (!ok && lane == 0) sm.flag = 1;
       __syncwarp();
-      // (b) lane = column of [G | h]: forward substitution Y = L^{-1}[G|h] (kept for P -= Y'Y), then back substitution K = -L^{-T} Y.
-      //     Factor entries are warp-uniform broadcasts, the running column lives in registers.
-      double y[MU]; double* Yb = sm.PB;   // PB is free after phase 2; Y uses leading dimension LDX
-#pragma unroll
-      for (int a = 0; a < MU; ++a) y[a] = sm.G[a * LDG + lane];
-#pragma unroll
-      for (int a = 0; a < MU; ++a) {       // right-looking: finish y[a], then subtract column a of L from the rows below
-        asm volatile("" ::: "memory");   // keep the factor loads of later columns from being hoisted (register pressure)
-        y[a] *= sm.dut[a]; Yb[a * LDX + lane] = y[a];
-#pragma unroll
-        for (int c = a + 1; c < MU; ++c) y[c] = fma(-sm.Lt[a * MU + c], y[a], y[c]);
-      }
+      // (b) back substitution K = -L^{-T} Y, lane = column: factor entries are warp-uniform broadcasts, the running column lives in registers.
       double* gk = gb + (size_t)k * GAIN_DBL;
 #pragma unroll
       for (int a = MU - 1; a >= 0; --a) {  // L' z = y, right-looking over row a of L'
