@@ -131,6 +131,23 @@ __device__ __forceinline__ void euler_rate_map_dot_times(double z, double y, con
   o[1] = (-sz * zd) * ed[1] + (-sy * yd * sz + cy * cz * zd) * ed[2];
   o[2] = (-cy * yd) * ed[2];
 }
+// Variants taking precomputed trig values tr = {sin z, cos z, sin y, cos y, sin x, cos x} (one warp-wide sincos pass serves all users)
+__device__ __forceinline__ void rot_zyx_sc(const double* tr, double* R) {
+  const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3], sx = tr[4], cx = tr[5];
+  R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
+  R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
+  R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
+}
+__device__ __forceinline__ void euler_rate_map_sc(const double* tr, double* T) {
+  const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3];
+  T[0] = 0; T[1] = -sz; T[2] = cy * cz; T[3] = 0; T[4] = cz; T[5] = cy * sz; T[6] = 1; T[7] = 0; T[8] = -sy;
+}
+__device__ __forceinline__ void euler_rate_map_dot_times_sc(const double* tr, const double* ed, double* o) {
+  const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3]; const double zd = ed[0], yd = ed[1];
+  o[0] = (-cz * zd) * ed[1] + (-sy * yd * cz - cy * sz * zd) * ed[2];
+  o[1] = (-sz * zd) * ed[1] + (-sy * yd * sz + cy * cz * zd) * ed[2];
+  o[2] = (-cy * yd) * ed[2];
+}
 __device__ __forceinline__ void inv3(const double* m, double* o) {
   const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
   const double id = 1.0 / (m[0] * c00 + m[1] * c01 + m[2] * c02);

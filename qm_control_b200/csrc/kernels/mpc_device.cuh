@@ -31,30 +31,45 @@ struct PointWs {
 __device__ __forceinline__ int foot_of_leg_joint(const DevModel* __restrict__ mdl, int j) { return mdl->leg_foot[j / 3]; }
 
 // Evaluate the flow map (and its Jacobian rows if with_jac) at (ws->x, ws->u).
+// max_depth: 6 = whole tree, 3 = base + legs (the flow map does not see the arm links; only the end-effector cost does).
+// The base-frame algebra is spread over lanes wherever it is data parallel (entries of 3x3 products, the three euler columns): a
+// single-lane restatement costs ~4x the instructions and the LQ / line-search kernels are issue-latency bound.
 template <bool with_jac>
-__device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, PointWs* ws, int lane) {
-  rbd_kinematics<false>(mdl, ws->x + 6, (const double*)nullptr, &ws->kin, lane);
-  const double m = mdl->total_mass;
-  if (lane == 0) {
-    const double* R = ws->kin.R[0]; const double z = ws->x[9], y = ws->x[10];
-    euler_rate_map(z, y, ws->T); inv3(ws->T, ws->Tinv);
-    double RIi[9]; matmul3(R, mdl->I_nom_inv, RIi); matmul3_nt(RIi, R, ws->W); for (int i = 0; i < 9; ++i) ws->W[i] *= m;
-    matvec3(R, mdl->c_nom, ws->c); for (int a = 0; a < 3; ++a) ws->rcom[a] = ws->x[6 + a] - ws->c[a];
-    const double* ha = ws->x + 3; matvec3(ws->W, ha, ws->omega); matvec3(ws->Tinv, ws->omega, ws->thd);
-    if (with_jac) {
-      double sz, cz, sy, cy; sincos(z, &sz, &cz); sincos(y, &sy, &cy);
-      const double* om = ws->omega; const double* th = ws->thd;
-      const double dT[3][3] = {{-cz * th[1] - cy * sz * th[2], -sz * th[1] + cy * cz * th[2], 0.0}, {-sy * cz * th[2], -sy * sz * th[2], -cy * th[2]}, {0.0, 0.0, 0.0}};
-      for (int k = 0; k < 3; ++k) {
-        const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double t1[3], t2[3], t3[3];
-        cross3(Tk, om, t1); cross3(Tk, ha, t2); matvec3(ws->W, t2, t3);
-        for (int a = 0; a < 3; ++a) ws->dom[k][a] = t1[a] - t3[a];                       // d omega / d theta_k
-        double tc[3]; cross3(Tk, ws->c, tc); cross3(ws->dom[k], ws->c, ws->vp[k]); cross3_add(om, tc, ws->vp[k]);   // d(omega x c)/d theta_k
-        const double tmp[3] = {ws->dom[k][0] - dT[k][0], ws->dom[k][1] - dT[k][1], ws->dom[k][2] - dT[k][2]}; matvec3(ws->Tinv, tmp, ws->vt[k]);
-      }
-      const double* c = ws->c; const double Sc[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
-      matmul3(Sc, ws->W, ws->Mpc); for (int i = 0; i < 9; ++i) ws->Mpc[i] = -ws->Mpc[i];
-      matmul3(ws->Tinv, ws->W, ws->Mtw);
+__device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, PointWs* ws, int lane, int max_depth = 6) {
+  rbd_kinematics<false>(mdl, ws->x + 6, (const double*)nullptr, &ws->kin, lane, max_depth);
+  const double m = mdl->total_mass; const double* tr = ws->kin.trig; const double* R = ws->kin.R[0]; const double* ha = ws->x + 3;
+  if (lane == 0) { euler_rate_map_sc(tr, ws->T); inv3(ws->T, ws->Tinv); }
+  if (lane < 9) {   // W = m R I_nom^{-1} R' , entry (i, jj)
+    const int i = lane / 3, jj = lane - 3 * i; const double* Ii = mdl->I_nom_inv; double acc = 0.0;
+#pragma unroll
+    for (int bq = 0; bq < 3; ++bq) { const double rib = R[3 * i] * Ii[bq] + R[3 * i + 1] * Ii[3 + bq] + R[3 * i + 2] * Ii[6 + bq]; acc = fma(rib, R[3 * jj + bq], acc); }
+    ws->W[lane] = m * acc;
+  }
+  if (lane < 3) { const double cv = R[3 * lane] * mdl->c_nom[0] + R[3 * lane + 1] * mdl->c_nom[1] + R[3 * lane + 2] * mdl->c_nom[2]; ws->c[lane] = cv; ws->rcom[lane] = ws->x[6 + lane] - cv; }
+  __syncwarp();
+  double om = 0.0; if (lane < 3) om = ws->W[3 * lane] * ha[0] + ws->W[3 * lane + 1] * ha[1] + ws->W[3 * lane + 2] * ha[2];
+  const double o0 = __shfl_sync(FULL, om, 0), o1 = __shfl_sync(FULL, om, 1), o2 = __shfl_sync(FULL, om, 2);
+  double thl = 0.0; if (lane < 3) { thl = ws->Tinv[3 * lane] * o0 + ws->Tinv[3 * lane + 1] * o1 + ws->Tinv[3 * lane + 2] * o2; ws->omega[lane] = om; ws->thd[lane] = thl; }
+  if (with_jac) {
+    const double th1 = __shfl_sync(FULL, thl, 1), th2 = __shfl_sync(FULL, thl, 2);
+    if (lane < 3) {   // lane = euler column k
+      const int k = lane; const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3]; const double omv[3] = {o0, o1, o2};
+      double dT[3];
+      if (k == 0) { dT[0] = -cz * th1 - cy * sz * th2; dT[1] = -sz * th1 + cy * cz * th2; dT[2] = 0.0; }
+      else if (k == 1) { dT[0] = -sy * cz * th2; dT[1] = -sy * sz * th2; dT[2] = -cy * th2; }
+      else { dT[0] = 0.0; dT[1] = 0.0; dT[2] = 0.0; }
+      const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double t1[3], t2[3], t3[3];
+      cross3(Tk, omv, t1); cross3(Tk, ha, t2); matvec3(ws->W, t2, t3);
+      double domk[3]; for (int a = 0; a < 3; ++a) { domk[a] = t1[a] - t3[a]; ws->dom[k][a] = domk[a]; }          // d omega / d theta_k
+      double tc[3], vpk[3]; cross3(Tk, ws->c, tc); cross3(domk, ws->c, vpk); cross3_add(omv, tc, vpk);           // d(omega x c)/d theta_k
+      for (int a = 0; a < 3; ++a) ws->vp[k][a] = vpk[a];
+      const double tmp[3] = {domk[0] - dT[0], domk[1] - dT[1], domk[2] - dT[2]}; matvec3(ws->Tinv, tmp, ws->vt[k]);
+    }
+    if (lane < 9) {   // Mpc = -S(c) W ; Mtw = Tinv W , entry (i, jj)
+      const int i = lane / 3, jj = lane - 3 * i; const double* c = ws->c; const double* W = ws->W;
+      const double s0 = (i == 0) ? 0.0 : (i == 1 ? c[2] : -c[1]), s1 = (i == 0) ? -c[2] : (i == 1 ? 0.0 : c[0]), s2 = (i == 0) ? c[1] : (i == 1 ? -c[0] : 0.0);
+      ws->Mpc[lane] = -(s0 * W[jj] + s1 * W[3 + jj] + s2 * W[6 + jj]);
+      ws->Mtw[lane] = ws->Tinv[3 * i] * W[jj] + ws->Tinv[3 * i + 1] * W[3 + jj] + ws->Tinv[3 * i + 2] * W[6 + jj];
     }
   }
   __syncwarp();

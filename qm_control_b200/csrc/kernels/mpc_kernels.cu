@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   // instruction-fetch sensitive (straight-line code of several hundred KB), so the pass loop is deliberately not unrolled.
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-  point_eval<true>(mdl, &sm.pt, lane);
+  point_eval<true>(mdl, &sm.pt, lane, pass == 0 ? 6 : 3);   // the second RK2 stage needs the flow map only: no arm links
   LQ_LOCKSTEP();
   if (pass == 1) break;
   // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
@@ -595,7 +595,7 @@ __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax
   for (int k = 1; k < n; ++k) { const bool copy = (k == n - 1) || (ge[k] == 1); if (copy) { for (int i = tid; i < NU; i += nthreads) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i]; } __syncthreads(); }
 }
 
-__global__ void __launch_bounds__(32 * LS_WARPS) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
+__global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
                                                                      const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[LS_WARPS][3]; __shared__ int decision;
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(32 * LS_WARPS) mpc_linesearch_kernel(const Dev
       bool done = false;
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {   // one inlined copy of the flow map for both RK2 stages (instruction-fetch footprint)
-        point_eval<false>(mdl, &sm.pt, lane);
+        point_eval<false>(mdl, &sm.pt, lane, pass == 0 ? 6 : 3);
         if (pass == 1) break;
         TargetRef ref = target_reference(tt, ts, nk, t, lane);
         cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, terminal, lane);

@@ -21,6 +21,7 @@ struct RbdWs {
   double A[NB][6];      // spatial bias acceleration (qddot = 0, gravity NOT included)
   double Ic[NB][10];    // (composite) inertia about world origin: m, h=m*c (3), IO (xx,xy,xz,yy,yz,zz)
   double F[NB][6];      // (composite) spatial force [nO; f]
+  double trig[6];       // sin/cos of the base euler angles z, y, x (one sincos pass per kinematics call)
 };
 
 // y = I * [w; vO] → [nO; f]
@@ -36,16 +37,36 @@ __device__ __forceinline__ void inertia_apply(const double* I, const double* mv,
 __device__ __forceinline__ double dot6(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
 
 // Pass 1: kinematics (+ optional velocities / bias accelerations).  q,v are in shared memory (24 each).
-// Lane L < 19 owns body L.  with_vel: 0 = positions only, 1 = V and A as well.
+// Lane L < 19 owns body L.  with_vel: 0 = positions only, 1 = V and A as well.  max_depth limits the tree levels that are updated
+// (3 = base + legs, 6 = arm as well).
+// All trigonometry happens in ONE warp-wide pass (lanes 1..18: joint angles, folded straight into the joint-local rotation
+// Rj * Rq(q_j); lanes 19..21: base euler angles -> ws->trig), so the level loop below is one 3x3 product per body.
 template <bool with_vel, class WS>
-__device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl, const double* q, const double* v, WS* ws, int lane) {
+__device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl, const double* q, const double* v, WS* ws, int lane, int max_depth = 6) {
+  const int body = lane; const int j = body - 1;
+  const int my_depth = (body >= 1 && body < NB) ? mdl->depth[body] : -1;
+  double Rlq[9]; int ax = 0;
+  {
+    const bool is_joint = body >= 1 && body < NB, is_euler = lane >= NB && lane < NB + 3;
+    double s = 0.0, c = 1.0; if (is_joint || is_euler) sincos(is_joint ? q[6 + j] : q[3 + lane - NB], &s, &c);
+    if (is_euler) { ws->trig[2 * (lane - NB)] = s; ws->trig[2 * (lane - NB) + 1] = c; }
+    if (is_joint) {
+      ax = mdl->axis[j]; const double* Rl = mdl->Rj[j];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { const double r0 = Rl[3 * i], r1 = Rl[3 * i + 1], r2 = Rl[3 * i + 2];   // Rl * Rq(axis, q_j): Rq mixes the two columns after the axis
+        if (ax == 0) { Rlq[3 * i] = r0; Rlq[3 * i + 1] = c * r1 + s * r2; Rlq[3 * i + 2] = -s * r1 + c * r2; }
+        else if (ax == 1) { Rlq[3 * i] = c * r0 - s * r2; Rlq[3 * i + 1] = r1; Rlq[3 * i + 2] = s * r0 + c * r2; }
+        else { Rlq[3 * i] = c * r0 + s * r1; Rlq[3 * i + 1] = -s * r0 + c * r1; Rlq[3 * i + 2] = r2; } }
+    }
+  }
+  __syncwarp();
   // base (lane 0) and the 6 base columns of S
   if (lane == 0) {
-    double R[9]; rot_zyx(q[3], q[4], q[5], R);
+    double R[9]; rot_zyx_sc(ws->trig, R);
 #pragma unroll
     for (int i = 0; i < 9; ++i) ws->R[0][i] = R[i];
     ws->p[0][0] = q[0]; ws->p[0][1] = q[1]; ws->p[0][2] = q[2];
-    double T[9]; euler_rate_map(q[3], q[4], T);
+    double T[9]; euler_rate_map_sc(ws->trig, T);
     const double pb[3] = {q[0], q[1], q[2]};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {   // translation columns: w = 0, vO = e_k
@@ -55,7 +76,7 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
     }
     if constexpr (with_vel) {
       const double ed[3] = {v[3], v[4], v[5]}; double w[3]; matvec3(T, ed, w);
-      double wd[3]; euler_rate_map_dot_times(q[3], q[4], ed, wd);
+      double wd[3]; euler_rate_map_dot_times_sc(ws->trig, ed, wd);
       const double pd[3] = {v[0], v[1], v[2]};
       double vo[3]; cross3(pb, w, vo); vo[0] += pd[0]; vo[1] += pd[1]; vo[2] += pd[2];
       double ao[3]; cross3(pd, w, ao); cross3_add(pb, wd, ao);
@@ -64,19 +85,13 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
     }
   }
   __syncwarp();
-  const int body = lane; const int j = body - 1;
-  const int my_depth = (body >= 1 && body < NB) ? mdl->depth[body] : -1;
-  for (int d = 1; d <= 6; ++d) {
+  for (int d = 1; d <= max_depth; ++d) {
     if (my_depth == d) {
       const int pb = mdl->parent[j];
-      double Rp[9], Rl[9], Rw[9];
+      double Rp[9], Rw[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { Rp[i] = ws->R[pb][i]; Rl[i] = mdl->Rj[j][i]; }
-      double R0[9]; matmul3(Rp, Rl, R0);
-      double s, c; sincos(q[6 + j], &s, &c); const int ax = mdl->axis[j];
-      double Rq[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-      if (ax == 0) { Rq[4] = c; Rq[5] = -s; Rq[7] = s; Rq[8] = c; } else if (ax == 1) { Rq[0] = c; Rq[2] = s; Rq[6] = -s; Rq[8] = c; } else { Rq[0] = c; Rq[1] = -s; Rq[3] = s; Rq[4] = c; }
-      matmul3(R0, Rq, Rw);
+      for (int i = 0; i < 9; ++i) Rp[i] = ws->R[pb][i];
+      matmul3(Rp, Rlq, Rw);
       double pl[3] = {mdl->pj[j][0], mdl->pj[j][1], mdl->pj[j][2]}, pw[3]; matvec3(Rp, pl, pw);
       pw[0] += ws->p[pb][0]; pw[1] += ws->p[pb][1]; pw[2] += ws->p[pb][2];
 #pragma unroll
@@ -98,7 +113,7 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
 }
 
 // positions-only workspace (MPC kernels)
-struct KinWs { double R[NB][9]; double p[NB][3]; double S[NQ][6]; };
+struct KinWs { double R[NB][9]; double p[NB][3]; double S[NQ][6]; double trig[6]; };
 
 // Pass 2: per-body world inertias; optionally RNEA body forces (gravity: +9.81 z base acceleration trick).
 // with_force: 0 none, 1 = F = I (A + Ag) + V x* I V with gravity, 2 = same without gravity (centroidal momentum rate bias)
