@@ -120,6 +120,54 @@ int qmb200_centroidal_state_from_rbd(const qmb200_handle* h, int32_t n, const do
 int qmb200_gait_schedule(const char* gait_file, const char* gait_name, double t_start, double lo, double hi,
                          double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
 
+/* ---- controller side of the path: the steps of QMController::update around evaluatePolicy / WbcBase::update and the
+ *      publisher that feeds the solver, batched on the device.  The caller owns the per-robot controller state these functions read and
+ *      write (the members of QMController / QmTargetTrajectoriesInteractiveMarker they mirror); `_dev` variants take device pointers. */
+#define QMB200_TARGET_CMD_VEL 0      /* cmdVelToTargetTrajectories      (QmTargetTrajectoriesPublisher_node.cpp:73-113): cmd = vx, vy, vz, yaw rate */
+#define QMB200_TARGET_EE_CMD_VEL 1   /* EeCmdVelToTargetTrajectories    (:118-165): cmd = vx, vy, vz of the end effector */
+#define QMB200_TARGET_EE_GOAL 2      /* EEgoalPoseToTargetTrajectories  (:172-208) + processFeedback (QmTargetTrajectoriesPublisher.cpp:94-109): cmd = pos(3), quat xyzw(4) */
+#define QMB200_JOINT_CMD 5           /* HybridJointHandle::setCommand(posDes, velDes, kp, kd, ff) (HybridJointInterface.h:55-61) */
+#define QMB200_ST_SAFETY 0x10000     /* SafetyChecker::check failed (SafetyChecker.h:22-35): the reference stops the controller */
+#define QMB200_ST_HW_RING_FULL 2     /* qmb200_hw_write: more than 32 commands inside the delay window (the oldest was dropped) */
+
+/* QMController::updateStateEstimation tail (QMController.cpp:236-243): t_obs += period; x_obs = computeCentroidalStateFromRbdModel(rbd) with
+ * the yaw unwrapped against the previous x_obs[9] (angles::shortest_angular_distance). */
+int qmb200_observation_update(qmb200_handle* h, const double* rbd /*[B][55]*/, const double* period /*[B]*/, double* t_obs /*[B] in-out*/, double* x_obs /*[B][30] in-out*/);
+int qmb200_observation_update_dev(qmb200_handle* h, const double* rbd, const double* period, double* t_obs, double* x_obs, void* cuda_stream);
+
+/* TargetTrajectories from a command (QmTargetTrajectoriesPublisher_node.cpp:44-208) in the layout qmb200_mpc_solve takes; constants from
+ * reference.info (comHeight, defaultJointState, target*Velocity) and task.info (mpc.timeHorizon).  last_ee_target mirrors lastEeTarget_
+ * (initial value qmb200_initial_ee_target: QmTargetTrajectoriesPublisher.h:55-57). */
+int qmb200_target_trajectories(qmb200_handle* h, int32_t kind, const double* cmd /*[B][7]*/, const double* t_obs /*[B]*/, const double* x_obs /*[B][30]*/, const double* ee_state /*[B][7] pos, quat xyzw*/,
+                               double* last_ee_target /*[B][7] in-out*/, int32_t* n_target /*[B]*/, double* target_times /*[B][KMAX]*/, double* target_states /*[B][KMAX][37]*/);
+int qmb200_target_trajectories_dev(qmb200_handle* h, int32_t kind, const double* cmd, const double* t_obs, const double* x_obs, const double* ee_state, double* last_ee_target,
+                                   int32_t* n_target, double* target_times, double* target_states, void* cuda_stream);
+void qmb200_initial_ee_target(double* last_ee_target7);
+
+/* SafetyChecker::check + QMController::updateControlLaw (QMController.cpp:159-165,177-190) or, for a handle created with
+ * QMB200_WBC_HIERARCHICAL_MPC, QMMpcController::updateControlLaw (:427-445).  joint_cmd entries the reference does not write in a given call
+ * (legs before t = 10 s; the position-controlled arm of QMMpcController) keep their previous value, as the joint handles do. */
+int qmb200_control_law(qmb200_handle* h, const double* x_des /*[B][30]*/, const double* u_des /*[B][30]*/, const double* wbc_cmd /*[B][54]*/, const double* t_obs /*[B]*/, const double* x_obs /*[B][30]*/,
+                       double* joint_cmd /*[B][18][5] in-out*/, double* arm_pos_cmd /*[B][6] in-out*/, double* last_time /*[B] in-out*/, int32_t* status /*[B]*/);
+int qmb200_control_law_dev(qmb200_handle* h, const double* x_des, const double* u_des, const double* wbc_cmd, const double* t_obs, const double* x_obs, double* joint_cmd, double* arm_pos_cmd,
+                           double* last_time, int32_t* status, void* cuda_stream);
+/* dynamic_reconfigure kp_arm_wbc / kd_arm_wbc (QMController.cpp:357-362; defaults 0.0 / 0.5, qm_controllers/cfg/weight.cfg:7-8) */
+int qmb200_set_arm_gains(qmb200_handle* h, double kp_arm_wbc, double kd_arm_wbc);
+
+/* Plant stand-in, QMHWSim::writeSim (qm_gazebo/src/QMHWSim.cpp:98-116): the commands pass a per-robot delay FIFO (kept in the handle) and
+ * the joint effort is kp (posDes - q) + kd (velDes - qd) + ff.  time == period clears the FIFO (simulation reset). */
+int qmb200_hw_write(qmb200_handle* h, const double* time /*[B]*/, const double* period /*[B]*/, const double* joint_cmd /*[B][18][5]*/, const double* joint_pos /*[B][18]*/, const double* joint_vel /*[B][18]*/,
+                    double* effort /*[B][18]*/, int32_t* status /*[B]*/);
+int qmb200_hw_write_dev(qmb200_handle* h, const double* time, const double* period, const double* joint_cmd, const double* joint_pos, const double* joint_vel, double* effort, int32_t* status, void* cuda_stream);
+/* gazebo/delay (qm_gazebo/config/default.yaml:2; QMHWSim.cpp:33-35 defaults to 0); clears the FIFO */
+int qmb200_hw_set_delay(qmb200_handle* h, double delay);
+
+/* The whole QMController::update (QMController.cpp:128-175) on the stored policy: observation update → evaluatePolicy(t_obs) → WbcBase::update
+ * (period, t_obs) → safety check + control law.  cmd = the WBC 54-vector, status = WBC status | QMB200_ST_SAFETY. */
+int qmb200_update(qmb200_handle* h, const double* rbd /*[B][55]*/, const double* period /*[B]*/, double* t_obs /*[B] in-out*/, double* x_obs /*[B][30] in-out*/, double* joint_cmd /*[B][18][5] in-out*/,
+                  double* arm_pos_cmd /*[B][6] in-out*/, double* last_time /*[B] in-out*/, double* cmd /*[B][54]*/, int32_t* status /*[B]*/);
+int qmb200_update_dev(qmb200_handle* h, const double* rbd, const double* period, double* t_obs, double* x_obs, double* joint_cmd, double* arm_pos_cmd, double* last_time, double* cmd, int32_t* status, void* cuda_stream);
+
 /* ---- tick pipeline: qmb200_tick / qmb200_tick_dev cut the batch into `chunks` (1..8) robot ranges and run each range's
  *      MPC solve → evaluatePolicy → WbcBase::update chain on its own CUDA stream (forked from / joined into the caller's stream), so
  *      kernels with different bottlenecks overlap on the SMs.  Robots are independent (the reference runs one controller per robot,

@@ -11,6 +11,7 @@
 #include "mpc.h"
 #include "wbc.h"
 
+namespace orc { void observation_update(const Model& m, const double* rbd55, double period, double* t_obs, double* x_obs30); }
 using namespace orc;
 
 namespace {
@@ -70,6 +71,12 @@ int orc_rbd(void* hp, const double* q, const double* v, double* M, double* nle, 
 int orc_centroidal_state_from_rbd(void* hp, const double* rbd48, double* x30) {
   Handle* h = static_cast<Handle*>(hp);
   return guarded([&] { centroidal_state_from_rbd(h->model, rbd48, x30); });
+}
+
+// QMController::updateStateEstimation tail (QMController.cpp:236-243), see ctrl.cpp
+int orc_observation_update(void* hp, const double* rbd55, double period, double* t_obs, double* x_obs30) {
+  Handle* h = static_cast<Handle*>(hp);
+  return guarded([&] { observation_update(h->model, rbd55, period, t_obs, x_obs30); });
 }
 
 int orc_wbc_update(void* hp, const double* x_des, const double* u_des, const double* rbd, int mode, double period, double time, double* input_last, int variant,

@@ -9,5 +9,6 @@ from ._lib import LIB_PATH, ASSETS, load_library, QmbError  # noqa: F401
 from .interface import QMInterface, Solver  # noqa: F401
 from .wbc import HierarchicalWbc, HierarchicalMpcWbc  # noqa: F401
 from .mpc import SqpMpc  # noqa: F401
+from .controller import QMController, QMMpcController  # noqa: F401
 
-__all__ = ["QMInterface", "Solver", "HierarchicalWbc", "HierarchicalMpcWbc", "SqpMpc", "load_library", "QmbError", "LIB_PATH", "ASSETS"]
+__all__ = ["QMInterface", "Solver", "HierarchicalWbc", "HierarchicalMpcWbc", "SqpMpc", "QMController", "QMMpcController", "load_library", "QmbError", "LIB_PATH", "ASSETS"]

@@ -11,6 +11,7 @@
 #include "../../include/qmb200.h"
 #include "host/qm_config.h"
 #include "kernels/mpc_api.cuh"
+#include "kernels/ctrl_api.cuh"
 
 namespace qmb {
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
@@ -38,6 +39,11 @@ struct qmb200_handle {
   // tick pipeline: the batch is cut into `chunks` robot ranges, each running its MPC → policy → WBC chain on its own stream, so that
   // kernels with different bottlenecks (LQ: instruction latency, Riccati: shared-memory bandwidth, WBC) share the SMs
   static constexpr int MAX_CHUNKS = 8;
+  // controller-side constants and staging (capi_ctrl.inc)
+  TargetParams target_prm{}; ControlLawParams law_prm{0, 0.0, 0.5};
+  bool c_ready = false; double *c_tobs = nullptr, *c_xobs = nullptr, *c_jcmd = nullptr, *c_armpos = nullptr, *c_lasttime = nullptr, *c_cmd7 = nullptr, *c_ee = nullptr, *c_lastee = nullptr,
+                               *c_jpos = nullptr, *c_jvel = nullptr, *c_effort = nullptr, *c_ttimes = nullptr, *c_tstates = nullptr; int32_t *c_status = nullptr, *c_ntarget = nullptr;
+  double hw_delay = 0.0; double *hw_ring_cmd = nullptr, *hw_ring_stamp = nullptr; int32_t* hw_ring_state = nullptr;   // QMHWSim command-delay FIFO
   int chunks = 1; cudaStream_t cs[MAX_CHUNKS] = {nullptr}; cudaEvent_t fork_ev = nullptr, join_ev[MAX_CHUNKS] = {nullptr};
 };
 
@@ -60,10 +66,15 @@ int qmb200_create(const qmb200_config* cfg, qmb200_handle** out) {
   qmb200_handle* h = new qmb200_handle();
   try {
     h->hm = build_host_model(cfg->task_file, cfg->urdf_file, cfg->reference_file, cfg->wbc_gains_file ? cfg->wbc_gains_file : "");
+    // constants of the target publisher node (QmTargetTrajectoriesPublisher_node.cpp:225-229)
+    InfoFile ref(cfg->reference_file), task(cfg->task_file);
+    h->target_prm.com_height = ref.number("comHeight"); h->target_prm.target_displacement_velocity = ref.number("targetDisplacementVelocity");
+    h->target_prm.target_rotation_velocity = ref.number("targetRotationVelocity"); h->target_prm.time_to_target = task.number("mpc.timeHorizon");
+    for (int j = 0; j < NJ; ++j) h->target_prm.default_joint_state[j] = h->hm.default_joint_state[j];
   } catch (const std::exception& e) { g_create_error = e.what(); delete h; return -2; }
   if (cfg->time_horizon > 0) h->hm.dev.time_horizon = cfg->time_horizon;
   if (cfg->dt > 0) h->hm.dev.dt = cfg->dt;
-  h->B = cfg->batch; h->variant = cfg->wbc_variant; h->device = cfg->device;
+  h->B = cfg->batch; h->variant = cfg->wbc_variant; h->device = cfg->device; h->law_prm.variant = cfg->wbc_variant == QMB200_WBC_HIERARCHICAL_MPC ? 1 : 0;
   const int nint = (int)std::ceil(h->hm.dev.time_horizon / h->hm.dev.dt - 1e-9);
   h->nmax = cfg->max_nodes > 0 ? cfg->max_nodes : nint + 1 + 20;
   int ndev = 0; cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -143,3 +154,4 @@ int qmb200_wbc_get_input_last(qmb200_handle* h, double* input_last) {
 }  // extern "C"
 
 #include "capi_mpc.inc"
+#include "capi_ctrl.inc"

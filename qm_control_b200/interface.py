@@ -182,6 +182,47 @@ class Solver:
         B, N = self.batch, self.nmax; dx = np.zeros((B, N, NX)); du = np.zeros((B, N, NU)); robot = np.zeros((B, 8))
         self._chk(self.lib.qmb200_debug_get_step(self.h, _p(dx), _p(du), _p(robot)), "qmb200_debug_get_step"); return dx, du, robot
 
+    # ---------------- controller side: observation, targets, control law, plant law, QMController::update ----------------
+    def observation_update(self, rbd, period, t_obs, x_obs):
+        """QMController::updateStateEstimation tail (QMController.cpp:236-243) → (t_obs, x_obs) advanced."""
+        B = self.batch; rbd = _f64(rbd, (B, RBD)); period = _f64(period, (B,)); t = _f64(t_obs, (B,)).copy(); x = _f64(x_obs, (B, NX)).copy()
+        self._chk(self.lib.qmb200_observation_update(self.h, _p(rbd), _p(period), _p(t), _p(x)), "qmb200_observation_update"); return t, x
+
+    def target_trajectories(self, kind, cmd, t_obs, x_obs, ee_state, last_ee_target):
+        """QmTargetTrajectoriesPublisher_node.cpp:44-208 → (n_target, target_times, target_states, last_ee_target)."""
+        B = self.batch; c = np.zeros((B, 7)); cmd = np.asarray(cmd, dtype=np.float64).reshape(B, -1); c[:, :cmd.shape[1]] = cmd
+        t = _f64(t_obs, (B,)); x = _f64(x_obs, (B, NX)); ee = _f64(ee_state, (B, 7)); le = _f64(last_ee_target, (B, 7)).copy()
+        nt = np.zeros(B, dtype=np.int32); tt = np.zeros((B, KMAX)); ts = np.zeros((B, KMAX, TARGET))
+        self._chk(self.lib.qmb200_target_trajectories(self.h, int(kind), _p(c), _p(t), _p(x), _p(ee), _p(le), _p(nt), _p(tt), _p(ts)), "qmb200_target_trajectories"); return nt, tt, ts, le
+
+    def initial_ee_target(self):
+        v = np.zeros(7); self.lib.qmb200_initial_ee_target(_p(v)); return np.tile(v, (self.batch, 1))
+
+    def set_arm_gains(self, kp, kd):
+        self._chk(self.lib.qmb200_set_arm_gains(self.h, float(kp), float(kd)), "qmb200_set_arm_gains")
+
+    def control_law(self, x_des, u_des, wbc_cmd, t_obs, x_obs, joint_cmd, arm_pos_cmd, last_time):
+        """SafetyChecker + updateControlLaw (QMController.cpp:159-190 / 427-445) → (joint_cmd, arm_pos_cmd, last_time, status)."""
+        B = self.batch; jc = _f64(joint_cmd, (B, 18, 5)).copy(); ap = _f64(arm_pos_cmd, (B, 6)).copy(); lt = _f64(last_time, (B,)).copy(); st = np.zeros(B, dtype=np.int32)
+        self._chk(self.lib.qmb200_control_law(self.h, _p(_f64(x_des, (B, NX))), _p(_f64(u_des, (B, NU))), _p(_f64(wbc_cmd, (B, CMD))), _p(_f64(t_obs, (B,))), _p(_f64(x_obs, (B, NX))), _p(jc), _p(ap), _p(lt), _p(st)),
+                  "qmb200_control_law"); return jc, ap, lt, st
+
+    def hw_set_delay(self, delay):
+        self._chk(self.lib.qmb200_hw_set_delay(self.h, float(delay)), "qmb200_hw_set_delay")
+
+    def hw_write(self, time, period, joint_cmd, joint_pos, joint_vel):
+        """QMHWSim::writeSim (QMHWSim.cpp:98-116) → (effort[B,18], status)."""
+        B = self.batch; eff = np.zeros((B, 18)); st = np.zeros(B, dtype=np.int32)
+        self._chk(self.lib.qmb200_hw_write(self.h, _p(_f64(time, (B,))), _p(_f64(period, (B,))), _p(_f64(joint_cmd, (B, 18, 5))), _p(_f64(joint_pos, (B, 18))), _p(_f64(joint_vel, (B, 18))), _p(eff), _p(st)), "qmb200_hw_write")
+        return eff, st
+
+    def update(self, rbd, period, t_obs, x_obs, joint_cmd, arm_pos_cmd, last_time):
+        """QMController::update (QMController.cpp:128-175) on the stored policy → (t_obs, x_obs, joint_cmd, arm_pos_cmd, last_time, cmd[B,54], status)."""
+        B = self.batch; t = _f64(t_obs, (B,)).copy(); x = _f64(x_obs, (B, NX)).copy(); jc = _f64(joint_cmd, (B, 18, 5)).copy(); ap = _f64(arm_pos_cmd, (B, 6)).copy(); lt = _f64(last_time, (B,)).copy()
+        cmd = np.zeros((B, CMD)); st = np.zeros(B, dtype=np.int32)
+        self._chk(self.lib.qmb200_update(self.h, _p(_f64(rbd, (B, RBD))), _p(_f64(period, (B,))), _p(t), _p(x), _p(jc), _p(ap), _p(lt), _p(cmd), _p(st)), "qmb200_update")
+        return t, x, jc, ap, lt, cmd, st
+
     # ---------------- utilities ----------------
     def centroidal_state_from_rbd(self, rbd):
         rbd = _f64(rbd); n = rbd.shape[0]; x = np.empty((n, NX))

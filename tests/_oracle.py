@@ -171,3 +171,45 @@ class Oracle:
         et = f64(event_times); md = i32(modes); zp = C.c_double(); zv = C.c_double()
         self._chk(self.lib.orc_swing_reference(self.h, C.c_int(len(et)), _d(et), _i(md), C.c_int(leg), C.c_double(t), C.byref(zp), C.byref(zv)))
         return zp.value, zv.value
+
+    # ---- controller side (oracle/src/ctrl.cpp) ----
+    def observation_update(self, rbd, period, t_obs, x_obs):
+        t = C.c_double(float(t_obs)); x = f64(x_obs).copy()
+        self._chk(self.lib.orc_observation_update(self.h, _d(f64(rbd)), C.c_double(float(period)), C.byref(t), _d(x)))
+        return t.value, x
+
+    def control_law(self, variant, arm_kp, arm_kd, x_des, u_des, wbc_cmd, time, x_obs, joint_cmd, arm_pos, last_time):
+        jc = f64(joint_cmd).copy(); ap = f64(arm_pos).copy(); lt = C.c_double(float(last_time))
+        safe = self.lib.orc_control_law(C.c_int(variant), C.c_double(arm_kp), C.c_double(arm_kd), _d(f64(x_des)), _d(f64(u_des)), _d(f64(wbc_cmd)), C.c_double(float(time)), _d(f64(x_obs)), _d(jc), _d(ap), C.byref(lt))
+        return jc, ap, lt.value, bool(safe)
+
+
+class TargetOracle:
+    """QmTargetTrajectoriesPublisher_node.cpp restated (oracle/src/ctrl.cpp)."""
+
+    def __init__(self, task=TASK, reference=REFERENCE):
+        if not os.path.exists(LIB_PATH):
+            build_oracle()
+        self.lib = C.CDLL(LIB_PATH); self.lib.orc_ctrl_create.restype = C.c_void_p
+        self.c = C.c_void_p(self.lib.orc_ctrl_create(task.encode(), reference.encode()))
+        assert self.c
+
+    def target(self, kind, cmd, t_obs, x_obs, ee_state, last_ee):
+        c7 = np.zeros(7); cmd = f64(cmd); c7[:len(cmd)] = cmd; le = f64(last_ee).copy(); times = np.zeros(2); states = np.zeros((2, 37))
+        self.lib.orc_target_trajectories(self.c, C.c_int(kind), _d(c7), C.c_double(float(t_obs)), _d(f64(x_obs)), _d(f64(ee_state)), _d(le), _d(times), _d(states))
+        return times, states, le
+
+
+class HwSimOracle:
+    """QMHWSim::writeSim restated with a std::deque (oracle/src/ctrl.cpp)."""
+
+    def __init__(self, delay):
+        if not os.path.exists(LIB_PATH):
+            build_oracle()
+        self.lib = C.CDLL(LIB_PATH); self.lib.orc_hw_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.lib.orc_hw_create(C.c_double(delay)))
+
+    def write(self, time, period, joint_cmd, pos, vel):
+        eff = np.zeros(18)
+        self.lib.orc_hw_write(self.h, C.c_double(float(time)), C.c_double(float(period)), _d(f64(joint_cmd)), _d(f64(pos)), _d(f64(vel)), _d(eff))
+        return eff
