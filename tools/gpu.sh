@@ -3,6 +3,6 @@
 set -e
 cd "$(dirname "$0")/.."
 make -s -C oracle
-make -s -C qm_control_b200/csrc 2>&1 | grep -E "error|undefined" && exit 1
+make -s -j8 -C qm_control_b200/csrc 2>&1 | grep -E "error|undefined" && exit 1
 T=$1; shift
 exec timeout $((T + 1900)) /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
