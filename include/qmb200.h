@@ -120,6 +120,19 @@ int qmb200_centroidal_state_from_rbd(const qmb200_handle* h, int32_t n, const do
 int qmb200_gait_schedule(const char* gait_file, const char* gait_name, double t_start, double lo, double hi,
                          double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
 
+/* ---- stateful gait front-end: ocs2::legged_robot::GaitSchedule as QMInterface::loadGaitSchedule builds it (QMInterface.cpp:455-480) and
+ *      GaitReceiver / SwitchedModelReferenceManager drive it [upstream ocs2_legged_robot, recalled]: the schedule starts as
+ *      reference.info:initialModeSchedule with defaultModeSequenceTemplate as the active template; a gait command
+ *      (GaitJoyPublisher.cpp:35-60 → a gait.info template) is inserted at the end of the current horizon after phaseTransitionStanceTime
+ *      of stance (task.info:9); every solve asks for the window [t0 - T, tf + T] (trim + tile).  Host object, one per robot. */
+typedef struct qmb200_gait qmb200_gait;
+int qmb200_gait_create(const char* task_file, const char* reference_file, qmb200_gait** out);
+void qmb200_gait_destroy(qmb200_gait* g);
+/* GaitSchedule::insertModeSequenceTemplate(template, startTime, finalTime); GaitReceiver passes (finalTime of the solve, timeHorizon) */
+int qmb200_gait_insert_template(qmb200_gait* g, const char* gait_file, const char* gait_name, double start_time, double final_time);
+/* GaitSchedule::getModeSchedule(lowerBoundTime, upperBoundTime): returns the number of events written (<= EMAX) or negative */
+int qmb200_gait_get_mode_schedule(qmb200_gait* g, double lower_bound_time, double upper_bound_time, double* event_times /*[EMAX]*/, int32_t* mode_sequence /*[EMAX+1]*/);
+
 /* ---- controller side of the path: the steps of QMController::update around evaluatePolicy / WbcBase::update and the
  *      publisher that feeds the solver, batched on the device.  The caller owns the per-robot controller state these functions read and
  *      write (the members of QMController / QmTargetTrajectoriesInteractiveMarker they mirror); `_dev` variants take device pointers. */

@@ -28,6 +28,7 @@ SYMBOLS = ["qmb200_create", "qmb200_destroy", "qmb200_last_error", "qmb200_get_d
            "qmb200_mpc_solve", "qmb200_mpc_solve_dev", "qmb200_mpc_reset", "qmb200_mpc_set_solution", "qmb200_mpc_get_solution",
            "qmb200_policy_eval", "qmb200_policy_eval_dev", "qmb200_tick", "qmb200_tick_dev", "qmb200_centroidal_state_from_rbd",
            "qmb200_gait_schedule", "qmb200_launch_count", "qmb200_stream", "qmb200_debug_get_step",
+           "qmb200_gait_create", "qmb200_gait_destroy", "qmb200_gait_insert_template", "qmb200_gait_get_mode_schedule",
            "qmb200_observation_update", "qmb200_observation_update_dev", "qmb200_target_trajectories", "qmb200_target_trajectories_dev", "qmb200_initial_ee_target",
            "qmb200_control_law", "qmb200_control_law_dev", "qmb200_set_arm_gains", "qmb200_hw_write", "qmb200_hw_write_dev", "qmb200_hw_set_delay", "qmb200_update", "qmb200_update_dev",
            "qmb200_set_pipeline", "qmb200_set_profiling", "qmb200_collect_kernel_times", "qmb200_get_kernel_times", "qmb200_measure_fp64_peak"]
@@ -55,6 +56,10 @@ def load_library():
     lib.qmb200_set_arm_gains.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.qmb200_hw_set_delay.argtypes = [C.c_void_p, C.c_double]
     lib.qmb200_initial_ee_target.restype = None
+    lib.qmb200_gait_destroy.restype = None
+    lib.qmb200_gait_destroy.argtypes = [C.c_void_p]
+    lib.qmb200_gait_insert_template.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double]
+    lib.qmb200_gait_get_mode_schedule.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib

@@ -2,6 +2,7 @@
 // kernel launches.  No CPU fallback: every compute entry point launches the sm_100a kernels or fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>

@@ -236,3 +236,30 @@ def gait_schedule(gait_name, t_start, lo, hi, gait_file=None):
     if n < 0:
         raise QmbError("qmb200_gait_schedule failed: " + lib.qmb200_last_error(None).decode())
     return ev, md, n
+
+
+class GaitSchedule:
+    """ocs2::legged_robot::GaitSchedule as QMInterface::loadGaitSchedule builds it (QMInterface.cpp:455-480): stateful host object, one per robot."""
+
+    def __init__(self, interface=None):
+        self.lib = _lib.load_library(); self.interface = interface or QMInterface(); g = C.c_void_p()
+        if self.lib.qmb200_gait_create(self.interface.taskFile.encode(), self.interface.referenceFile.encode(), C.byref(g)) != 0:
+            raise QmbError("qmb200_gait_create failed: " + self.lib.qmb200_last_error(None).decode())
+        self.g = g
+
+    def __del__(self):
+        try:
+            self.lib.qmb200_gait_destroy(self.g)
+        except Exception:
+            pass
+
+    def insertModeSequenceTemplate(self, gait_name, startTime, finalTime, gait_file=None):
+        if self.lib.qmb200_gait_insert_template(self.g, (gait_file or self.interface.gaitFile).encode(), gait_name.encode(), float(startTime), float(finalTime)) != 0:
+            raise QmbError("qmb200_gait_insert_template failed: " + self.lib.qmb200_last_error(None).decode())
+
+    def getModeSchedule(self, lowerBoundTime, upperBoundTime):
+        ev = np.zeros(EMAX); md = np.full(EMAX + 1, 15, dtype=np.int32)
+        n = self.lib.qmb200_gait_get_mode_schedule(self.g, float(lowerBoundTime), float(upperBoundTime), _p(ev), _p(md))
+        if n < 0:
+            raise QmbError("qmb200_gait_get_mode_schedule failed: " + self.lib.qmb200_last_error(None).decode())
+        return ev, md, n

@@ -69,3 +69,57 @@ def test_shard_ranges_cover_the_batch():
     for total, world in ((8192, 8), (10, 4), (7, 8), (1, 1)):
         spans = [shard_range(total, r, world) for r in range(world)]
         assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+class _GaitTwin:
+    """List-based restatement of GaitSchedule [upstream, recalled] used to cross-check the C++ host object."""
+
+    def __init__(self):
+        self.ev = [0.5]; self.md = [15, 15]; self.tmpl = ([0.0, 1.0], [15]); self.pts = 0.1   # reference.info:27-52, task.info:9
+
+    def tile(self, start, final):
+        times, modes = self.tmpl; self.ev.append(start)
+        while self.ev[-1] < final:
+            for i, m in enumerate(modes):
+                self.md.append(m); self.ev.append(self.ev[-1] + (times[i + 1] - times[i]))
+        self.md.append(15)
+
+    def insert(self, tmpl, start, final):
+        self.tmpl = tmpl; idx = int(np.searchsorted(self.ev, start, side="left"))
+        if idx < len(self.ev):
+            del self.ev[idx:]; del self.md[idx + 1:]
+        stance = 0.0 if self.md[-1] == 15 else self.pts
+        if stance > 0:
+            self.ev.append(start); self.md.append(15)
+        self.tile(start + stance, final)
+
+    def get(self, lo, hi):
+        idx = int(np.searchsorted(self.ev, lo, side="left"))
+        if idx > 0:
+            del self.ev[:idx - 1]; del self.md[:idx - 1]; self.md[0] = 15
+        start = self.ev[-1]; self.ev.pop(); self.md.pop(); self.tile(start, hi)
+        return list(self.ev), list(self.md)
+
+
+def test_stateful_gait_schedule_follows_the_controller_protocol():
+    """MPC ticks ask for [t0 - T, tf + T] (SwitchedModelReferenceManager::modifyReferences); gait commands arrive through
+    GaitReceiver::preSolverRun → insertModeSequenceTemplate(template, finalTime, timeHorizon)."""
+    from qm_control_b200.interface import GaitSchedule
+    gs = GaitSchedule(); tw = _GaitTwin(); T = 1.0
+    tmpl = {g: synthetic._gait_template(_lib.asset("qm_gait.info"), g) for g in ("trot", "flying_trot", "stance")}
+    t0 = 0.0
+    for tick in range(400):
+        t0 = 0.01 * tick
+        if tick == 50:
+            gs.insertModeSequenceTemplate("trot", t0 + T, T); tw.insert((list(tmpl["trot"][0]), tmpl["trot"][1]), t0 + T, T)
+        if tick == 200:
+            gs.insertModeSequenceTemplate("flying_trot", t0 + T, T); tw.insert((list(tmpl["flying_trot"][0]), tmpl["flying_trot"][1]), t0 + T, T)
+        ev, md, n = gs.getModeSchedule(t0 - T, t0 + 2 * T); ev_t, md_t = tw.get(t0 - T, t0 + 2 * T)
+        assert n == len(ev_t); np.testing.assert_allclose(ev[:n], ev_t, rtol=0, atol=1e-12); assert list(md[:n + 1]) == md_t
+        assert md[0] == 15 and md[n] == 15 and np.all(np.diff(ev[:n]) > 0) and ev[n - 1] >= t0 + 2 * T
+        if tick == 49:
+            assert set(md[:n + 1]) == {15}                              # standing until the first gait command
+        if tick == 120:                                                 # trot since t = 1.5: LF_RH / RF_LH alternate every 0.35 s
+            k = int(np.searchsorted(ev[:n], 1.5 + 1e-9)); assert list(md[k:k + 4]) == [9, 6, 9, 6]; np.testing.assert_allclose(np.diff(ev[k - 1:k + 3]), 0.35)
+        if tick == 300:                                                 # the switch trot → flying trot passes through phaseTransitionStanceTime of stance
+            k = int(np.searchsorted(ev[:n], 3.0 - 1e-9)); assert md[k + 1] == 15 and abs(ev[k + 1] - ev[k] - 0.1) < 1e-12
