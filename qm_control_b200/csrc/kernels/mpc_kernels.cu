@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   LQ_LOCKSTEP();
   // ---- projected dynamics rows (lane = state row): A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
   if (lane < NX) {
-    const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; double* Brow = sg + ST_B + (size_t)r * MU; double bt = sm.el.l.bvec[r];
+    const int r = lane; double bt = sm.el.l.bvec[r];
     if (r >= 3 && r < 6) {       // h_ang rows pick up the dependent joint velocities: + sum_legs BrdJ[r][joint] * Px_joint (accumulated in the shared-memory row, own thread)
       double* arow = sm.A1r + (r - 3) * NX; double acc[12];
 #pragma unroll
@@ -241,30 +241,35 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
         for (int c = 0; c < 12; ++c) arow[sup_col(c, L.first)] += acc[c];
       }
     }
-    if (r >= 3 && r < 12) {
-#pragma unroll 6
-      for (int c = 0; c < NX; ++c) Arow[c] = sm.A1r[(r - 3) * NX + c] + ((c == r) ? 1.0 : 0.0);
-    } else {
-#pragma unroll 6
-      for (int c = 0; c < NX; ++c) Arow[c] = (c == r) ? 1.0 : 0.0;
-    }
     if (r >= 12 && r < 24) {     // dependent joint-velocity rows: I + dtw * Px
       const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3;
-      if (L.dep[j]) { bt += dtw * L.Pe[j]; for (int c = 0; c < 12; ++c) { const int col = sup_col(c, L.first); Arow[col] = ((col == r) ? 1.0 : 0.0) + dtw * L.Px[j][c]; } }
+      if (L.dep[j]) bt += dtw * L.Pe[j];
     }
     if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw / mass) * sm.Pe_full[3 * f + r];
     if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.el.l.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
-    // B~ row
-    for (int a = 0; a < MU; ++a) {
-      double v = 0.0;
-      if (a < m) { const int fa = sm.free_idx[a];
-        if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw / mass : 0.0;
-        else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(mdl, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
-        else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
-      }
-      Brow[a] = v;
-    }
     sg[ST_b + r] = bt;
+  }
+  __syncwarp();   // the h_ang rows of A1r were updated by their own lanes above
+  // A~ (30x30) and B~ (30x18) leave as flat row-major sweeps: consecutive lanes write consecutive doubles (8 sectors per store instruction
+  // instead of the 30 a lane-per-row store touches)
+  for (int e = lane; e < NX * NX; e += 32) {
+    const int r = e / NX, c = e - r * NX; double v = (c == r) ? 1.0 : 0.0;
+    if (r >= 3 && r < 12) v += sm.A1r[(r - 3) * NX + c];
+    else if (r >= 12 && r < 24) {
+      const LegWs& L = sm.leg[foot_of_leg_joint(mdl, r - 12)]; const int j = (r - 12) % 3;
+      const int pos = c < 6 ? c : ((c >= 9 && c < 12) ? c - 3 : ((c >= 12 + L.first && c < 15 + L.first) ? 9 + c - 12 - L.first : -1));   // inverse of sup_col
+      if (L.dep[j] && pos >= 0) v += dtw * L.Px[j][pos];
+    }
+    sg[ST_A + e] = v;
+  }
+  for (int e = lane; e < NX * MU; e += 32) {
+    const int r = e / MU, a = e - r * MU; double v = 0.0;
+    if (a < m) { const int fa = sm.free_idx[a];
+      if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw / mass : 0.0;
+      else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(mdl, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
+      else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
+    }
+    sg[ST_B + e] = v;
   }
   LQ_LOCKSTEP();
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
@@ -300,16 +305,17 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
           for (int c = 0; c < 3; ++c) acc[12 + 3 * l + c] += blk[9 + c]; }
       }
     }
-    double* Qrow = sg + ST_Q + (size_t)r * NX; const double dq = sm.quad.qdiag[r];
+    // Q~ is symmetric: lane r stores its row as COLUMN r, so every store instruction writes one contiguous 240-byte row
+    double* Qcol = sg + ST_Q + r; const double dq = sm.quad.qdiag[r];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) Qrow[c] = dt * (acc[c] + ((c == r) ? dq : 0.0));
+    for (int c = 0; c < NX; ++c) Qcol[(size_t)c * NX] = dt * (acc[c] + ((c == r) ? dq : 0.0));
     sg[ST_q + r] = dt * qv;
   }
   LQ_LOCKSTEP();
-  if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu
-    const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rrow = sg + ST_R + (size_t)a * MU;
-#pragma unroll 6
-    for (int c = 0; c < NX; ++c) Srow[c] = 0.0;
+  for (int e = lane; e < MU * NX; e += 32) sg[ST_S + e] = 0.0;   // S~ is zero except the swing-joint rows written below
+  __syncwarp();
+  if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu (symmetric: lane a stores column a, one contiguous row per store instruction)
+    const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rcol = sg + ST_R + a;
     if (a < m) {
       const int fa = sm.free_idx[a]; double rv = sm.rs[fa]; int li = -1, jf = -1;
       if (fa >= 12 && fa < 24) { li = foot_of_leg_joint(mdl, fa - 12); jf = (fa - 12) % 3; }
@@ -326,9 +332,9 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
         if (c < m) { const int fc = sm.free_idx[c]; v = quad_R(mdl, &sm.quad, fa, fc);
           if (swing_joint && fc >= 12 + sm.leg[li].first && fc < 15 + sm.leg[li].first) { const LegWs& L = sm.leg[li]; const int pv = L.pivot; const int jc = fc - 12 - L.first; const double pa = L.Pu2[jf > pv ? jf - 1 : jf], pc = L.Pu2[jc > pv ? jc - 1 : jc];
             v += pa * L.Rl[3 * pv + jc] + L.Rl[3 * jf + pv] * pc + pa * L.Rl[3 * pv + pv] * pc; } }
-        Rrow[c] = dt * v;
+        Rcol[(size_t)c * MU] = dt * v;
       }
-    } else { sg[ST_r + a] = 0.0; for (int c = 0; c < MU; ++c) Rrow[c] = (c == a) ? 1.0 : 0.0; }
+    } else { sg[ST_r + a] = 0.0; for (int c = 0; c < MU; ++c) Rcol[(size_t)c * MU] = (c == a) ? 1.0 : 0.0; }
   }
   // projection data for the forward pass: dense rows of Px / Pu / Pe of the dependent inputs
   for (int e = lane; e < MAXDEP * NX; e += 32) sg[ST_PXD + e] = 0.0;

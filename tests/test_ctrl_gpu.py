@@ -105,7 +105,7 @@ def test_controller_update_matches_oracle_chain(oracle, variant):
             t_o[b], x_o[b] = oracle.observation_update(rbd[b], period, t_o[b], x_o[b])
             n = ref["n_nodes"][b]; ne = p["n_events"][b]
             xd, ud, mode = oracle.evaluate_policy(ref["t"][b, :n], ref["event"][b, :n], ref["x"][b, :n], ref["u"][b, :n], p["event_times"][b, :ne], p["modes"][b, :ne + 1], t_o[b])
-            c, il[b], _ = oracle.wbc_update(xd, ud, rbd[b], mode, period, t_o[b], input_last=il[b], variant=variant)
+            cb, ilb = oracle.wbc_update_batch(xd[None], ud[None], rbd[b][None], [mode], [period], [t_o[b]], il[b][None], variant=variant); c = cb[0]; il[b] = ilb[0]   # (the batch entry tolerates the oracle's QP iteration cap in the free arm directions)
             jc_o[b], ap_o[b], lt_o[b], safe = oracle.control_law(variant, 0.0, 0.5, xd, ud, c, t_o[b], x_o[b], jc_o[b], ap_o[b], lt_o[b])
             det = np.r_[0:18, 24:36] if variant else np.arange(54)     # HierarchicalMpcWbc leaves the arm accelerations - and with them every torque - undetermined (tests/test_wbc_gpu.py)
             err = np.max(np.abs(cmd[b, det] - c[det])) / max(1.0, np.max(np.abs(c[det])))

@@ -2,7 +2,9 @@
 """Summarise an ncu report's source page per CUDA source line: tools/ncu_hot.py <file.ncu-rep> [top_n]"""
 import csv, subprocess, sys, io, collections
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
+import os
+KSEL = (["--kernel-name", os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else [])
+txt = subprocess.run(["ncu", "-i", rep] + KSEL + ["--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 agg = collections.OrderedDict(); cur_file = None; H = None
 for r in rows:

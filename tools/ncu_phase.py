@@ -3,7 +3,9 @@
 line of `anchor_file` seen in SASS address order): tools/ncu_phase.py <file.ncu-rep> <anchor_file> [bucket]"""
 import csv, subprocess, sys, io, collections
 rep, anchor = sys.argv[1], sys.argv[2]; bucket = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
+import os
+KSEL = (["--kernel-name", os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else [])
+txt = subprocess.run(["ncu", "-i", rep] + KSEL + ["--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 insts = []; cur_file = None; H = None; cur_line = None
 for r in rows:
