@@ -553,35 +553,36 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
     for (int k = 0; k < N; ++k) {
       const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sib + (size_t)k * STAGE_INT; const int type = si[SI_TYPE], ndep = si[SI_NDEP];
       double* dxk = dxo + ((size_t)b * nmax + k) * NX; double* duk = duo + ((size_t)b * nmax + k) * NU;
+      // dx is double buffered (sm.dx / sm.tmp): the next state is written into the other buffer, and the barrier at the top of the next
+      // iteration publishes it - two barriers per node instead of four
+      const double* dxc = (k & 1) ? sm.tmp : sm.dx; double* dxn = (k & 1) ? sm.dx : sm.tmp;
+      cp_async_wait<0>(); __syncthreads();   // stage record k has landed; dx(k) (written by other threads in the previous iteration) is visible; nobody reads buffer set (k+1)&1 any more
       issue_fwd(k + 1);
-      if (tid < NX) { const double dxi = sm.dx[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
-      if (type == 1) { if (tid < NX) { duk[tid] = 0.0; sm.tmp[tid] = sm.dx[tid] + sg[ST_b + tid]; } __syncthreads(); if (tid < NX) sm.dx[tid] = sm.tmp[tid]; __syncthreads(); continue; }
+      if (tid < NX) { const double dxi = dxc[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
+      if (type == 1) { if (tid < NX) { duk[tid] = 0.0; dxn[tid] = dxc[tid] + sg[ST_b + tid]; } continue; }
       const bool o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* Ab = o ? sm.P : sm.A; const double* Bb = o ? sm.PB : sm.Bm;
       const double* bv = o ? sm.pPb : sm.b; const double* qv = o ? sm.p : sm.q; const double* rv = o ? sm.h : sm.r; const double* kv = o ? sm.kff2 : sm.kff;
-      cp_async_wait<1>(); __syncthreads();
       { double s = 0.0;   // all lanes take part in the quad reduction (shfl_sync needs the full mask)
-        if (ti < MU) { const double* kr = Kb + ti * LDG + jb * 8; const double* dx = sm.dx + jb * 8;
+        if (ti < MU) { const double* kr = Kb + ti * LDG + jb * 8; const double* dx = dxc + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(kr[v], dx[v], s); }
         s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + kv[ti]; }
       __syncthreads();
       { double s = 0.0;
-        if (ti < NX) { const double* ar = Ab + ti * LDX + jb * 8; const double* dx = sm.dx + jb * 8;
+        if (ti < NX) { const double* ar = Ab + ti * LDX + jb * 8; const double* dx = dxc + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(ar[v], dx[v], s);
           if (jb < 3) { const double* br = Bb + ti * LDB + jb * 8; const double* du = sm.dut + jb * 8;
 #pragma unroll
             for (int v = 0; v < 8; ++v) s = fma(br[v], du[v], s); } }
-        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) sm.tmp[ti] = s + bv[ti]; }
-      if (tid < NX) armijo += qv[tid] * sm.dx[tid];
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) dxn[ti] = s + bv[ti]; }
+      if (tid < NX) armijo += qv[tid] * dxc[tid];
       if (tid < MU) { const double dut = sm.dut[tid]; armijo += rv[tid] * dut; const int fi = si[SI_FREE + tid]; if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; } }
       if (tid >= 64 && tid < 64 + MAXDEP) { const int d = tid - 64; if (d < ndep) { double s = sg[ST_PED + d]; const double* px = sg + ST_PXD + (size_t)d * NX; const double* pu = sg + ST_PUD + (size_t)d * MU;
-          for (int j = 0; j < NX; ++j) s = fma(px[j], sm.dx[j], s); for (int a = 0; a < MU; ++a) s = fma(pu[a], sm.dut[a], s); duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
-      __syncthreads();
-      if (tid < NX) sm.dx[tid] = sm.tmp[tid];
-      __syncthreads();
+          for (int j = 0; j < NX; ++j) s = fma(px[j], dxc[j], s); for (int a = 0; a < MU; ++a) s = fma(pu[a], sm.dut[a], s); duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
     }
-    if (tid < NX) { const double dxi = sm.dx[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_q + tid] * dxi; }
+    __syncthreads();
+    if (tid < NX) { const double dxi = ((N & 1) ? sm.tmp : sm.dx)[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_q + tid] * dxi; }
   }
   armijo = warp_sum(armijo); dxn2 = warp_sum(dxn2); dun2 = warp_sum(dun2);
   __syncthreads();
