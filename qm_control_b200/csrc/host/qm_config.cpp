@@ -258,7 +258,8 @@ HostModel build_host_model(const std::string& task_file, const std::string& urdf
     for (int i = 0; i < NU; ++i) for (int j = 0; j < NU; ++j) { const bool in_block = (i < 24 && j < 24) ? (i / 3 == j / 3) : (i == j);
       if (!in_block && std::fabs(d.R[i * NU + j]) > 1e-12 * rmax) throw std::runtime_error("task.info R: entry (" + std::to_string(i) + "," + std::to_string(j) + ") couples different feet/legs; only the block structure of QMInterface::initializeInputCostWeight is supported"); }
     for (int bq = 0; bq < 8; ++bq) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) d.Rblk[bq][3 * a + b] = d.R[(3 * bq + a) * NU + 3 * bq + b];
-    for (int i = 0; i < 6; ++i) d.Rarm[i] = d.R[(24 + i) * NU + 24 + i]; }
+    for (int i = 0; i < 6; ++i) d.Rarm[i] = d.R[(24 + i) * NU + 24 + i];
+    d.q_is_diag = 1; for (int i = 0; i < NX; ++i) { d.Qdiag[i] = d.Q[i * NX + i]; for (int j = 0; j < NX; ++j) if (i != j && d.Q[i * NX + j] != 0.0) d.q_is_diag = 0; } }
   d.mu_ee_pos = task.number("endEffector.muPosition", 1.0); d.mu_ee_ori = task.number("endEffector.muOrientation", 1.0);
   d.mu_final_ee_pos = task.number("finalEndEffector.muPosition", 1.0); d.mu_final_ee_ori = task.number("finalEndEffector.muOrientation", 1.0);
   d.friction_mu = task.number("frictionConeSoftConstraint.frictionCoefficient", 1.0); d.friction_barrier_mu = task.number("frictionConeSoftConstraint.mu", 0.1); d.friction_barrier_delta = task.number("frictionConeSoftConstraint.delta", 5.0);

@@ -42,6 +42,7 @@ struct DevModel {
   double wbc_friction;
   // MPC settings (task.info:75-92,138-147,192-343)
   double Q[NX * NX], R[NU * NU];
+  double Qdiag[NX]; int q_is_diag;   // Q of task.info:192-233 is diagonal: fast path when the loaded matrix really is (checked at create), dense fallback otherwise
   double Rblk[8][9], Rarm[6];   // R is block diagonal (QMInterface.cpp:274-299): 3x3 blocks per foot force / per leg, diagonal for the arm; checked at create
   double mu_ee_pos, mu_ee_ori, mu_final_ee_pos, mu_final_ee_ori;
   double friction_mu, friction_barrier_mu, friction_barrier_delta, friction_reg, friction_hess_shift;

@@ -118,7 +118,7 @@ __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, Poi
 // ---- reference signals -------------------------------------------------------------------------------
 // ocs2::lookup::findIndexInTimeArray (std::lower_bound)
 __device__ __forceinline__ int lower_bound_idx(const double* a, int n, double t) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < t) lo = mid + 1; else hi = mid; } return lo; }
-__device__ __forceinline__ int mode_at_time(const double* ev, const int32_t* modes, int ne, double t) { return modes[lower_bound_idx(ev, ne, t)]; }
+template <class MT> __device__ __forceinline__ int mode_at_time(const double* ev, const MT* modes, int ne, double t) { return modes[lower_bound_idx(ev, ne, t)]; }
 // ocs2::LinearInterpolation::timeSegment
 __device__ __forceinline__ void time_segment(const double* times, int n, double t, int& index, double& alpha) {
   if (n <= 1) { index = 0; alpha = 1.0; return; }
@@ -130,7 +130,7 @@ __device__ __forceinline__ void time_segment(const double* times, int n, double 
   index = 0; alpha = 1.0;
 }
 // SwingTrajectoryPlanner::getZvelocityConstraint / getZpositionConstraint [upstream]: status=false when the swing phase is not enclosed
-__device__ __forceinline__ bool swing_reference(const DevModel* __restrict__ mdl, const double* ev, const int32_t* modes, int ne, int leg, double t, double& zp, double& zv) {
+template <class MT> __device__ __forceinline__ bool swing_reference(const DevModel* __restrict__ mdl, const double* ev, const MT* modes, int ne, int leg, double t, double& zp, double& zv) {
   const int np = ne + 1; const int p = lower_bound_idx(ev, ne, t); zp = 0.0; zv = 0.0;
   if (contact_flag(modes[p], leg)) return true;
   int start = -1; for (int ip = p - 1; ip >= 0; --ip) if (contact_flag(modes[ip], leg)) { start = ip; break; }
@@ -227,9 +227,14 @@ __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, c
     double dx = 0.0, du = 0.0;
     if (lane < NX) { dx = ws->x[lane] - ref.xnom; double un = 0.0; if (lane < 12 && (lane % 3) == 2 && ((flagmask >> (lane / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du = ws->u[lane] - un; }
     double qd = 0.0, rd = 0.0;
-    const double* Qr = mdl->Q + (lane < NX ? lane : 0) * NX; const double* Rr = mdl->R + (lane < NU ? lane : 0) * NU;
+    if (mdl->q_is_diag) { if (lane < NX) qd = mdl->Qdiag[lane] * dx; }
+    else { const double* Qr = mdl->Q + (lane < NX ? lane : 0) * NX;
 #pragma unroll 6
-    for (int j = 0; j < NX; ++j) { const double dxj = __shfl_sync(FULL, dx, j), duj = __shfl_sync(FULL, du, j); qd = fma(Qr[j], dxj, qd); rd = fma(Rr[j], duj, rd); }
+      for (int j = 0; j < NX; ++j) qd = fma(Qr[j], __shfl_sync(FULL, dx, j), qd); }
+    { // R is block diagonal (checked at create): 3x3 blocks over the 8 force / leg-joint triples, diagonal over the arm
+      const int blk = lane < 24 ? lane / 3 : 0, row = lane - 3 * blk; const double* Rb = mdl->Rblk[blk] + 3 * (lane < 24 ? row : 0);
+      const double d0 = __shfl_sync(FULL, du, 3 * blk), d1 = __shfl_sync(FULL, du, 3 * blk + 1), d2 = __shfl_sync(FULL, du, 3 * blk + 2);
+      if (lane < 24) rd = fma(Rb[0], d0, fma(Rb[1], d1, Rb[2] * d2)); else if (lane < NU) rd = mdl->Rarm[lane - 24] * du; }
     value += 0.5 * warp_sum(lane < NX ? dx * qd + du * rd : 0.0);
     if (with_quad && lane < NX) { qw->qf[lane] = qd; qw->rf[lane] = rd; }
     __syncwarp();

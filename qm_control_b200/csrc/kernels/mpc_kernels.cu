@@ -92,7 +92,9 @@ struct LqSmem {
   double xs[NX], xnext[NX], f1[NX], A1r[9 * NX], B1h[36];             // A1r becomes A_d - I (rows 3:12) in place
   double Pe_full[NU], rs[NU];
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
+  double ev[EMAX]; unsigned char modes[EMAX + 8];   // the robot's mode schedule, staged once per node: the binary searches and the swing-interval scans then hit shared memory
 };
+static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep two CTAs per SM");
 
 // The LQ kernel is ~220 KB of straight-line code executed once per node: warps of a CTA are re-aligned at a few phase
 // boundaries so that they share instruction-cache lines (exited warps - event / terminal / padding nodes - no longer take part).
@@ -105,7 +107,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp];
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL; int32_t* si = stage_i + ((size_t)b * nmax + k) * STAGE_INT;
-  const int ne = p.n_events[b]; const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
+  const int ne = p.n_events[b]; const double* ev = sm.ev; const unsigned char* modes = sm.modes;
+  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
   const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
   const bool terminal = (k == n - 1);
@@ -275,9 +278,13 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
   if (lane < NX) {   // q~ = q + Px' rs ; Q~ = Q + Px' R Px : per leg a 12x12 block on its support columns
     const int r = lane; double acc[NX];
+    if (mdl->q_is_diag) { const double qrr = mdl->Qdiag[r];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) acc[c] = mdl->Q[r * NX + c];
-    acc[0] += 0.0; double qv = sm.quad.qf[r];
+      for (int c = 0; c < NX; ++c) acc[c] = (c == r) ? qrr : 0.0; }
+    else {
+#pragma unroll
+      for (int c = 0; c < NX; ++c) acc[c] = mdl->Q[r * NX + c]; }
+    double qv = sm.quad.qf[r];
     const int ea = ee_pos(r);
     if (ea >= 0) {
 #pragma unroll
@@ -594,7 +601,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
 
 // =====================================================================================================
 // K4: filter line search (one CTA per robot; warps stride over nodes) + trajectory update + input fix-up
-struct LsSmem { PointWs pt; CostWs cost; ConWs con; double xa[NX], ua[NU], xna[NX], f1[NX]; };
+struct LsSmem { PointWs pt; CostWs cost; ConWs con; double xa[NX], ua[NU], xna[NX], f1[NX]; double ev[EMAX]; unsigned char modes[EMAX + 8]; };   // ev / modes: the robot's mode schedule (one copy per warp)
 
 __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax, int n, int tid, int nthreads) {
   // toPrimalSolution [upstream]: input at a pre-event node repeats the previous one; last input repeated
@@ -611,7 +618,8 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const 
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* gx = sol.x + (size_t)b * nmax * NX; double* gu = sol.u + (size_t)b * nmax * NU; const double* gdx = dxo + (size_t)b * nmax * NX; const double* gdu = duo + (size_t)b * nmax * NU;
-  const int ne = p.n_events[b]; const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
+  const int ne = p.n_events[b]; const double* ev = sm.ev; const unsigned char* modes = sm.modes;
+  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
   const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* rb = robot + (size_t)b * ROBOT_DBL; const double armijo = rb[0], base_cost = rb[1], base_viol = sqrt(rb[2] + rb[3]), dxn = rb[4], dun = rb[5];
   const bool failed = (status[b] & MST_NOT_PD) != 0;

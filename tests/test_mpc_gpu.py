@@ -144,3 +144,22 @@ def test_not_positive_definite_is_reported_like_the_oracle(oracle):
     with pytest.raises(RuntimeError, match="not positive definite"):
         oracle.mpc_solve_batch({k: v[:1] for k, v in prob.items()}, solver.nmax, nthreads=1)
     oracle.mpc_solve_batch({k: v[1:] for k, v in prob.items()}, solver.nmax, nthreads=1)
+
+
+def test_dense_state_weight_falls_back_to_the_general_path(tmp_path):
+    """task.info's Q is diagonal and the kernels use that (DevModel::q_is_diag); a Q with off-diagonal entries is still a legal input of
+    QMInterface (loadEigenMatrix reads a dense 30x30): the general path must give the oracle's answer for it."""
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic, _lib
+    from _oracle import Oracle, URDF, REFERENCE, GAINS
+    import re
+    txt = open(_lib.asset("qm_task.info")).read()
+    m = re.search(r"(?m)^Q\s*\n?\{", txt); assert m
+    txt = txt[:m.end()] + "\n  (0,1) 3.0\n  (1,0) 3.0\n  (6,9) 20.0\n  (9,6) 20.0\n" + txt[m.end():]
+    task = tmp_path / "task_dense_q.info"; task.write_text(txt)
+    B = 4; solver = q.Solver(q.QMInterface(taskFile=str(task)), batch=B, dt=0.015); orc = Oracle(URDF, str(task), REFERENCE, GAINS); orc.mpc_set(dt=0.015, horizon=1.0)
+    Q, _ = orc.mpc_weights(); assert Q[0, 1] != 0 and Q[6, 9] != 0
+    prob, _ = synthetic.make_batch(np.arange(B), config=4)
+    out = solver.mpc_solve(prob); ref = orc.mpc_solve_batch(prob, solver.nmax, nthreads=4)
+    assert np.all((out["status"] & ~16) == 0); np.testing.assert_array_equal(out["step_info"][:, 0], ref["dbg"][:, 0])
+    assert _traj_err(out, ref).max() < RTOL
