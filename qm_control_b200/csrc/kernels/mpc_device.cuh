@@ -28,14 +28,17 @@ struct PointWs {
   double pf[4][3], d[4][3], Jl[4][9], al[4][9];   // Jl[i][3*j + a]: component a of leg-Jacobian column j of foot i
 };
 
-__device__ __forceinline__ int foot_of_leg_joint(const DevModel* __restrict__ mdl, int j) { return mdl->leg_foot[j / 3]; }
+// leg (joint order LF, LH, RF, RH) → foot (contact order) map packed two bits per leg: loaded once per kernel, every lookup is then pure ALU
+// (the map sits in front of shared-memory indexing in the flat stage-record sweeps, so a global load per lookup is a dependent chain)
+__device__ __forceinline__ int pack_leg_foot(const DevModel* __restrict__ mdl) { return mdl->leg_foot[0] | (mdl->leg_foot[1] << 2) | (mdl->leg_foot[2] << 4) | (mdl->leg_foot[3] << 6); }
+__device__ __forceinline__ int foot_of_leg_joint(int lfp, int j) { return (lfp >> (2 * (j / 3))) & 3; }
 
 // Evaluate the flow map (and its Jacobian rows if with_jac) at (ws->x, ws->u).
 // max_depth: 6 = whole tree, 3 = base + legs (the flow map does not see the arm links; only the end-effector cost does).
 // The base-frame algebra is spread over lanes wherever it is data parallel (entries of 3x3 products, the three euler columns): a
 // single-lane restatement costs ~4x the instructions and the LQ / line-search kernels are issue-latency bound.
 template <bool with_jac>
-__device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, PointWs* ws, int lane, int max_depth = 6) {
+__device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, PointWs* ws, int lane, int lfp, int max_depth = 6) {
   rbd_kinematics<false>(mdl, ws->x + 6, (const double*)nullptr, &ws->kin, lane, max_depth);
   const double m = mdl->total_mass; const double* tr = ws->kin.trig; const double* R = ws->kin.R[0]; const double* ha = ws->x + 3;
   if (lane == 0) { euler_rate_map_sc(tr, ws->T); inv3(ws->T, ws->Tinv); }
@@ -102,7 +105,7 @@ __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, Poi
       const int r = e / NX, col = e % NX; double v = 0.0;
       if (r < 3) {
         if (col >= 9 && col < 12) v = ws->hth[col - 9][r];
-        else if (col >= 12 && col < 24) { const int j = col - 12; const int i = foot_of_leg_joint(mdl, j); const double* J = ws->Jl[i] + 3 * (j % 3); const double* F = ws->u + 3 * i;
+        else if (col >= 12 && col < 24) { const int j = col - 12; const int i = foot_of_leg_joint(lfp, j); const double* J = ws->Jl[i] + 3 * (j % 3); const double* F = ws->u + 3 * i;
           v = ((r == 0) ? J[1] * F[2] - J[2] * F[1] : (r == 1 ? J[2] * F[0] - J[0] * F[2] : J[0] * F[1] - J[1] * F[0])) / m; }
       } else if (r < 6) {
         const int a = r - 3; if (col < 3) v = (a == col) ? 1.0 : 0.0; else if (col < 6) v = ws->Mpc[3 * a + col - 3]; else if (col >= 9 && col < 12) v = ws->vp[col - 9][a];

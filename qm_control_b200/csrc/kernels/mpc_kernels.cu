@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL; int32_t* si = stage_i + ((size_t)b * nmax + k) * STAGE_INT;
   const int ne = p.n_events[b]; const double* ev = sm.ev; const unsigned char* modes = sm.modes;
   { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
+  const int lfp = pack_leg_foot(mdl);
   const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
   const bool terminal = (k == n - 1);
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   // instruction-fetch sensitive (straight-line code of several hundred KB), so the pass loop is deliberately not unrolled.
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-  point_eval<true>(mdl, &sm.pt, lane, pass == 0 ? 6 : 3);   // the second RK2 stage needs the flow map only: no arm links
+  point_eval<true>(mdl, &sm.pt, lane, lfp, pass == 0 ? 6 : 3);   // the second RK2 stage needs the flow map only: no arm links
   LQ_LOCKSTEP();
   if (pass == 1) break;
   // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   if (lane < NU) {
     double sv = sm.quad.rf[lane];
     if (lane < 12) { const int f = lane / 3; for (int a = 0; a < 3; ++a) sv += quad_R(mdl, &sm.quad, lane, 3 * f + a) * sm.Pe_full[3 * f + a]; }
-    else if (lane < 24) { const int i = foot_of_leg_joint(mdl, lane - 12); sv = sm.leg[i].rs[(lane - 12) % 3]; }
+    else if (lane < 24) { const int i = foot_of_leg_joint(lfp, lane - 12); sv = sm.leg[i].rs[(lane - 12) % 3]; }
     sm.rs[lane] = sv;
   }
   LQ_LOCKSTEP();
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
       }
     }
     if (r >= 12 && r < 24) {     // dependent joint-velocity rows: I + dtw * Px
-      const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3;
+      const int i = foot_of_leg_joint(lfp, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3;
       if (L.dep[j]) bt += dtw * L.Pe[j];
     }
     if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw / mass) * sm.Pe_full[3 * f + r];
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     const int r = e / NX, c = e - r * NX; double v = (c == r) ? 1.0 : 0.0;
     if (r >= 3 && r < 12) v += sm.A1r[(r - 3) * NX + c];
     else if (r >= 12 && r < 24) {
-      const LegWs& L = sm.leg[foot_of_leg_joint(mdl, r - 12)]; const int j = (r - 12) % 3;
+      const LegWs& L = sm.leg[foot_of_leg_joint(lfp, r - 12)]; const int j = (r - 12) % 3;
       const int pos = c < 6 ? c : ((c >= 9 && c < 12) ? c - 3 : ((c >= 12 + L.first && c < 15 + L.first) ? 9 + c - 12 - L.first : -1));   // inverse of sup_col
       if (L.dep[j] && pos >= 0) v += dtw * L.Px[j][pos];
     }
@@ -269,8 +270,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     const int r = e / MU, a = e - r * MU; double v = 0.0;
     if (a < m) { const int fa = sm.free_idx[a];
       if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw / mass : 0.0;
-      else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(mdl, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
-      else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(mdl, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
+      else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
+      else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(lfp, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
     }
     sg[ST_B + e] = v;
   }
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rcol = sg + ST_R + a;
     if (a < m) {
       const int fa = sm.free_idx[a]; double rv = sm.rs[fa]; int li = -1, jf = -1;
-      if (fa >= 12 && fa < 24) { li = foot_of_leg_joint(mdl, fa - 12); jf = (fa - 12) % 3; }
+      if (fa >= 12 && fa < 24) { li = foot_of_leg_joint(lfp, fa - 12); jf = (fa - 12) % 3; }
       const bool swing_joint = li >= 0 && !sm.leg[li].stance;
       if (swing_joint) {   // free joint of a swing leg: coupled to the pivot through R_leg and Pu
         const LegWs& L = sm.leg[li]; const int pv = L.pivot; const double pu = L.Pu2[jf > pv ? jf - 1 : jf];
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   if (lane < MAXDEP) {
     const int d = lane; double pe = 0.0; int di = -1;
     if (d < ndep) { di = sm.dep_idx[d]; pe = sm.Pe_full[di];
-      if (di >= 12) { const int i = foot_of_leg_joint(mdl, di - 12); const LegWs& L = sm.leg[i]; const int j = (di - 12) % 3;
+      if (di >= 12) { const int i = foot_of_leg_joint(lfp, di - 12); const LegWs& L = sm.leg[i]; const int j = (di - 12) % 3;
         for (int c = 0; c < 12; ++c) sg[ST_PXD + (size_t)d * NX + sup_col(c, L.first)] = L.Px[j][c];
         if (!L.stance) { int nf = 0; for (int jj = 0; jj < 3; ++jj) if (jj != L.pivot) { sg[ST_PUD + (size_t)d * MU + L.free_col[jj]] = L.Pu2[nf++]; } } } }
     sg[ST_PED + d] = pe; si[SI_DEP + d] = di;
@@ -620,6 +621,7 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const 
   double* gx = sol.x + (size_t)b * nmax * NX; double* gu = sol.u + (size_t)b * nmax * NU; const double* gdx = dxo + (size_t)b * nmax * NX; const double* gdu = duo + (size_t)b * nmax * NU;
   const int ne = p.n_events[b]; const double* ev = sm.ev; const unsigned char* modes = sm.modes;
   { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
+  const int lfp = pack_leg_foot(mdl);
   const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* rb = robot + (size_t)b * ROBOT_DBL; const double armijo = rb[0], base_cost = rb[1], base_viol = sqrt(rb[2] + rb[3]), dxn = rb[4], dun = rb[5];
   const bool failed = (status[b] & MST_NOT_PD) != 0;
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const 
       bool done = false;
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {   // one inlined copy of the flow map for both RK2 stages (instruction-fetch footprint)
-        point_eval<false>(mdl, &sm.pt, lane, pass == 0 ? 6 : 3);
+        point_eval<false>(mdl, &sm.pt, lane, lfp, pass == 0 ? 6 : 3);
         if (pass == 1) break;
         TargetRef ref = target_reference(tt, ts, nk, t, lane);
         cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, terminal, lane);
