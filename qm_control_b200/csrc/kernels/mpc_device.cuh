@@ -40,7 +40,8 @@ __device__ __forceinline__ int foot_of_leg_joint(int lfp, int j) { return (lfp >
 template <bool with_jac>
 __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, PointWs* ws, int lane, int lfp, int max_depth = 6) {
   rbd_kinematics<false>(mdl, ws->x + 6, (const double*)nullptr, &ws->kin, lane, max_depth);
-  const double m = mdl->total_mass; const double* tr = ws->kin.trig; const double* R = ws->kin.R[0]; const double* ha = ws->x + 3;
+  // fp64 division is a ~30-instruction subroutine: divide once (im), multiply everywhere
+  const double m = mdl->total_mass, im = 1.0 / m; const double* tr = ws->kin.trig; const double* R = ws->kin.R[0]; const double* ha = ws->x + 3;
   if (lane == 0) { euler_rate_map_sc(tr, ws->T); inv3(ws->T, ws->Tinv); }
   if (lane < 9) {   // W = m R I_nom^{-1} R' , entry (i, jj)
     const int i = lane / 3, jj = lane - 3 * i; const double* Ii = mdl->I_nom_inv; double acc = 0.0;
@@ -82,18 +83,18 @@ __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, Poi
     const int first = mdl->foot_leg[i];
     for (int j = 0; j < 3; ++j) { const double* S = ws->kin.S[6 + first + j]; const double* o = ws->kin.p[first + j + 1]; const double r[3] = {pw[0] - o[0], pw[1] - o[1], pw[2] - o[2]}; double col[3]; cross3(S, r, col);
       for (int a = 0; a < 3; ++a) { ws->Jl[i][3 * j + a] = col[a]; ws->al[i][3 * j + a] = S[a]; } }
-    if (with_jac) { for (int a = 0; a < 3; ++a) { const double ea[3] = {a == 0 ? 1.0 : 0.0, a == 1 ? 1.0 : 0.0, a == 2 ? 1.0 : 0.0}; double col[3]; cross3(ws->d[i], ea, col); for (int r = 0; r < 3; ++r) ws->Bh[r * 12 + 3 * i + a] = col[r] / m; } }
+    if (with_jac) { for (int a = 0; a < 3; ++a) { const double ea[3] = {a == 0 ? 1.0 : 0.0, a == 1 ? 1.0 : 0.0, a == 2 ? 1.0 : 0.0}; double col[3]; cross3(ws->d[i], ea, col); for (int r = 0; r < 3; ++r) ws->Bh[r * 12 + 3 * i + a] = col[r] * im; } }
   }
   __syncwarp();
   if (with_jac && lane < 3) {   // sum_i (T_k x d_i) x F_i / m
     const int k = lane; const double Tk[3] = {ws->T[k], ws->T[3 + k], ws->T[6 + k]}; double acc[3] = {0, 0, 0};
     for (int i = 0; i < 4; ++i) { double t[3]; cross3(Tk, ws->d[i], t); cross3_add(t, ws->u + 3 * i, acc); }
-    for (int a = 0; a < 3; ++a) ws->hth[k][a] = acc[a] / m;
+    for (int a = 0; a < 3; ++a) ws->hth[k][a] = acc[a] * im;
   }
   if (lane < NX) {
     double val;
-    if (lane < 3) { val = (ws->u[lane] + ws->u[3 + lane] + ws->u[6 + lane] + ws->u[9 + lane]) / m + (lane == 2 ? -9.81 : 0.0); }
-    else if (lane < 6) { const int a = lane - 3; double acc = 0.0; for (int i = 0; i < 4; ++i) { const double* d = ws->d[i]; const double* F = ws->u + 3 * i; acc += (a == 0) ? d[1] * F[2] - d[2] * F[1] : (a == 1 ? d[2] * F[0] - d[0] * F[2] : d[0] * F[1] - d[1] * F[0]); } val = acc / m; }
+    if (lane < 3) { val = (ws->u[lane] + ws->u[3 + lane] + ws->u[6 + lane] + ws->u[9 + lane]) * im + (lane == 2 ? -9.81 : 0.0); }
+    else if (lane < 6) { const int a = lane - 3; double acc = 0.0; for (int i = 0; i < 4; ++i) { const double* d = ws->d[i]; const double* F = ws->u + 3 * i; acc += (a == 0) ? d[1] * F[2] - d[2] * F[1] : (a == 1 ? d[2] * F[0] - d[0] * F[2] : d[0] * F[1] - d[1] * F[0]); } val = acc * im; }
     else if (lane < 9) { const int a = lane - 6; const double* o = ws->omega; const double* c = ws->c; const double oc = (a == 0) ? o[1] * c[2] - o[2] * c[1] : (a == 1 ? o[2] * c[0] - o[0] * c[2] : o[0] * c[1] - o[1] * c[0]); val = ws->x[a] + oc; }
     else if (lane < 12) val = ws->thd[lane - 9];
     else val = ws->u[lane];
@@ -106,7 +107,7 @@ __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, Poi
       if (r < 3) {
         if (col >= 9 && col < 12) v = ws->hth[col - 9][r];
         else if (col >= 12 && col < 24) { const int j = col - 12; const int i = foot_of_leg_joint(lfp, j); const double* J = ws->Jl[i] + 3 * (j % 3); const double* F = ws->u + 3 * i;
-          v = ((r == 0) ? J[1] * F[2] - J[2] * F[1] : (r == 1 ? J[2] * F[0] - J[0] * F[2] : J[0] * F[1] - J[1] * F[0])) / m; }
+          v = ((r == 0) ? J[1] * F[2] - J[2] * F[1] : (r == 1 ? J[2] * F[0] - J[0] * F[2] : J[0] * F[1] - J[1] * F[0])) * im; }
       } else if (r < 6) {
         const int a = r - 3; if (col < 3) v = (a == col) ? 1.0 : 0.0; else if (col < 6) v = ws->Mpc[3 * a + col - 3]; else if (col >= 9 && col < 12) v = ws->vp[col - 9][a];
       } else {
@@ -142,12 +143,12 @@ template <class MT> __device__ __forceinline__ bool swing_reference(const DevMod
   const double t0 = ev[start], t1 = ev[fin]; const double scaling = fmin(1.0, (t1 - t0) / mdl->swing_time_scale); const double tm = 0.5 * (t0 + t1), zm = scaling * mdl->swing_height;
   double ta, pa, va, tb, pb, vb;
   if (t < tm) { ta = t0; pa = 0.0; va = scaling * mdl->lift_off_velocity; tb = tm; pb = zm; vb = 0.0; } else { ta = tm; pa = zm; va = 0.0; tb = t1; pb = 0.0; vb = scaling * mdl->touch_down_velocity; }
-  const double dtt = tb - ta, dp = pb - pa, dv = vb - va; const double c0 = pa, c1 = va * dtt, c2 = -(3.0 * va + dv) * dtt + 3.0 * dp, c3 = (2.0 * va + dv) * dtt - 2.0 * dp; const double tn = (t - ta) / dtt;
-  zp = ((c3 * tn + c2) * tn + c1) * tn + c0; zv = ((3.0 * c3 * tn + 2.0 * c2) * tn + c1) / dtt; return true;
+  const double dtt = tb - ta, dp = pb - pa, dv = vb - va; const double c0 = pa, c1 = va * dtt, c2 = -(3.0 * va + dv) * dtt + 3.0 * dp, c3 = (2.0 * va + dv) * dtt - 2.0 * dp; const double idt = 1.0 / dtt, tn = (t - ta) * idt;
+  zp = ((c3 * tn + c2) * tn + c1) * tn + c0; zv = ((3.0 * c3 * tn + 2.0 * c2) * tn + c1) * idt; return true;
 }
 // ocs2 RelaxedBarrierPenalty [upstream]
 __device__ __forceinline__ void relaxed_barrier(double mu, double delta, double h, double& p0, double& p1, double& p2) {
-  if (h > delta) { p0 = -mu * log(h); p1 = -mu / h; p2 = mu / (h * h); }
+  if (h > delta) { const double ih = 1.0 / h; p0 = -mu * log(h); p1 = -mu * ih; p2 = mu * ih * ih; }
   else { const double t = (h - 2.0 * delta) / delta; p0 = mu * (-log(delta) + 0.5 * t * t - 0.5); p1 = mu * (h - 2.0 * delta) / (delta * delta); p2 = mu / (delta * delta); }
 }
 
@@ -164,7 +165,7 @@ __device__ __forceinline__ TargetRef target_reference(const double* tt, const do
   if (nk > 1) {
     const double* ql = l + 33; const double* qr = rr + 33; const double tq = 1.0 - a; double d = 0.0; for (int i = 0; i < 4; ++i) d += ql[i] * qr[i];
     const double ad = fabs(d); double s0, s1;
-    if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - tq; s1 = tq; } else { const double th = acos(ad), st = sin(th); s0 = sin((1.0 - tq) * th) / st; s1 = sin(tq * th) / st; }
+    if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - tq; s1 = tq; } else { const double th = acos(ad), st = sin(th); const double ist = 1.0 / st; s0 = sin((1.0 - tq) * th) * ist; s1 = sin(tq * th) * ist; }
     if (d < 0.0) s1 = -s1; for (int i = 0; i < 4; ++i) r.qref[i] = s0 * ql[i] + s1 * qr[i];
   } else { for (int i = 0; i < 4; ++i) r.qref[i] = l[33 + i]; }
   return r;
@@ -194,10 +195,10 @@ __device__ __forceinline__ void ee_error(const DevModel* __restrict__ mdl, const
     for (int a = 0; a < 3; ++a) { pw[a] += ws->kin.p[body][a]; cw->pee[a] = pw[a]; cw->e[a] = pw[a] - ref.pref[a]; }
     // rotation → quaternion (w,x,y,z); sign free (quadratic penalty), same q used for e and its Jacobian
     double q[4]; const double tr = R[0] + R[4] + R[8];
-    if (tr > 0.0) { const double s = sqrt(tr + 1.0) * 2.0; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
-    else if (R[0] > R[4] && R[0] > R[8]) { const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
-    else if (R[4] > R[8]) { const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
-    else { const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+    if (tr > 0.0) { const double s = sqrt(tr + 1.0) * 2.0, is = 1.0 / s; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) * is; q[2] = (R[2] - R[6]) * is; q[3] = (R[3] - R[1]) * is; }
+    else if (R[0] > R[4] && R[0] > R[8]) { const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0, is = 1.0 / s; q[0] = (R[7] - R[5]) * is; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) * is; q[3] = (R[2] + R[6]) * is; }
+    else if (R[4] > R[8]) { const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0, is = 1.0 / s; q[0] = (R[2] - R[6]) * is; q[1] = (R[1] + R[3]) * is; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) * is; }
+    else { const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0, is = 1.0 / s; q[0] = (R[3] - R[1]) * is; q[1] = (R[2] + R[6]) * is; q[2] = (R[5] + R[7]) * is; q[3] = 0.25 * s; }
     for (int i = 0; i < 4; ++i) cw->quat[i] = q[i];
     const double* rv = ref.qref; const double rw = ref.qref[3]; const double* qv = q + 1; double cr[3]; cross3(qv, rv, cr);
     for (int a = 0; a < 3; ++a) cw->e[3 + a] = q[0] * rv[a] - rw * qv[a] + cr[a];   // ocs2 quaternionDistance(q, qRef) [upstream]
@@ -269,10 +270,10 @@ __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, c
     if (lane >= 12 && lane < 16) {
       const int i = lane - 12;
       if ((flagmask >> i) & 1) {
-        const double Fx = ws->u[3 * i], Fy = ws->u[3 * i + 1], Fz = ws->u[3 * i + 2]; const double n2 = Fx * Fx + Fy * Fy + mdl->friction_reg, n = sqrt(n2), n32 = n * n2;
+        const double Fx = ws->u[3 * i], Fy = ws->u[3 * i + 1], Fz = ws->u[3 * i + 2]; const double n2 = Fx * Fx + Fy * Fy + mdl->friction_reg, n = sqrt(n2), in = 1.0 / n, in32 = in * in * in;
         const double h = mdl->friction_mu * Fz - n; double p0, p1, p2; relaxed_barrier(mdl->friction_barrier_mu, mdl->friction_barrier_delta, h, p0, p1, p2); bv = p0;
         if (with_quad) {
-          const double g[3] = {-Fx / n, -Fy / n, mdl->friction_mu}; const double H2[9] = {-(Fy * Fy + mdl->friction_reg) / n32, Fx * Fy / n32, 0, Fx * Fy / n32, -(Fx * Fx + mdl->friction_reg) / n32, 0, 0, 0, 0};
+          const double g[3] = {-Fx * in, -Fy * in, mdl->friction_mu}; const double H2[9] = {-(Fy * Fy + mdl->friction_reg) * in32, Fx * Fy * in32, 0, Fx * Fy * in32, -(Fx * Fx + mdl->friction_reg) * in32, 0, 0, 0, 0};
           for (int a = 0; a < 3; ++a) { qw->rf[3 * i + a] += p1 * g[a]; for (int b = 0; b < 3; ++b) qw->fric[i * 9 + 3 * a + b] = p2 * g[a] * g[b] + p1 * H2[3 * a + b]; }
           shift = -p1 * mdl->friction_hess_shift;
         }

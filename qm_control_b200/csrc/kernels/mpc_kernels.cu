@@ -183,10 +183,10 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
         for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.el.e.con.C[i][a][c]; L.Px[j][c] = sv; } }
     } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
       for (int a = 0; a < 3; ++a) sm.Pe_full[3 * i + a] = -sm.pt.u[3 * i + a];
-      const double piv = sm.pt.Jl[i][3 * pivot + 2];
-      L.Pe[pivot] = -sm.el.e.con.e[i][2] / piv; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
-      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = -sm.el.e.con.C[i][2][c] / piv;
-      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = -sm.pt.Jl[i][3 * j + 2] / piv;
+      const double piv = sm.pt.Jl[i][3 * pivot + 2], nip = -1.0 / piv;
+      L.Pe[pivot] = sm.el.e.con.e[i][2] * nip; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
+      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = sm.el.e.con.C[i][2][c] * nip;
+      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = sm.pt.Jl[i][3 * j + 2] * nip;
     }
     // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
     for (int a = 0; a < 3; ++a) { double sv = sm.quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   if (lane < NX) sm.pt.x[lane] = sm.xs[lane] + mdl->rk_c * dt * sm.f1[lane];
   __syncwarp();
   }
-  const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2);
+  const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2), imass = 1.0 / mass;
   double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.el.l.bvec[lane] = bb; }   // defect
   const double dyn_ss = warp_sum(bb * bb);
   // A_d - I (rows 3:12) = dt (w1 A1 + w2 (A2 + c dt A2 A1)) ; B_d rows 3:12 = dt (w1 B1 + w2 (B2 + c dt A2 B1)): force columns (9x12), joint columns only in the h_ang rows (3x18)
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
 #pragma unroll
       for (int q = 0; q < 9; ++q) aa = fma(a2[3 + q], a1[q], aa);
       out[r] = dt * (w1 * a1[r] + w2 * (a2[c] + cdt * aa));
-      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } double ab = a2[c % 3] / mass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; sm.el.l.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
+      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } double ab = a2[c % 3] * imass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; sm.el.l.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
       else if (r < 3) sm.el.l.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c]; }
 #pragma unroll
     for (int r = 0; r < 9; ++r) sm.A1r[r * NX + c] = out[r];
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
       const int i = foot_of_leg_joint(lfp, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3;
       if (L.dep[j]) bt += dtw * L.Pe[j];
     }
-    if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw / mass) * sm.Pe_full[3 * f + r];
+    if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw * imass) * sm.Pe_full[3 * f + r];
     if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.el.l.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
     sg[ST_b + r] = bt;
   }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   for (int e = lane; e < NX * MU; e += 32) {
     const int r = e / MU, a = e - r * MU; double v = 0.0;
     if (a < m) { const int fa = sm.free_idx[a];
-      if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw / mass : 0.0;
+      if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw * imass : 0.0;
       else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
       else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(lfp, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
     }
