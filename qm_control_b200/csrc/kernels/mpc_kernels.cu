@@ -320,9 +320,10 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     sg[ST_q + r] = dt * qv;
   }
   LQ_LOCKSTEP();
-  for (int e = lane; e < MU * NX; e += 32) sg[ST_S + e] = 0.0;   // S~ is zero except the swing-joint rows written below
+  static_assert(ST_S == ST_R + MU * MU, "R~ and S~ are zero-filled in one sweep");
+  for (int e = lane; e < MU * MU + MU * NX; e += 32) sg[ST_R + e] = 0.0;   // R~ (block sparse) and S~ (swing-joint rows only) are mostly zero: coalesced fill, sparse entries below
   __syncwarp();
-  if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu (symmetric: lane a stores column a, one contiguous row per store instruction)
+  if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu (symmetric: lane a stores into column a)
     const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rcol = sg + ST_R + a;
     if (a < m) {
       const int fa = sm.free_idx[a]; double rv = sm.rs[fa]; int li = -1, jf = -1;
@@ -335,14 +336,15 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
         for (int c = 0; c < 12; ++c) Srow[sup_col(c, L.first)] = dt * (coef * L.Px[pv][c] + pu * L.U[pv][c]);
       }
       sg[ST_r + a] = dt * rv;
-      for (int c = 0; c < MU; ++c) {
-        double v = 0.0;
-        if (c < m) { const int fc = sm.free_idx[c]; v = quad_R(mdl, &sm.quad, fa, fc);
-          if (swing_joint && fc >= 12 + sm.leg[li].first && fc < 15 + sm.leg[li].first) { const LegWs& L = sm.leg[li]; const int pv = L.pivot; const int jc = fc - 12 - L.first; const double pa = L.Pu2[jf > pv ? jf - 1 : jf], pc = L.Pu2[jc > pv ? jc - 1 : jc];
-            v += pa * L.Rl[3 * pv + jc] + L.Rl[3 * jf + pv] * pc + pa * L.Rl[3 * pv + pv] * pc; } }
-        Rcol[(size_t)c * MU] = dt * v;
-      }
-    } else { sg[ST_r + a] = 0.0; for (int c = 0; c < MU; ++c) Rcol[(size_t)c * MU] = (c == a) ? 1.0 : 0.0; }
+      // R is block diagonal (3x3 blocks over force / leg-joint triples, diagonal over the arm): only the free inputs of fa's own block contribute to row a
+      if (fa >= 24) Rcol[(size_t)a * MU] = dt * quad_R(mdl, &sm.quad, fa, fa);
+      else { const int bi = fa / 3;
+        for (int jc = 0; jc < 3; ++jc) { const int fc = 3 * bi + jc; const int c = sm.col_of_input[fc]; if (c < 0) continue;
+          double v = quad_R(mdl, &sm.quad, fa, fc);
+          if (swing_joint) { const LegWs& L = sm.leg[li]; const int pv = L.pivot; const double pa = L.Pu2[jf > pv ? jf - 1 : jf], pc = L.Pu2[jc > pv ? jc - 1 : jc];
+            v += pa * L.Rl[3 * pv + jc] + L.Rl[3 * jf + pv] * pc + pa * L.Rl[3 * pv + pv] * pc; }
+          Rcol[(size_t)c * MU] = dt * v; } }
+    } else { sg[ST_r + a] = 0.0; Rcol[(size_t)a * MU] = 1.0; }
   }
   // projection data for the forward pass: dense rows of Px / Pu / Pe of the dependent inputs
   for (int e = lane; e < MAXDEP * NX; e += 32) sg[ST_PXD + e] = 0.0;
@@ -391,9 +393,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 // rows x cols doubles (cols even, 16-B aligned rows on both sides) global → shared, spread over threads tid = 0..nthr-1
+// (every caller copies a dense block, gs == cols: the global side is one contiguous run of 16-byte chunks, chunk e at g + 2e; only the padded
+// shared-memory side needs the (row, chunk) split.  The shared-window address is converted once per call, not once per chunk.)
 __device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, int cols, int gs, double* s, int ls, int tid, int nthr = RIC_THREADS) {
-  const int cpr = cols >> 1;
-  for (int e = tid; e < rows * cpr; e += nthr) { const int i = e / cpr, c = e - i * cpr; cp_async16(s + i * ls + 2 * c, g + (size_t)i * gs + 2 * c); }
+  const int cpr = cols >> 1; const unsigned sbase = (unsigned)__cvta_generic_to_shared(s); (void)gs;
+  for (int e = tid; e < rows * cpr; e += nthr) { const int i = e / cpr, c = e - i * cpr;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + 8u * (unsigned)(i * ls + 2 * c)), "l"(g + 2 * e)); }
 }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
