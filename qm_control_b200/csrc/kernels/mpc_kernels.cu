@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
 // broadcasts), stage records prefetched with cp.async while the previous phases compute, Cholesky + triangular solves
 // warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
 // LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
-constexpr int RIC_THREADS = 128;
+constexpr int RIC_THREADS = 128, RIC_NTYPE = 512;
 // Leading dimensions.  MMA operands are fetched as X[(k0 + t) * ld + c0 + g] (t = lane % 4, g = lane / 4): 2 * ld = 8 (mod 32) or
 // 24 (mod 32) puts the four k-rows of a half-warp on disjoint bank octets, i.e. every fragment load is conflict free.
 constexpr int LDX = 36, LDB = 28, LDG = 34, LDH = 24;
@@ -383,7 +383,9 @@ struct RicSmem {
   double Lt[MU * MU];                       // Cholesky factor of H, transposed: Lt[c][a] = L[a][c] (strict lower part; pivots live as reciprocals in dut)
   double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32], kff2[32];   // rollout vectors (two buffer sets)
   double red[RIC_THREADS / 32][4];
-  int flag;
+  int flag; int pad_;
+  alignas(16) int32_t sib[2][STAGE_INT];    // forward pass: the node's integer record (type, m, ndep, dependent / free input indices), prefetched with the matrices
+  unsigned char ntype[RIC_NTYPE];           // node types of the whole horizon, loaded once: the sweep's control flow never waits on a global load
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -452,6 +454,9 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
   for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
   __syncthreads();
+  const bool types_in_smem = n <= RIC_NTYPE;
+  if (types_in_smem) for (int k = tid; k < n; k += RIC_THREADS) sm.ntype[k] = (unsigned char)sib[(size_t)k * STAGE_INT + SI_TYPE];   // published by the barrier below
+  auto node_type = [&](int k) -> int { return types_in_smem ? (int)sm.ntype[k] : sib[(size_t)k * STAGE_INT + SI_TYPE]; };
   auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDX, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
     if (tid < NX) cp_async8(sm.A + tid * LDX + NX, sg + ST_b + tid); cp_async_commit(); };                                 // b~ rides in column 30 of A~
   auto issue_sr = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_S, MU, NX, NX, sm.G, LDG, tid); cp_rows(sg + ST_R, MU, MU, MU, sm.H, LDH, tid);
@@ -477,7 +482,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   // the matrices (b~, p + P b~, h, q~, p), so no separate matrix-vector products are needed.
   const int g = lane >> 2, t = lane & 3;
   for (int k = N - 1; k >= 0; --k) {
-    const int type = sib[(size_t)k * STAGE_INT + SI_TYPE];
+    const int type = node_type(k);
     cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed; P of node k+1 is complete
     if (type == 1) {                                // event node: A = I, no input: p += P b
       if (tid < NX) { double sv = sm.P[tid * LDX + NX]; for (int j = 0; j < NX; ++j) sv = fma(sm.P[tid * LDX + j], sm.A[j * LDX + NX], sv); sm.tmp[tid] = sv; }
@@ -555,7 +560,8 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   if (!(st & MST_NOT_PD)) {
     // two buffer sets (k & 1): {G, A, Bm, b, q, r, kff} and {W, P, PB, pPb, p, h, kff2}; node k+1 streams in while node k is applied
     auto issue_fwd = [&](int k) {
-      if (k < N && sib[(size_t)k * STAGE_INT + SI_TYPE] != 1) {
+      if (k < N && tid < STAGE_INT / 4) cp_async16(sm.sib[k & 1] + 4 * tid, sib + (size_t)k * STAGE_INT + 4 * tid);
+      if (k < N && node_type(k) != 1) {
         const double* sg = sgb + (size_t)k * STAGE_DBL; const double* gk = gb + (size_t)k * GAIN_DBL; const bool o = k & 1;
         cp_rows(gk, MU, NX, NX, o ? sm.W : sm.G, LDG, tid); cp_rows(sg + ST_A, NX, NX, NX, o ? sm.P : sm.A, LDX, tid); cp_rows(sg + ST_B, NX, MU, MU, o ? sm.PB : sm.Bm, LDB, tid);
         if (tid < 15) cp_async16((o ? sm.pPb : sm.b) + 2 * tid, sg + ST_b + 2 * tid); else if (tid < 30) cp_async16((o ? sm.p : sm.q) + 2 * (tid - 15), sg + ST_q + 2 * (tid - 15));
@@ -564,13 +570,14 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       cp_async_commit(); };
     issue_fwd(0);
     for (int k = 0; k < N; ++k) {
-      const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sib + (size_t)k * STAGE_INT; const int type = si[SI_TYPE], ndep = si[SI_NDEP];
+      const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sm.sib[k & 1]; const int type = node_type(k);
       double* dxk = dxo + ((size_t)b * nmax + k) * NX; double* duk = duo + ((size_t)b * nmax + k) * NU;
       // dx is double buffered (sm.dx / sm.tmp): the next state is written into the other buffer, and the barrier at the top of the next
       // iteration publishes it - two barriers per node instead of four
       const double* dxc = (k & 1) ? sm.tmp : sm.dx; double* dxn = (k & 1) ? sm.dx : sm.tmp;
       cp_async_wait<0>(); __syncthreads();   // stage record k has landed; dx(k) (written by other threads in the previous iteration) is visible; nobody reads buffer set (k+1)&1 any more
       issue_fwd(k + 1);
+      const int ndep = si[SI_NDEP];
       if (tid < NX) { const double dxi = dxc[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
       if (type == 1) { if (tid < NX) { duk[tid] = 0.0; dxn[tid] = dxc[tid] + sg[ST_b + tid]; } continue; }
       const bool o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* Ab = o ? sm.P : sm.A; const double* Bb = o ? sm.PB : sm.Bm;
