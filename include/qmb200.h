@@ -81,6 +81,15 @@ int qmb200_wbc_update_dev(qmb200_handle* h, const double* x_des, const double* u
 int qmb200_wbc_set_input_last(qmb200_handle* h, const double* input_last /*[B][30] or NULL*/);
 int qmb200_wbc_get_input_last(qmb200_handle* h, double* input_last /*[B][30]*/);
 
+/* WbcBase::dynamicCallback (qm_wbc/src/WbcBase.cpp:69-117, qm_wbc/cfg/wbcWigeht.cfg:7-47): the PD gains of the task formulators, replaceable at run time.
+ * Takes effect for the next wbc_update / tick / update call on the handle's stream. */
+typedef struct {
+  double kp_swing, kd_swing, base_height_kp, base_height_kd, kp_base_linear, kd_base_linear, kp_base_angular, kd_base_angular;
+  double kp_arm_joint[6], kd_arm_joint[6], kp_ee_linear[3], kd_ee_linear[3], kp_ee_angular[3], kd_ee_angular[3];
+} qmb200_wbc_gains;
+int qmb200_wbc_get_gains(const qmb200_handle* h, qmb200_wbc_gains* out);
+int qmb200_wbc_set_gains(qmb200_handle* h, const qmb200_wbc_gains* gains);
+
 /* ---- MPC seam: ocs2::MPC_BASE::run → SqpSolver::run(t0, x0, t0+T), one SQP iteration (QMController.cpp:287-288,315-332),
  *      with the inputs the reference manager holds: mode schedule (SwitchedModelReferenceManager) and TargetTrajectories.
  *      The previous PrimalSolution (warm start, mpc.coldStart=false) lives in the handle. */

@@ -1,4 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and its stack (OCS2 / Pinocchio / qpOASES / HPIPM) cannot be
+// built here, so this restatement is not checked against reference outputs; DESIGN.md section 5 lists the pins used instead
+// (known answers from the reference's own config, an independent numpy/scipy twin, finite-difference identities, tests/golden).
 // C entry points (ctypes) of the CPU oracle.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load this library; the product never does.
 #include <atomic>

@@ -1,4 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and its stack (OCS2 / Pinocchio / qpOASES / HPIPM) cannot be
+// built here, so this restatement is not checked against reference outputs; DESIGN.md section 5 lists the pins used instead
+// (known answers from the reference's own config, an independent numpy/scipy twin, finite-difference identities, tests/golden).
 // Single-rigid-body centroidal model helpers [upstream ocs2_centroidal_model, recalled — SURVEY.md App. A.2]:
 // updateCentroidalDynamics (SRBD branch), computeFloatingBaseCentroidalMomentumMatrixInverse,
 // CentroidalModelPinocchioMapping::getPinocchioJointVelocity, getNormalizedCentroidalMomentumRate and the

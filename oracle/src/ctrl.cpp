@@ -1,4 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// Parity of this file: the functions restated here are reference-OWNED sources (cited line by line), pinned by the independent scipy
+// transliteration in tests/test_ctrl_cpu.py; the upstream helpers they call (angles, ocs2 rotations) are recalled, i.e. PARITY UNPINNED.
 // CPU restatement of the controller steps either side of the MPC+WBC path, one robot per call, written against the
 // reference sources line by line (they are reference-owned code, not upstream):
 //   observation_update      QMController::updateStateEstimation tail           qm_controllers/src/QMController.cpp:236-243

@@ -1,4 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and its stack (OCS2 / Pinocchio / qpOASES / HPIPM) cannot be
+// built here, so this restatement is not checked against reference outputs; DESIGN.md section 5 lists the pins used instead
+// (known answers from the reference's own config, an independent numpy/scipy twin, finite-difference identities, tests/golden).
 // URDF → Model (see model.h) and Jacobian-based rigid-body quantities via dual numbers.
 #include "model.h"
 

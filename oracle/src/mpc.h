@@ -1,4 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and its stack (OCS2 / Pinocchio / qpOASES / HPIPM) cannot be
+// built here, so this restatement is not checked against reference outputs; DESIGN.md section 5 lists the pins used instead
+// (known answers from the reference's own config, an independent numpy/scipy twin, finite-difference identities, tests/golden).
 // Restatement of the MPC tick: the OCP that qm_interface defines (QMInterface.cpp:79-142) solved by ONE
 // multiple-shooting SQP iteration as the controller configures it (QMController.cpp:287-288, task.info:75-92).
 // All upstream OCS2 pieces are [recalled] — see SURVEY.md Appendix A and DESIGN.md for the conventions fixed here.

@@ -1,4 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and its stack (OCS2 / Pinocchio / qpOASES / HPIPM) cannot be
+// built here, so this restatement is not checked against reference outputs; DESIGN.md section 5 lists the pins used instead
+// (known answers from the reference's own config, an independent numpy/scipy twin, finite-difference identities, tests/golden).
 // Dense convex QP   min 1/2 z'Hz + c'z   s.t.  A z <= ub      (the form HoQp hands to qpOASES:
 // qm_wbc/src/HoQp.cpp:135-150 — QProblem(nV,nC), init(H,g,A,nullptr,nullptr,nullptr,ubA), no bounds,
 // no lower constraint limits).  qpOASES@268b2f2 is not available offline (qpoases_catkin/CMakeLists.txt:27-29),

@@ -1,4 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY UNPINNED: the reference ships no tests or golden vectors for this path and its stack (OCS2 / Pinocchio / qpOASES / HPIPM) cannot be
+// built here, so this restatement is not checked against reference outputs; DESIGN.md section 5 lists the pins used instead
+// (known answers from the reference's own config, an independent numpy/scipy twin, finite-difference identities, tests/golden).
 // Restatement of qm_wbc: WbcBase (qm_wbc/src/WbcBase.cpp:118-563), Task (include/qm_wbc/Task.h:17-66),
 // HoQp (src/HoQp.cpp:12-159), HierarchicalWbc (src/HierarchicalWbc.cpp:18-44) and
 // HierarchicalMpcWbc (src/HierarchicalMpcWbc.cpp:18-34).

@@ -152,6 +152,25 @@ int qmb200_wbc_get_input_last(qmb200_handle* h, double* input_last) {
   QMB_CUDA(h, cudaMemcpyAsync(input_last, h->d_input_last, (size_t)h->B * NU * 8, cudaMemcpyDeviceToHost, h->stream)); QMB_CUDA(h, cudaStreamSynchronize(h->stream)); return 0;
 }
 
+int qmb200_wbc_get_gains(const qmb200_handle* h, qmb200_wbc_gains* g) {
+  if (!h || !g) return -1; const DevModel& d = h->hm.dev;
+  g->kp_swing = d.kp_swing; g->kd_swing = d.kd_swing; g->base_height_kp = d.base_height_kp; g->base_height_kd = d.base_height_kd; g->kp_base_linear = d.base_linear_kp; g->kd_base_linear = d.base_linear_kd;
+  g->kp_base_angular = d.base_angular_kp; g->kd_base_angular = d.base_angular_kd;
+  for (int i = 0; i < 6; ++i) { g->kp_arm_joint[i] = d.arm_joint_kp[i]; g->kd_arm_joint[i] = d.arm_joint_kd[i]; }
+  for (int i = 0; i < 3; ++i) { g->kp_ee_linear[i] = d.ee_linear_kp[i]; g->kd_ee_linear[i] = d.ee_linear_kd[i]; g->kp_ee_angular[i] = d.ee_angular_kp[i]; g->kd_ee_angular[i] = d.ee_angular_kd[i]; }
+  return 0;
+}
+int qmb200_wbc_set_gains(qmb200_handle* h, const qmb200_wbc_gains* g) {
+  if (!h) return -1; if (!g) return fail(h, "qmb200_wbc_set_gains: null gains");
+  QMB_CUDA(h, cudaSetDevice(h->device)); DevModel& d = h->hm.dev;
+  d.kp_swing = g->kp_swing; d.kd_swing = g->kd_swing; d.base_height_kp = g->base_height_kp; d.base_height_kd = g->base_height_kd; d.base_linear_kp = g->kp_base_linear; d.base_linear_kd = g->kd_base_linear;
+  d.base_angular_kp = g->kp_base_angular; d.base_angular_kd = g->kd_base_angular;
+  for (int i = 0; i < 6; ++i) { d.arm_joint_kp[i] = g->kp_arm_joint[i]; d.arm_joint_kd[i] = g->kd_arm_joint[i]; }
+  for (int i = 0; i < 3; ++i) { d.ee_linear_kp[i] = g->kp_ee_linear[i]; d.ee_linear_kd[i] = g->kd_ee_linear[i]; d.ee_angular_kp[i] = g->kp_ee_angular[i]; d.ee_angular_kd[i] = g->kd_ee_angular[i]; }
+  // stream-ordered update of the replicated constants: kernels already queued keep the old gains, later ones see the new
+  QMB_CUDA(h, cudaMemcpyAsync(h->d_model, &h->hm.dev, sizeof(DevModel), cudaMemcpyHostToDevice, h->stream)); QMB_CUDA(h, cudaStreamSynchronize(h->stream)); return 0;
+}
+
 }  // extern "C"
 
 #include "capi_mpc.inc"

@@ -109,6 +109,23 @@ class Solver:
     def wbc_update_dev(self, x_des, u_des, rbd, mode, period, time, cmd, status, stream=None):
         self._chk(self.lib.qmb200_wbc_update_dev(self.h, _p(x_des), _p(u_des), _p(rbd), _p(mode), _p(period), _p(time), _p(cmd), _p(status), C.c_void_p(stream) if stream else None), "qmb200_wbc_update_dev")
 
+    def wbc_get_gains(self):
+        """→ dict of the task-formulator PD gains (WbcBase::dynamicCallback fields)."""
+        g = _lib.WbcGains(); self._chk(self.lib.qmb200_wbc_get_gains(self.h, C.byref(g)), "qmb200_wbc_get_gains")
+        return {n: (list(getattr(g, n)) if hasattr(getattr(g, n), "__len__") else getattr(g, n)) for n, _ in _lib.WbcGains._fields_}
+
+    def wbc_set_gains(self, **gains):
+        """Dynamic reconfigure of the WBC gains: keyword per field of qmb200_wbc_gains; unspecified fields keep their value."""
+        g = _lib.WbcGains(); self._chk(self.lib.qmb200_wbc_get_gains(self.h, C.byref(g)), "qmb200_wbc_get_gains")
+        for k, v in gains.items():
+            cur = getattr(g, k)
+            if hasattr(cur, "__len__"):
+                for i, x in enumerate(v):
+                    cur[i] = float(x)
+            else:
+                setattr(g, k, float(v))
+        self._chk(self.lib.qmb200_wbc_set_gains(self.h, C.byref(g)), "qmb200_wbc_set_gains")
+
     def wbc_set_input_last(self, input_last=None):
         self._chk(self.lib.qmb200_wbc_set_input_last(self.h, _p(_f64(input_last, (self.batch, NU))) if input_last is not None else None), "qmb200_wbc_set_input_last")
 

@@ -106,3 +106,42 @@ def test_wbc_equation_of_motion_and_limits(oracle):
 def test_wbc_batch_one(oracle):
     """B = 1 must work (plugin use, config 1)."""
     _run(oracle, config=1, B=1, variant=0, time=12.0)
+
+
+def test_wbc_dynamic_reconfigure_matches_an_oracle_built_with_those_gains(tmp_path):
+    """WbcBase::dynamicCallback (WbcBase.cpp:69-117): gains replaced at run time through qmb200_wbc_set_gains give the result of a controller
+    constructed with those gains; reading them back returns what was set."""
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    from _oracle import Oracle, URDF, TASK, REFERENCE
+    new = dict(kp_swing=300.0, kd_swing=30.0, base_height_kp=350.0, base_height_kd=120.0, kp_base_linear=380.0, kd_base_linear=90.0, kp_base_angular=420.0, kd_base_angular=150.0,
+               kp_arm_joint=[3000, 3100, 3200, 3300, 3400, 3500], kd_arm_joint=[60, 61, 62, 63, 64, 65], kp_ee_linear=[2500, 2600, 2700], kd_ee_linear=[70, 71, 72],
+               kp_ee_angular=[1500, 1600, 1700], kd_ee_angular=[50, 51, 52])
+    lines = ["wbcGains", "{"]
+    for k in ("kp_swing", "kd_swing"):
+        lines.append("  %s %r" % (k, new[k]))
+    lines += ["  baseHeightKp %r" % new["base_height_kp"], "  baseHeightKd %r" % new["base_height_kd"], "  kp_base_linear %r" % new["kp_base_linear"], "  kd_base_linear %r" % new["kd_base_linear"],
+              "  kp_base_angular %r" % new["kp_base_angular"], "  kd_base_angular %r" % new["kd_base_angular"]]
+    for i in range(6):
+        lines += ["  kp_arm_joint_%d %r" % (i + 1, float(new["kp_arm_joint"][i])), "  kd_arm_joint_%d %r" % (i + 1, float(new["kd_arm_joint"][i]))]
+    for i, ax in enumerate("xyz"):
+        lines += ["  kp_ee_linear_%s %r" % (ax, float(new["kp_ee_linear"][i])), "  kd_ee_linear_%s %r" % (ax, float(new["kd_ee_linear"][i])),
+                  "  kp_ee_angular_%s %r" % (ax, float(new["kp_ee_angular"][i])), "  kd_ee_angular_%s %r" % (ax, float(new["kd_ee_angular"][i]))]
+    lines.append("}"); gfile = tmp_path / "gains.info"; gfile.write_text("\n".join(lines) + "\n")
+    orc = Oracle(URDF, TASK, REFERENCE, str(gfile))
+    B = 48; solver = q.Solver(batch=B); prob, wbc = synthetic.make_batch(np.arange(B), config=5)
+    x_des, u_des, mode = synthetic.nominal_wbc_inputs(prob, solver.robot_mass)
+    u_des = u_des + synthetic.uniform(77, np.arange(B), 1, 30, -1.0, 1.0) * np.r_[np.full(12, 5.0), np.full(18, 0.2)]
+    for b in range(B):
+        for f in range(4):
+            if not (mode[b] >> (3 - f)) & 1:
+                u_des[b, 3 * f:3 * f + 3] = 0.0
+    il = synthetic.uniform(78, np.arange(B), 2, 30, -0.1, 0.1); tarr = np.full(B, 12.0)
+    solver.wbc_set_input_last(il); before, _ = solver.wbc_update(x_des, u_des, wbc["rbd"], mode, wbc["period"], tarr)
+    solver.wbc_set_gains(**new); got = solver.wbc_get_gains()
+    for k, v in new.items():
+        assert np.allclose(got[k], v, rtol=0, atol=0), k
+    solver.wbc_set_input_last(il); after, status = solver.wbc_update(x_des, u_des, wbc["rbd"], mode, wbc["period"], tarr); assert np.all(status == 0)
+    ref, _ = orc.wbc_update_batch(x_des, u_des, wbc["rbd"], mode, wbc["period"], tarr, il, variant=0, nthreads=8)
+    err = _rel_err(after, ref); assert err.max() < RTOL, err.max()
+    assert np.max(np.abs(after - before)) > 1e-3     # the new gains did change the command
