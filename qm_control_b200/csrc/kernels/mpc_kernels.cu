@@ -253,27 +253,34 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.el.l.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
     sg[ST_b + r] = bt;
   }
-  __syncwarp();   // the h_ang rows of A1r were updated by their own lanes above
-  // A~ (30x30) and B~ (30x18) leave as flat row-major sweeps: consecutive lanes write consecutive doubles (8 sectors per store instruction
-  // instead of the 30 a lane-per-row store touches)
-  for (int e = lane; e < NX * NX; e += 32) {
-    const int r = e / NX, c = e - r * NX; double v = (c == r) ? 1.0 : 0.0;
-    if (r >= 3 && r < 12) v += sm.A1r[(r - 3) * NX + c];
-    else if (r >= 12 && r < 24) {
-      const LegWs& L = sm.leg[foot_of_leg_joint(lfp, r - 12)]; const int j = (r - 12) % 3;
-      const int pos = c < 6 ? c : ((c >= 9 && c < 12) ? c - 3 : ((c >= 12 + L.first && c < 15 + L.first) ? 9 + c - 12 - L.first : -1));   // inverse of sup_col
-      if (L.dep[j] && pos >= 0) v += dtw * L.Px[j][pos];
-    }
-    sg[ST_A + e] = v;
+  if (lane >= 3 && lane < 12) sm.A1r[(lane - 3) * NX + lane] += 1.0;   // A1r rows become rows 3:12 of A~ themselves (own row of each lane: no hazard with the h_ang update above)
+  __syncwarp();
+  // A~ (30x30) and B~ (30x18) leave as flat row-major sweeps (consecutive lanes write consecutive doubles: 8 sectors per store instruction instead
+  // of the 30 a lane-per-row store touches).  Both are identity/zero outside a dense band - rows 3:12 - and a handful of structured entries, so
+  // the sweeps carry no index arithmetic: zero/copy fill first, then the sparse entries by their owning lanes.
+  for (int e = lane; e < NX * NX; e += 32) sg[ST_A + e] = (e >= 3 * NX && e < 12 * NX) ? sm.A1r[e - 3 * NX] : 0.0;
+  for (int e = lane; e < NX * MU; e += 32) sg[ST_B + e] = 0.0;
+  __syncwarp();
+  if (lane < NX && (lane < 3 || lane >= 12)) {   // identity rows of A~, plus I + dtw * Px on the support columns of a dependent joint-velocity row
+    const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; Arow[r] = 1.0;
+    if (r >= 12 && r < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, r - 12)]; const int j = (r - 12) % 3;
+      if (L.dep[j]) for (int c = 0; c < 12; ++c) { const int col = sup_col(c, L.first); Arow[col] = ((col == r) ? 1.0 : 0.0) + dtw * L.Px[j][c]; } }
   }
-  for (int e = lane; e < NX * MU; e += 32) {
-    const int r = e / MU, a = e - r * MU; double v = 0.0;
+  for (int e = lane; e < 9 * MU; e += 32) {      // dense band of B~: rows 3:12 (force columns; joint columns reach the h_ang rows only)
+    const int r = 3 + e / MU, a = e - (r - 3) * MU; double v = 0.0;
     if (a < m) { const int fa = sm.free_idx[a];
-      if (r < 3) v = (fa < 12 && fa % 3 == r) ? dtw * imass : 0.0;
-      else if (r < 12) { if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa]; else if (fa < 24 && r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } else if (fa >= 24 && r < 6) v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12]; }
-      else { if (fa == r) v = dtw; else if (r < 24 && fa >= 12 && fa < 24) { const int i = foot_of_leg_joint(lfp, r - 12); const LegWs& L = sm.leg[i]; const int j = (r - 12) % 3; if (!L.stance && j == L.pivot && fa >= 12 + L.first && fa < 15 + L.first) { const int jf = fa - 12 - L.first; v = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
+      if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa];
+      else if (r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12];
+        if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
     }
-    sg[ST_B + e] = v;
+    sg[ST_B + 3 * MU + e] = v;
+  }
+  if (lane < m) {                                 // sparse entries of B~, by column (lane = projected input a)
+    const int a = lane, fa = sm.free_idx[a];
+    if (fa < 12) sg[ST_B + (size_t)(fa % 3) * MU + a] = dtw * imass;                              // h_lin rows: F / m
+    else { sg[ST_B + (size_t)fa * MU + a] = dtw;                                                   // joint position rows: own joint velocity
+      if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)];
+        if (!L.stance) { const int jf = fa - 12 - L.first; sg[ST_B + (size_t)(12 + L.first + L.pivot) * MU + a] = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }   // eliminated pivot joint of a swing leg
   }
   LQ_LOCKSTEP();
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
