@@ -102,18 +102,17 @@ __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, Poi
   }
   __syncwarp();
   if (with_jac) {
-    for (int e = lane; e < 9 * NX; e += 32) {
-      const int r = e / NX, col = e % NX; double v = 0.0;
-      if (r < 3) {
-        if (col >= 9 && col < 12) v = ws->hth[col - 9][r];
-        else if (col >= 12 && col < 24) { const int j = col - 12; const int i = foot_of_leg_joint(lfp, j); const double* J = ws->Jl[i] + 3 * (j % 3); const double* F = ws->u + 3 * i;
-          v = ((r == 0) ? J[1] * F[2] - J[2] * F[1] : (r == 1 ? J[2] * F[0] - J[0] * F[2] : J[0] * F[1] - J[1] * F[0])) * im; }
-      } else if (r < 6) {
-        const int a = r - 3; if (col < 3) v = (a == col) ? 1.0 : 0.0; else if (col < 6) v = ws->Mpc[3 * a + col - 3]; else if (col >= 9 && col < 12) v = ws->vp[col - 9][a];
-      } else {
-        const int a = r - 6; if (col >= 3 && col < 6) v = ws->Mtw[3 * a + col - 3]; else if (col >= 9 && col < 12) v = ws->vt[col - 9][a];
-      }
-      ws->Ar[e] = v;
+    // Ar (9 x 30: the non-trivial rows 3:12 of df/dx = d[hdot_ang; pdot; thetadot]/dx) is two thirds zeros: fill, then lane = column writes its own non-zeros
+    // (no per-element index arithmetic; the fill and the column writes are separated by a warp barrier)
+    for (int e = lane; e < 9 * NX; e += 32) ws->Ar[e] = 0.0;
+    __syncwarp();
+    if (lane < 24) {
+      const int col = lane;
+      if (col < 3) ws->Ar[(3 + col) * NX + col] = 1.0;                                                         // d pdot / d h_lin = I
+      else if (col < 6) { for (int a = 0; a < 3; ++a) { ws->Ar[(3 + a) * NX + col] = ws->Mpc[3 * a + col - 3]; ws->Ar[(6 + a) * NX + col] = ws->Mtw[3 * a + col - 3]; } }   // d / d h_ang
+      else if (col >= 9 && col < 12) { for (int a = 0; a < 3; ++a) { ws->Ar[a * NX + col] = ws->hth[col - 9][a]; ws->Ar[(3 + a) * NX + col] = ws->vp[col - 9][a]; ws->Ar[(6 + a) * NX + col] = ws->vt[col - 9][a]; } }   // d / d theta
+      else if (col >= 12) { const int j = col - 12; const int i = foot_of_leg_joint(lfp, j); const double* J = ws->Jl[i] + 3 * (j % 3); const double* F = ws->u + 3 * i;   // d hdot_ang / d q_leg = (J_j x F) / m
+        ws->Ar[col] = (J[1] * F[2] - J[2] * F[1]) * im; ws->Ar[NX + col] = (J[2] * F[0] - J[0] * F[2]) * im; ws->Ar[2 * NX + col] = (J[0] * F[1] - J[1] * F[0]) * im; }
     }
     __syncwarp();
   }
