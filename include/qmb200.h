@@ -40,6 +40,7 @@ extern "C" {
 #define QMB200_ST_NAN 4
 #define QMB200_ST_NOT_PD 8
 #define QMB200_ST_NO_STEP 16      /* line search rejected every step size (solution = initial guess, as in SqpSolver::takeStep) */
+#define QMB200_ST_CONVERGED 32    /* informational: SqpSolver::checkConvergence ended the SQP loop before sqp.sqpIteration (only when sqpIteration > 1) */
 
 typedef struct qmb200_handle qmb200_handle;
 
@@ -100,6 +101,10 @@ int qmb200_mpc_solve(qmb200_handle* h, const double* t0 /*[B]*/, const double* x
                      double* x_traj /*[B][NMAX][30]*/, double* u_traj /*[B][NMAX][30]*/, int32_t* status /*[B]*/, double* step_info /*[B][4] or NULL: alpha, cost, dyn SSE, eq SSE after the step*/);
 int qmb200_mpc_solve_dev(qmb200_handle* h, const double* t0, const double* x0, const int32_t* n_events, const double* event_times, const int32_t* mode_sequence,
                          const int32_t* n_target, const double* target_times, const double* target_states, void* cuda_stream);
+/* sqp.sqpIteration / costTol of the handle (task.info:28; the create-time values come from task.info): SqpSolver::runImpl runs up to that many
+ * LQ → QP → line-search iterations per solve and leaves the loop early per robot on checkConvergence (step size, metrics, primal step) [upstream ocs2_sqp].
+ * sqp_iterations <= 0 / cost_tol <= 0 keep the current value. */
+int qmb200_mpc_set_iterations(qmb200_handle* h, int32_t sqp_iterations, double cost_tol);
 /* drop the stored PrimalSolution: next solve starts from QMInitializer (qm_interface/src/initialization/QMInitializer.cpp:33-41) */
 int qmb200_mpc_reset(qmb200_handle* h);
 /* load a PrimalSolution as warm start (n_nodes[b] < 2 → cold start for robot b) */

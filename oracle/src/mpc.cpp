@@ -171,7 +171,7 @@ Perf compute_performance(const Model& m, const MpcSettings& s, const ModeSchedul
 MpcSettings load_mpc_settings(const Model& model, const std::string& task_file, const std::string& reference_file) {
   (void)reference_file;
   auto root = info_parse_file(task_file); MpcSettings s;
-  s.dt = root->num_or("sqp.dt", s.dt); s.time_horizon = root->num_or("mpc.timeHorizon", s.time_horizon); s.delta_tol = root->num_or("sqp.deltaTol", s.delta_tol);
+  s.dt = root->num_or("sqp.dt", s.dt); s.time_horizon = root->num_or("mpc.timeHorizon", s.time_horizon); s.delta_tol = root->num_or("sqp.deltaTol", s.delta_tol); s.sqp_iterations = std::max(1, (int)root->num_or("sqp.sqpIteration", 1.0)); s.cost_tol = root->num_or("sqp.costTol", s.cost_tol);
   s.g_max = root->num_or("sqp.g_max", s.g_max); s.g_min = root->num_or("sqp.g_min", s.g_min);
   s.Q = info_matrix(*root, "Q", NX, NX);
   Mat Rt = info_matrix(*root, "R", NU, NU);
@@ -256,6 +256,9 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
       bool fl[4]; mode_to_contact_flags(mode_at_time(sched, t), fl); Vec ui(NU); weight_compensating_input(m, fl, ui.data()); u.push_back(ui); x.push_back(x.back());
     } else { u.push_back(interpolate(t, ptimes, pu)); x.push_back(interpolate(tn, ptimes, prev->x)); }
   }
+  // ---- SqpSolver::runImpl [upstream ocs2_sqp, recalled]: for (iter < sqpIteration) { setupQuadraticSubproblem; getOCPSolution; takeStep; checkConvergence } ----
+  for (int iteration = 0; iteration < s.sqp_iterations; ++iteration) {
+  if (dbg) { dbg->A.clear(); dbg->B.clear(); dbg->b.clear(); }
   // ---- setupQuadraticSubproblem ----
   struct Stage { bool event = false; int nu = 0; Mat A, B; Vec b; Mat Q, R, P; Vec q, r; Mat Px, Pu; Vec Pe; };
   std::vector<Stage> st(N); Quad qN; Perf base;
@@ -326,6 +329,15 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
   } while (alpha >= s.alpha_min);
   if (accepted) { x = xn; u = un; } else alpha = 0.0;
   if (dbg) { dbg->alpha = alpha; dbg->base_cost = base.cost; dbg->base_dyn_sse = base.dyn; dbg->base_eq_sse = base.eq; dbg->step_cost = stepPerf.cost; dbg->step_dyn_sse = stepPerf.dyn; dbg->step_eq_sse = stepPerf.eq; dbg->armijo = armijo; dbg->trials = trials; dbg->dx = dx; dbg->du = du; }
+  // checkConvergence [upstream ocs2_sqp SqpSolver.cpp, recalled]
+  int conv = -1;
+  if (iteration + 1 >= s.sqp_iterations) conv = 0;
+  else if (alpha < s.alpha_min) conv = 1;                                                                                   // a rejected step has stepSize 0
+  else if (std::fabs((accepted ? stepPerf.cost : base.cost) - base.cost) < s.cost_tol && violation(accepted ? stepPerf : base) < s.g_min) conv = 2;
+  else if (alpha * dxn < s.delta_tol && alpha * dun < s.delta_tol) conv = 3;
+  if (dbg) { dbg->iterations = iteration + 1; dbg->convergence = conv < 0 ? 0 : conv; }
+  if (conv >= 0) break;
+  }
   return sol;
 }
 

@@ -16,6 +16,7 @@ struct MpcSettings {
   // sqp{} / mpc{} (task.info:75-92,138-147)
   double dt = 0.015, time_horizon = 1.0, delta_tol = 1e-4, g_max = 1e-2, g_min = 1e-6;
   double alpha_decay = 0.5, alpha_min = 1e-4, gamma_c = 1e-6, armijo_factor = 1e-4;     // [upstream defaults]
+  int sqp_iterations = 1; double cost_tol = 1e-4;   // sqp.sqpIteration (task.info:28), costTol [upstream ocs2_sqp default]: SqpSolver::runImpl loop + checkConvergence
   // RK2 form x+ = x + dt (w1 k1 + w2 k2), k2 = f(x + c dt k1): Heun (c=1,w=1/2,1/2) is OCS2's SensitivityIntegrator rk2 [recalled]
   double rk_c = 1.0, rk_w1 = 0.5, rk_w2 = 0.5;
   // cost (task.info:192-287, QMInterface.cpp:274-319)
@@ -43,7 +44,7 @@ struct TargetTrajectories { std::vector<double> times; std::vector<Vec> states; 
 struct NodeInfo { double t; int event; /*0 none, 1 pre-event, 2 post-event*/ };
 struct MpcSolution { std::vector<NodeInfo> grid; std::vector<Vec> x, u; };
 
-struct MpcDebug { double alpha = 0; double base_cost = 0, base_dyn_sse = 0, base_eq_sse = 0, step_cost = 0, step_dyn_sse = 0, step_eq_sse = 0, armijo = 0; int trials = 0;
+struct MpcDebug { int iterations = 0; int convergence = 0; /* 0 ITERATIONS, 1 STEPSIZE, 2 METRICS, 3 PRIMAL */ double alpha = 0; double base_cost = 0, base_dyn_sse = 0, base_eq_sse = 0, step_cost = 0, step_dyn_sse = 0, step_eq_sse = 0, armijo = 0; int trials = 0;
   std::vector<Mat> A, B; std::vector<Vec> b; std::vector<Vec> dx, du; };
 
 // One SqpSolver::run(t0, x0, t0 + horizon) with sqpIteration = 1.  `previous` may be empty (cold start → QMInitializer).

@@ -18,7 +18,7 @@ namespace qmb {
 #define QMB_LQ_WARPS 6
 #endif
 constexpr int LQ_WARPS = QMB_LQ_WARPS, LS_WARPS = 4, SETUP_WARPS = 4;
-enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16 };
+enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16, MST_CONVERGED = 32 };   // CONVERGED: checkConvergence stopped the SQP loop before sqpIteration
 
 __device__ __forceinline__ double interval_start(double t, int ev) { return ev == 2 ? t + WEAK_EPS : t; }
 __device__ __forceinline__ double interval_end(double t, int ev) { return ev == 1 ? t - WEAK_EPS : t; }
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
   const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax); if (b >= B) return;
   const int n = sol.n_nodes[b]; if (k >= n) return;
+  if (status[b] & MST_CONVERGED) return;   // SqpSolver::runImpl left the iteration loop for this robot
   LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp];
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL; int32_t* si = stage_i + ((size_t)b * nmax + k) * STAGE_INT;
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RicSmem& sm = *reinterpret_cast<RicSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ti = tid >> 2, jb = tid & 3; const int b = b0 + blockIdx.x;
+  if (status[b] & MST_CONVERGED) return;
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
   for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
@@ -630,10 +632,11 @@ __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax
 }
 
 __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
-                                                                     const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info) {
+                                                                     const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int iteration) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[LS_WARPS][3]; __shared__ int decision;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x; if (b >= B) return;
+  if (status[b] & MST_CONVERGED) return;
   LsSmem& sm = reinterpret_cast<LsSmem*>(smem_raw)[warp];
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
@@ -705,7 +708,16 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const 
   } else { alpha = 0.0; sc = base_cost; sd = rb[2]; se = rb[3]; }
   __syncthreads();
   fixup_inputs(sol, b, nmax, n, threadIdx.x, blockDim.x);
-  if (threadIdx.x == 0) { if (!accepted) atomicOr(&status[b], MST_NO_STEP); double* si = step_info + (size_t)b * 4; si[0] = alpha; si[1] = sc; si[2] = sd; si[3] = se; }
+  if (threadIdx.x == 0) {
+    int flags = accepted ? 0 : MST_NO_STEP;
+    if (iteration + 1 < mdl->sqp_iterations) {   // SqpSolver::checkConvergence [upstream ocs2_sqp, recalled]: STEPSIZE, METRICS, PRIMAL (ITERATIONS = the host loop bound)
+      const bool stepsize = alpha < mdl->alpha_min;                                                       // a rejected step reports stepSize 0
+      const bool metrics = fabs(sc - base_cost) < mdl->cost_tol && sqrt(sd + se) < mdl->g_min;
+      const bool primal = alpha * dxn < mdl->delta_tol && alpha * dun < mdl->delta_tol;
+      if (stepsize || metrics || primal) flags |= MST_CONVERGED;
+    }
+    if (flags) atomicOr(&status[b], flags);
+    double* si = step_info + (size_t)b * 4; si[0] = alpha; si[1] = sc; si[2] = sd; si[3] = se; }
 }
 
 __global__ void mpc_fixup_kernel(int B, int nmax, MpcSolutionDev sol) { const int b = blockIdx.x; if (b >= B) return; const int n = sol.n_nodes[b]; if (n >= 2) fixup_inputs(sol, b, nmax, n, threadIdx.x, blockDim.x); }
@@ -741,20 +753,24 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
     configured = true;
   }
-  (void)hm;
   const int nb = b1 - b0, nmax = m.nmax; if (nb <= 0) return 0;
   MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];   // the caller flips m.cur once all ranges are queued
   if (ev) cudaEventRecord(ev[0], stream);
   mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
   if (ev) cudaEventRecord(ev[1], stream);
-  const long long nodes = (long long)nb * nmax;
-  mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.status);
-  if (ev) cudaEventRecord(ev[2], stream);
-  mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
-  if (ev) cudaEventRecord(ev[3], stream);
-  mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info);
+  const long long nodes = (long long)nb * nmax; const int iters = hm.sqp_iterations < 1 ? 1 : hm.sqp_iterations; int launched = 1;
+  // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
+  // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
+  for (int it = 0; it < iters; ++it) {
+    mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.status);
+    if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);
+    mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
+    if (ev && it == iters - 1) cudaEventRecord(ev[3], stream);
+    mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
+    launched += 3;
+  }
   if (ev) cudaEventRecord(ev[4], stream);
-  return 4;
+  return launched;
 }
 
 int mpc_policy_eval_launch(const MpcBuffers& m, const double* t, double* x_des, double* u_des, int32_t* mode, cudaStream_t stream, int b0, int b1) {

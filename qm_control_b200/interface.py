@@ -149,6 +149,10 @@ class Solver:
         keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
         self._chk(self.lib.qmb200_mpc_solve_dev(self.h, *[_p(prob_dev[k]) for k in keys], C.c_void_p(stream) if stream else None), "qmb200_mpc_solve_dev")
 
+    def mpc_set_iterations(self, sqp_iterations=0, cost_tol=0.0):
+        """sqp.sqpIteration / costTol (SqpSolver::runImpl loop bound and checkConvergence tolerance)."""
+        self._chk(self.lib.qmb200_mpc_set_iterations(self.h, int(sqp_iterations), float(cost_tol)), "qmb200_mpc_set_iterations")
+
     def mpc_reset(self):
         self._chk(self.lib.qmb200_mpc_reset(self.h), "qmb200_mpc_reset")
 

@@ -115,6 +115,9 @@ class Oracle:
     def mpc_set(self, dt=-1.0, horizon=-1.0, rk=(-1.0, 0.0, 0.0)):
         self.lib.orc_mpc_set(self.h, C.c_double(dt), C.c_double(horizon), C.c_double(rk[0]), C.c_double(rk[1]), C.c_double(rk[2]))
 
+    def mpc_set_sqp(self, sqp_iterations=0, cost_tol=0.0):
+        self.lib.orc_mpc_set_sqp(self.h, C.c_int(int(sqp_iterations)), C.c_double(float(cost_tol)))
+
     def mpc_weights(self):
         Q = np.zeros((30, 30)); R = np.zeros((30, 30))
         self.lib.orc_mpc_get_weights(self.h, _d(Q), _d(R))
@@ -130,7 +133,7 @@ class Oracle:
         prev: dict(n_nodes[B], t[B,nmax], event[B,nmax], x[B,nmax,30], u[B,nmax,30]) or None."""
         B = prob["t0"].shape[0]
         out = dict(n_nodes=np.zeros(B, dtype=np.int32), t=np.zeros((B, nmax)), event=np.zeros((B, nmax), dtype=np.int32), x=np.zeros((B, nmax, 30)), u=np.zeros((B, nmax, 30)))
-        dbg = np.zeros((B, 9)) if want_dbg else None
+        dbg = np.zeros((B, 11)) if want_dbg else None
         pa = [None] * 5 if prev is None else [_i(i32(prev["n_nodes"])), _d(f64(prev["t"])), _i(i32(prev["event"])), _d(f64(prev["x"])), _d(f64(prev["u"]))]
         keep = [f64(prob["t0"]), f64(prob["x0"]), i32(prob["n_events"]), f64(prob["event_times"]), i32(prob["modes"]), i32(prob["n_target"]), f64(prob["target_times"]), f64(prob["target_states"])]
         emax = keep[3].shape[1]; kmax = keep[6].shape[1]

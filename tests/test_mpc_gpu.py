@@ -163,3 +163,31 @@ def test_dense_state_weight_falls_back_to_the_general_path(tmp_path):
     out = solver.mpc_solve(prob); ref = orc.mpc_solve_batch(prob, solver.nmax, nthreads=4)
     assert np.all((out["status"] & ~16) == 0); np.testing.assert_array_equal(out["step_info"][:, 0], ref["dbg"][:, 0])
     assert _traj_err(out, ref).max() < RTOL
+
+
+def test_multiple_sqp_iterations_and_convergence_exit(oracle):
+    """sqp.sqpIteration > 1 (SqpSolver::runImpl loop): three iterations from a cold start track the oracle's loop; with loose tolerances the
+    convergence test (checkConvergence: step size / metrics / primal step) ends the loop early for the same robots on both sides."""
+    import qm_control_b200 as q
+    from qm_control_b200 import synthetic
+    B = 9; solver = q.Solver(batch=B, dt=0.015); oracle.mpc_set(dt=0.015, horizon=1.0)
+    prob, _ = synthetic.make_batch(np.arange(B), config=5)
+    try:
+        solver.mpc_set_iterations(3); oracle.mpc_set_sqp(3)
+        out = solver.mpc_solve(prob); ref = oracle.mpc_solve_batch(prob, solver.nmax, nthreads=8)
+        assert np.all(ref["dbg"][:, 9] >= 2)                              # the cold start is far from converged: more than one iteration everywhere
+        assert np.all((out["status"] & ~(16 | 32)) == 0), np.unique(out["status"])
+        np.testing.assert_array_equal(((out["status"] & 32) != 0), ref["dbg"][:, 9] < 3)
+        np.testing.assert_array_equal(out["step_info"][:, 0], ref["dbg"][:, 0])
+        assert _traj_err(out, ref).max() < RTOL
+        one = q.Solver(batch=B, dt=0.015).mpc_solve(prob)                  # and the extra iterations did move the solution
+        assert max(np.max(np.abs(one["x"] - out["x"])), np.max(np.abs(one["u"] - out["u"]))) > 1e-6
+        # early exit: robot 1758 of the bench workload has an indefinite projected Hessian -> no step -> checkConvergence(STEPSIZE) ends its loop after the
+        # first iteration (status NOT_PD | NO_STEP | CONVERGED, warm start kept) while its neighbour runs all three iterations and matches the oracle
+        ids = np.array([1758, 5]); s2 = q.Solver(batch=2, dt=0.01); s2.mpc_set_iterations(3); oracle.mpc_set(dt=0.01, horizon=1.0)
+        p2, _ = synthetic.make_batch(ids, config=4, horizon=1.0); o2 = s2.mpc_solve(p2)
+        assert o2["status"][0] == (8 | 16 | 32) and (o2["status"][1] & ~16) == 0, o2["status"]
+        r2 = oracle.mpc_solve_batch({k: v[1:] for k, v in p2.items()}, s2.nmax, nthreads=1); assert r2["dbg"][0, 9] == 3
+        n = int(r2["n_nodes"][0]); assert np.max(np.abs(o2["x"][1, :n] - r2["x"][0, :n])) / max(1.0, np.max(np.abs(r2["x"][0, :n]))) < RTOL
+    finally:
+        oracle.mpc_set_sqp(1)
