@@ -607,8 +607,15 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
         s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) dxn[ti] = s + bv[ti]; }
       if (tid < NX) armijo += qv[tid] * dxc[tid];
       if (tid < MU) { const double dut = sm.dut[tid]; armijo += rv[tid] * dut; const int fi = si[SI_FREE + tid]; if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; } }
-      if (tid >= 64 && tid < 64 + MAXDEP) { const int d = tid - 64; if (d < ndep) { double s = sg[ST_PED + d]; const double* px = sg + ST_PXD + (size_t)d * NX; const double* pu = sg + ST_PUD + (size_t)d * MU;
-          for (int j = 0; j < NX; ++j) s = fma(px[j], dxc[j], s); for (int a = 0; a < MU; ++a) s = fma(pu[a], sm.dut[a], s); duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
+      { // dependent inputs du_d = Px_d dx + Pu_d du~ + Pe_d: 8 threads per row (MAXDEP * 8 = all 128 threads), 6 of the 48 terms each, so the
+        // global loads of a row are one short burst instead of a 48-long dependent chain on one lane that the next barrier has to wait for
+        static_assert(MAXDEP * 8 == RIC_THREADS, "one 8-thread group per dependent input");
+        const int d = tid >> 3, q8 = tid & 7; double s = 0.0;
+        if (d < ndep) { const double* px = sg + ST_PXD + (size_t)d * NX; const double* pu = sg + ST_PUD + (size_t)d * MU;
+#pragma unroll
+          for (int idx = q8; idx < NX + MU; idx += 8) s = fma(idx < NX ? px[idx] : pu[idx - NX], idx < NX ? dxc[idx] : sm.dut[idx - NX], s); }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); s += __shfl_xor_sync(FULL, s, 4);
+        if (d < ndep && q8 == 0) { s += sg[ST_PED + d]; duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
     }
     __syncthreads();
     if (tid < NX) { const double dxi = ((N & 1) ? sm.tmp : sm.dx)[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_q + tid] * dxi; }
