@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevMo
   __syncwarp();
   // ---- initializeStateInputTrajectories [upstream ocs2_oc/multiple_shooting/Initialization.cpp] ----
   const int np = prev.n_nodes ? prev.n_nodes[b] : 0; const bool has_prev = np >= 2;
-  const double* pt = prev.t + (size_t)b * nmax; const double* px = prev.x + (size_t)b * nmax * NX; const double* pu = prev.u + (size_t)b * nmax * NU;
+  // the previous grid is staged in shared memory: every interpolation below starts with a binary search over it (7 dependent loads)
+  extern __shared__ double s_prev_t[]; double* spt = s_prev_t + (size_t)warp * nmax;
+  { const double* gpt = prev.t + (size_t)b * nmax; for (int i = lane; i < np && i < nmax; i += 32) spt[i] = gpt[i]; __syncwarp(); }
+  const double* pt = spt; const double* px = prev.x + (size_t)b * nmax * NX; const double* pu = prev.u + (size_t)b * nmax * NU;
   const double state_till = has_prev ? pt[np - 1] : t0, input_till = has_prev ? pt[np - 2] : t0;
   double* gx = next.x + (size_t)b * nmax * NX; double* gu = next.u + (size_t)b * nmax * NU;
   auto interp = [&](const double* traj, double t) { int idx; double a; time_segment(pt, np, t, idx, a); return (lane < NX) ? a * traj[(size_t)idx * NX + lane] + (1.0 - a) * traj[(size_t)(idx + 1 < np ? idx + 1 : idx) * NX + lane] : 0.0; };
@@ -763,7 +766,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   const int nb = b1 - b0, nmax = m.nmax; if (nb <= 0) return 0;
   MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];   // the caller flips m.cur once all ranges are queued
   if (ev) cudaEventRecord(ev[0], stream);
-  mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
+  mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, sizeof(double) * SETUP_WARPS * nmax, stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
   if (ev) cudaEventRecord(ev[1], stream);
   const long long nodes = (long long)nb * nmax; const int iters = hm.sqp_iterations < 1 ? 1 : hm.sqp_iterations; int launched = 1;
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
