@@ -123,3 +123,26 @@ def test_stateful_gait_schedule_follows_the_controller_protocol():
             k = int(np.searchsorted(ev[:n], 1.5 + 1e-9)); assert list(md[k:k + 4]) == [9, 6, 9, 6]; np.testing.assert_allclose(np.diff(ev[k - 1:k + 3]), 0.35)
         if tick == 300:                                                 # the switch trot → flying trot passes through phaseTransitionStanceTime of stance
             k = int(np.searchsorted(ev[:n], 3.0 - 1e-9)); assert md[k + 1] == 15 and abs(ev[k + 1] - ev[k] - 0.1) < 1e-12
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_python_binding(tmp_path):
+    """include/qmb200.h must compile as C (the boundary a cgo / JNI / C++ maintainer binds) and the ctypes mirrors of its structs must have
+    the same size and field offsets."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields_cfg = [n for n, _ in _lib.Config._fields_]; fields_g = [n for n, _ in _lib.WbcGains._fields_]
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "qmb200.h"', 'int main(void) {', '  printf("%zu\\n", sizeof(qmb200_config));']
+    body += ['  printf("%%zu\\n", offsetof(qmb200_config, %s));' % f for f in fields_cfg]
+    body += ['  printf("%zu\\n", sizeof(qmb200_wbc_gains));'] + ['  printf("%%zu\\n", offsetof(qmb200_wbc_gains, %s));' % f for f in fields_g]
+    body += ['  printf("%d %d %d %d %d %d %d\\n", QMB200_NX, QMB200_NU, QMB200_RBD, QMB200_CMD, QMB200_TARGET, QMB200_EMAX, QMB200_KMAX);', '  return 0; }']
+    src.write_text("\n".join(body) + "\n"); exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    it = iter(out)
+    assert int(next(it)) == C.sizeof(_lib.Config)
+    for f in fields_cfg:
+        assert int(next(it)) == getattr(_lib.Config, f).offset, f
+    assert int(next(it)) == C.sizeof(_lib.WbcGains)
+    for f in fields_g:
+        assert int(next(it)) == getattr(_lib.WbcGains, f).offset, f
+    assert [int(v) for v in next(it).split()] == [_lib.NX, _lib.NU, _lib.RBD, _lib.CMD, _lib.TARGET, _lib.EMAX, _lib.KMAX]
