@@ -258,14 +258,16 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
   }
   // ---- SqpSolver::runImpl [upstream ocs2_sqp, recalled]: for (iter < sqpIteration) { setupQuadraticSubproblem; getOCPSolution; takeStep; checkConvergence } ----
   for (int iteration = 0; iteration < s.sqp_iterations; ++iteration) {
-  if (dbg) { dbg->A.clear(); dbg->B.clear(); dbg->b.clear(); }
+  if (dbg) { dbg->A.clear(); dbg->B.clear(); dbg->b.clear(); dbg->Q.clear(); dbg->R.clear(); dbg->P.clear(); dbg->C.clear(); dbg->D.clear(); dbg->q.clear(); dbg->r.clear(); dbg->e.clear(); dbg->is_event.clear(); }
   // ---- setupQuadraticSubproblem ----
   struct Stage { bool event = false; int nu = 0; Mat A, B; Vec b; Mat Q, R, P; Vec q, r; Mat Px, Pu; Vec Pe; };
   std::vector<Stage> st(N); Quad qN; Perf base;
   for (int i = 0; i < NX; ++i) { const double d = x0[i] - x[0][i]; base.dyn += d * d; }
   for (int k = 0; k < N; ++k) {
     Stage& S = st[k];
-    if (grid[k].event == 1) { S.event = true; S.nu = 0; S.A = Mat::identity(NX); S.b = x[k] - x[k + 1]; base.dyn += norm2(S.b); continue; }
+    if (grid[k].event == 1) { S.event = true; S.nu = 0; S.A = Mat::identity(NX); S.b = x[k] - x[k + 1]; base.dyn += norm2(S.b);
+      if (dbg) { dbg->A.push_back(S.A); dbg->B.push_back(Mat(NX, NU)); dbg->b.push_back(S.b); dbg->Q.push_back(Mat(NX, NX)); dbg->R.push_back(Mat(NU, NU)); dbg->P.push_back(Mat(NU, NX)); dbg->C.push_back(Mat(0, NX)); dbg->D.push_back(Mat(0, NU)); dbg->q.push_back(Vec(NX, 0.0)); dbg->r.push_back(Vec(NU, 0.0)); dbg->e.push_back(Vec()); dbg->is_event.push_back(1); }
+      continue; }
     const double t = interval_start(grid[k]), dt = interval_end(grid[k + 1]) - t; bool fl[4]; mode_to_contact_flags(mode_at_time(sched, t), fl);
     D60 z[60]; for (int i = 0; i < 60; ++i) z[i] = D60::variable(i < 30 ? x[k][i] : u[k][i - 30], i);
     D60 xn[NX]; rk2_step<D60>(m, s, z, z + 30, dt, xn);
@@ -276,7 +278,7 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
     D60 g[16]; const int ng = equality_constraints<D60>(m, s, sched, t, fl, z, z + 30, g);
     Mat C(ng, NX), D(ng, NU); Vec e(ng); for (int i = 0; i < ng; ++i) { e[i] = g[i].v; for (int j = 0; j < 30; ++j) { C(i, j) = g[i].d[j]; D(i, j) = g[i].d[30 + j]; } }
     base.eq += dt * norm2(e);
-    if (dbg) { dbg->A.push_back(A); dbg->B.push_back(B); dbg->b.push_back(b); }
+    if (dbg) { dbg->A.push_back(A); dbg->B.push_back(B); dbg->b.push_back(b); dbg->Q.push_back(c.Q); dbg->R.push_back(c.R); dbg->P.push_back(c.P); dbg->C.push_back(C); dbg->D.push_back(D); dbg->q.push_back(c.q); dbg->r.push_back(c.r); dbg->e.push_back(e); dbg->is_event.push_back(0); }
     // luConstraintProjection + changeOfInputVariables [upstream ocs2_core/misc/LinearAlgebra, recalled]
     FullPivLU lu(D); S.Pu = lu.kernel(); S.Px = -1.0 * lu.solve(C); S.Pe = colvec(-1.0 * lu.solve(col(e))); S.nu = S.Pu.c;
     S.A = A + B * S.Px; S.b = b + B * S.Pe; S.B = B * S.Pu;
@@ -287,6 +289,7 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
     S.P = S.Pu.T() * (c.P + RPx); S.r = tmul(S.Pu, rs); S.R = S.Pu.T() * (c.R * S.Pu);
   }
   base.cost += final_cost(m, s, tt, interval_start(grid[N]), x[N].data(), &qN);
+  if (dbg) { dbg->QN = qN.Q; dbg->qN = qN.q; }
   // ---- QP: Riccati backward / forward (HPIPM with no inequality rows ≡ exact LQ solve) ----
   std::vector<Mat> K(N); std::vector<Vec> kff(N);
   Mat P = qN.Q; Vec p = qN.q;
@@ -339,6 +342,13 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
   if (conv >= 0) break;
   }
   return sol;
+}
+
+double stage_probe(const Model& m, const MpcSettings& s, const ModeSchedule& sched, const TargetTrajectories& tt, double t, const double* x, const double* u, double* q, double* r, double* g, int* ng) {
+  bool fl[4]; mode_to_contact_flags(mode_at_time(sched, t), fl); Quad c; const double f = stage_cost(m, s, tt, t, fl, x, u, (q || r) ? &c : nullptr);
+  if (q) for (int i = 0; i < NX; ++i) q[i] = c.q[i]; if (r) for (int i = 0; i < NU; ++i) r[i] = c.r[i];
+  if (g && ng) *ng = equality_constraints<double>(m, s, sched, t, fl, x, u, g);
+  return f;
 }
 
 void evaluate_policy(const MpcSolution& sol, const ModeSchedule& sched, double t, double* xd, double* ud, int* mode) {

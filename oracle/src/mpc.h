@@ -35,6 +35,10 @@ struct MpcSettings {
 MpcSettings load_mpc_settings(const Model& model, const std::string& task_file, const std::string& reference_file);
 
 void centroidal_state_from_rbd(const Model& m, const double* rbd48, double* x30);
+struct ModeSchedule; struct TargetTrajectories;
+// one evaluation of the intermediate cost and the equality constraints at (t, x, u) for finite-difference checks of their derivatives: returns the cost value,
+// fills gradient q[30], r[30] (if non-null), constraint values g[<=16] and their count
+double stage_probe(const Model& m, const MpcSettings& s, const ModeSchedule& sched, const TargetTrajectories& tt, double t, const double* x, const double* u, double* q, double* r, double* g, int* ng);
 
 // ocs2::ModeSchedule: modeSequence.size() == eventTimes.size() + 1
 struct ModeSchedule { std::vector<double> event_times; std::vector<int> mode_sequence; };
@@ -45,7 +49,10 @@ struct NodeInfo { double t; int event; /*0 none, 1 pre-event, 2 post-event*/ };
 struct MpcSolution { std::vector<NodeInfo> grid; std::vector<Vec> x, u; };
 
 struct MpcDebug { int iterations = 0; int convergence = 0; /* 0 ITERATIONS, 1 STEPSIZE, 2 METRICS, 3 PRIMAL */ double alpha = 0; double base_cost = 0, base_dyn_sse = 0, base_eq_sse = 0, step_cost = 0, step_dyn_sse = 0, step_eq_sse = 0, armijo = 0; int trials = 0;
-  std::vector<Mat> A, B; std::vector<Vec> b; std::vector<Vec> dx, du; };
+  std::vector<Mat> A, B; std::vector<Vec> b; std::vector<Vec> dx, du;
+  // the QP of the (last) SQP iteration as setupQuadraticSubproblem built it, per interval (cost already scaled by dt): ½ dx'Q dx + du'P dx + ½ du'R du + q'dx + r'du,
+  // C dx + D du + e = 0; event nodes carry empty matrices; QN, qN = final cost
+  std::vector<Mat> Q, R, P, C, D; std::vector<Vec> q, r, e; std::vector<int> is_event; Mat QN; Vec qN; };
 
 // One SqpSolver::run(t0, x0, t0 + horizon) with sqpIteration = 1.  `previous` may be empty (cold start → QMInitializer).
 MpcSolution mpc_solve(const Model& model, const MpcSettings& s, double t0, const double* x0, const ModeSchedule& schedule, const TargetTrajectories& target,

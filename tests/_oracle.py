@@ -216,3 +216,28 @@ class HwSimOracle:
         eff = np.zeros(18)
         self.lib.orc_hw_write(self.h, C.c_double(float(time)), C.c_double(float(period)), _d(f64(joint_cmd)), _d(f64(pos)), _d(f64(vel)), _d(eff))
         return eff
+
+
+def _mpc_qp(self, prob, nmax, max_k=200):
+    """QP of the tick for robot 0 of `prob` (cold start): dict of per-interval blocks, see orc_mpc_qp."""
+    keep = [f64(prob["t0"][:1]), f64(prob["x0"][:1]), i32(prob["n_events"][:1]), f64(prob["event_times"][:1]), i32(prob["modes"][:1]), i32(prob["n_target"][:1]), f64(prob["target_times"][:1]), f64(prob["target_states"][:1])]
+    emax = keep[3].shape[1]; kmax = keep[6].shape[1]; K = max_k
+    o = dict(A=np.zeros((K, 30, 30)), B=np.zeros((K, 30, 30)), b=np.zeros((K, 30)), Q=np.zeros((K, 30, 30)), R=np.zeros((K, 30, 30)), P=np.zeros((K, 30, 30)), q=np.zeros((K, 30)), r=np.zeros((K, 30)),
+             C=np.zeros((K, 16, 30)), D=np.zeros((K, 16, 30)), e=np.zeros((K, 16)), ng=np.zeros(K, dtype=np.int32), is_event=np.zeros(K, dtype=np.int32), QN=np.zeros((30, 30)), qN=np.zeros(30),
+             dx=np.zeros((K + 1, 30)), du=np.zeros((K, 30)))
+    n = C.c_int()
+    self._chk(self.lib.orc_mpc_qp(self.h, C.c_int(emax), C.c_int(kmax), C.c_int(nmax), _d(keep[0]), _d(keep[1]), _i(keep[2]), _d(keep[3]), _i(keep[4]), _i(keep[5]), _d(keep[6]), _d(keep[7]), C.c_int(K),
+                                  *[_d(o[k]) for k in ("A", "B", "b", "Q", "R", "P", "q", "r", "C", "D", "e")], _i(o["ng"]), _i(o["is_event"]), _d(o["QN"]), _d(o["qN"]), _d(o["dx"]), _d(o["du"]), C.byref(n)))
+    o["n_nodes"] = n.value
+    return o
+
+
+def _stage_probe(self, event_times, modes, target_times, target_states, t, x, u, want_grad=True):
+    et = f64(event_times); md = i32(modes); tt = f64(target_times); ts = f64(target_states); f = C.c_double(); q = np.zeros(30); r = np.zeros(30); g = np.zeros(16); ng = C.c_int()
+    self._chk(self.lib.orc_stage_probe(self.h, C.c_int(len(et)), _d(et), _i(md), C.c_int(len(tt)), _d(tt), _d(ts), C.c_double(float(t)), _d(f64(x)), _d(f64(u)), C.byref(f),
+                                       _d(q) if want_grad else None, _d(r) if want_grad else None, _d(g), C.byref(ng)))
+    return f.value, q, r, g[:ng.value].copy()
+
+
+Oracle.mpc_qp = _mpc_qp
+Oracle.stage_probe = _stage_probe
