@@ -67,3 +67,31 @@ def test_cost_gradient_and_constraint_jacobians_by_finite_differences(oracle):
         assert np.max(np.abs(fd_C - qp["C"][k, :ng])) < 1e-6 * (1.0 + np.max(np.abs(qp["C"][k]))) and np.max(np.abs(fd_D - qp["D"][k, :ng])) < 1e-6 * (1.0 + np.max(np.abs(qp["D"][k])))
         checked += 1
     assert checked >= 5
+
+
+def test_discrete_dynamics_sensitivities_by_finite_differences(oracle):
+    """A_d, B_d and the defect b of the multiple-shooting nodes against central differences of a numpy RK2 (Heun) step built from the
+    oracle's continuous flow map only - pins the sensitivity integrator independently of the dual-number propagation the oracle uses."""
+    oracle.mpc_set(dt=0.015, horizon=1.0); prob, _ = synthetic.make_batch(np.array([1]), config=5)      # trot
+    qp = oracle.mpc_qp(prob, NMAX); sol = oracle.mpc_solve_batch(prob, NMAX, nthreads=1); n = int(sol["n_nodes"][0]); t = sol["t"][0, :n]; ev = sol["event"][0, :n]
+    ne = int(prob["n_events"][0]); et = prob["event_times"][0, :ne]; md = prob["modes"][0, :ne + 1]; mass = oracle.model_info()["mass"]; x = prob["x0"][0].copy()
+
+    def step(xx, uu, dt):
+        k1 = oracle.flow_map(xx, uu)[0]; k2 = oracle.flow_map(xx + dt * k1, uu)[0]; return xx + 0.5 * dt * (k1 + k2)
+
+    checked = 0
+    for k in range(3, n - 2, 13):
+        if ev[k] != 0 or ev[k + 1] != 0 or qp["is_event"][k]:
+            continue
+        dt = t[k + 1] - t[k]; mode = md[int(np.searchsorted(et, t[k], side="left"))]; flags = [(mode >> (3 - f)) & 1 for f in range(4)]; u = np.zeros(30)
+        for f in range(4):
+            if flags[f]:
+                u[3 * f + 2] = mass * 9.81 / sum(flags)
+        np.testing.assert_allclose(step(x, u, dt) - x, qp["b"][k], rtol=0, atol=1e-12)                      # defect against the held state of the cold start
+        h = 1e-6; A = np.zeros((30, 30)); B = np.zeros((30, 30))
+        for i in range(30):
+            d = np.zeros(30); d[i] = h
+            A[:, i] = (step(x + d, u, dt) - step(x - d, u, dt)) / (2 * h); B[:, i] = (step(x, u + d, dt) - step(x, u - d, dt)) / (2 * h)
+        assert np.max(np.abs(A - qp["A"][k])) < 1e-7 and np.max(np.abs(B - qp["B"][k])) < 1e-7, (k, np.max(np.abs(A - qp["A"][k])), np.max(np.abs(B - qp["B"][k])))
+        checked += 1
+    assert checked >= 4
