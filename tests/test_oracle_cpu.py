@@ -212,3 +212,51 @@ def test_cold_start_mpc_grid_and_feasibility(oracle):
         alpha, base_cost, base_dyn, base_eq, step_cost, step_dyn, step_eq = out["dbg"][b, :7]
         assert alpha > 0 and (step_cost < base_cost or step_dyn + step_eq < base_dyn + base_eq)   # filter line search: cost or violation improves
         assert step_eq < 0.1 * base_eq and step_dyn < 0.1 * base_dyn   # the projected QP step satisfies the linearised constraints: residuals drop to second order
+
+
+def test_srbd_flow_map_matches_independent_twin(oracle, twin):
+    """The continuous dynamics of the OCP (QMDynamicsAD.cpp:22-33 → PinocchioCentroidalDynamicsAD, SRBD) restated with the twin's own FK and its own
+    nominal constants: hdot/m = [g + sum F/m ; sum (p_foot - r_com) x F / m], qdot_base = A_b^{-1} m h, A_b = [[m I, m S(R c) T], [0, R I_nom R' T]], r_com = p - R c."""
+    info = oracle.model_info(); qn = info["q_nominal"]; bodies = twin.com_and_bodies(qn); mass = sum(b[0] for b in bodies)
+    com = sum(b[0] * b[1] for b in bodies) / mass; c_nom = qn[0:3] - com                                     # comToBasePositionNominal (base orientation is zero at the nominal pose)
+    I_nom = sum(b[2] + b[0] * ((b[1] - com) @ (b[1] - com) * np.eye(3) - np.outer(b[1] - com, b[1] - com)) for b in bodies)
+    np.testing.assert_allclose(mass, info["mass"], rtol=1e-12); np.testing.assert_allclose(c_nom, info["com_to_base"], atol=1e-12); np.testing.assert_allclose(I_nom, info["inertia_nominal"], atol=1e-10)
+    feet = ("LF_FOOT", "RF_FOOT", "LH_FOOT", "RH_FOOT")                                                       # contact order (ModelSettings.h:38)
+    for seed in range(5):
+        q, _ = _rand_q(oracle, 40 + seed); rng = np.random.default_rng(seed); h = rng.uniform(-0.3, 0.3, 6); u = np.r_[rng.uniform(-30, 60, 12), rng.uniform(-1, 1, 18)]
+        x = np.r_[h, q]; f, _, _ = oracle.flow_map(x, u)
+        pose = twin.fk(q); R = pose[twin.root][0]; z, y = q[3], q[4]
+        T = np.array([[0, -np.sin(z), np.cos(y) * np.cos(z)], [0, np.cos(z), np.cos(y) * np.sin(z)], [1, 0, -np.sin(y)]])
+        c = R @ c_nom; r_com = q[0:3] - c; S = np.array([[0, -c[2], c[1]], [c[2], 0, -c[0]], [-c[1], c[0], 0]])
+        Ab = np.block([[mass * np.eye(3), mass * S @ T], [np.zeros((3, 3)), R @ I_nom @ R.T @ T]])
+        F = u[:12].reshape(4, 3); lin = np.array([0, 0, -9.81]) + F.sum(0) / mass; ang = sum(np.cross(pose[n][1] - r_com, F[i]) for i, n in enumerate(feet)) / mass
+        ref = np.r_[lin, ang, np.linalg.solve(Ab, mass * h), u[12:]]
+        np.testing.assert_allclose(f, ref, rtol=0, atol=1e-10)
+
+
+def test_equality_constraint_values_match_independent_twin(oracle, twin):
+    """ZeroVelocityConstraintCppAd (stance: foot velocity = 0), ZeroForceConstraint (swing: F = 0) and NormalVelocityConstraintCppAd (swing: v_z - zdot_ref = 0,
+    NormalVelocityConstraintCppAd.cpp:37-66, positionErrorGain 0): the residuals the oracle stacks per node against foot velocities obtained by differentiating the
+    twin's own FK along qdot = [A_b^{-1} m h ; joint velocities]."""
+    from qm_control_b200 import synthetic
+    info = oracle.model_info(); mass = info["mass"]; c_nom = info["com_to_base"]; I_nom = info["inertia_nominal"]; feet = ("LF_FOOT", "RF_FOOT", "LH_FOOT", "RH_FOOT")
+    prob, _ = synthetic.make_batch(np.array([2]), config=5); ne = int(prob["n_events"][0]); et = prob["event_times"][0, :ne]; md = prob["modes"][0, :ne + 1]
+    tt = prob["target_times"][0, :2]; ts = prob["target_states"][0, :2]; checked = set()
+    for j, t in enumerate(np.linspace(12.01, 12.9, 12)):
+        q, _ = _rand_q(oracle, 60 + j); rng = np.random.default_rng(j); h = rng.uniform(-0.3, 0.3, 6); u = np.r_[rng.uniform(-30, 60, 12), rng.uniform(-1, 1, 18)]; x = np.r_[h, q]
+        mode = md[int(np.searchsorted(et, t, side="left"))]; flags = [(mode >> (3 - f)) & 1 for f in range(4)]
+        _, _, _, g = oracle.stage_probe(et, md, tt, ts, t, x, u, want_grad=False)
+        R = twin.fk(q)[twin.root][0]; z, y = q[3], q[4]; T = np.array([[0, -np.sin(z), np.cos(y) * np.cos(z)], [0, np.cos(z), np.cos(y) * np.sin(z)], [1, 0, -np.sin(y)]])
+        c = R @ c_nom; S = np.array([[0, -c[2], c[1]], [c[2], 0, -c[0]], [-c[1], c[0], 0]]); Ab = np.block([[mass * np.eye(3), mass * S @ T], [np.zeros((3, 3)), R @ I_nom @ R.T @ T]])
+        v = np.r_[np.linalg.solve(Ab, mass * h), u[12:]]; eps = 1e-6; pa = twin.fk(q + eps * v); pb = twin.fk(q - eps * v)
+        ref = []
+        for i, n in enumerate(feet):                                        # constraint order: per foot in contact order, stance → 3 velocity rows; swing → 3 force rows + 1 normal-velocity row
+            vf = (pa[n][1] - pb[n][1]) / (2 * eps)
+            if flags[i]:
+                ref += list(vf)
+            else:
+                zp, zv = oracle.swing_reference(et, md, i, t); ref += list(u[3 * i:3 * i + 3]) + [vf[2] - zv]
+        ref = np.array(ref); assert len(g) == len(ref) == 3 * sum(flags) + 4 * (4 - sum(flags))
+        # the oracle stacks the rows by constraint type, the twin by foot: compare the residuals as multisets
+        np.testing.assert_allclose(np.sort(g), np.sort(ref), rtol=0, atol=2e-8); checked.add(sum(flags))
+    assert checked >= {0, 2}
