@@ -260,3 +260,54 @@ def test_equality_constraint_values_match_independent_twin(oracle, twin):
         # the oracle stacks the rows by constraint type, the twin by foot: compare the residuals as multisets
         np.testing.assert_allclose(np.sort(g), np.sort(ref), rtol=0, atol=2e-8); checked.add(sum(flags))
     assert checked >= {0, 2}
+
+
+def _barrier(mu, delta, h):   # ocs2 RelaxedBarrierPenalty [upstream]
+    return -mu * np.log(h) if h > delta else mu * (-np.log(delta) + 0.5 * ((h - 2.0 * delta) / delta) ** 2 - 0.5)
+
+
+def test_input_weight_and_stage_cost_value_match_independent_twin(oracle, twin):
+    """(a) initializeInputCostWeight (QMInterface.cpp:274-299): R[12:24,12:24] = J' R_task J with J = d(foot positions)/d(leg joints) at initialState, J from central
+    differences of the twin's FK.  (b) the intermediate cost VALUE at random points from its published pieces: quadratic tracking (LeggedRobotQuadraticTrackingCost.h:34-40),
+    end-effector penalty 1/2 mu |e|^2 (task.info:118-122), relaxed barriers on the arm joint box (task.info:165-200, URDF limits) and on the friction cone
+    (task.info:159-164, regularisation 25 [upstream default]); EE pose from the twin's FK, quaternions from scipy."""
+    from scipy.spatial.transform import Rotation
+    from qm_control_b200 import synthetic, _lib
+    info = oracle.model_info(); Q, R = oracle.mpc_weights(); qn = info["q_nominal"]; feet = ("LF_FOOT", "RF_FOOT", "LH_FOOT", "RH_FOOT")
+    txt = open(_lib.asset("qm_task.info")).read(); import re as _re
+    blk = _re.search(r"(?m)^R\s*\n?\{(.*?)^\}", txt, _re.S).group(1); scaling = float(_re.search(r"scaling\s+([-+.\deE]+)", blk).group(1))
+    Rtask = np.zeros(30)
+    for i, j, v in _re.findall(r"\((\d+),(\d+)\)\s+([-+.\deE]+)", blk):
+        assert i == j; Rtask[int(i)] = scaling * float(v)
+    eps = 1e-6; J = np.zeros((12, 12))
+    for k in range(12):
+        d = np.zeros(24); d[6 + k] = eps; pa = twin.fk(qn + d); pb = twin.fk(qn - d)
+        J[:, k] = np.concatenate([(pa[n][1] - pb[n][1]) / (2 * eps) for n in feet])
+    Rref = np.diag(Rtask); Rref[12:24, 12:24] = J.T @ np.diag(Rtask[12:24]) @ J
+    np.testing.assert_allclose(R, Rref, rtol=0, atol=1e-9)
+    Qblk = _re.search(r"(?m)^Q\s*\n?\{(.*?)^\}", txt, _re.S).group(1); Qs = float(_re.search(r"scaling\s+([-+.\deE]+)", Qblk).group(1)); Qref = np.zeros((30, 30))
+    for i, j, v in _re.findall(r"\((\d+),(\d+)\)\s+([-+.\deE]+)", Qblk):
+        Qref[int(i), int(j)] = Qs * float(v)
+    np.testing.assert_allclose(Q, Qref, rtol=0, atol=0)
+    # (b) cost value
+    prob, _ = synthetic.make_batch(np.array([4]), config=4); ne = int(prob["n_events"][0]); et = prob["event_times"][0, :ne]; md = prob["modes"][0, :ne + 1]
+    tt = prob["target_times"][0, :2]; ts = prob["target_states"][0, :2]; lo = info["lower"][12:]; hi = info["upper"][12:]; vlim = np.array([0.628, 0.628, 0.628, 0.837, 0.837, 0.837])
+    for j, t in enumerate(np.linspace(12.05, 12.95, 6)):
+        q, _ = _rand_q(oracle, 80 + j); rng = np.random.default_rng(100 + j); q[18:24] = np.clip(q[18:24], lo + 0.05, hi - 0.05)
+        x = np.r_[rng.uniform(-0.2, 0.2, 6), q]; u = np.r_[np.tile([3.0, -4.0, 60.0], 4) + rng.uniform(-2, 2, 12), rng.uniform(-0.5, 0.5, 18)]
+        mode = md[int(np.searchsorted(et, t, side="left"))]; flags = [(mode >> (3 - f)) & 1 for f in range(4)]
+        f_or, _, _, _ = oracle.stage_probe(et, md, tt, ts, t, x, u, want_grad=False)
+        a = (tt[1] - t) / (tt[1] - tt[0]); xref = a * ts[0, :30] + (1 - a) * ts[1, :30]; un = np.zeros(30)
+        for f in range(4):
+            if flags[f]:
+                un[3 * f + 2] = info["mass"] * 9.81 / sum(flags)
+        val = 0.5 * (x - xref) @ Q @ (x - xref) + 0.5 * (u - un) @ R @ (u - un)
+        Ree, pee = twin.fk(q)["j2n6s300_end_effector"]; pref = ts[0, 30:33]; qref = ts[0, 33:37]                     # constant EE target over the horizon
+        qe = Rotation.from_matrix(Ree).as_quat(); dist = qe[3] * qref[:3] - qref[3] * qe[:3] + np.cross(qe[:3], qref[:3])    # quaternionDistance(q_ee, q_ref)
+        val += 0.5 * 2000.0 * np.sum((pee - pref) ** 2) + 0.5 * 1000.0 * np.sum(dist ** 2)
+        for i in range(6):
+            val += _barrier(0.1, 1e-3, x[24 + i] - lo[i]) + _barrier(0.1, 1e-3, hi[i] - x[24 + i]) + _barrier(0.1, 1e-3, u[24 + i] + vlim[i]) + _barrier(0.1, 1e-3, vlim[i] - u[24 + i])
+        for f in range(4):
+            if flags[f]:
+                F = u[3 * f:3 * f + 3]; val += _barrier(0.1, 5.0, 0.3 * F[2] - np.sqrt(F[0] ** 2 + F[1] ** 2 + 25.0))
+        np.testing.assert_allclose(f_or, val, rtol=1e-10, atol=1e-8)
