@@ -34,13 +34,22 @@ extern "C" {
 #define QMB200_WBC_HIERARCHICAL 0      /* qm::HierarchicalWbc      (qm_wbc/src/HierarchicalWbc.cpp:18-44)    */
 #define QMB200_WBC_HIERARCHICAL_MPC 1  /* qm::HierarchicalMpcWbc   (qm_wbc/src/HierarchicalMpcWbc.cpp:18-34) */
 
-/* per-robot status bits (the reference ignores solver status, HoQp.cpp:143; here it is reported) */
+/* per-robot status bits (the reference ignores solver status, HoQp.cpp:143; here it is reported).
+ * Layout of a status word:  bits 0..7   WBC flags (QMB200_ST_ITER_CAP | _OVERFLOW | _NAN) — qmb200_wbc_update, qmb200_update, qmb200_tick
+ *                           bits 8..15  MPC flags shifted left by 8 — only in the merged word qmb200_tick / qmb200_tick_dev return
+ *                                       (qmb200_mpc_solve / qmb200_mpc_get_solution report the MPC flags unshifted in their own status array)
+ *                           bit 16      QMB200_ST_SAFETY — qmb200_update / qmb200_control_law
+ * Nothing else is ever OR-ed into a status word: the WBC's iteration counts live in qmb200_wbc_get_diagnostics. */
 #define QMB200_ST_ITER_CAP 1
-#define QMB200_ST_OVERFLOW 2
+#define QMB200_ST_OVERFLOW 2      /* WBC: more rows than the working-set / level-0 buffers hold; MPC: node count > NMAX, event / target count out of range, swing phase not enclosed */
 #define QMB200_ST_NAN 4
 #define QMB200_ST_NOT_PD 8
 #define QMB200_ST_NO_STEP 16      /* line search rejected every step size (solution = initial guess, as in SqpSolver::takeStep) */
 #define QMB200_ST_CONVERGED 32    /* informational: SqpSolver::checkConvergence ended the SQP loop before sqp.sqpIteration (only when sqpIteration > 1) */
+#define QMB200_ST_NEG_DT 64       /* an interval of the time grid has a non-positive duration: a pre-/post-event node within weakEpsilon (1e-6 s) of its neighbour but
+                                     further than dt_min (1e-8 s), so getIntervalEnd - getIntervalStart < 0 [upstream ocs2_oc TimeDiscretization]; the stage cost is then
+                                     weighted by a negative dt and the QP is not convex (comes with QMB200_ST_NOT_PD) */
+#define QMB200_MPC_STATUS_SHIFT 8
 
 typedef struct qmb200_handle qmb200_handle;
 
@@ -90,6 +99,11 @@ typedef struct {
 } qmb200_wbc_gains;
 int qmb200_wbc_get_gains(const qmb200_handle* h, qmb200_wbc_gains* out);
 int qmb200_wbc_set_gains(qmb200_handle* h, const qmb200_wbc_gains* gains);
+/* Per-robot diagnostics of the last WBC update on this handle (the reference prints nothing: HoQp.cpp:143 drops qpOASES' return value):
+ * diag[b] = it0 | it1 << 8 | it2 << 16 | nw << 24 — level-0 semismooth passes, active-set iterations of levels 1 and 2, final working-set size. */
+int qmb200_wbc_get_diagnostics(qmb200_handle* h, int32_t* diag /*[B]*/);
+/* Iteration caps of the WBC solver (defaults 30 / 80 ≙ nWSR = 100 of HoQp.cpp:141); a robot that hits one carries QMB200_ST_ITER_CAP.  <= 0 keeps the value. */
+int qmb200_wbc_set_iteration_caps(qmb200_handle* h, int32_t level0_passes, int32_t active_set_iterations);
 
 /* ---- MPC seam: ocs2::MPC_BASE::run → SqpSolver::run(t0, x0, t0+T), one SQP iteration (QMController.cpp:287-288,315-332),
  *      with the inputs the reference manager holds: mode schedule (SwitchedModelReferenceManager) and TargetTrajectories.
@@ -210,6 +224,11 @@ int qmb200_measure_fp64_peak(qmb200_handle* h, double* tflops);
 
 /* diagnostics: the QP step (dx, du) of the last solve and per-robot scalars [armijo, baseline cost, dyn SSE, eq SSE, |dx|, |du|, -, -] */
 int qmb200_debug_get_step(qmb200_handle* h, double* dx /*[B][NMAX][30]*/, double* du /*[B][NMAX][30]*/, double* robot /*[B][8]*/);
+/* Host-only (no CUDA device needed): run the constructor chain's parsers (QMInterface::setupModel / setupOptimalControlProblem inputs: task.info, robot.urdf,
+ * reference.info, optional gains file — batch / device of cfg are ignored) and copy the resulting model + settings constants (the block replicated to every GPU)
+ * into out.  Returns the block size in bytes (also when out is NULL or capacity is too small: nothing is copied then), negative on a parse error
+ * (qmb200_last_error(NULL)).  Used to check that two sets of input files define the same problem, bit for bit. */
+int64_t qmb200_debug_model_blob(const qmb200_config* cfg, void* out, int64_t capacity);
 
 /* number of kernels this library launched since create (bench.py's gpu_launches) */
 int64_t qmb200_launch_count(const qmb200_handle* h);

@@ -30,14 +30,14 @@ class WbcGains(C.Structure):
 
 # every symbol include/qmb200.h declares (checked by the CPU test-suite)
 SYMBOLS = ["qmb200_create", "qmb200_destroy", "qmb200_last_error", "qmb200_get_dims", "qmb200_get_model_info", "qmb200_get_joint_name",
-           "qmb200_wbc_update", "qmb200_wbc_update_dev", "qmb200_wbc_set_input_last", "qmb200_wbc_get_input_last", "qmb200_wbc_get_gains", "qmb200_wbc_set_gains",
+           "qmb200_wbc_update", "qmb200_wbc_update_dev", "qmb200_wbc_set_input_last", "qmb200_wbc_get_input_last", "qmb200_wbc_get_gains", "qmb200_wbc_set_gains", "qmb200_wbc_get_diagnostics", "qmb200_wbc_set_iteration_caps",
            "qmb200_mpc_solve", "qmb200_mpc_solve_dev", "qmb200_mpc_set_iterations", "qmb200_mpc_reset", "qmb200_mpc_set_solution", "qmb200_mpc_get_solution",
            "qmb200_policy_eval", "qmb200_policy_eval_dev", "qmb200_tick", "qmb200_tick_dev", "qmb200_centroidal_state_from_rbd",
            "qmb200_gait_schedule", "qmb200_launch_count", "qmb200_stream", "qmb200_debug_get_step",
            "qmb200_gait_create", "qmb200_gait_destroy", "qmb200_gait_insert_template", "qmb200_gait_get_mode_schedule",
            "qmb200_observation_update", "qmb200_observation_update_dev", "qmb200_target_trajectories", "qmb200_target_trajectories_dev", "qmb200_initial_ee_target",
            "qmb200_control_law", "qmb200_control_law_dev", "qmb200_set_arm_gains", "qmb200_hw_write", "qmb200_hw_write_dev", "qmb200_hw_set_delay", "qmb200_update", "qmb200_update_dev",
-           "qmb200_set_pipeline", "qmb200_set_profiling", "qmb200_collect_kernel_times", "qmb200_get_kernel_times", "qmb200_measure_fp64_peak"]
+           "qmb200_debug_model_blob", "qmb200_set_pipeline", "qmb200_set_profiling", "qmb200_collect_kernel_times", "qmb200_get_kernel_times", "qmb200_measure_fp64_peak"]
 
 _lib = None
 
@@ -55,6 +55,8 @@ def load_library():
     lib.qmb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.qmb200_destroy.argtypes = [C.c_void_p]
     lib.qmb200_destroy.restype = None
+    lib.qmb200_debug_model_blob.restype = C.c_int64
+    lib.qmb200_debug_model_blob.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64]
     lib.qmb200_launch_count.restype = C.c_int64
     lib.qmb200_launch_count.argtypes = [C.c_void_p]
     lib.qmb200_stream.restype = C.c_void_p

@@ -273,6 +273,7 @@ HostModel build_host_model(const std::string& task_file, const std::string& urdf
   d.sqp_iterations = (int)task.number("sqp.sqpIteration", 1.0); if (d.sqp_iterations < 1) d.sqp_iterations = 1; d.cost_tol = task.number("sqp.costTol", 1e-4);
   d.dt = task.number("sqp.dt", 0.015); d.time_horizon = task.number("mpc.timeHorizon", 1.0); d.delta_tol = task.number("sqp.deltaTol", 1e-4); d.g_max = task.number("sqp.g_max", 1e-2); d.g_min = task.number("sqp.g_min", 1e-6);
   d.alpha_decay = 0.5; d.alpha_min = 1e-4; d.gamma_c = 1e-6; d.armijo_factor = 1e-4;   // ocs2 sqp::Settings defaults [upstream]
+  d.wbc_iter_cap0 = 30; d.wbc_iter_cap = 80;
   d.rk_c = 1.0; d.rk_w1 = 0.5; d.rk_w2 = 0.5;                                          // Heun (ocs2 SensitivityIntegrator rk2 [upstream])
   return hm;
 }

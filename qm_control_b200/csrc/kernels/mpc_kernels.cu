@@ -18,18 +18,22 @@ namespace qmb {
 #define QMB_LQ_WARPS 6
 #endif
 constexpr int LQ_WARPS = QMB_LQ_WARPS, LS_WARPS = 4, SETUP_WARPS = 4;
-enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16, MST_CONVERGED = 32 };   // CONVERGED: checkConvergence stopped the SQP loop before sqpIteration
+enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16, MST_CONVERGED = 32, MST_NEG_DT = 64 };   // NEG_DT: an interval with non-positive duration (include/qmb200.h)   // CONVERGED: checkConvergence stopped the SQP loop before sqpIteration
 
 __device__ __forceinline__ double interval_start(double t, int ev) { return ev == 2 ? t + WEAK_EPS : t; }
 __device__ __forceinline__ double interval_end(double t, int ev) { return ev == 1 ? t - WEAK_EPS : t; }
+// caller-provided counts are clamped on every use (the _dev entry points take arbitrary device arrays); K1 flags an out-of-range count with MST_OVERFLOW
+__device__ __forceinline__ int clamp_events(int ne) { return ne < 0 ? 0 : (ne > EMAX ? EMAX : ne); }
+__device__ __forceinline__ int clamp_targets(int nk) { return nk < 1 ? 1 : (nk > KMAX ? KMAX : nk); }
 __device__ __forceinline__ int flag_mask(int mode) { int m = 0; for (int i = 0; i < 4; ++i) if (contact_flag(mode, i)) m |= 1 << i; return m; }
 
 // =====================================================================================================
 // K1: time grid + initial guess
 __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev prev, MpcSolutionDev next, int32_t* __restrict__ status) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x * SETUP_WARPS + warp; if (b >= B) return;
-  const double t0 = p.t0[b], tf = t0 + mdl->time_horizon, dt = mdl->dt; const int ne = p.n_events[b]; const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
+  const double t0 = p.t0[b], tf = t0 + mdl->time_horizon, dt = mdl->dt; const int ne = clamp_events(p.n_events[b]); const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
   double* gt = next.t + (size_t)b * nmax; int32_t* ge = next.event + (size_t)b * nmax; int st = 0;
+  if (ne != p.n_events[b] || clamp_targets(p.n_target[b]) != p.n_target[b]) st |= MST_OVERFLOW;
   // ---- timeDiscretizationWithEvents [upstream ocs2_oc/oc_data/TimeDiscretization.cpp] ----
   int n = 0;
   if (lane == 0) {
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevMo
     }
     next.n_nodes[b] = n;
   }
-  n = __shfl_sync(FULL, n, 0); st = __shfl_sync(FULL, st, 0);
+  n = __shfl_sync(FULL, n, 0); st |= __shfl_sync(FULL, st, 0);
   __syncwarp();
   // ---- initializeStateInputTrajectories [upstream ocs2_oc/multiple_shooting/Initialization.cpp] ----
   const int np = prev.n_nodes ? prev.n_nodes[b] : 0; const bool has_prev = np >= 2;
@@ -111,10 +115,10 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp];
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL; int32_t* si = stage_i + ((size_t)b * nmax + k) * STAGE_INT;
-  const int ne = p.n_events[b]; const double* ev = sm.ev; const unsigned char* modes = sm.modes;
+  const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
   { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
   const int lfp = pack_leg_foot(mdl);
-  const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
+  const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
   const bool terminal = (k == n - 1);
   if (lane < NX) { sm.xs[lane] = xk[lane]; sm.pt.u[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
@@ -130,6 +134,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   __syncwarp();
   const double dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
   const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
+  if (!terminal && !(dt > 0.0) && lane == 0) atomicOr(&status[b], MST_NEG_DT);   // getIntervalDuration <= 0: an event within weakEpsilon of a grid node (QMB200_ST_NEG_DT)
   double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0;
   // One inlined copy of the flow-map evaluation serves both RK2 stages (and the terminal node): the kernel is
   // instruction-fetch sensitive (straight-line code of several hundred KB), so the pass loop is deliberately not unrolled.
@@ -651,10 +656,10 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const 
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* gx = sol.x + (size_t)b * nmax * NX; double* gu = sol.u + (size_t)b * nmax * NU; const double* gdx = dxo + (size_t)b * nmax * NX; const double* gdu = duo + (size_t)b * nmax * NU;
-  const int ne = p.n_events[b]; const double* ev = sm.ev; const unsigned char* modes = sm.modes;
+  const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
   { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
   const int lfp = pack_leg_foot(mdl);
-  const int nk = p.n_target[b]; const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
+  const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* rb = robot + (size_t)b * ROBOT_DBL; const double armijo = rb[0], base_cost = rb[1], base_viol = sqrt(rb[2] + rb[3]), dxn = rb[4], dun = rb[5];
   const bool failed = (status[b] & MST_NOT_PD) != 0;
   double alpha = 1.0; bool accepted = false; double sc = base_cost, sd = rb[2], se = rb[3];
@@ -741,13 +746,13 @@ __global__ void mpc_policy_eval_kernel(int b0, int B, int nmax, MpcSolutionDev s
   int idx; double a; time_segment(gt, n, t, idx, a); const int i2 = (idx + 1 < n) ? idx + 1 : idx;
   const double* gx = sol.x + (size_t)b * nmax * NX; const double* gu = sol.u + (size_t)b * nmax * NU;
   if (lane < NX) { x_des[(size_t)b * NX + lane] = a * gx[(size_t)idx * NX + lane] + (1.0 - a) * gx[(size_t)i2 * NX + lane]; u_des[(size_t)b * NU + lane] = a * gu[(size_t)idx * NU + lane] + (1.0 - a) * gu[(size_t)i2 * NU + lane]; }
-  if (lane == 0) mode_out[b] = mode_at_time(event_times + (size_t)b * EMAX, modes + (size_t)b * (EMAX + 1), n_events[b], t);
+  if (lane == 0) mode_out[b] = mode_at_time(event_times + (size_t)b * EMAX, modes + (size_t)b * (EMAX + 1), clamp_events(n_events[b]), t);
 }
 
 // =====================================================================================================
-bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<void*>& allocs) {
+bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<void*>& allocs, cudaStream_t stream) {
   m.B = B; m.nmax = nmax; m.cur = 0;
-  auto A = [&](auto** p, size_t count) { void* q = nullptr; const size_t bytes = count * sizeof(**p); cudaError_t e = cudaMalloc(&q, bytes); if (e != cudaSuccess) { err = std::string("cudaMalloc (MPC buffers) failed: ") + cudaGetErrorString(e); return false; } cudaMemset(q, 0, bytes); allocs.push_back(q); *p = static_cast<std::remove_reference_t<decltype(**p)>*>(q); return true; };
+  auto A = [&](auto** p, size_t count) { void* q = nullptr; const size_t bytes = count * sizeof(**p); cudaError_t e = cudaMalloc(&q, bytes); if (e != cudaSuccess) { err = std::string("cudaMalloc (MPC buffers) failed: ") + cudaGetErrorString(e); return false; } cudaMemsetAsync(q, 0, bytes, stream); allocs.push_back(q); *p = static_cast<std::remove_reference_t<decltype(**p)>*>(q); return true; };
   const size_t Bn = (size_t)B * nmax;
   bool ok = A(&m.t0, B) && A(&m.x0, (size_t)B * NX) && A(&m.n_events, B) && A(&m.event_times, (size_t)B * EMAX) && A(&m.modes, (size_t)B * (EMAX + 1)) && A(&m.n_target, B) && A(&m.target_times, (size_t)B * KMAX) && A(&m.target_states, (size_t)B * KMAX * TARGET_DIM);
   for (int s = 0; s < 2 && ok; ++s) ok = A(&m.sol[s].n_nodes, B) && A(&m.sol[s].t, Bn) && A(&m.sol[s].event, Bn) && A(&m.sol[s].x, Bn * NX) && A(&m.sol[s].u, Bn * NU);
@@ -755,14 +760,14 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
   return ok;
 }
 
+int mpc_configure_device() {
+  cudaError_t e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
+  return (int)e;
+}
+
 int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, const MpcProblemDev& p, int b0, int b1, cudaStream_t stream, cudaEvent_t* ev) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
-    cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
-    cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
-    configured = true;
-  }
   const int nb = b1 - b0, nmax = m.nmax; if (nb <= 0) return 0;
   MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];   // the caller flips m.cur once all ranges are queued
   if (ev) cudaEventRecord(ev[0], stream);

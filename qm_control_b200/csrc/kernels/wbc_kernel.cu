@@ -190,11 +190,11 @@ __device__ __forceinline__ void project_task(QpWs& qp, int rows, int off, int nz
 }
 
 // One hierarchy level >= 1: primal active set over the hard inequalities, equality residual minimised in the window.
-__device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, int& nw, int lane, int& iters_out) {
+__device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, int& nw, int lane, int& iters_out, int iter_cap) {
   QpWs& qp = sm.u.qp; const int nz = 36 - off; const int nineq = 36 + 5 * ic.nc; int status = 0;
   if (nz <= 0) return 0;
   bool converged = false;
-  for (int iter = 0; iter < 80; ++iter) {
+  for (int iter = 0; iter < iter_cap; ++iter) {
     iters_out = iter + 1;
     // (1) working-set constraints in window coordinates: Wc[c + k*LDZ] = G_{w_k} . Z[:, off+c]
     int kc = 0;
@@ -271,7 +271,7 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
 __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevModel* __restrict__ mdl, int b0, int B, const double* __restrict__ x_des, const double* __restrict__ u_des,
                                                                    const double* __restrict__ rbd_meas, const int32_t* __restrict__ mode_in, const double* __restrict__ period_in,
                                                                    const double* __restrict__ time_in, double* __restrict__ input_last, int variant,
-                                                                   double* __restrict__ cmd_out, int32_t* __restrict__ status_out) {
+                                                                   double* __restrict__ cmd_out, int32_t* __restrict__ status_out, int32_t* __restrict__ diag_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = b0 + blockIdx.x * WBC_WARPS + warp;
@@ -371,8 +371,9 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   int rows0 = build_level(sm, mdl, 0, mode, variant, init_phase, lane);
   const int nineq = 36 + 5 * nc;
   unsigned vmask0 = 0, vmask1 = 0;   // violated set, bit per inequality (lane-uniform)
-  for (int it = 0; it < 30; ++it) {
-    int r = rows0;
+  const int cap0 = mdl->wbc_iter_cap0, cap = mdl->wbc_iter_cap; int it0 = 0;
+  for (int it = 0; it < cap0; ++it) {
+    int r = rows0; it0 = it + 1;
     // append violated rows
     for (int i = 0; i < nineq; ++i) { const bool in = (i < 32) ? ((vmask0 >> i) & 1u) : ((vmask1 >> (i - 32)) & 1u); if (in) { if (r >= MAXR) { status |= ST_TOO_MANY_ROWS; break; }
         for (int k = lane; k < 36; k += 32) qp.Ap[r * LDZ + k] = ineq_row_elem(ic, i, k); if (lane == 0) qp.bp[r] = ineq_rhs(ic, i); ++r; } }
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
     for (int o = 16; o > 0; o >>= 1) { n0 |= __shfl_xor_sync(FULL, n0, o); n1 |= __shfl_xor_sync(FULL, n1, o); }
     if (n0 == vmask0 && n1 == vmask1) break;
     vmask0 = n0; vmask1 = n1;
-    if (it == 29) status |= ST_ITER_CAP;
+    if (it == cap0 - 1) status |= ST_ITER_CAP;
   }
   // optimal slack of level 0 and the null space of A0 (HoQp::buildZMatrix, HoQp.cpp:126-133)
   for (int i = lane; i < nineq; i += 32) { const double val = ineq_row_dot(ic, i, qp.xbar) - ineq_rhs(ic, i); sm.vstar[i] = val > 0.0 ? val : 0.0; }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
     const int rows = build_level(sm, mdl, level, mode, variant, init_phase, lane);
     const int nz = 36 - off;
     if (nz <= 0) break;                                   // trivial kernel (the reference keeps one zero column, HoQp.cpp:129)
-    status |= solve_level(sm, ic, rows, off, nw, lane, level == 1 ? it1 : it2);
+    status |= solve_level(sm, ic, rows, off, nw, lane, level == 1 ? it1 : it2, cap);
     if (level == 1) {                                    // Z <- Z * kernel(A_1 Z)
       project_task(qp, rows, off, nz, lane);
       const int k = w_qrcp(qp.W, nz, rows, LDZ, qp.tau, qp.perm, 1e-11, lane);
@@ -420,21 +421,23 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   bool bad = false;
   if (lane < NJ) { const double* Mr = sm.M + (6 + lane) * LDM; double s = sm.nle[6 + lane]; for (int k = 0; k < NQ; ++k) s += Mr[k] * qp.xbar[k]; for (int k = 0; k < 12; ++k) s -= sm.Jf[k * LDM + 6 + lane] * qp.xbar[NQ + k]; out[36 + lane] = s; bad = !isfinite(s); }
   if (__any_sync(FULL, bad)) status |= ST_NAN;
-  if (status) status |= (it1 << 8) | (it2 << 16) | (nw << 24);   // diagnostics ride in the high bits of a failed robot's status
-  if (lane == 0) status_out[b] = status;
+  // status word: WBC flags only, in the low byte (bits 8..15 carry the MPC flags after qmb200_tick's merge, bit 16 = QMB200_ST_SAFETY: include/qmb200.h);
+  // iteration counts / working-set size go to the separate diagnostics word: it0 | it1 << 8 | it2 << 16 | nw << 24
+  if (lane == 0) { status_out[b] = status; if (diag_out) diag_out[b] = (it0 & 0xff) | ((it1 & 0xff) << 8) | ((it2 & 0xff) << 16) | ((nw & 0xff) << 24); }
 }
 
 static_assert(sizeof(WbcSmem) * WBC_WARPS <= 227 * 1024, "WBC shared-memory budget exceeded");
 size_t wbc_smem_bytes() { return sizeof(WbcSmem) * WBC_WARPS; }
 
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
-                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0, int b1) {
-  static bool configured = false;
+                       double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0, int b1, int32_t* diag) {
   const size_t smem = wbc_smem_bytes();
-  if (!configured) { cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
   if (b1 < 0) b1 = B; if (b1 <= b0) return;
   const int grid = (b1 - b0 + WBC_WARPS - 1) / WBC_WARPS;
-  wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status);
+  wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status, diag);
 }
+
+// cudaFuncSetAttribute is per device: called from qmb200_create after cudaSetDevice (one handle per GPU, several handles / devices per process allowed)
+int wbc_configure_device() { return (int)cudaFuncSetAttribute(wbc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbc_smem_bytes()); }
 
 }  // namespace qmb

@@ -129,6 +129,14 @@ class Solver:
     def wbc_set_input_last(self, input_last=None):
         self._chk(self.lib.qmb200_wbc_set_input_last(self.h, _p(_f64(input_last, (self.batch, NU))) if input_last is not None else None), "qmb200_wbc_set_input_last")
 
+    def wbc_get_diagnostics(self):
+        """→ dict(level0_passes, level1_iterations, level2_iterations, working_set) of the last WBC update, per robot."""
+        d = np.zeros(self.batch, dtype=np.int32); self._chk(self.lib.qmb200_wbc_get_diagnostics(self.h, _p(d)), "qmb200_wbc_get_diagnostics")
+        return dict(level0_passes=d & 0xFF, level1_iterations=(d >> 8) & 0xFF, level2_iterations=(d >> 16) & 0xFF, working_set=(d >> 24) & 0xFF)
+
+    def wbc_set_iteration_caps(self, level0_passes=0, active_set_iterations=0):
+        self._chk(self.lib.qmb200_wbc_set_iteration_caps(self.h, int(level0_passes), int(active_set_iterations)), "qmb200_wbc_set_iteration_caps")
+
     def wbc_get_input_last(self):
         out = np.empty((self.batch, NU)); self._chk(self.lib.qmb200_wbc_get_input_last(self.h, _p(out)), "qmb200_wbc_get_input_last"); return out
 

@@ -6,16 +6,9 @@
 import numpy as np
 import pytest
 
+from _parity import MPC_TOL, TICK_TOL, WBC_TOL, assert_cmd, assert_traj
+
 pytestmark = pytest.mark.gpu
-RTOL = 1e-5
-
-
-def _traj_err(out, ref, b_out, b_ref):
-    n = int(ref["n_nodes"][b_ref]); assert int(out["n_nodes"][b_out]) == n
-    ex = np.max(np.abs(out["x"][b_out, :n] - ref["x"][b_ref, :n])) / max(1.0, np.max(np.abs(ref["x"][b_ref, :n])))
-    k = np.nonzero(ref["event"][b_ref, :n - 1] != 1)[0]
-    eu = np.max(np.abs(out["u"][b_out, k] - ref["u"][b_ref, k])) / max(1.0, np.max(np.abs(ref["u"][b_ref, k])))
-    return max(ex, eu)
 
 
 def test_config2_mpc_b1024_n100(oracle):
@@ -36,7 +29,7 @@ def test_config2_mpc_b1024_n100(oracle):
     sel = np.array([0, 7, 100, 511, 512, 777, 1000, 1023]); sub = {k: v[sel] for k, v in prob.items()}
     ref = oracle.mpc_solve_batch(sub, solver.nmax, nthreads=8)
     for i, b in enumerate(sel):
-        assert out["step_info"][b, 0] == ref["dbg"][i, 0]; err = _traj_err(out, ref, b, i); assert err < RTOL, (b, err)
+        assert out["step_info"][b, 0] == ref["dbg"][i, 0]; assert_traj(out, ref, MPC_TOL, tag="config2 b1024 robot %d" % b, b_out=b, b_ref=i)
     # batch-position invariance: reverse the batch
     solver2 = q.Solver(batch=B, dt=0.01); rev = ids[::-1].copy(); prob_r, _ = synthetic.make_batch(rev, config=2, horizon=1.0)
     out_r = solver2.mpc_solve(prob_r)
@@ -60,7 +53,7 @@ def test_config3_wbc_b4096(oracle):
     assert np.all(status == 0), np.unique(status)
     sel = np.arange(0, B, 128)
     ref, _ = oracle.wbc_update_batch(x_des[sel], u_des[sel], wbc["rbd"][sel], mode[sel], wbc["period"][sel], np.full(len(sel), 12.0), il[sel], variant=0, nthreads=8)
-    err = np.max(np.abs(cmd[sel] - ref), axis=1) / np.maximum(1.0, np.max(np.abs(ref), axis=1)); assert err.max() < RTOL, err.max()
+    assert_cmd(cmd[sel], ref, WBC_TOL, tag="config3 wbc b4096")
     eff = oracle.model_info()["effort"]; lim = np.r_[np.tile(eff[:3], 4), eff[12:]]
     assert np.all(np.abs(cmd[:, 36:]) <= lim + 1e-6)                                  # torque limits, every robot
     F = cmd[:, 24:36].reshape(B, 4, 3); assert np.all(F[:, :, 2] >= -1e-7) and np.all(np.abs(F[:, :, :2]) <= 0.3 * F[:, :, 2:3] + 1e-6)   # friction pyramid
@@ -87,10 +80,8 @@ def test_config4_full_tick_b8192_rows_do_not_depend_on_the_batch(oracle):
     cmd_s, status_s = small.tick(ps, ps["t0"] + 0.002, ws["rbd"], ws["period"])
     assert np.array_equal(cmd[sel], cmd_s) and np.array_equal(status[sel], status_s)
     ref = oracle.tick_batch(ps, small.nmax, ps["t0"] + 0.002, ws["rbd"], ws["period"], np.zeros((len(sel), 30)), nthreads=8)
-    err = np.max(np.abs(cmd_s - ref["cmd"]), axis=1) / np.maximum(1.0, np.max(np.abs(ref["cmd"]), axis=1)); assert err.max() < 1e-4, err   # WBC gains amplify the 1e-5 MPC tolerance
-    sol = small.mpc_get_solution()
-    for i in range(len(sel)):
-        assert _traj_err(sol, ref, i, i) < RTOL
+    assert_cmd(cmd_s, ref["cmd"], TICK_TOL, tag="config4 b8192 tick cmd")
+    assert_traj(small.mpc_get_solution(), ref, MPC_TOL, tag="config4 b8192 tick traj")
 
 
 def test_config4_twenty_warm_started_ticks(oracle):
@@ -110,13 +101,11 @@ def test_config4_twenty_warm_started_ticks(oracle):
         t_eval = prob["t0"] + 0.002
         cmd, status = solver.tick(prob, t_eval, wbc["rbd"], wbc["period"]); assert np.all((status & ~(16 << 8)) == 0), (tick, np.unique(status))
         ref = oracle.tick_batch(prob, solver.nmax, t_eval, wbc["rbd"], wbc["period"], il, prev=prev, nthreads=6)
-        sol = solver.mpc_get_solution()
-        for b in range(B):
-            worst = max(worst, _traj_err(sol, ref, b, b))
-        err = np.max(np.abs(cmd - ref["cmd"]), axis=1) / np.maximum(1.0, np.max(np.abs(ref["cmd"]), axis=1)); assert err.max() < 1e-4, (tick, err)
+        lv = assert_traj(solver.mpc_get_solution(), ref, MPC_TOL, tag="config4 20 ticks: tick %d traj" % tick); worst = max(worst, max(lv.values()))
+        assert_cmd(cmd, ref["cmd"], TICK_TOL, tag="config4 20 ticks: tick %d cmd" % tick)
         np.testing.assert_allclose(solver.wbc_get_input_last(), ref["input_last"], rtol=0, atol=1e-6)   # = the policy input of each side's own solution
         prev = {k: ref[k] for k in ("n_nodes", "t", "event", "x", "u")}; il = ref["input_last"]
-    assert worst < RTOL, worst
+    assert worst < MPC_TOL, worst
 
 
 def test_config5_mixed_gaits_per_gpu_share(oracle):
@@ -137,7 +126,5 @@ def test_config5_mixed_gaits_per_gpu_share(oracle):
     cmd_s, status_s = small.tick(ps, ps["t0"] + 0.002, ws["rbd"], ws["period"])
     assert np.array_equal(cmd[sel], cmd_s) and np.array_equal(status[sel], status_s)
     ref = oracle.tick_batch(ps, small.nmax, ps["t0"] + 0.002, ws["rbd"], ws["period"], np.zeros((len(sel), 30)), nthreads=9)
-    err = np.max(np.abs(cmd_s - ref["cmd"]), axis=1) / np.maximum(1.0, np.max(np.abs(ref["cmd"]), axis=1)); assert err.max() < 1e-4, err
-    sol_s = small.mpc_get_solution()
-    for i in range(len(sel)):
-        assert _traj_err(sol_s, ref, i, i) < RTOL
+    assert_cmd(cmd_s, ref["cmd"], TICK_TOL, tag="config5 b2048 tick cmd")
+    assert_traj(small.mpc_get_solution(), ref, MPC_TOL, tag="config5 b2048 tick traj")

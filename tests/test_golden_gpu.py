@@ -1,5 +1,5 @@
 """The CUDA path (through the C-ABI) against the committed golden fixtures (tests/golden/*.npz) — no oracle build involved.
-Tolerance: 1e-5 relative on trajectories and the WBC vector (BASELINE.json north_star), 1e-12 on the target front-end."""
+Contract 1e-5 relative on trajectories and the WBC vector (BASELINE.json north_star); asserted 1e-8 per block (tests/_parity.py), 1e-12 on the target front-end."""
 import os
 import sys
 
@@ -10,6 +10,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 sys.path.insert(0, GOLD)
 import make_golden as mg  # noqa: E402
+from _parity import MPC_TOL, WBC_TOL, assert_cmd, assert_traj  # noqa: E402
 
 
 def test_wbc_against_golden():
@@ -18,7 +19,7 @@ def test_wbc_against_golden():
     x_des, u_des, mode, wbc, il = mg.wbc_inputs(ids, solver.robot_mass)
     solver.wbc_set_input_last(il)
     cmd, status = solver.wbc_update(x_des, u_des, wbc["rbd"], mode, wbc["period"], np.full(B, 12.0)); assert np.all(status == 0)
-    err = np.max(np.abs(cmd - g["cmd"]), axis=1) / np.maximum(1.0, np.max(np.abs(g["cmd"]), axis=1)); assert err.max() < 1e-5, err
+    assert_cmd(cmd, g["cmd"], WBC_TOL, tag="golden wbc_config5")
     np.testing.assert_array_equal(solver.wbc_get_input_last(), g["input_last"])
 
 
@@ -33,11 +34,7 @@ def test_mpc_against_golden():
             solver.mpc_set_solution({k: g["t1_" + k] for k in ("n_nodes", "t", "event", "x", "u")})
         out = solver.mpc_solve(prob)
         np.testing.assert_array_equal(out["n_nodes"], g[pre + "n_nodes"]); np.testing.assert_array_equal(out["step_info"][:, 0], g[pre + "dbg"][:, 0])
-        for b in range(B):
-            n = int(out["n_nodes"][b]); np.testing.assert_array_equal(out["event"][b, :n], g[pre + "event"][b, :n]); np.testing.assert_allclose(out["t"][b, :n], g[pre + "t"][b, :n], rtol=0, atol=1e-12)
-            gx = g[pre + "x"][b, :n]; ex = np.max(np.abs(out["x"][b, :n] - gx)) / max(1.0, np.max(np.abs(gx)))
-            k = np.nonzero(g[pre + "event"][b, :n - 1] != 1)[0]; gu = g[pre + "u"][b, k]; eu = np.max(np.abs(out["u"][b, k] - gu)) / max(1.0, np.max(np.abs(gu)))
-            assert max(ex, eu) < 1e-5, (tick, b, ex, eu)
+        assert_traj(out, {k: g[pre + k] for k in ("n_nodes", "t", "event", "x", "u")}, MPC_TOL, tag="golden mpc_config5 tick %d" % tick)
 
 
 def test_target_against_golden():
