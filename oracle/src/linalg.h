@@ -161,6 +161,52 @@ inline void householder_qr(const Mat& A, Mat& Q, Mat& R) {
   }
 }
 
+// Householder QR with column pivoting: A P = Q [R; 0].  Returns the numerical rank (pivots below tol * largest pivot are treated as zero).
+// Q is m x m, R is m x n (upper trapezoidal in its first `rank` rows), perm[j] = original index of the column now at position j.
+inline int householder_qrcp(const Mat& A, Mat& Q, Mat& R, std::vector<int>& perm, double tol = 1e-11) {
+  const int m = A.r, n = A.c; R = A; Q = Mat::identity(m); perm.resize(n); for (int j = 0; j < n; ++j) perm[j] = j;
+  int rank = 0; double first = 0.0;
+  for (int k = 0; k < std::min(m, n); ++k) {
+    int piv = k; double best = -1.0;
+    for (int j = k; j < n; ++j) { double s = 0; for (int i = k; i < m; ++i) s += R(i, j) * R(i, j); if (s > best) { best = s; piv = j; } }
+    const double nrm = std::sqrt(std::max(best, 0.0)); if (k == 0) first = nrm;
+    if (!(nrm > tol * first) || nrm == 0.0) break;
+    if (piv != k) { for (int i = 0; i < m; ++i) std::swap(R(i, k), R(i, piv)); std::swap(perm[k], perm[piv]); }
+    const double alpha = R(k, k) > 0 ? -nrm : nrm;
+    Vec v(m, 0.0); for (int i = k; i < m; ++i) v[i] = R(i, k); v[k] -= alpha;
+    double vn = 0; for (int i = k; i < m; ++i) vn += v[i] * v[i];
+    if (vn > 0.0) {
+      for (int j = k; j < n; ++j) { double s = 0; for (int i = k; i < m; ++i) s += v[i] * R(i, j); s *= 2.0 / vn; for (int i = k; i < m; ++i) R(i, j) -= s * v[i]; }
+      for (int j = 0; j < m; ++j) { double s = 0; for (int i = k; i < m; ++i) s += v[i] * Q(j, i); s *= 2.0 / vn; for (int i = k; i < m; ++i) Q(j, i) -= s * v[i]; }
+    }
+    ++rank;
+  }
+  return rank;
+}
+// Equality-constrained least squares  min |A x - b|  s.t.  E x = e  (E may have dependent rows; the system is assumed consistent) by the
+// null-space method with orthogonal factorisations only (no normal equations): x = Q1 y1 + Q2 y2, E' P = Q [R; 0].
+// In flat directions of the reduced problem the minimum-norm solution is taken.
+inline Vec constrained_lstsq(const Mat& A, const Vec& b, const Mat& E, const Vec& e) {
+  const int n = A.c; Mat Q = Mat::identity(n); int k = 0; Vec y1;
+  if (E.r > 0) { Mat R; std::vector<int> perm; k = householder_qrcp(E.T(), Q, R, perm);
+    y1.assign(k, 0.0);   // R11' y1 = (P' e)[0:k]  (lower triangular, forward substitution)
+    for (int i = 0; i < k; ++i) { double s = e[perm[i]]; for (int l = 0; l < i; ++l) s -= R(l, i) * y1[l]; y1[i] = s / R(i, i); } }
+  Vec x(n, 0.0); for (int i = 0; i < n; ++i) for (int l = 0; l < k; ++l) x[i] += Q(i, l) * y1[l];
+  const int nf = n - k; if (nf == 0 || A.r == 0) return x;
+  Mat Q2 = Q.block(0, k, n, nf); Mat AQ = A * Q2; Vec r = b - A * x;
+  Mat Qa, Ra; std::vector<int> pa; const int ka = householder_qrcp(AQ, Qa, Ra, pa);
+  Vec c = tmul(Qa, r); Vec z(nf, 0.0);
+  if (ka == nf) { for (int i = ka - 1; i >= 0; --i) { double s = c[i]; for (int l = i + 1; l < ka; ++l) s -= Ra(i, l) * z[pa[l]]; z[pa[i]] = s / Ra(i, i); } }
+  else if (ka > 0) {   // rank deficient: minimum-norm solution of [R11 R12] w = c1 through the QR of the transposed trapezoid (complete orthogonal decomposition)
+    Mat Tt(nf, ka); for (int i = 0; i < ka; ++i) for (int j = 0; j < nf; ++j) Tt(j, i) = Ra(i, j);
+    Mat Qb, Rb; householder_qr(Tt, Qb, Rb); Vec u(ka, 0.0);
+    for (int i = 0; i < ka; ++i) { double s = c[i]; for (int l = 0; l < i; ++l) s -= Rb(l, i) * u[l]; u[i] = s / Rb(i, i); }
+    for (int j = 0; j < nf; ++j) { double w = 0; for (int l = 0; l < ka; ++l) w += Qb(j, l) * u[l]; z[pa[j]] = w; }
+  }
+  for (int i = 0; i < n; ++i) for (int l = 0; l < nf; ++l) x[i] += Q2(i, l) * z[l];
+  return x;
+}
+
 // ---- small fixed-size templated types for kinematics ----
 template <class T> struct V3 { T x, y, z; V3() : x(T(0.0)), y(T(0.0)), z(T(0.0)) {} V3(T a, T b, T c) : x(a), y(b), z(c) {}
   T& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); } const T& operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); } };

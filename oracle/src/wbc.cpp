@@ -49,7 +49,8 @@ struct HoQp {
   Mat stackedZPrev, stackedZ; Vec stackedSlackPrev, xPrev; Mat h, d; Vec c, f; Vec stackedSlack, slackSol, decSol; int iterations = 0, status = 0;
 
   HoQp(Task t, std::shared_ptr<HoQp> hp) : task(std::move(t)), higher(std::move(hp)) { initVars(); formulate(); solve(); buildZ(); stackSlack(); }
-  Vec getSolutions() const { return xPrev + stackedZPrev * decSol; }   // HoQp.h:31-34
+  Vec xPolished;   // see polish()
+  Vec getSolutions() const { return xPolished.empty() ? xPrev + stackedZPrev * decSol : xPolished; }   // HoQp.h:31-34
 
   void initVars() {  // HoQp.cpp:21-51
     numSlack = task.d.r; hasEq = task.a.r > 0; hasIneq = numSlack > 0;
@@ -77,7 +78,26 @@ struct HoQp {
     for (int i = 0; i < s; ++i) z0[n + i] = std::max(0.0, -f[s + numPrevSlack + i]);
     QpResult r = solve_qp_active_set(h, c, d, f, z0); iterations = r.iterations; status = r.status;
     decSol = seg(r.z, 0, n); slackSol = seg(r.z, n, s);
+    polish(r.active);
   }
+  // Numerical refinement, not a different optimum.  The literal level problem works in the coordinates of a fullPivLu kernel (HoQp.cpp:126-133) on the
+  // normal-equation Hessian Z'A'AZ + 1e-12 I (HoQp.cpp:60-66): its condition number is the square of the task's, and where a level leaves directions almost
+  // free (HierarchicalMpcWbc gives the arm no task; level 2 then trades 1e4 rad/s^2 of arm acceleration against the contact forces through a 3e3-conditioned
+  // block) the active-set iterate carries 1e-6..1e-4 of noise.  With the active set W the QP has identified, the level optimum is the equality-constrained least
+  // squares  min |A_p x - b_p|  s.t.  A_higher x = A_higher x_prev,  D_W x = f_W + v*_W  in the 36-dim decision space; it is re-solved here with Householder
+  // factorisations only, as a minimum-norm CORRECTION of the QP's iterate (free directions keep the QP's feasible choice).  Levels that own slack variables (level 0) are left as the QP returns them.
+  void polish(const std::vector<int>& active) {
+    if (!higher || numSlack != 0 || !hasEq) return;
+    std::vector<int> rows; for (int i : active) if (i >= numSlack && i < numSlack + numPrevSlack) rows.push_back(i - numSlack);
+    Mat E(stackedTasksPrev.a.r + (int)rows.size(), numDecX()); Vec e(E.r, 0.0);
+    Vec ax = stackedTasksPrev.a.r ? stackedTasksPrev.a * xPrev : Vec();
+    for (int i = 0; i < stackedTasksPrev.a.r; ++i) { for (int j = 0; j < E.c; ++j) E(i, j) = stackedTasksPrev.a(i, j); e[i] = ax[i]; }
+    for (size_t k = 0; k < rows.size(); ++k) { const int i = rows[k], o = stackedTasksPrev.a.r + (int)k; for (int j = 0; j < E.c; ++j) E(o, j) = stackedTasksPrev.d(i, j); e[o] = stackedTasksPrev.f[i] + stackedSlackPrev[i]; }
+    // correction form: x = x_qp + delta with the minimum-norm delta, so that directions the level leaves free keep the QP's (feasible) choice
+    const Vec xq = xPrev + stackedZPrev * decSol; const Vec delta = constrained_lstsq(task.a, task.b - task.a * xq, E, e - E * xq);
+    xPolished = xq + delta;
+  }
+  int numDecX() const { return (int)xPrev.size(); }
   void buildZ() {  // HoQp.cpp:126-133
     if (hasEq) { FullPivLU lu(task.a * stackedZPrev); stackedZ = stackedZPrev * lu.kernel(); } else stackedZ = stackedZPrev;
   }

@@ -31,11 +31,26 @@ def wbc_inputs(ids, mass):
     return x_des, u_des, mode, wbc, il
 
 
+WBC_MPC_IDS = np.arange(16)
+
+
+def wbc_mpc_inputs(ids, mass):
+    prob, wbc = synthetic.make_batch(ids, config=3)
+    x_des, u_des, mode = synthetic.nominal_wbc_inputs(prob, mass)
+    u_des = u_des + synthetic.uniform(77, ids, 1, 30, -1.0, 1.0) * np.r_[np.full(12, 5.0), np.full(18, 0.2)]
+    il = u_des + synthetic.uniform(78, ids, 2, 30, -0.002, 0.002)
+    return x_des, u_des, mode, wbc, il
+
+
 def main():
     o = Oracle(); mass = o.model_info()["mass"]
     x_des, u_des, mode, wbc, il = wbc_inputs(WBC_IDS, mass)
     cmd, il_out = o.wbc_update_batch(x_des, u_des, wbc["rbd"], mode, wbc["period"], np.full(len(WBC_IDS), 12.0), il, variant=0, nthreads=4)
     np.savez_compressed(os.path.join(HERE, "wbc_config5.npz"), ids=WBC_IDS, mode=mode, cmd=cmd, input_last=il_out)
+    # HierarchicalMpcWbc (QMMpcController's WBC): stance, realistic joint accelerations; the 12 leg torques cmd[:, 36:48] are what the controller consumes
+    x_des, u_des, mode, wbc, il = wbc_mpc_inputs(WBC_MPC_IDS, mass)
+    cmd, il_out = o.wbc_update_batch(x_des, u_des, wbc["rbd"], mode, wbc["period"], np.full(len(WBC_MPC_IDS), 12.0), il, variant=1, nthreads=4)
+    np.savez_compressed(os.path.join(HERE, "wbc_mpc_variant_config3.npz"), ids=WBC_MPC_IDS, mode=mode, cmd=cmd, input_last=il_out)
 
     o.mpc_set(dt=0.015, horizon=1.0)
     prob, _ = synthetic.make_batch(MPC_IDS, config=5)

@@ -21,6 +21,13 @@ def test_wbc_golden(oracle):
     _close(cmd, g["cmd"], 1e-8); _close(il_out, g["input_last"])
 
 
+def test_wbc_mpc_variant_golden(oracle):
+    g = np.load(os.path.join(GOLD, "wbc_mpc_variant_config3.npz")); x_des, u_des, mode, wbc, il = mg.wbc_mpc_inputs(g["ids"], oracle.model_info()["mass"])
+    cmd, il_out = oracle.wbc_update_batch(x_des, u_des, wbc["rbd"], mode, wbc["period"], np.full(len(mode), 12.0), il, variant=1, nthreads=2)
+    _close(cmd[:, 36:48], g["cmd"][:, 36:48], 1e-8); _close(cmd[:, 24:36], g["cmd"][:, 24:36], 1e-8); _close(cmd[:, :18], g["cmd"][:, :18], 1e-7)   # leg torques, forces, base / leg accelerations
+    _close(cmd[:, 18:24], g["cmd"][:, 18:24], 1e-6)                                                                                         # arm accelerations of O(1e4)
+
+
 def test_mpc_golden(oracle):
     from qm_control_b200 import synthetic
     g = np.load(os.path.join(GOLD, "mpc_config5_dt015.npz")); oracle.mpc_set(dt=0.015, horizon=1.0)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 sys.path.insert(0, GOLD)
 import make_golden as mg  # noqa: E402
-from _parity import MPC_TOL, WBC_TOL, assert_cmd, assert_traj  # noqa: E402
+from _parity import CMD_BLOCKS, MPC_TOL, MPCWBC_TOL, WBC_TOL, assert_cmd, assert_traj  # noqa: E402
 
 
 def test_wbc_against_golden():
@@ -21,6 +21,17 @@ def test_wbc_against_golden():
     cmd, status = solver.wbc_update(x_des, u_des, wbc["rbd"], mode, wbc["period"], np.full(B, 12.0)); assert np.all(status == 0)
     assert_cmd(cmd, g["cmd"], WBC_TOL, tag="golden wbc_config5")
     np.testing.assert_array_equal(solver.wbc_get_input_last(), g["input_last"])
+
+
+def test_wbc_mpc_variant_against_golden():
+    """HierarchicalMpcWbc: the 12 leg torques QMMpcController consumes (QMController.cpp:427-431), and every other block, against the fixture."""
+    import qm_control_b200 as q
+    g = np.load(os.path.join(GOLD, "wbc_mpc_variant_config3.npz")); ids = g["ids"]; B = len(ids); solver = q.Solver(batch=B, wbc_variant=1)
+    x_des, u_des, mode, wbc, il = mg.wbc_mpc_inputs(ids, solver.robot_mass)
+    solver.wbc_set_input_last(il)
+    cmd, status = solver.wbc_update(x_des, u_des, wbc["rbd"], mode, wbc["period"], np.full(B, 12.0)); assert np.all(status == 0)
+    blocks = dict(CMD_BLOCKS); blocks["arm_acc"] = (18, 24, 1e3)
+    assert_cmd(cmd, g["cmd"], MPCWBC_TOL, tag="golden wbc_mpc_variant", blocks=blocks)
 
 
 def test_mpc_against_golden():

@@ -91,7 +91,7 @@ def test_wbc_mpc_variant_matches_oracle(oracle):
         viol = D0 @ x - f0; assert viol.max() < 1e-6, (b, "inequalities", viol.max())
         active = viol > -1e-7 * (1.0 + np.abs(f0))
         r1 = tw._certificate(A1v.T @ (A1v @ x - b1v), A0, D0[active]); r2 = tw._certificate(A2v.T @ (A2v @ x - b2v), np.r_[A0, A1v], D0[active])
-        worst = max(worst, r1, r2); assert r1 < 1e-6 and r2 < 1e-6, (b, "KKT residual level 1 / 2", r1, r2)
+        worst = max(worst, r1, r2); assert r1 < 1e-9 and r2 < 1e-9, (b, "KKT residual level 1 / 2", r1, r2)   # observed 1e-11 .. 1e-15 (profiles/r02_mpcwbc_certificates.txt)
         tau = M["M"][6:] @ x[:24] - M["Jfoot"].T[6:] @ x[24:] + M["nle"][6:]
         np.testing.assert_allclose(cmd[b, 36:], tau, rtol=1e-10, atol=1e-9)                                 # updateCmd (WbcBase.cpp:548-563)
     print("HierarchicalMpcWbc: worst KKT residual of the CUDA result %.2e" % worst)
