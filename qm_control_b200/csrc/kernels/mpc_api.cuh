@@ -10,11 +10,29 @@
 namespace qmb {
 
 constexpr int EMAX = 32, KMAX = 4, TARGET_DIM = 37;
-// per-node projected LQ stage as the LQ kernel hands it to the Riccati kernel (doubles)
-constexpr int ST_A = 0, ST_B = 900, ST_b = 1440, ST_Q = 1470, ST_R = 2370, ST_S = 2694, ST_q = 3234, ST_r = 3264, ST_PXD = 3282, ST_PUD = 3762, ST_PED = 4050, ST_PERF = 4066, STAGE_DBL = 4072;
-// ints: [0] type (0 intermediate, 1 event, 2 terminal), [1] m (projected input dim), [2] ndep, [3..19) dep input index, [19..37) free input index
-constexpr int SI_TYPE = 0, SI_M = 1, SI_NDEP = 2, SI_DEP = 3, SI_FREE = 19, STAGE_INT = 40;
-constexpr int GAIN_DBL = 18 * 30 + 18 + 6;   // feedback K (m x 30), feedforward k (m)
+// Per-node projected LQ stage as the LQ kernel (K2) hands it to the Riccati kernel (K3): the STRUCTURED record (16,672 B instead of the 32,576 B of the dense
+// round-1 record).  The projected problem is stored in the model's sparsity, and every dense piece has the row pitch of the shared-memory matrix it lands in, so
+// that K3 fetches a node with four bulk copies (cp.async.bulk → SASS UBLKCP, one mbarrier each) instead of ~1700 16-byte cp.async:
+//   A~ = I + [rows 3:12 dense] + [leg-joint rows 12:24: dtw * Px on the 12 support columns of the leg]      B~ = [rows 0:3: dtw/m at free force columns]
+//   + [rows 3:12 dense] + [joint rows: dtw at the own free column, dtw * Pu2 in the eliminated pivot row of a swing leg]
+//   R~ is block diagonal over input triples (<= 3 entries per row), S~ has <= 8 non-zero rows (free joints of swing legs) of 12 support entries.
+constexpr int LDX = 36, LDB = 28, LDG = 34, LDH = 24;   // shared-memory pitches of the 30-, 18-column matrices of K3 (see mpc_kernels.cu)
+constexpr int ST_AR = 0;                 // 9 x LDX : rows 3:12 of A~ ; column 30 = b~[3:12] ; columns 31.. zero
+constexpr int ST_BR = ST_AR + 9 * LDX;   // 9 x LDB : rows 3:12 of B~ ; columns 18.. zero
+constexpr int ST_Q = ST_BR + 9 * LDB;    // 30 x LDX: Q~ (symmetric) ; column 30 = q~ ; columns 31.. zero      (terminal node: the final cost)
+constexpr int ST_TAIL = ST_Q + NX * LDX; // the small pieces, one contiguous block:
+constexpr int T_PXJ = 0;                 //   12 x 12: Px rows of the 12 leg-joint velocity inputs on their support columns (zero rows for free joints)
+constexpr int T_b = 144, T_q = 174, T_r = 204;   // b~ (30), q~ (30), r~ (18)
+constexpr int T_RT = 222;                //   18 x 3 : R~[a][column of input 3*(fa/3) + jc] (arm inputs: [a][0] = diagonal); rows a >= m: identity padding
+constexpr int T_SJ = 276;                //   8 x 12 : S~ rows of the free joints of swing legs (slot = 2 * foot + position among the leg's two free joints)
+constexpr int T_PU2 = 372, T_PED = 380;  //   Pu2 (4 feet x 2), P_e of the dependent inputs (16)
+constexpr int T_MISC = 396;              //   dtw = dt (w1 + w2), cost, dynamics SSE, equality SSE of the node
+constexpr int T_INT = 400;               //   int32[56]: type (0 intermediate, 1 event, 2 terminal), m, ndep, dep[16], free[18], pivot[4] (joint eliminated in a swing leg, -1 stance),
+                                         //   pcol[4][2] (projected columns of a swing leg's two free joints, -1 stance)
+constexpr int TAIL_DBL = 428, STAGE_DBL = ST_TAIL + TAIL_DBL;
+constexpr int SI_TYPE = 0, SI_M = 1, SI_NDEP = 2, SI_DEP = 3, SI_FREE = 19, SI_PIV = 37, SI_PCOL = 41;
+static_assert(STAGE_DBL == 2084 && (ST_BR % 2 == 0) && (ST_Q % 2 == 0) && (ST_TAIL % 2 == 0) && (TAIL_DBL % 2 == 0), "16-byte aligned pieces");
+constexpr int GAIN_DBL = 18 * LDG;       // feedback K (m x 30) with the pitch of its shared-memory target, feedforward k in column 30
 constexpr int ROBOT_DBL = 8;                 // armijo, base cost, base dyn SSE, base eq SSE, |dx|, |du|
 
 // PrimalSolution of every robot: node count, node times, event annotation (0 none, 1 pre-event, 2 post-event), x, u

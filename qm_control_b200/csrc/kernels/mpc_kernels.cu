@@ -105,16 +105,26 @@ static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep t
 
 // The LQ kernel is ~220 KB of straight-line code executed once per node: warps of a CTA are re-aligned at a few phase
 // boundaries so that they share instruction-cache lines (exited warps - event / terminal / padding nodes - no longer take part).
-#define LQ_LOCKSTEP() __syncthreads()
-__global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ stage_i, int32_t* __restrict__ status) {
+// Optional re-alignment of a CTA's warps at phase boundaries (instruction-cache sharing).  Measured on B200 with the structured record (profiles/r02_ab_k3.jsonl):
+// 21.88 ms with, 21.42 ms without - the kernel is no longer fetch bound, so it is OFF.  When enabled the barrier is taken only by CTAs whose six warps all hold
+// regular (intermediate) nodes - a CTA-uniform predicate established before any warp can exit - so no warp ever waits for one that has returned.
+#ifndef QMB_LQ_LOCKSTEP
+#define QMB_LQ_LOCKSTEP 0
+#endif
+#define LQ_LOCKSTEP() do { if (QMB_LQ_LOCKSTEP && lockstep) __syncthreads(); } while (0)
+__global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
-  const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax); if (b >= B) return;
-  const int n = sol.n_nodes[b]; if (k >= n) return;
-  if (status[b] & MST_CONVERGED) return;   // SqpSolver::runImpl left the iteration loop for this robot
+  const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax);
+  const int n = (b < B) ? sol.n_nodes[b] : 0;
+  const bool work = b < B && k < n && !(status[b] & MST_CONVERGED);   // MST_CONVERGED: SqpSolver::runImpl left the iteration loop for this robot
+  const bool regular = work && k < n - 1 && sol.event[(size_t)b * nmax + k] != 1;
+  const bool lockstep = __syncthreads_and(regular) != 0;                // every thread of the CTA is still here: the early exits come after this point
+  (void)lockstep;
+  if (!work) return;
   LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp];
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
-  double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL; int32_t* si = stage_i + ((size_t)b * nmax + k) * STAGE_INT;
+  double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL;
   const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
   { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
   const int lfp = pack_leg_foot(mdl);
@@ -124,9 +134,10 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   if (lane < NX) { sm.xs[lane] = xk[lane]; sm.pt.u[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
   __syncwarp();
   if (!terminal && ge[k] == 1) {   // event node: identity jump map, no input, no cost (setupEventNode)
-    double d = 0.0; if (lane < NX) { d = sm.xs[lane] - sm.xnext[lane]; sg[ST_b + lane] = d; }
+    double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
+    double d = 0.0; if (lane < NX) { d = sm.xs[lane] - sm.xnext[lane]; tl[T_b + lane] = d; }
     const double ss = warp_sum(d * d);
-    if (lane == 0) { si[SI_TYPE] = 1; si[SI_M] = 0; si[SI_NDEP] = 0; sg[ST_PERF] = 0.0; sg[ST_PERF + 1] = ss; sg[ST_PERF + 2] = 0.0; }
+    if (lane == 0) { si[SI_TYPE] = 1; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = 0.0; tl[T_MISC + 2] = ss; tl[T_MISC + 3] = 0.0; }
     return;
   }
   const double t = interval_start(gt[k], ge[k]);
@@ -147,9 +158,10 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   TargetRef ref = target_reference(tt, ts, nk, t, lane);
   cost_val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, fm, terminal, lane);
   if (terminal) {   // setupTerminalNode: finalEndEffector soft constraint only (QMInterface.cpp:104)
-    for (int e = lane; e < NX * NX; e += 32) { const int a = ee_pos(e / NX), c = ee_pos(e % NX); sg[ST_Q + e] = (a >= 0 && c >= 0) ? sm.quad.E[a * 12 + c] : 0.0; }
-    if (lane < NX) sg[ST_q + lane] = sm.quad.qf[lane];
-    if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; sg[ST_PERF] = cost_val; sg[ST_PERF + 1] = 0.0; sg[ST_PERF + 2] = 0.0; }
+    double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
+    for (int e = lane; e < NX * LDX; e += 32) { const int r = e / LDX, c = e - r * LDX; const int a = ee_pos(r), cc = (c < NX) ? ee_pos(c) : -1;
+      sg[ST_Q + e] = (c == NX) ? sm.quad.qf[r] : ((a >= 0 && cc >= 0) ? sm.quad.E[a * 12 + cc] : 0.0); }   // final cost: Hessian, gradient in column 30, zero padding
+    if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = cost_val; tl[T_MISC + 2] = 0.0; tl[T_MISC + 3] = 0.0; }
     return;
   }
   foot_velocity<true>(mdl, &sm.pt, &sm.el.e.con, lane);
@@ -238,10 +250,11 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   }
   __syncwarp();
   LQ_LOCKSTEP();
-  // ---- projected dynamics rows (lane = state row): A~ = A_d + B_d Px, B~ = B_d Pu, b~ = b + B_d Pe ----
+  // ---- projected dynamics: b~ = b + B_d Pe (lane = state row) ; rows 3:12 of A~ = A_d + B_d Px (the h_ang rows pick up the dependent joint velocities) ----
+  double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
   if (lane < NX) {
     const int r = lane; double bt = sm.el.l.bvec[r];
-    if (r >= 3 && r < 6) {       // h_ang rows pick up the dependent joint velocities: + sum_legs BrdJ[r][joint] * Px_joint (accumulated in the shared-memory row, own thread)
+    if (r >= 3 && r < 6) {       // + sum_legs BrdJ[r][joint] * Px_joint (accumulated in the shared-memory row, own thread)
       double* arow = sm.A1r + (r - 3) * NX; double acc[12];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const LegWs& L = sm.leg[i];
@@ -260,36 +273,26 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     }
     if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw * imass) * sm.Pe_full[3 * f + r];
     if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.el.l.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
-    sg[ST_b + r] = bt;
+    tl[T_b + r] = bt;
+    if (r >= 3 && r < 12) sg[ST_AR + (r - 3) * LDX + NX] = bt;   // b~[3:12] also rides in column 30 of the dense A~ rows (K3's vector recursion)
   }
   if (lane >= 3 && lane < 12) sm.A1r[(lane - 3) * NX + lane] += 1.0;   // A1r rows become rows 3:12 of A~ themselves (own row of each lane: no hazard with the h_ang update above)
   __syncwarp();
-  // A~ (30x30) and B~ (30x18) leave as flat row-major sweeps (consecutive lanes write consecutive doubles: 8 sectors per store instruction instead
-  // of the 30 a lane-per-row store touches).  Both are identity/zero outside a dense band - rows 3:12 - and a handful of structured entries, so
-  // the sweeps carry no index arithmetic: zero/copy fill first, then the sparse entries by their owning lanes.
-  for (int e = lane; e < NX * NX; e += 32) sg[ST_A + e] = (e >= 3 * NX && e < 12 * NX) ? sm.A1r[e - 3 * NX] : 0.0;
-  for (int e = lane; e < NX * MU; e += 32) sg[ST_B + e] = 0.0;
-  __syncwarp();
-  if (lane < NX && (lane < 3 || lane >= 12)) {   // identity rows of A~, plus I + dtw * Px on the support columns of a dependent joint-velocity row
-    const int r = lane; double* Arow = sg + ST_A + (size_t)r * NX; Arow[r] = 1.0;
-    if (r >= 12 && r < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, r - 12)]; const int j = (r - 12) % 3;
-      if (L.dep[j]) for (int c = 0; c < 12; ++c) { const int col = sup_col(c, L.first); Arow[col] = ((col == r) ? 1.0 : 0.0) + dtw * L.Px[j][c]; } }
-  }
-  for (int e = lane; e < 9 * MU; e += 32) {      // dense band of B~: rows 3:12 (force columns; joint columns reach the h_ang rows only)
-    const int r = 3 + e / MU, a = e - (r - 3) * MU; double v = 0.0;
+  // rows 3:12 of A~ with K3's shared-memory pitch (one 240-byte run per store instruction), zero padding columns 31..35
+#pragma unroll
+  for (int r = 0; r < 9; ++r) { if (lane < NX) sg[ST_AR + r * LDX + lane] = sm.A1r[r * NX + lane]; else if (lane == 31) sg[ST_AR + r * LDX + 31] = 0.0; }
+  for (int e = lane; e < 36; e += 32) sg[ST_AR + (e >> 2) * LDX + 32 + (e & 3)] = 0.0;
+  // Px rows of the 12 leg-joint velocity inputs on their support columns: K3 rebuilds rows 12:24 of A~ (I + dtw Px) and the dependent inputs of the rollout from them
+  for (int e = lane; e < 144; e += 32) { const int j12 = e / 12, c = e - 12 * j12; const LegWs& L = sm.leg[foot_of_leg_joint(lfp, j12)]; const int j = j12 % 3; tl[T_PXJ + e] = L.dep[j] ? L.Px[j][c] : 0.0; }
+  // rows 3:12 of B~ (force columns; joint columns reach the h_ang rows only), pitch LDB, zero padding; the remaining rows of B~ are structured (see mpc_api.cuh)
+  for (int e = lane; e < 9 * LDB; e += 32) {
+    const int rr = e / LDB, a = e - rr * LDB; const int r = 3 + rr; double v = 0.0;
     if (a < m) { const int fa = sm.free_idx[a];
-      if (fa < 12) v = sm.el.l.BrdF[(r - 3) * 12 + fa];
-      else if (r < 6) { v = sm.el.l.BrdJ[(r - 3) * NJ + fa - 12];
-        if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[(r - 3) * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
+      if (fa < 12) v = sm.el.l.BrdF[rr * 12 + fa];
+      else if (r < 6) { v = sm.el.l.BrdJ[rr * NJ + fa - 12];
+        if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[rr * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
     }
-    sg[ST_B + 3 * MU + e] = v;
-  }
-  if (lane < m) {                                 // sparse entries of B~, by column (lane = projected input a)
-    const int a = lane, fa = sm.free_idx[a];
-    if (fa < 12) sg[ST_B + (size_t)(fa % 3) * MU + a] = dtw * imass;                              // h_lin rows: F / m
-    else { sg[ST_B + (size_t)fa * MU + a] = dtw;                                                   // joint position rows: own joint velocity
-      if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)];
-        if (!L.stance) { const int jf = fa - 12 - L.first; sg[ST_B + (size_t)(12 + L.first + L.pivot) * MU + a] = dtw * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }   // eliminated pivot joint of a swing leg
+    sg[ST_BR + e] = v;
   }
   LQ_LOCKSTEP();
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
@@ -329,99 +332,106 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
           for (int c = 0; c < 3; ++c) acc[12 + 3 * l + c] += blk[9 + c]; }
       }
     }
-    // Q~ is symmetric: lane r stores its row as COLUMN r, so every store instruction writes one contiguous 240-byte row
+    // Q~ is symmetric: lane r stores its row as COLUMN r, so every store instruction writes one contiguous 240-byte row; q~ in column 30 (and in the tail for the rollout)
     double* Qcol = sg + ST_Q + r; const double dq = sm.quad.qdiag[r];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) Qcol[(size_t)c * NX] = dt * (acc[c] + ((c == r) ? dq : 0.0));
-    sg[ST_q + r] = dt * qv;
+    for (int c = 0; c < NX; ++c) Qcol[(size_t)c * LDX] = dt * (acc[c] + ((c == r) ? dq : 0.0));
+    sg[ST_Q + r * LDX + NX] = dt * qv; tl[T_q + r] = dt * qv;
   }
+  for (int e = lane; e < NX * 5; e += 32) sg[ST_Q + (e / 5) * LDX + 31 + (e % 5)] = 0.0;   // padding columns 31..35
   LQ_LOCKSTEP();
-  static_assert(ST_S == ST_R + MU * MU, "R~ and S~ are zero-filled in one sweep");
-  for (int e = lane; e < MU * MU + MU * NX; e += 32) sg[ST_R + e] = 0.0;   // R~ (block sparse) and S~ (swing-joint rows only) are mostly zero: coalesced fill, sparse entries below
+  for (int e = lane; e < 8 * 12; e += 32) tl[T_SJ + e] = 0.0;
   __syncwarp();
-  if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) ; R~ = Pu' R Pu (symmetric: lane a stores into column a)
-    const int a = lane; double* Srow = sg + ST_S + (size_t)a * NX; double* Rcol = sg + ST_R + a;
+  if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) (non-zero only for the free joints of swing legs) ; R~ = Pu' R Pu (block diagonal over the input triples)
+    const int a = lane; double rt[3] = {0.0, 0.0, 0.0}; double rtil = 0.0;
     if (a < m) {
       const int fa = sm.free_idx[a]; double rv = sm.rs[fa]; int li = -1, jf = -1;
       if (fa >= 12 && fa < 24) { li = foot_of_leg_joint(lfp, fa - 12); jf = (fa - 12) % 3; }
       const bool swing_joint = li >= 0 && !sm.leg[li].stance;
       if (swing_joint) {   // free joint of a swing leg: coupled to the pivot through R_leg and Pu
-        const LegWs& L = sm.leg[li]; const int pv = L.pivot; const double pu = L.Pu2[jf > pv ? jf - 1 : jf];
+        const LegWs& L = sm.leg[li]; const int pv = L.pivot; const int jfi = jf > pv ? jf - 1 : jf; const double pu = L.Pu2[jfi];
         rv += pu * L.rs[pv];
-        const double coef = L.Rl[3 * jf + pv];
-        for (int c = 0; c < 12; ++c) Srow[sup_col(c, L.first)] = dt * (coef * L.Px[pv][c] + pu * L.U[pv][c]);
+        const double coef = L.Rl[3 * jf + pv]; double* Srow = tl + T_SJ + (2 * li + jfi) * 12;
+        for (int c = 0; c < 12; ++c) Srow[c] = dt * (coef * L.Px[pv][c] + pu * L.U[pv][c]);
       }
-      sg[ST_r + a] = dt * rv;
+      rtil = dt * rv;
       // R is block diagonal (3x3 blocks over force / leg-joint triples, diagonal over the arm): only the free inputs of fa's own block contribute to row a
-      if (fa >= 24) Rcol[(size_t)a * MU] = dt * quad_R(mdl, &sm.quad, fa, fa);
+      if (fa >= 24) rt[0] = dt * quad_R(mdl, &sm.quad, fa, fa);
       else { const int bi = fa / 3;
-        for (int jc = 0; jc < 3; ++jc) { const int fc = 3 * bi + jc; const int c = sm.col_of_input[fc]; if (c < 0) continue;
+        for (int jc = 0; jc < 3; ++jc) { const int fc = 3 * bi + jc; if (sm.col_of_input[fc] < 0) continue;
           double v = quad_R(mdl, &sm.quad, fa, fc);
           if (swing_joint) { const LegWs& L = sm.leg[li]; const int pv = L.pivot; const double pa = L.Pu2[jf > pv ? jf - 1 : jf], pc = L.Pu2[jc > pv ? jc - 1 : jc];
             v += pa * L.Rl[3 * pv + jc] + L.Rl[3 * jf + pv] * pc + pa * L.Rl[3 * pv + pv] * pc; }
-          Rcol[(size_t)c * MU] = dt * v; } }
-    } else { sg[ST_r + a] = 0.0; Rcol[(size_t)a * MU] = 1.0; }
+          rt[jc] = dt * v; } }
+    }
+    tl[T_r + a] = rtil; tl[T_RT + 3 * a] = rt[0]; tl[T_RT + 3 * a + 1] = rt[1]; tl[T_RT + 3 * a + 2] = rt[2];
   }
-  // projection data for the forward pass: dense rows of Px / Pu / Pe of the dependent inputs
-  for (int e = lane; e < MAXDEP * NX; e += 32) sg[ST_PXD + e] = 0.0;
-  for (int e = lane; e < MAXDEP * MU; e += 32) sg[ST_PUD + e] = 0.0;
-  __syncwarp();
-  if (lane < MAXDEP) {
-    const int d = lane; double pe = 0.0; int di = -1;
-    if (d < ndep) { di = sm.dep_idx[d]; pe = sm.Pe_full[di];
-      if (di >= 12) { const int i = foot_of_leg_joint(lfp, di - 12); const LegWs& L = sm.leg[i]; const int j = (di - 12) % 3;
-        for (int c = 0; c < 12; ++c) sg[ST_PXD + (size_t)d * NX + sup_col(c, L.first)] = L.Px[j][c];
-        if (!L.stance) { int nf = 0; for (int jj = 0; jj < 3; ++jj) if (jj != L.pivot) { sg[ST_PUD + (size_t)d * MU + L.free_col[jj]] = L.Pu2[nf++]; } } } }
-    sg[ST_PED + d] = pe; si[SI_DEP + d] = di;
-  }
+  if (lane < 4) { const LegWs& L = sm.leg[lane]; tl[T_PU2 + 2 * lane] = L.Pu2[0]; tl[T_PU2 + 2 * lane + 1] = L.Pu2[1]; si[SI_PIV + lane] = L.stance ? -1 : L.pivot;
+    // projected columns of the leg's two free joints (swing legs): the rollout needs them for the eliminated pivot joint
+    int nf = 0; for (int jj = 0; jj < 3; ++jj) if (!L.stance && jj != L.pivot) si[SI_PCOL + 2 * lane + nf++] = L.free_col[jj]; if (L.stance) { si[SI_PCOL + 2 * lane] = -1; si[SI_PCOL + 2 * lane + 1] = -1; } }
+  if (lane < MAXDEP) { const int d = lane; double pe = 0.0; int di = -1; if (d < ndep) { di = sm.dep_idx[d]; pe = sm.Pe_full[di]; } tl[T_PED + d] = pe; si[SI_DEP + d] = di; }
   if (lane < MU) si[SI_FREE + lane] = (lane < m) ? sm.free_idx[lane] : -1;
-  if (lane == 0) { si[SI_TYPE] = 0; si[SI_M] = m; si[SI_NDEP] = ndep; sg[ST_PERF] = dt * cost_val; sg[ST_PERF + 1] = dt * dyn_ss; sg[ST_PERF + 2] = dt * eq_ss; }
+  if (lane == 0) { si[SI_TYPE] = 0; si[SI_M] = m; si[SI_NDEP] = ndep; tl[T_MISC] = dtw; tl[T_MISC + 1] = dt * cost_val; tl[T_MISC + 2] = dt * dyn_ss; tl[T_MISC + 3] = dt * eq_ss; }
 }
 
 // =====================================================================================================
 // K3: Riccati backward sweep + forward rollout of the projected LQ problem.
-// One CTA (4 warps) per robot.  Every 30x30 product is tiled 1x8 over 120 threads (thread t: row t/4, columns 8*(t%4)..+7),
-// operands in shared memory (row operand walked with an odd leading dimension, column-block operand read as 16-byte
-// broadcasts), stage records prefetched with cp.async while the previous phases compute, Cholesky + triangular solves
-// warp-specialised on warp 0 with the factor in registers.  The projected input dimension is padded to MU=18 by the
-// LQ kernel (identity rows in R~, zero rows in S~/B~), so nothing here depends on the contact mode.
+// One CTA (4 warps) per robot.  Every product of the backward sweep is a set of 8x8x4 fp64 tensor-core tiles (DMMA) on dense 30x30 / 30x18 matrices in shared
+// memory; the Cholesky + triangular solves are warp-specialised with the factor in registers.  The structured stage record of K2 (mpc_api.cuh) reaches shared
+// memory through the TMA engine: per node four bulk copies (cp.async.bulk: rows 3:12 of A~ and of B~, the Q~ block, the 3.4 KB tail) signalled on mbarriers,
+// issued by one thread one node ahead; the sparse remainder of A~ / B~ (identity, dtw * Px on support columns, dtw at free columns) is rebuilt in place from the
+// tail while the previous node's phase 4 runs.  -DQMB_TMA=0 replaces the bulk copies by 16-byte cp.async spread over the CTA (same record, same schedule; the A/B
+// measurement is in profiles/).  The projected input dimension is padded to MU = 18 (identity rows in R~, zero rows in S~ / B~), so nothing depends on the mode.
+#ifndef QMB_TMA
+#define QMB_TMA 1
+#endif
 constexpr int RIC_THREADS = 128, RIC_NTYPE = 512;
-// Leading dimensions.  MMA operands are fetched as X[(k0 + t) * ld + c0 + g] (t = lane % 4, g = lane / 4): 2 * ld = 8 (mod 32) or
+// Leading dimensions (mpc_api.cuh).  MMA operands are fetched as X[(k0 + t) * ld + c0 + g] (t = lane % 4, g = lane / 4): 2 * ld = 8 (mod 32) or
 // 24 (mod 32) puts the four k-rows of a half-warp on disjoint bank octets, i.e. every fragment load is conflict free.
-constexpr int LDX = 36, LDB = 28, LDG = 34, LDH = 24;
 struct RicSmem {
   double P[NX * LDX];                       // value function: Hessian in columns 0..29, gradient p in column 30; receives Q~ (C operand of phase 3) in between
   double A[NX * LDX];                       // A~ (column 30: b~)
   double W[NX * LDX];                       // W = P'A (column 30: p + P b~)
   double Bm[NX * LDB], PB[NX * LDB];        // B~ ; P'B~, later Y = L^{-1}[G | h] (18 x LDX)
-  double G[MU * LDG];                       // S~ (column 30: r~), then G = S~ + B~'W (column 30: h)
-  double H[MU * LDH];                       // R~, then H = R~ + B~'P B~
+  double G[MU * LDG];                       // G = S~ + B~'W (column 30: h = r~ + B~'(p + P b~))
+  double H[MU * LDH];                       // H = R~ + B~'P B~
   double Lt[MU * MU];                       // Cholesky factor of H, transposed: Lt[c][a] = L[a][c] (strict lower part; pivots live as reciprocals in dut)
-  double p[32], b[32], q[32], r[32], pPb[32], h[32], dx[32], dut[32], tmp[32], kff[32], kff2[32];   // rollout vectors (two buffer sets)
+  alignas(16) double tail[TAIL_DBL];        // backward sweep: the node's small pieces (Px rows, b~, q~, r~, R~ / S~ entries, index lists)
+  double dx[32], dut[32], tmp[32];
   double red[RIC_THREADS / 32][4];
+  alignas(8) unsigned long long bar[4];     // mbarriers: 0 = A~/B~ rows (forward: buffer set 0), 1 = tail, 2 = Q~, 3 = forward buffer set 1
   int flag; int pad_;
-  alignas(16) int32_t sib[2][STAGE_INT];    // forward pass: the node's integer record (type, m, ndep, dependent / free input indices), prefetched with the matrices
+  signed char srow[MU + 2], sfirst[MU + 2]; // projected input a: S~ slot (2 * foot + position) and first joint of its leg when a is a free joint of a swing leg, else -1
   unsigned char ntype[RIC_NTYPE];           // node types of the whole horizon, loaded once: the sweep's control flow never waits on a global load
 };
+static_assert(sizeof(RicSmem) <= 57344 - 64, "Riccati kernel must keep four CTAs per SM");
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-// rows x cols doubles (cols even, 16-B aligned rows on both sides) global → shared, spread over threads tid = 0..nthr-1
-// (every caller copies a dense block, gs == cols: the global side is one contiguous run of 16-byte chunks, chunk e at g + 2e; only the padded
-// shared-memory side needs the (row, chunk) split.  The shared-window address is converted once per call, not once per chunk.)
-__device__ __forceinline__ void cp_rows(const double* __restrict__ g, int rows, int cols, int gs, double* s, int ls, int tid, int nthr = RIC_THREADS) {
-  const int cpr = cols >> 1; const unsigned sbase = (unsigned)__cvta_generic_to_shared(s); (void)gs;
-  for (int e = tid; e < rows * cpr; e += nthr) { const int i = e / cpr, c = e - i * cpr;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + 8u * (unsigned)(i * ls + 2 * c)), "l"(g + 2 * e)); }
+// one contiguous run global -> shared through the TMA engine (bytes: multiple of 16, both addresses 16-byte aligned); completion is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
-}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// A "copy group": with QMB_TMA one elected thread arms the mbarrier and issues the bulk copies; without it every thread copies its share with cp.async and the
+// group is closed by cp.async.wait_all + a CTA barrier at the point where the TMA path waits on the mbarrier.
+struct CopyGroup {
+  unsigned long long* bar; unsigned phase;
+  __device__ __forceinline__ void begin(unsigned bytes, int tid) { if (QMB_TMA && tid == 0) mbar_expect_tx(bar, bytes); }
+  __device__ __forceinline__ void copy(void* dst, const void* src, unsigned bytes, int tid, int nthr = RIC_THREADS, int t0 = 0) {
+    if (QMB_TMA) { if (tid == 0) bulk_g2s(dst, src, bytes, bar); }
+    else { const int me = tid - t0; if (me >= 0 && me < nthr) for (unsigned o = 16u * me; o < bytes; o += 16u * nthr) cp_async16((char*)dst + o, (const char*)src + o); }
+  }
+  // returns after the group's bytes are visible to the calling thread (TMA) / to the whole CTA (cp.async path: includes a barrier, so every thread must call it)
+  __device__ __forceinline__ void wait() { if (QMB_TMA) mbar_wait(bar, phase & 1u); else { cp_async_wait_all(); __syncthreads(); } ++phase; }
+  __device__ __forceinline__ void skip() { ++phase; }
+};
+
 // ---- fp64 tensor-core tiles (DMMA.8x8x4, mma.sync m8n8k4 f64: measured 37 TFLOP/s on B200, the same rate as the DFMA pipe at 1/8 of
 // the issue slots and ~1/3 of the shared-memory operand traffic of a 4x4 register tile).  C(8x8) += A(8x4) B(4x8) with
 // A[i][k] = X[k][i0 + i], B[k][j] = Y[k][j0 + j]: lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g], C[g][2t], C[g][2t + 1].
@@ -460,55 +470,78 @@ __device__ __forceinline__ void cfrag_store(double* M, int ld, int i0, int j0, i
 #pragma unroll
     for (int n = 0; n < NT; ++n) { const int ri = i0 + 8 * m + g; if (ri < rows) *reinterpret_cast<double2*>(M + ri * ld + j0 + 8 * n + 2 * t) = make_double2(c[m][n][0], c[m][n][1]); }
 }
+// support position (0..11) of state column j for the leg whose first joint is `first`, -1 outside the support (inverse of sup_col)
+__device__ __forceinline__ int sup_pos(int j, int first) { return j < 6 ? j : ((j >= 9 && j < 12) ? j - 3 : (((unsigned)(j - 12 - first) < 3u) ? 9 + j - 12 - first : -1)); }
 
-__global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const int32_t* __restrict__ stage_i,
+__global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage,
                                                                   double* __restrict__ gains, double* __restrict__ dxo, double* __restrict__ duo, double* __restrict__ robot, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RicSmem& sm = *reinterpret_cast<RicSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ti = tid >> 2, jb = tid & 3; const int b = b0 + blockIdx.x;
   if (status[b] & MST_CONVERGED) return;
   const int n = sol.n_nodes[b]; const int N = n - 1;
-  const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const int32_t* sib = stage_i + (size_t)b * nmax * STAGE_INT; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
-  for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero padding columns once
+  const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; double* gb = gains + (size_t)b * nmax * GAIN_DBL;
+  const int lfp = pack_leg_foot(mdl); const double imass = 1.0 / mdl->total_mass;
+  for (int e = tid; e < (int)(sizeof(RicSmem) / 8); e += RIC_THREADS) reinterpret_cast<double*>(&sm)[e] = 0.0;   // zero everything once (padding columns, static zero rows)
   __syncthreads();
+  if (tid < NX && (tid < 3 || tid >= 24)) sm.A[tid * LDX + tid] = 1.0;   // identity rows of A~ that no node ever changes
+  if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&sm.bar[i], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");           // the zero fill (generic proxy) is ordered before the first bulk copy (async proxy) by this fence + the barrier below
   const bool types_in_smem = n <= RIC_NTYPE;
-  if (types_in_smem) for (int k = tid; k < n; k += RIC_THREADS) sm.ntype[k] = (unsigned char)sib[(size_t)k * STAGE_INT + SI_TYPE];   // published by the barrier below
-  auto node_type = [&](int k) -> int { return types_in_smem ? (int)sm.ntype[k] : sib[(size_t)k * STAGE_INT + SI_TYPE]; };
-  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_A, NX, NX, NX, sm.A, LDX, tid); cp_rows(sg + ST_B, NX, MU, MU, sm.Bm, LDB, tid);
-    if (tid < NX) cp_async8(sm.A + tid * LDX + NX, sg + ST_b + tid); cp_async_commit(); };                                 // b~ rides in column 30 of A~
-  auto issue_sr = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; cp_rows(sg + ST_S, MU, NX, NX, sm.G, LDG, tid); cp_rows(sg + ST_R, MU, MU, MU, sm.H, LDH, tid);
-    if (tid < MU) cp_async8(sm.G + tid * LDG + NX, sg + ST_r + tid); cp_async_commit(); };                                 // r~ in column 30 of S~
-  // Q~, q~ land in the (dead) P buffer as the C operand of phase 3.  Only the three helper warps of node k issue (and later wait for) these
-  // copies, so the factorisation warp never waits on them; it still commits an empty group to keep the group count uniform.
-  auto issue_q = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; const int hw = (warp - ((k + b) & 3) - 1) & 3;
-    if (hw < 3) { const int ht = hw * 32 + lane; cp_rows(sg + ST_Q, NX, NX, NX, sm.P, LDX, ht, 96); if (ht < NX) cp_async8(sm.P + ht * LDX + NX, sg + ST_q + ht); }
-    cp_async_commit(); };
+  auto rec_type = [&](int k) -> int { return reinterpret_cast<const int32_t*>(sgb + (size_t)k * STAGE_DBL + ST_TAIL + T_INT)[SI_TYPE]; };
+  if (types_in_smem) for (int k = tid; k < n; k += RIC_THREADS) sm.ntype[k] = (unsigned char)rec_type(k);   // published by the barrier below
+  auto node_type = [&](int k) -> int { return types_in_smem ? (int)sm.ntype[k] : rec_type(k); };
+  CopyGroup gAB{&sm.bar[0], 0u}, gT{&sm.bar[1], 0u}, gQ{&sm.bar[2], 0u}, gF1{&sm.bar[3], 0u};
+  auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; gAB.begin((9 * LDX + 9 * LDB) * 8, tid);
+    gAB.copy(sm.A + 3 * LDX, sg + ST_AR, 9 * LDX * 8, tid); gAB.copy(sm.Bm + 3 * LDB, sg + ST_BR, 9 * LDB * 8, tid); };     // rows 3:12 of A~ (with b~ in column 30) and of B~
+  auto issue_tail = [&](int k) { gT.begin(TAIL_DBL * 8, tid); gT.copy(sm.tail, sgb + (size_t)k * STAGE_DBL + ST_TAIL, TAIL_DBL * 8, tid); };
+  // Q~, q~ land in the (dead) P buffer as the C operand of phase 3; only the three helper warps of node k wait for them
+  auto issue_q = [&](int k) { gQ.begin(NX * LDX * 8, tid); gQ.copy(sm.P, sgb + (size_t)k * STAGE_DBL + ST_Q, NX * LDX * 8, tid); };
+  // rebuild the structured part of A~ / B~ of the node whose tail sits in sm.tail (all threads; A~ rows 3:12 and B~ rows 3:12 arrive by copy)
+  auto expand = [&]() {
+    const double* tl = sm.tail; const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const double dtw = tl[T_MISC];
+    for (int e = tid; e < 144; e += RIC_THREADS) { const int j12 = e / 12, c = e - 12 * j12; const int col = sup_col(c, 3 * (j12 / 3));   // rows 12:24: I + dtw * Px on the leg's support columns
+      sm.A[(12 + j12) * LDX + col] = ((col == 12 + j12) ? 1.0 : 0.0) + dtw * tl[T_PXJ + e]; }
+    if (tid < NX && (tid < 3 || tid >= 12)) sm.A[tid * LDX + NX] = tl[T_b + tid];                                                    // b~ (rows 3:12 came with the dense rows)
+    for (int e = tid; e < 21 * MU; e += RIC_THREADS) {   // B~ rows 0:3 and 12:30, every element evaluated (no zero fill + scatter: no ordering between threads needed)
+      const int rr = e / MU, a = e - rr * MU; const int r = rr < 3 ? rr : rr + 9; const int fa = si[SI_FREE + a]; double v = 0.0;
+      if (fa >= 0) {
+        if (r < 3) { if (fa < 12 && fa - 3 * (fa / 3) == r) v = dtw * imass; }                                                       // h_lin rows: F / m
+        else if (fa == r) v = dtw;                                                                                                  // joint position rows: own joint velocity
+        else if (fa >= 12 && fa < 24) { const int j = fa - 12, lg = j / 3, foot = (lfp >> (2 * lg)) & 3; const int pv = si[SI_PIV + foot];   // eliminated pivot joint of a swing leg
+          if (pv >= 0 && r == 12 + 3 * lg + pv) { const int jf = j - 3 * lg; v = dtw * tl[T_PU2 + 2 * foot + (jf > pv ? jf - 1 : jf)]; } }
+      }
+      sm.Bm[r * LDB + a] = v;
+    }
+    if (tid < MU) { const int fa = si[SI_FREE + tid]; int slot = -1, first = 0;
+      if (fa >= 12 && fa < 24) { const int j = fa - 12, lg = j / 3, foot = (lfp >> (2 * lg)) & 3; const int pv = si[SI_PIV + foot]; if (pv >= 0) { const int jf = j - 3 * lg; slot = 2 * foot + (jf > pv ? jf - 1 : jf); first = 3 * lg; } }
+      sm.srow[tid] = (signed char)slot; sm.sfirst[tid] = (signed char)first; }
+  };
   // terminal value function and baseline performance
-  for (int e = tid; e < NX * NX; e += RIC_THREADS) sm.P[(e / NX) * LDX + (e % NX)] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
-  if (tid < NX) sm.P[tid * LDX + NX] = sgb[(size_t)N * STAGE_DBL + ST_q + tid];
+  for (int e = tid; e < NX * LDX; e += RIC_THREADS) sm.P[e] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
   double perf0 = 0, perf1 = 0, perf2 = 0;
-  for (int k = tid; k < n; k += RIC_THREADS) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_PERF; perf0 += pf[0]; perf1 += pf[1]; perf2 += pf[2]; }
+  for (int k = tid; k < n; k += RIC_THREADS) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_TAIL + T_MISC + 1; perf0 += pf[0]; perf1 += pf[1]; perf2 += pf[2]; }
   if (tid < NX) { const double d = p.x0[(size_t)b * NX + tid] - sol.x[(size_t)b * nmax * NX + tid]; sm.dx[tid] = d; perf1 += d * d; }
   perf0 = warp_sum(perf0); perf1 = warp_sum(perf1); perf2 = warp_sum(perf2);
   if (lane == 0) { sm.red[warp][0] = perf0; sm.red[warp][1] = perf1; sm.red[warp][2] = perf2; }
-  if (N >= 1) { issue_ab(N - 1); issue_sr(N - 1); }
   __syncthreads();
   double perf[3]; for (int i = 0; i < 3; ++i) perf[i] = sm.red[0][i] + sm.red[1][i] + sm.red[2][i] + sm.red[3][i];
+  if (N >= 1) { issue_tail(N - 1); if (node_type(N - 1) != 1) issue_ab(N - 1); gT.wait(); if (node_type(N - 1) != 1) expand(); }
   int st = 0;
   // backward sweep: every product is a set of 8x8 DMMA tiles spread over the four warps.  The vector recursion rides in column 30 of
   // the matrices (b~, p + P b~, h, q~, p), so no separate matrix-vector products are needed.
   const int g = lane >> 2, t = lane & 3;
   for (int k = N - 1; k >= 0; --k) {
-    const int type = node_type(k);
-    cp_async_wait<1>(); __syncthreads();          // A~, B~, b~ of node k have landed; P of node k+1 is complete
-    if (type == 1) {                                // event node: A = I, no input: p += P b
-      if (tid < NX) { double sv = sm.P[tid * LDX + NX]; for (int j = 0; j < NX; ++j) sv = fma(sm.P[tid * LDX + j], sm.A[j * LDX + NX], sv); sm.tmp[tid] = sv; }
-      cp_async_wait<0>(); __syncthreads();
-      if (tid < NX) sm.P[tid * LDX + NX] = sm.tmp[tid];
+    const int type = node_type(k); const int tnext = k > 0 ? node_type(k - 1) : 1;
+    if (type == 1) {                                // event node: A = I, no input: p += P b   (b~ of the node is in the tail, which expand-time waited for)
+      __syncthreads();                              // P of node k+1 is complete
+      if (tid < NX) { double sv = sm.P[tid * LDX + NX]; for (int j = 0; j < NX; ++j) sv = fma(sm.P[tid * LDX + j], sm.tail[T_b + j], sv); sm.tmp[tid] = sv; }
       __syncthreads();
-      if (k > 0) { issue_ab(k - 1); issue_sr(k - 1); }
+      if (tid < NX) sm.P[tid * LDX + NX] = sm.tmp[tid];
+      if (k > 0) { issue_tail(k - 1); if (tnext != 1) issue_ab(k - 1); gT.wait(); if (tnext != 1) expand(); }
       continue;
     }
+    gAB.wait(); if (QMB_TMA) __syncthreads();     // rows 3:12 of A~, B~ have landed; the rebuilt rows and P of node k+1 are visible to everybody
     // ---- phase 1: W = P'A (32x32: warp = 16x16 block; column 30: p + P b~) ; PB = P'B~ (32x24: warp = row tile) ----
     { const int i0 = 16 * (warp >> 1), j0 = 16 * (warp & 1);
       double c[2][2][2] = {}; warp_mma<NX, 2, 2, false>(sm.P, LDX, i0, sm.A, LDX, j0, c, g, t);
@@ -518,16 +551,37 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       cfrag_store<2, 2>(sm.W, LDX, i0, j0, NX, c, g, t);
       double d[1][3][2] = {}; warp_mma<NX, 1, 3, false>(sm.P, LDX, 8 * warp, sm.Bm, LDB, 0, d, g, t);
       cfrag_store<1, 3>(sm.PB, LDB, 8 * warp, 0, NX, d, g, t); }
-    cp_async_wait<0>(); __syncthreads();           // S~, R~, r~ have landed; W, PB visible; P is dead until phase 3
+    __syncthreads();                                 // W, PB visible; P is dead until phase 3
     issue_q(k);
-    // ---- phase 2: G = S~ + B~'W (24x32: warp = column tile; column 30: h = r~ + B~'(p + P b~)) ; H = R~ + B~'PB (24x24: warps 0-2) ----
-    { double c[3][1][2]; cfrag_load<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t); warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.W, LDX, 8 * warp, c, g, t); cfrag_store<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t);
-      if (warp < 3) { double d[3][1][2]; cfrag_load<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.PB, LDB, 8 * warp, d, g, t); cfrag_store<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); } }
+    // ---- phase 2: G = S~ + B~'W (24x32: warp = column tile; column 30: h = r~ + B~'(p + P b~)) ; H = R~ + B~'PB (24x24: warps 0-2).  S~, r~ and R~ are
+    //      not stored densely: the C fragments are initialised from the structured entries of the tail ----
+    { const double* tl = sm.tail; const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const int mm = si[SI_M];
+      double c[3][1][2];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) { const int a = 8 * mt + g; const bool rowok = a < MU; const int slot = rowok ? sm.srow[a] : -1, first = rowok ? sm.sfirst[a] : 0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { const int j = 8 * warp + 2 * t + e; double v = 0.0;
+          if (rowok) { if (j == NX) v = tl[T_r + a]; else if (slot >= 0 && j < NX) { const int ps = sup_pos(j, first); if (ps >= 0) v = tl[T_SJ + slot * 12 + ps]; } }
+          c[mt][0][e] = v; } }
+      warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.W, LDX, 8 * warp, c, g, t); cfrag_store<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t);
+      if (warp < 3) { double d[3][1][2];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) { const int a = 8 * mt + g; const int fa = (a < MU) ? si[SI_FREE + a] : -1;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) { const int cc = 8 * warp + 2 * t + e; double v = 0.0;
+            if (a < MU && cc < MU) { if (a >= mm) v = (a == cc) ? 1.0 : 0.0;                                  // identity padding of the projected input
+              else if (fa >= 24) v = (a == cc) ? tl[T_RT + 3 * a] : 0.0;                                      // arm: diagonal
+              else { const int fc = si[SI_FREE + cc]; if (fc >= 0 && fc / 3 == fa / 3) v = tl[T_RT + 3 * a + fc - 3 * (fc / 3)]; } }   // own input triple
+            d[mt][0][e] = v; } }
+        warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.PB, LDB, 8 * warp, d, g, t); cfrag_store<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); } }
     __syncthreads();
+    if (k > 0) issue_tail(k - 1);                   // the tail buffer is free: next node's small pieces stream in during phase 3
     // ---- phase 3: one warp factors H and solves for Y and the gains ; the other three compute P <- Q~ + A~'W (column 30: q~ + A~'(p + P b~)).
     // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
     const int sw = (k + b) & 3;
+    if (!QMB_TMA) gQ.wait();                        // cp.async path: the wait contains a CTA barrier, so all four warps take it
     if (warp == sw) {
+      if (QMB_TMA) gQ.skip();
       // (a) Cholesky of H with the factor in registers (lane = row, read from the upper triangle: column access is bank-conflict free;
       //     pivot and column broadcasts by shuffle) fused with the forward substitution Y = L^{-1}[G | h] (lane = column of [G | h]):
       //     the broadcast L[c][j] that updates row c of the factor is exactly the multiplier of the right-looking substitution step,
@@ -549,84 +603,84 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       if (!ok && lane == 0) sm.flag = 1;
       __syncwarp();
       // (b) back substitution K = -L^{-T} Y, lane = column: factor entries are warp-uniform broadcasts, the running column lives in registers.
+      //     The gains leave with the pitch of their shared-memory target in the rollout (K rows of LDG doubles, feed-forward k in column 30).
       double* gk = gb + (size_t)k * GAIN_DBL;
 #pragma unroll
       for (int a = MU - 1; a >= 0; --a) {  // L' z = y, right-looking over row a of L'
         asm volatile("" ::: "memory");
         y[a] *= sm.dut[a];
-        if (lane < NX) gk[a * NX + lane] = -y[a]; else if (lane == NX) gk[MU * NX + a] = -y[a];
+        gk[a * LDG + lane] = -y[a];
 #pragma unroll
         for (int c = 0; c < a; ++c) y[c] = fma(-sm.Lt[c * MU + a], y[a], y[c]);
       }
     } else {
-      cp_async_wait<0>(); asm volatile("bar.sync 1, 96;\n" ::: "memory");   // Q~ (this thread's and the other helpers' copies) is in the P buffer
+      if (QMB_TMA) gQ.wait();                                                  // Q~ is in the P buffer
       const int hi = (warp - sw - 1) & 3;                                      // helper index 0..2: 8x8 tiles hi, hi+3, ... of the 4x4 tile grid
       for (int tile = hi; tile < 16; tile += 3) { const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3);
         double c[1][1][2]; cfrag_load<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); warp_mma<NX, 1, 1, false>(sm.A, LDX, i0, sm.W, LDX, j0, c, g, t); cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); }
     }
     __syncthreads();
-    if (sm.flag) { st |= MST_NOT_PD; break; }
-    if (k > 0) { issue_ab(k - 1); issue_sr(k - 1); }   // A~/B~ and S~/R~ buffers are free: prefetch the next node
+    if (sm.flag) { st |= MST_NOT_PD; if (k > 0) gT.wait(); break; }            // (an in-flight copy must land before the CTA may exit)
+    if (k > 0) { if (tnext != 1) issue_ab(k - 1); gT.wait(); if (tnext != 1) expand(); }   // A~/B~ buffers are free: fetch and rebuild the next node while phase 4 runs
     // ---- phase 4: P -= Y'Y, column 30: p -= Y' yh (warp = 16x16 block; the top-of-loop barrier closes this phase) ----
     { const double* Yb = sm.PB; const int i0 = 16 * (warp >> 1), j0 = 16 * (warp & 1);
       double c[2][2][2]; cfrag_load<2, 2>(sm.P, LDX, i0, j0, NX, c, g, t); warp_mma<MU, 2, 2, true>(Yb, LDX, i0, Yb, LDX, j0, c, g, t); cfrag_store<2, 2>(sm.P, LDX, i0, j0, NX, c, g, t); }
   }
-  cp_async_wait<0>(); __syncthreads();
-  // ---- forward rollout: du~ = K dx + k ; dx+ = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~ ----
+  __syncthreads();
+  // ---- forward rollout: du~ = K dx + k ; dx+ = A~ dx + B~ du~ + b~ ; du = Px dx + Pu du~ + Pe ; armijo = sum q~'dx + r~'du~.  Works on the structured
+  //      record directly (no dense A~ / B~): per node four copies - gains, rows 3:12 of A~ and B~, tail - into one of two buffer sets ----
   double armijo = 0.0, dxn2 = 0.0, dun2 = 0.0;
   if (!(st & MST_NOT_PD)) {
-    // two buffer sets (k & 1): {G, A, Bm, b, q, r, kff} and {W, P, PB, pPb, p, h, kff2}; node k+1 streams in while node k is applied
+    // buffer set 0: {G, A[0:9 rows], Bm[0:9 rows], A + 9 rows} ; set 1: {W, P, PB, P + 9 rows}
     auto issue_fwd = [&](int k) {
-      if (k < N && tid < STAGE_INT / 4) cp_async16(sm.sib[k & 1] + 4 * tid, sib + (size_t)k * STAGE_INT + 4 * tid);
-      if (k < N && node_type(k) != 1) {
-        const double* sg = sgb + (size_t)k * STAGE_DBL; const double* gk = gb + (size_t)k * GAIN_DBL; const bool o = k & 1;
-        cp_rows(gk, MU, NX, NX, o ? sm.W : sm.G, LDG, tid); cp_rows(sg + ST_A, NX, NX, NX, o ? sm.P : sm.A, LDX, tid); cp_rows(sg + ST_B, NX, MU, MU, o ? sm.PB : sm.Bm, LDB, tid);
-        if (tid < 15) cp_async16((o ? sm.pPb : sm.b) + 2 * tid, sg + ST_b + 2 * tid); else if (tid < 30) cp_async16((o ? sm.p : sm.q) + 2 * (tid - 15), sg + ST_q + 2 * (tid - 15));
-        else if (tid < 39) cp_async16((o ? sm.h : sm.r) + 2 * (tid - 30), sg + ST_r + 2 * (tid - 30)); else if (tid < 48) cp_async16((o ? sm.kff2 : sm.kff) + 2 * (tid - 39), gk + MU * NX + 2 * (tid - 39));
-      }
-      cp_async_commit(); };
+      if (k >= N) return; const int o = k & 1; CopyGroup& cg = o ? gF1 : gAB; const double* sg = sgb + (size_t)k * STAGE_DBL; const bool ev = node_type(k) == 1;
+      cg.begin((ev ? 0 : (GAIN_DBL + 9 * LDX + 9 * LDB) * 8) + TAIL_DBL * 8, tid);
+      cg.copy((o ? sm.P : sm.A) + 9 * LDX, sg + ST_TAIL, TAIL_DBL * 8, tid);
+      if (!ev) { cg.copy(o ? sm.W : sm.G, gb + (size_t)k * GAIN_DBL, GAIN_DBL * 8, tid); cg.copy(o ? sm.P : sm.A, sg + ST_AR, 9 * LDX * 8, tid); cg.copy(o ? sm.PB : sm.Bm, sg + ST_BR, 9 * LDB * 8, tid); } };
     issue_fwd(0);
     for (int k = 0; k < N; ++k) {
-      const double* sg = sgb + (size_t)k * STAGE_DBL; const int32_t* si = sm.sib[k & 1]; const int type = node_type(k);
+      const int o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* ARb = o ? sm.P : sm.A; const double* BRb = o ? sm.PB : sm.Bm; const double* tl = (o ? sm.P : sm.A) + 9 * LDX;
       double* dxk = dxo + ((size_t)b * nmax + k) * NX; double* duk = duo + ((size_t)b * nmax + k) * NU;
       // dx is double buffered (sm.dx / sm.tmp): the next state is written into the other buffer, and the barrier at the top of the next
       // iteration publishes it - two barriers per node instead of four
       const double* dxc = (k & 1) ? sm.tmp : sm.dx; double* dxn = (k & 1) ? sm.dx : sm.tmp;
-      cp_async_wait<0>(); __syncthreads();   // stage record k has landed; dx(k) (written by other threads in the previous iteration) is visible; nobody reads buffer set (k+1)&1 any more
+      if (o) gF1.wait(); else gAB.wait();
+      if (QMB_TMA) __syncthreads();              // record k has landed; dx(k) (written by other threads in the previous iteration) is visible; nobody reads buffer set (k+1)&1 any more
       issue_fwd(k + 1);
-      const int ndep = si[SI_NDEP];
+      const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const int type = si[SI_TYPE], ndep = si[SI_NDEP], mm = si[SI_M]; const double dtw = tl[T_MISC];
       if (tid < NX) { const double dxi = dxc[tid]; dxk[tid] = dxi; dxn2 += dxi * dxi; }
-      if (type == 1) { if (tid < NX) { duk[tid] = 0.0; dxn[tid] = dxc[tid] + sg[ST_b + tid]; } continue; }
-      const bool o = k & 1; const double* Kb = o ? sm.W : sm.G; const double* Ab = o ? sm.P : sm.A; const double* Bb = o ? sm.PB : sm.Bm;
-      const double* bv = o ? sm.pPb : sm.b; const double* qv = o ? sm.p : sm.q; const double* rv = o ? sm.h : sm.r; const double* kv = o ? sm.kff2 : sm.kff;
-      { double s = 0.0;   // all lanes take part in the quad reduction (shfl_sync needs the full mask)
+      if (type == 1) { if (tid < NX) { duk[tid] = 0.0; dxn[tid] = dxc[tid] + tl[T_b + tid]; } continue; }
+      { double s = 0.0;   // du~ = K dx + k: 4 threads per row (all lanes take part in the quad reduction); columns 30 / 31 of K meet dx[30] = dx[31] = 0
         if (ti < MU) { const double* kr = Kb + ti * LDG + jb * 8; const double* dx = dxc + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(kr[v], dx[v], s); }
-        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + kv[ti]; }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < MU && jb == 0) sm.dut[ti] = s + Kb[ti * LDG + NX]; }
       __syncthreads();
-      { double s = 0.0;
-        if (ti < NX) { const double* ar = Ab + ti * LDX + jb * 8; const double* dx = dxc + jb * 8;
+      { // dependent inputs du_d = Px_d dx + Pu_d du~ + Pe_d, 8 threads per input (MAXDEP * 8 = all 128 threads); a dependent joint also owns its row of the dynamics:
+        // dx+[joint] = dx[joint] + dtw * (Px dx + Pu du~) + b~[joint]
+        static_assert(MAXDEP * 8 == RIC_THREADS, "one 8-thread group per dependent input");
+        const int d = tid >> 3, q8 = tid & 7; double s = 0.0; const int di = (d < ndep) ? si[SI_DEP + d] : -1;
+        if (di >= 12) { const int j = di - 12, lg = j / 3, first = 3 * lg; const double* px = tl + T_PXJ + j * 12;
+          s = px[q8] * dxc[sup_col(q8, first)]; if (q8 < 4) s = fma(px[q8 + 8], dxc[sup_col(q8 + 8, first)], s);
+          if (q8 >= 4 && q8 < 6) { const int foot = (lfp >> (2 * lg)) & 3; const int col = si[SI_PCOL + 2 * foot + q8 - 4]; if (si[SI_PIV + foot] >= 0 && col >= 0) s = fma(tl[T_PU2 + 2 * foot + q8 - 4], sm.dut[col], s); } }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); s += __shfl_xor_sync(FULL, s, 4);
+        if (di >= 0 && q8 == 0) { const double full = s + tl[T_PED + d]; duk[di] = full; dun2 += full * full; if (di >= 12) dxn[di] = dxc[di] + dtw * s + tl[T_b + di]; } }
+      if (tid < NX) armijo += tl[T_q + tid] * dxc[tid];
+      if (tid < MU) { const double dut = sm.dut[tid]; armijo += tl[T_r + tid] * dut; const int fi = si[SI_FREE + tid];
+        if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; if (fi >= 12) dxn[fi] = dxc[fi] + dtw * dut + tl[T_b + fi]; } }   // free joint: dx+ = dx + dtw du + b~
+      if (warp == 1 && lane < 3) { double acc = 0.0; for (int a = 0; a < mm; ++a) { const int fa = si[SI_FREE + a]; if (fa < 12 && fa - 3 * (fa / 3) == lane) acc += sm.dut[a]; }   // h_lin rows: forces / m
+        dxn[lane] = dxc[lane] + dtw * imass * acc + tl[T_b + lane]; }
+      if (warp >= 2) { const int rr = (tid - 64) >> 2; double s = 0.0;   // dense rows 3:12: A~ row . dx + B~ row . du~  (4 threads per row; column 30 of the A~ row is b~ and meets dx[30] = 0)
+        if (rr < 9) { const double* ar = ARb + rr * LDX + jb * 8; const double* dx = dxc + jb * 8;
 #pragma unroll
           for (int v = 0; v < 8; ++v) s = fma(ar[v], dx[v], s);
-          if (jb < 3) { const double* br = Bb + ti * LDB + jb * 8; const double* du = sm.dut + jb * 8;
+          if (jb < 3) { const double* br = BRb + rr * LDB + jb * 8; const double* du = sm.dut + jb * 8;
 #pragma unroll
             for (int v = 0; v < 8; ++v) s = fma(br[v], du[v], s); } }
-        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (ti < NX && jb == 0) dxn[ti] = s + bv[ti]; }
-      if (tid < NX) armijo += qv[tid] * dxc[tid];
-      if (tid < MU) { const double dut = sm.dut[tid]; armijo += rv[tid] * dut; const int fi = si[SI_FREE + tid]; if (fi >= 0) { duk[fi] = dut; dun2 += dut * dut; } }
-      { // dependent inputs du_d = Px_d dx + Pu_d du~ + Pe_d: 8 threads per row (MAXDEP * 8 = all 128 threads), 6 of the 48 terms each, so the
-        // global loads of a row are one short burst instead of a 48-long dependent chain on one lane that the next barrier has to wait for
-        static_assert(MAXDEP * 8 == RIC_THREADS, "one 8-thread group per dependent input");
-        const int d = tid >> 3, q8 = tid & 7; double s = 0.0;
-        if (d < ndep) { const double* px = sg + ST_PXD + (size_t)d * NX; const double* pu = sg + ST_PUD + (size_t)d * MU;
-#pragma unroll
-          for (int idx = q8; idx < NX + MU; idx += 8) s = fma(idx < NX ? px[idx] : pu[idx - NX], idx < NX ? dxc[idx] : sm.dut[idx - NX], s); }
-        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); s += __shfl_xor_sync(FULL, s, 4);
-        if (d < ndep && q8 == 0) { s += sg[ST_PED + d]; duk[si[SI_DEP + d]] = s; dun2 += s * s; } }
+        s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (rr < 9 && jb == 0) dxn[3 + rr] = s + tl[T_b + 3 + rr]; }
     }
     __syncthreads();
-    if (tid < NX) { const double dxi = ((N & 1) ? sm.tmp : sm.dx)[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_q + tid] * dxi; }
+    if (tid < NX) { const double dxi = ((N & 1) ? sm.tmp : sm.dx)[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_Q + tid * LDX + NX] * dxi; }
   }
   armijo = warp_sum(armijo); dxn2 = warp_sum(dxn2); dun2 = warp_sum(dun2);
   __syncthreads();
@@ -756,7 +810,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
   const size_t Bn = (size_t)B * nmax;
   bool ok = A(&m.t0, B) && A(&m.x0, (size_t)B * NX) && A(&m.n_events, B) && A(&m.event_times, (size_t)B * EMAX) && A(&m.modes, (size_t)B * (EMAX + 1)) && A(&m.n_target, B) && A(&m.target_times, (size_t)B * KMAX) && A(&m.target_states, (size_t)B * KMAX * TARGET_DIM);
   for (int s = 0; s < 2 && ok; ++s) ok = A(&m.sol[s].n_nodes, B) && A(&m.sol[s].t, Bn) && A(&m.sol[s].event, Bn) && A(&m.sol[s].x, Bn * NX) && A(&m.sol[s].u, Bn * NU);
-  ok = ok && A(&m.stage, Bn * STAGE_DBL) && A(&m.stage_i, Bn * STAGE_INT) && A(&m.gains, Bn * GAIN_DBL) && A(&m.dx, Bn * NX) && A(&m.du, Bn * NU) && A(&m.robot, (size_t)B * ROBOT_DBL) && A(&m.status, B) && A(&m.step_info, (size_t)B * 4);
+  ok = ok && A(&m.stage, Bn * STAGE_DBL) && A(&m.gains, Bn * GAIN_DBL) && A(&m.dx, Bn * NX) && A(&m.du, Bn * NU) && A(&m.robot, (size_t)B * ROBOT_DBL) && A(&m.status, B) && A(&m.step_info, (size_t)B * 4);
   return ok;
 }
 
@@ -777,9 +831,9 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
   // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
   for (int it = 0; it < iters; ++it) {
-    mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.status);
+    mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);
-    mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.stage_i, m.gains, m.dx, m.du, m.robot, m.status);
+    mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[3], stream);
     mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
     launched += 3;

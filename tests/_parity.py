@@ -18,8 +18,8 @@ import numpy as np
 CONTRACT = 1e-5          # north_star tolerance
 MPC_TOL = 1e-8           # asserted: one SQP iteration (LQ + projection + Riccati + line search), per block
 WBC_TOL = 1e-8           # asserted: one WbcBase::update on identical inputs, per block
-MPCWBC_TOL = 1e-7        # asserted: HierarchicalMpcWbc (arm torque limits active, 1e4 rad/s^2 arm accelerations through a 3e3-conditioned 6x6 block: one decade of the
-                         # conditioning is granted; both sides are KKT points to 1e-11, see tests/test_wbc_gpu.py and profiles/r02_mpcwbc_certificates.txt)
+MPCWBC_TOL = 1e-8        # asserted: HierarchicalMpcWbc (arm torque limits active, arm accelerations of 1e4 rad/s^2 behind a 3e3-conditioned 6x6 block); both sides are KKT
+                         # points to 1e-11 once the oracle refines its levels on the active set (profiles/r02_mpcwbc_certificates.txt), observed agreement ~1e-11
 TICK_TOL = 1e-6          # asserted: MPC -> evaluatePolicy -> WBC chain (the WBC's PD laws multiply the MPC's ~1e-11 by gains up to 6000: still a decade below the contract)
 
 # name -> (lo, hi, floor)
