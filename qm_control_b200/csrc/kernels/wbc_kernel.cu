@@ -25,30 +25,45 @@ namespace qmb {
 
 constexpr int LDM = 25;   // leading dimension of 24-column matrices (odd → conflict-free column walks)
 constexpr int LDZ = 37;   // leading dimension of 36-column / 36-row matrices
+constexpr int LZ = 19;    // leading dimension of matrices in null-space coordinates (at most 18 columns: level 0 always has 18 independent rows)
 constexpr int MAXR = 24;  // max rows of one level's equality task (22 in flight mode) or 18 + violated rows at level 0
 constexpr int MAXW = 20;  // max size of the inequality working set
-constexpr int WBC_WARPS = 4;
+#ifndef QMB_WBC_WARPS
+#define QMB_WBC_WARPS 7
+#endif
+constexpr int WBC_WARPS = QMB_WBC_WARPS;   // robots (= warps) per CTA, one CTA per SM: the kernel is latency bound, its speed is the number of warps an SM holds
 
 enum { ST_OK = 0, ST_ITER_CAP = 1, ST_TOO_MANY_ROWS = 2, ST_NAN = 4 };
 
+// end-effector quantities: produced by the rigid-body passes, consumed when the level-1 rows are built - they live where the projected rows go afterwards
+struct EeWs { double Jee[6 * LDM], djv_ee[6], ee_m_pos[3], ee_m_vel[3], ee_m_rot[9], ee_m_w[3], ee_d_pos[3], ee_d_vel[3], ee_d_rot[9]; };
+// QP workspace, 22 KB per robot (round 1: 44 KB, which capped the SM at four warps):
+//   * the null-space basis is kept in null-space width (36 x <= 18) instead of 36 x 36,
+//   * the level-0 factorisation runs in place on the task rows (row i of the task IS column i of the column-major QR workspace),
+//   * levels >= 1 iterate in null-space coordinates on the projected rows A_p Z (<= 22 x 18), so the 36-wide rows are only a build area that the
+//     factorisation workspaces of the level reuse; working-set rows are regenerated from M / J instead of being cached.
 struct QpWs {
-  double Ap[MAXR * LDZ];       // current level's task rows (r x 36)
-  double Z[36 * LDZ];          // orthonormal basis; active window = columns [off, 36)
-  double W[LDZ * MAXR];        // COD workspace (n_z x r, column-major)
-  double Wc[LDZ * MAXW];       // working-set constraint COD workspace (n_z x nw)
-  double Gw[MAXW * LDZ];       // explicit rows of the working-set constraints (filled when a row enters the set)
+  union ZA { struct Q { double Z[36 * LZ];        // orthonormal basis of the current null space, active columns [off, nzc)
+                        double AR[MAXR * LDZ];    // level 0: task rows / their in-place QR.  levels >= 1: raw task rows while they are built, then the
+                      } q;                        //   step workspace W1 (LZ x MAXR, at AR) and the working-set factorisation Wc (LZ x MAXW, behind it)
+             RbdWs rbd;                           // rigid-body passes (before the hierarchy starts)
+             __device__ ZA() {} } za;
+  union AH { double Ah[MAXR * LZ];                // projected task rows A_p Z (rows x nz, pitch LZ) = column-major nz x rows for the null-space QR of the level
+             EeWs ee; __device__ AH() {} } ah;
+  double G[18 * 19];                              // normal equations of an overdetermined / rank-deficient step (k <= 18 at levels >= 1; level 0 borrows Z)
   double tau[MAXR], tauc[MAXW];
-  double xbar[36], dx[36], g[36], y[36], s[36], rhs[MAXR], bp[MAXR], lam[MAXW], G[MAXR * (MAXR + 1)], t18[MAXR];
+  double xbar[36], dx[36], g[36], y[36], s[36], zac[LZ + 1], rhs[MAXR], bp[MAXR], bh[MAXR], lam[MAXW], t18[MAXR];
   int perm[MAXR], permc[MAXW], wset[MAXW];
 };
+static_assert(LZ * MAXR + LZ * MAXW <= MAXR * LDZ, "W1 and Wc share the row build area");
+static_assert(sizeof(RbdWs) <= sizeof(double) * (36 * LZ + MAXR * LDZ), "rigid-body workspace overlays Z + AR only");
 
 struct WbcSmem {
   double q[NQ], v[NQ], qd[NQ], vd[NQ];
   double M[NQ * LDM], nle[NQ];
   double Jf[12 * LDM], djv_f[12], fpos_m[12], fvel_m[12], fpos_d[12], fvel_d[12];
-  double Jee[6 * LDM], djv_ee[6], ee_m_pos[3], ee_m_vel[3], ee_m_rot[9], ee_m_w[3], ee_d_pos[3], ee_d_vel[3], ee_d_rot[9];
-  double Tm[9], wdot_base[3], base_acc[6], xdes[NX], udes[NU], lim[NJ], vstar[64];
-  union U { RbdWs rbd; QpWs qp; __device__ U() {} } u;
+  double Tm[9], wdot_base[3], base_acc[6], xdes[NX], udes[NU], lim[NJ], vstar[56];
+  QpWs qp;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -89,64 +104,64 @@ __device__ __forceinline__ double ineq_row_elem(const IneqCtx& c, int i, int k) 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Minimum-norm least squares  min || Abar y - rhs ||  with Abar^T stored column-wise in W (n x r): COD.
-// On exit y[0..n) holds the solution in the coordinates of W's rows; returns rank.  Uses qp.tau/perm/G/t18.
-__device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, const double* rhs, double* y, int lane) {
-  const int k = w_qrcp(W, n, r, LDZ, qp.tau, qp.perm, 1e-11, lane);
+// Minimum-norm least squares  min || Abar y - rhs ||  with Abar^T stored column-wise in W (n x r, leading dimension ldw): COD.
+// On exit y[0..n) holds the solution in the coordinates of W's rows; returns rank.  Uses qp.tau/perm/t18 and the k x k scratch G (leading dimension ldg).
+__device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, int ldw, const double* rhs, double* y, double* G, int ldg, int lane) {
+  const int k = w_qrcp(W, n, r, ldw, qp.tau, qp.perm, 1e-11, lane);
   // Abar = P R^T Q^T  →  residual_c = sum_{i<=min(c,k-1)} R[i][c] y_i - rhs[perm[c]]
   for (int i = lane; i < n; i += 32) y[i] = 0.0;
   __syncwarp();
   if (k == 0) return 0;
   if (k == r) {   // square lower-triangular system R11^T y1 = P^T rhs
     for (int c = 0; c < k; ++c) {
-      double part = 0.0; if (lane < c) part = W[lane + c * LDZ] * y[lane];
+      double part = 0.0; if (lane < c) part = W[lane + c * ldw] * y[lane];
       const double s = warp_sum(part);
-      if (lane == 0) y[c] = (rhs[qp.perm[c]] - s) / W[c + c * LDZ];
+      if (lane == 0) y[c] = (rhs[qp.perm[c]] - s) / W[c + c * ldw];
       __syncwarp();
     }
   } else {        // overdetermined / rank deficient: normal equations on the k x k triangular factor
-    for (int e = lane; e < k * k; e += 32) { const int a = e / k, b = e % k; double s = 0.0; for (int c = (a > b ? a : b); c < r; ++c) s += W[a + c * LDZ] * W[b + c * LDZ]; qp.G[a * (MAXR + 1) + b] = s; }
-    if (lane < k) { double s = 0.0; for (int c = lane; c < r; ++c) s += W[lane + c * LDZ] * rhs[qp.perm[c]]; qp.t18[lane] = s; }
+    for (int e = lane; e < k * k; e += 32) { const int a = e / k, b = e % k; double s = 0.0; for (int c = (a > b ? a : b); c < r; ++c) s += W[a + c * ldw] * W[b + c * ldw]; G[a * ldg + b] = s; }
+    if (lane < k) { double s = 0.0; for (int c = lane; c < r; ++c) s += W[lane + c * ldw] * rhs[qp.perm[c]]; qp.t18[lane] = s; }
     __syncwarp();
-    w_cholesky(qp.G, k, MAXR + 1, lane);
-    w_chol_solve(qp.G, k, MAXR + 1, qp.t18, lane);
+    w_cholesky(G, k, ldg, lane);
+    w_chol_solve(G, k, ldg, qp.t18, lane);
     if (lane < k) y[lane] = qp.t18[lane];
     __syncwarp();
   }
-  w_apply_q(W, n, k, LDZ, qp.tau, y, lane);
+  w_apply_q(W, n, k, ldw, qp.tau, y, lane);
   return k;
 }
 
-// Build the task rows of one hierarchy level into qp.Ap / qp.bp.  Returns the row count.
+// Build the task rows of one hierarchy level into the row build area qp.za.q.AR (pitch LDZ) / qp.bp.  Returns the row count.
 //   level 0: floating-base EoM + no-contact-motion + swing zero-force           (WbcBase.cpp:338-356, 386-401, 407-415)
 //   level 1: HierarchicalWbc: height, base angular, EE linear, EE angular, 100*swing (t>=10) | arm joint tracking (t<10)
 //            HierarchicalMpcWbc: height, base angular, base linear, 100*swing
 //   level 2: contact force + base linear | contact force
 __device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int level, int mode, int variant, bool init_phase, int lane) {
-  QpWs& qp = sm.u.qp; int nc = 0; for (int f = 0; f < 4; ++f) nc += contact_flag(mode, f);
+  QpWs& qp = sm.qp; double* Ap = qp.za.q.AR; const EeWs& ee = qp.ah.ee; int nc = 0; for (int f = 0; f < 4; ++f) nc += contact_flag(mode, f);
   int rows = 0;
   if (level == 0) rows = 18;
   else if (level == 1) rows = (variant == 0) ? (init_phase ? 6 : 10 + 3 * (4 - nc)) : (6 + 3 * (4 - nc));
   else rows = (variant == 0) ? 14 : 12;
-  for (int e = lane; e < rows * LDZ; e += 32) qp.Ap[e] = 0.0;
+  for (int e = lane; e < rows * LDZ; e += 32) Ap[e] = 0.0;
   __syncwarp();
   if (level == 0) {
-    for (int e = lane; e < 6 * 36; e += 32) { const int r = e / 36, k = e % 36; qp.Ap[r * LDZ + k] = (k < NQ) ? sm.M[r * LDM + k] : -sm.Jf[(k - NQ) * LDM + r]; }
+    for (int e = lane; e < 6 * 36; e += 32) { const int r = e / 36, k = e % 36; Ap[r * LDZ + k] = (k < NQ) ? sm.M[r * LDM + k] : -sm.Jf[(k - NQ) * LDM + r]; }
     if (lane < 6) qp.bp[lane] = -sm.nle[lane];
     int row = 6;
-    for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; qp.Ap[(row + a) * LDZ + k] = sm.Jf[(3 * f + a) * LDM + k]; } if (lane < 3) qp.bp[row + lane] = -sm.djv_f[3 * f + lane]; row += 3; }
-    for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) { if (lane < 3) { qp.Ap[(row + lane) * LDZ + NQ + 3 * f + lane] = 1.0; qp.bp[row + lane] = 0.0; } row += 3; }
+    for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; Ap[(row + a) * LDZ + k] = sm.Jf[(3 * f + a) * LDM + k]; } if (lane < 3) qp.bp[row + lane] = -sm.djv_f[3 * f + lane]; row += 3; }
+    for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) { if (lane < 3) { Ap[(row + lane) * LDZ + NQ + 3 * f + lane] = 1.0; qp.bp[row + lane] = 0.0; } row += 3; }
   } else if (level == 1) {
     int row = 0;
     if (variant == 0 && init_phase) {   // formulateArmJointNomalTrackingTask (WbcBase.cpp:439-465)
-      if (lane < 6) { const int k = NQ - 6 + lane; qp.Ap[lane * LDZ + k] = 1.0; qp.bp[lane] = mdl->arm_joint_kp[lane] * (sm.qd[k] - sm.q[k]) + mdl->arm_joint_kd[lane] * (sm.vd[k] - sm.v[k]); }
+      if (lane < 6) { const int k = NQ - 6 + lane; Ap[lane * LDZ + k] = 1.0; qp.bp[lane] = mdl->arm_joint_kp[lane] * (sm.qd[k] - sm.q[k]) + mdl->arm_joint_kd[lane] * (sm.vd[k] - sm.v[k]); }
       row = 6;
     } else {
       // formulateBaseHeightMotionTask (WbcBase.cpp:296-308)
-      if (lane == 0) { qp.Ap[2] = 1.0; qp.bp[0] = sm.base_acc[2] + mdl->base_height_kp * (sm.qd[2] - sm.q[2]) + mdl->base_height_kd * (sm.vd[2] - sm.v[2]); }
+      if (lane == 0) { Ap[2] = 1.0; qp.bp[0] = sm.base_acc[2] + mdl->base_height_kp * (sm.qd[2] - sm.q[2]) + mdl->base_height_kd * (sm.vd[2] - sm.v[2]); }
       // formulateBaseAngularMotionTask (WbcBase.cpp:258-293): base_j angular rows are [0 | T | 0]
       if (lane < 3) {
-        const int r = lane; for (int k = 0; k < 3; ++k) qp.Ap[(1 + r) * LDZ + 3 + k] = sm.Tm[3 * r + k];
+        const int r = lane; for (int k = 0; k < 3; ++k) Ap[(1 + r) * LDZ + 3 + k] = sm.Tm[3 * r + k];
         double wM[3], wD[3]; matvec3(sm.Tm, sm.v + 3, wM); matvec3(sm.Tm, sm.vd + 3, wD);
         double Rm[9], Rr[9], err[3]; rot_zyx(sm.q[3], sm.q[4], sm.q[5], Rm); rot_zyx(sm.qd[3], sm.qd[4], sm.qd[5], Rr); rotation_error_world(Rr, Rm, err);
         // getGlobalAngularAccelerationFromEulerAnglesZyxDerivatives(eulerMeasured, eulerRatesDesired, eulerAccDesired) = T edd + Tdot(ed) ed
@@ -156,72 +171,83 @@ __device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int le
       row = 4;
       if (variant == 0) {
         // formulateEeLinearMotionTrackingTask (WbcBase.cpp:467-492) and formulateEeAngularMotionTrackingTask (:494-531)
-        for (int e = lane; e < 6 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; const bool zero = (a >= 3 && k >= 3 && k < 6); qp.Ap[(row + a) * LDZ + k] = zero ? 0.0 : sm.Jee[a * LDM + k]; }
-        if (lane < 3) qp.bp[row + lane] = mdl->ee_linear_kp[lane] * (sm.ee_d_pos[lane] - sm.ee_m_pos[lane]) + mdl->ee_linear_kd[lane] * (sm.ee_d_vel[lane] - sm.ee_m_vel[lane]) - sm.djv_ee[lane];
-        if (lane == 3) { double err[3]; rotation_error_world(sm.ee_d_rot, sm.ee_m_rot, err);
+        for (int e = lane; e < 6 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; const bool zero = (a >= 3 && k >= 3 && k < 6); Ap[(row + a) * LDZ + k] = zero ? 0.0 : ee.Jee[a * LDM + k]; }
+        if (lane < 3) qp.bp[row + lane] = mdl->ee_linear_kp[lane] * (ee.ee_d_pos[lane] - ee.ee_m_pos[lane]) + mdl->ee_linear_kd[lane] * (ee.ee_d_vel[lane] - ee.ee_m_vel[lane]) - ee.djv_ee[lane];
+        if (lane == 3) { double err[3]; rotation_error_world(ee.ee_d_rot, ee.ee_m_rot, err);
           // arm_dj_tmp zeroes columns 3:6 of the angular rows: Jdot_w v minus the base euler part (= Tdot ed = base angular bias acc)
-          for (int a = 0; a < 3; ++a) qp.bp[row + 3 + a] = mdl->ee_angular_kp[a] * err[a] - mdl->ee_angular_kd[a] * sm.ee_m_w[a] - (sm.djv_ee[3 + a] - sm.wdot_base[a]); }
+          for (int a = 0; a < 3; ++a) qp.bp[row + 3 + a] = mdl->ee_angular_kp[a] * err[a] - mdl->ee_angular_kd[a] * ee.ee_m_w[a] - (ee.djv_ee[3 + a] - sm.wdot_base[a]); }
         row += 6;
       } else {
         // formulateBaseLinearMotionTask (WbcBase.cpp:228-240)
-        if (lane < 2) { qp.Ap[(row + lane) * LDZ + lane] = 1.0; qp.bp[row + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
+        if (lane < 2) { Ap[(row + lane) * LDZ + lane] = 1.0; qp.bp[row + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
         row += 2;
       }
       // formulateSwingLegTask * 100 (WbcBase.cpp:311-334, HierarchicalWbc.cpp:29)
       for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) {
-        for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; qp.Ap[(row + a) * LDZ + k] = 100.0 * sm.Jf[(3 * f + a) * LDM + k]; }
+        for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; Ap[(row + a) * LDZ + k] = 100.0 * sm.Jf[(3 * f + a) * LDM + k]; }
         if (lane < 3) { const int i = 3 * f + lane; qp.bp[row + lane] = 100.0 * (mdl->kp_swing * (sm.fpos_d[i] - sm.fpos_m[i]) + mdl->kd_swing * (sm.fvel_d[i] - sm.fvel_m[i]) - sm.djv_f[i]); }
         row += 3;
       }
     }
   } else {
     // formulateContactForceTask (WbcBase.cpp:534-546)
-    if (lane < 12) { qp.Ap[lane * LDZ + NQ + lane] = 1.0; qp.bp[lane] = sm.udes[lane]; }
-    if (variant == 0 && lane < 2) { qp.Ap[(12 + lane) * LDZ + lane] = 1.0; qp.bp[12 + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
+    if (lane < 12) { Ap[lane * LDZ + NQ + lane] = 1.0; qp.bp[lane] = sm.udes[lane]; }
+    if (variant == 0 && lane < 2) { Ap[(12 + lane) * LDZ + lane] = 1.0; qp.bp[12 + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
   }
   __syncwarp();
   return rows;
 }
 
-// W[c + i*LDZ] = sum_k Ap[i][k] Z[k][off+c]   (n_z x rows)
+// Projected task of a level >= 1:  Ah = A_p Z[:, off:nzc] (rows x nz, pitch LZ),  bh = b_p - A_p xbar.  The 36-wide rows are dead afterwards.
 __device__ __forceinline__ void project_task(QpWs& qp, int rows, int off, int nz, int lane) {
-  for (int e = lane; e < rows * nz; e += 32) { const int i = e / nz, c = e % nz; const double* a = qp.Ap + i * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.Z[k * LDZ + off + c]; qp.W[c + i * LDZ] = s; }
+  const double* Ap = qp.za.q.AR; const double* Z = qp.za.q.Z;
+  for (int e = lane; e < rows * nz; e += 32) { const int i = e / nz, c = e - i * nz; const double* a = Ap + i * LDZ; double s0 = 0.0, s1 = 0.0;
+#pragma unroll 6
+    for (int k = 0; k < 36; k += 2) { s0 = fma(a[k], Z[k * LZ + off + c], s0); s1 = fma(a[k + 1], Z[(k + 1) * LZ + off + c], s1); }
+    qp.ah.Ah[i * LZ + c] = s0 + s1; }
+  if (lane < rows) { const double* a = Ap + lane * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s = fma(a[k], qp.xbar[k], s); qp.bh[lane] = qp.bp[lane] - s; }
   __syncwarp();
 }
 
-// One hierarchy level >= 1: primal active set over the hard inequalities, equality residual minimised in the window.
-__device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, int& nw, int lane, int& iters_out, int iter_cap) {
-  QpWs& qp = sm.u.qp; const int nz = 36 - off; const int nineq = 36 + 5 * ic.nc; int status = 0;
+// One hierarchy level >= 1 in null-space coordinates: primal active set over the hard inequalities, equality residual |Ah z - bh| minimised in the window.
+__device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, int nzc, int& nw, int lane, int& iters_out, int iter_cap) {
+  QpWs& qp = sm.qp; const int nz = nzc - off; const int nineq = 36 + 5 * ic.nc; int status = 0;
   if (nz <= 0) return 0;
+  const double* Z = qp.za.q.Z; const double* Ah = qp.ah.Ah; double* W1 = qp.za.q.AR; double* Wc = qp.za.q.AR + LZ * MAXR;
+  if (lane < LZ + 1) qp.zac[lane] = 0.0;   // accumulated step of this level in window coordinates
+  __syncwarp();
   bool converged = false;
   for (int iter = 0; iter < iter_cap; ++iter) {
     iters_out = iter + 1;
-    // (1) working-set constraints in window coordinates: Wc[c + k*LDZ] = G_{w_k} . Z[:, off+c]
+    // (1) working-set constraints in window coordinates: Wc[c + k*LZ] = D_{w_k} . Z[:, off+c]  (the row is regenerated from M / J, never stored)
     int kc = 0;
     if (nw > 0) {
-      for (int e = lane; e < nw * nz; e += 32) { const int k = e / nz, c = e % nz; const double* gr = qp.Gw + k * LDZ; double s = 0.0;
-#pragma unroll 4
-        for (int j = 0; j < 36; ++j) s = fma(gr[j], qp.Z[j * LDZ + off + c], s);
-        qp.Wc[c + k * LDZ] = s; }
-      __syncwarp();
-      kc = w_qrcp(qp.Wc, nz, nw, LDZ, qp.tauc, qp.permc, 1e-10, lane);
+      for (int k = 0; k < nw; ++k) {
+        const int wi = qp.wset[k]; qp.y[lane] = ineq_row_elem(ic, wi, lane); if (lane < 4) qp.y[32 + lane] = ineq_row_elem(ic, wi, 32 + lane);
+        __syncwarp();
+        if (lane < nz) { double s0 = 0.0, s1 = 0.0;
+#pragma unroll 6
+          for (int j = 0; j < 36; j += 2) { s0 = fma(qp.y[j], Z[j * LZ + off + lane], s0); s1 = fma(qp.y[j + 1], Z[(j + 1) * LZ + off + lane], s1); }
+          Wc[lane + k * LZ] = s0 + s1; }
+        __syncwarp();
+      }
+      kc = w_qrcp(Wc, nz, nw, LZ, qp.tauc, qp.permc, 1e-10, lane);
       if (kc < nw) {   // dependent rows in this window: keep an independent subset and refactor
         int keep = (lane < kc) ? qp.wset[qp.permc[lane]] : -1; __syncwarp(); if (lane < kc) qp.wset[lane] = keep; nw = kc; __syncwarp();
-        for (int k2 = 0; k2 < nw; ++k2) for (int j = lane; j < 36; j += 32) qp.Gw[k2 * LDZ + j] = ineq_row_elem(ic, qp.wset[k2], j);
-        __syncwarp(); continue;
+        continue;
       }
     }
     // (2) least squares for the step in the free directions
-    project_task(qp, rows, off, nz, lane);
-    if (lane < rows) { const double* a = qp.Ap + lane * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.xbar[k]; qp.rhs[lane] = qp.bp[lane] - s; }
+    for (int e = lane; e < rows * LZ; e += 32) W1[e] = Ah[e];   // W1 (nz x rows, column-major) has the memory layout of Ah (rows x nz, row-major)
+    if (lane < rows) { const double* a = Ah + lane * LZ; double s = 0.0; for (int c = 0; c < nz; ++c) s = fma(a[c], qp.zac[c], s); qp.rhs[lane] = qp.bh[lane] - s; }
     __syncwarp();
-    if (kc > 0) w_apply_qt_cols(qp.Wc, nz, kc, LDZ, qp.tauc, qp.W, rows, LDZ, lane);
+    if (kc > 0) w_apply_qt_cols(Wc, nz, kc, LZ, qp.tauc, W1, rows, LZ, lane);
     const int nfree = nz - kc;
     for (int i = lane; i < nz; i += 32) qp.s[i] = 0.0;
     __syncwarp();
-    if (nfree > 0) cod_lstsq(qp, qp.W + kc, nfree, rows, qp.rhs, qp.s + kc, lane);
-    if (kc > 0) w_apply_q(qp.Wc, nz, kc, LDZ, qp.tauc, qp.s, lane);
-    for (int i = lane; i < 36; i += 32) { double d = 0.0; for (int c = 0; c < nz; ++c) d += qp.Z[i * LDZ + off + c] * qp.s[c]; qp.dx[i] = d; }
+    if (nfree > 0) cod_lstsq(qp, W1 + kc, nfree, rows, LZ, qp.rhs, qp.s + kc, qp.G, 19, lane);
+    if (kc > 0) w_apply_q(Wc, nz, kc, LZ, qp.tauc, qp.s, lane);
+    for (int i = lane; i < 36; i += 32) { double d = 0.0; for (int c = 0; c < nz; ++c) d = fma(Z[i * LZ + off + c], qp.s[c], d); qp.dx[i] = d; }
     __syncwarp();
     double dmax = 0.0, xmax = 0.0; for (int i = lane; i < 36; i += 32) { dmax = fmax(dmax, fabs(qp.dx[i])); xmax = fmax(xmax, fabs(qp.xbar[i])); }
     dmax = warp_max(dmax); xmax = warp_max(xmax);
@@ -237,31 +263,29 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
       }
       { double a = alpha; int b = (blk < 0) ? 0x7fffffff : blk; warp_argmin(a, b); alpha = a; blk = (alpha < 1.0) ? b : -1; }
       for (int i = lane; i < 36; i += 32) qp.xbar[i] += alpha * qp.dx[i];
+      if (lane < nz) qp.zac[lane] += alpha * qp.s[lane];
       __syncwarp();
-      if (blk >= 0) { if (nw >= MAXW) { status |= ST_TOO_MANY_ROWS; break; } if (lane == 0) qp.wset[nw] = blk; for (int j = lane; j < 36; j += 32) qp.Gw[nw * LDZ + j] = ineq_row_elem(ic, blk, j); nw += 1; __syncwarp(); full_step = false; }
+      if (blk >= 0) { if (nw >= MAXW) { status |= ST_TOO_MANY_ROWS; break; } if (lane == 0) qp.wset[nw] = blk; nw += 1; __syncwarp(); full_step = false; }
     }
     if (!full_step) continue;
     if (nw == 0) { converged = true; break; }
-    // (4) multipliers of the working set at the face minimiser:  C^T lam = -g,  g = Zw^T Ap^T (Ap xbar - bp)
-    if (lane < rows) { const double* a = qp.Ap + lane * LDZ; double s = 0.0; for (int k = 0; k < 36; ++k) s += a[k] * qp.xbar[k]; qp.rhs[lane] = s - qp.bp[lane]; }
+    // (4) multipliers of the working set at the face minimiser:  C^T lam = -g,  g = Ah^T (Ah z - bh)
+    if (lane < rows) { const double* a = Ah + lane * LZ; double s = 0.0; for (int c = 0; c < nz; ++c) s = fma(a[c], qp.zac[c], s); qp.rhs[lane] = s - qp.bh[lane]; }
     __syncwarp();
-    for (int i = lane; i < 36; i += 32) { double s = 0.0; for (int r = 0; r < rows; ++r) s += qp.Ap[r * LDZ + i] * qp.rhs[r]; qp.y[i] = s; }
+    for (int c = lane; c < nz; c += 32) { double s = 0.0; for (int r = 0; r < rows; ++r) s = fma(Ah[r * LZ + c], qp.rhs[r], s); qp.g[c] = s; }
     __syncwarp();
-    for (int c = lane; c < nz; c += 32) { double s = 0.0; for (int j = 0; j < 36; ++j) s += qp.Z[j * LDZ + off + c] * qp.y[j]; qp.g[c] = s; }
-    __syncwarp();
-    w_apply_qt(qp.Wc, nz, kc, LDZ, qp.tauc, qp.g, lane);
+    w_apply_qt(Wc, nz, kc, LZ, qp.tauc, qp.g, lane);
     double gmax = 0.0; for (int i = lane; i < nz; i += 32) gmax = fmax(gmax, fabs(qp.g[i])); gmax = warp_max(gmax);
     for (int c = kc - 1; c >= 0; --c) {   // back substitution R lam_p = -g[0:kc]
-      double part = 0.0; if (lane > c && lane < kc) part = qp.Wc[c + lane * LDZ] * qp.lam[lane];
+      double part = 0.0; if (lane > c && lane < kc) part = Wc[c + lane * LZ] * qp.lam[lane];
       const double s = warp_sum(part);
-      if (lane == 0) qp.lam[c] = (-qp.g[c] - s) / qp.Wc[c + c * LDZ];
+      if (lane == 0) qp.lam[c] = (-qp.g[c] - s) / Wc[c + c * LZ];
       __syncwarp();
     }
     double lmin = (lane < kc) ? qp.lam[lane] : 1e300; int li = lane; warp_argmin(lmin, li);
     if (lmin >= -1e-9 * (1.0 + gmax)) { converged = true; break; }
     // drop the constraint with the most negative multiplier (position li in pivoted order)
     { const int drop = qp.permc[li]; int keep = -1; if (lane < nw) { int src = lane < drop ? lane : lane + 1; keep = (src < nw) ? qp.wset[src] : -1; } __syncwarp(); if (lane < nw - 1) qp.wset[lane] = keep;
-      for (int k2 = drop; k2 < nw - 1; ++k2) { double v0 = 0.0, v1 = 0.0; if (lane < 36) v0 = qp.Gw[(k2 + 1) * LDZ + lane]; if (lane < 4) v1 = qp.Gw[(k2 + 1) * LDZ + 32 + lane]; __syncwarp(); if (lane < 36) qp.Gw[k2 * LDZ + lane] = v0; if (lane < 4) qp.Gw[k2 * LDZ + 32 + lane] = v1; __syncwarp(); }
       nw -= 1; __syncwarp(); }
   }
   if (!converged) status |= ST_ITER_CAP;
@@ -286,14 +310,14 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   // updateMeasured (WbcBase.cpp:138-144): rbd = [zyx(3), pos(3), joints(18), w_world(3), v_lin(3), joint vel(18), ...]
   if (lane < 3) { sm.q[lane] = rb[3 + lane]; sm.q[3 + lane] = rb[lane]; sm.v[lane] = rb[NQ + 3 + lane]; }
   if (lane < NJ) { sm.q[6 + lane] = rb[6 + lane]; sm.v[6 + lane] = rb[NQ + 6 + lane]; sm.lim[lane] = (lane < 12) ? mdl->effort[lane % 3] : mdl->effort[lane]; }
-  for (int i = lane; i < 64; i += 32) sm.vstar[i] = 0.0;
+  for (int i = lane; i < 56; i += 32) sm.vstar[i] = 0.0;
   __syncwarp();
   if (lane == 0) { euler_rate_map(sm.q[3], sm.q[4], sm.Tm); double Ti[9]; inv3(sm.Tm, Ti); const double w[3] = {rb[NQ], rb[NQ + 1], rb[NQ + 2]}; matvec3(Ti, w, sm.v + 3); }
   if (lane < NQ) sm.qd[lane] = sm.xdes[6 + lane];
   __syncwarp();
 
   // ---- measured side: M, nle, foot/EE Jacobians and bias accelerations ----
-  RbdWs* ws = &sm.u.rbd;
+  RbdWs* ws = &sm.qp.za.rbd; EeWs& ee = sm.qp.ah.ee;   // the end-effector block sits outside the rigid-body overlay
   rbd_kinematics<true>(mdl, sm.q, sm.v, ws, lane);
   rbd_inertias(mdl, ws, lane, 1);
   rbd_accumulate(mdl, ws, lane, true);
@@ -307,10 +331,10 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   {
     const int body = mdl->ee_body; double pl[3] = {mdl->ee_p[0], mdl->ee_p[1], mdl->ee_p[2]}, pw[3]; matvec3(ws->R[body], pl, pw);
     pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
-    point_jacobian(ws, pw, 12, 17, sm.Jee, LDM, lane);
-    if (lane < NQ) { const bool on = (lane < 6) || (lane >= 18); for (int a = 0; a < 3; ++a) sm.Jee[(3 + a) * LDM + lane] = on ? ws->S[lane][a] : 0.0; }
-    if (lane == 0) { double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.ee_m_pos[a] = pw[a]; sm.ee_m_vel[a] = vel[a]; sm.djv_ee[a] = acc[a]; sm.djv_ee[3 + a] = ws->A[body][a]; sm.ee_m_w[a] = ws->V[body][a]; sm.wdot_base[a] = ws->A[0][a]; }
-      matmul3(ws->R[body], mdl->ee_R, sm.ee_m_rot); }
+    point_jacobian(ws, pw, 12, 17, ee.Jee, LDM, lane);
+    if (lane < NQ) { const bool on = (lane < 6) || (lane >= 18); for (int a = 0; a < 3; ++a) ee.Jee[(3 + a) * LDM + lane] = on ? ws->S[lane][a] : 0.0; }
+    if (lane == 0) { double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { ee.ee_m_pos[a] = pw[a]; ee.ee_m_vel[a] = vel[a]; ee.djv_ee[a] = acc[a]; ee.djv_ee[3 + a] = ws->A[body][a]; ee.ee_m_w[a] = ws->V[body][a]; sm.wdot_base[a] = ws->A[0][a]; }
+      matmul3(ws->R[body], mdl->ee_R, ee.ee_m_rot); }
   }
   __syncwarp();
 
@@ -346,8 +370,8 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   if (lane == 0) {
     const int body = mdl->ee_body; double pl[3] = {mdl->ee_p[0], mdl->ee_p[1], mdl->ee_p[2]}, pw[3]; matvec3(ws->R[body], pl, pw);
     pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
-    double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.ee_d_pos[a] = pw[a]; sm.ee_d_vel[a] = vel[a]; }
-    matmul3(ws->R[body], mdl->ee_R, sm.ee_d_rot);
+    double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { ee.ee_d_pos[a] = pw[a]; ee.ee_d_vel[a] = vel[a]; }
+    matmul3(ws->R[body], mdl->ee_R, ee.ee_d_rot);
     // centroidalMomentumRate = m*getNormalizedCentroidalMomentumRate(u) [true COM] - dAg v - Aj qdd_j ; baseAcc = AbInv(SRBD) * that
     const double mt = ws->Ic[0][0]; const double com[3] = {ws->Ic[0][1] / mt, ws->Ic[0][2] / mt, ws->Ic[0][3] / mt};
     double lin[3] = {0, 0, -9.81 * mdl->total_mass}, ang[3] = {0, 0, 0};
@@ -362,25 +386,23 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   __syncwarp();
 
   // ---- hierarchy ----
-  QpWs& qp = sm.u.qp; IneqCtx ic{&sm, mode, nc, mdl->wbc_friction}; int status = 0;
+  QpWs& qp = sm.qp; IneqCtx ic{&sm, mode, nc, mdl->wbc_friction}; int status = 0;
   const bool init_phase = time < 10.0;   // HierarchicalWbc.cpp:32
-  for (int e = lane; e < 36 * LDZ; e += 32) qp.Z[e] = ((e / LDZ) == (e % LDZ)) ? 1.0 : 0.0;
+  double* AR = qp.za.q.AR; double* Z = qp.za.q.Z;
   for (int i = lane; i < 36; i += 32) qp.xbar[i] = 0.0;
   __syncwarp();
-  // level 0: min ||A0 x - b0||^2 + ||(D0 x - f0)_+||^2  — semismooth iteration on the violated set V
-  int rows0 = build_level(sm, mdl, 0, mode, variant, init_phase, lane);
-  const int nineq = 36 + 5 * nc;
+  // level 0: min ||A0 x - b0||^2 + ||(D0 x - f0)_+||^2  — semismooth iteration on the violated set V.  The rows are factorised IN PLACE (row i of the task is
+  // column i of the column-major QR workspace), so every pass rebuilds them from M / J (a few hundred element writes; the generic case takes one pass + one check)
+  const int nineq = 36 + 5 * nc; const int cap0 = mdl->wbc_iter_cap0, cap = mdl->wbc_iter_cap; int it0 = 0;
   unsigned vmask0 = 0, vmask1 = 0;   // violated set, bit per inequality (lane-uniform)
-  const int cap0 = mdl->wbc_iter_cap0, cap = mdl->wbc_iter_cap; int it0 = 0;
+  int k0 = 0;
   for (int it = 0; it < cap0; ++it) {
-    int r = rows0; it0 = it + 1;
+    int r = build_level(sm, mdl, 0, mode, variant, init_phase, lane); it0 = it + 1;
     // append violated rows
     for (int i = 0; i < nineq; ++i) { const bool in = (i < 32) ? ((vmask0 >> i) & 1u) : ((vmask1 >> (i - 32)) & 1u); if (in) { if (r >= MAXR) { status |= ST_TOO_MANY_ROWS; break; }
-        for (int k = lane; k < 36; k += 32) qp.Ap[r * LDZ + k] = ineq_row_elem(ic, i, k); if (lane == 0) qp.bp[r] = ineq_rhs(ic, i); ++r; } }
+        for (int k = lane; k < 36; k += 32) AR[r * LDZ + k] = ineq_row_elem(ic, i, k); if (lane == 0) qp.bp[r] = ineq_rhs(ic, i); ++r; } }
     __syncwarp();
-    for (int e = lane; e < r * 36; e += 32) { const int i = e / 36, c = e % 36; qp.W[c + i * LDZ] = qp.Ap[i * LDZ + c]; }
-    __syncwarp();
-    cod_lstsq(qp, qp.W, 36, r, qp.bp, qp.xbar, lane);
+    k0 = cod_lstsq(qp, AR, 36, r, LDZ, qp.bp, qp.xbar, Z, MAXR + 1, lane);   // Z is not in use yet: scratch of the rank-deficient branch
     __syncwarp();
     unsigned n0 = 0, n1 = 0;   // next violated set: strictly violated rows, plus rows of V sitting on their boundary
     for (int i = lane; i < nineq; i += 32) { const double val = ineq_row_dot(ic, i, qp.xbar) - ineq_rhs(ic, i); const double sc = 1e-9 * (1.0 + fabs(ineq_rhs(ic, i)));
@@ -394,24 +416,26 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   // optimal slack of level 0 and the null space of A0 (HoQp::buildZMatrix, HoQp.cpp:126-133)
   for (int i = lane; i < nineq; i += 32) { const double val = ineq_row_dot(ic, i, qp.xbar) - ineq_rhs(ic, i); sm.vstar[i] = val > 0.0 ? val : 0.0; }
   __syncwarp();
-  int off = 0, nw = 0, it1 = 0, it2 = 0;
+  int off = 0, nzc = 0, nw = 0, it1 = 0, it2 = 0;
   {
-    for (int e = lane; e < rows0 * 36; e += 32) { const int i = e / 36, c = e % 36; qp.W[c + i * LDZ] = qp.Ap[i * LDZ + c]; }
-    __syncwarp();
-    const int k = w_qrcp(qp.W, 36, rows0, LDZ, qp.tau, qp.perm, 1e-11, lane);
-    w_apply_q_right(qp.W, 36, k, LDZ, qp.tau, qp.Z, 36, LDZ, 0, lane);
-    off = k;
+    if (vmask0 | vmask1) {   // the last factorisation contains violated rows: factor A0 alone (otherwise the one in AR already is the QR of A0')
+      const int rows0 = build_level(sm, mdl, 0, mode, variant, init_phase, lane);
+      k0 = w_qrcp(AR, 36, rows0, LDZ, qp.tau, qp.perm, 1e-11, lane);
+    }
+    nzc = 36 - k0;
+    if (nzc > LZ - 1) { status |= ST_TOO_MANY_ROWS; nzc = 0; }   // (A0 has 18 independent rows for every physical model: the mass matrix and a contact Jacobian)
+    else w_form_q_tail(AR, 36, k0, LDZ, qp.tau, Z, LZ, lane);
   }
   // levels 1 and 2
-  for (int level = 1; level <= 2; ++level) {
+  for (int level = 1; level <= 2 && nzc > 0; ++level) {
     const int rows = build_level(sm, mdl, level, mode, variant, init_phase, lane);
-    const int nz = 36 - off;
+    const int nz = nzc - off;
     if (nz <= 0) break;                                   // trivial kernel (the reference keeps one zero column, HoQp.cpp:129)
-    status |= solve_level(sm, ic, rows, off, nw, lane, level == 1 ? it1 : it2, cap);
-    if (level == 1) {                                    // Z <- Z * kernel(A_1 Z)
-      project_task(qp, rows, off, nz, lane);
-      const int k = w_qrcp(qp.W, nz, rows, LDZ, qp.tau, qp.perm, 1e-11, lane);
-      w_apply_q_right(qp.W, nz, k, LDZ, qp.tau, qp.Z, 36, LDZ, off, lane);
+    project_task(qp, rows, off, nz, lane);
+    status |= solve_level(sm, ic, rows, off, nzc, nw, lane, level == 1 ? it1 : it2, cap);
+    if (level == 1) {                                    // Z <- Z * kernel(A_1 Z): QR of (A_1 Z)' in place on the projected rows
+      const int k = w_qrcp(qp.ah.Ah, nz, rows, LZ, qp.tau, qp.perm, 1e-11, lane);
+      w_apply_q_right(qp.ah.Ah, nz, k, LZ, qp.tau, Z, 36, LZ, off, lane);
       off += k;
     }
   }

@@ -87,6 +87,23 @@ __device__ __forceinline__ void w_apply_q_right(const double* W, int n, int k, i
   }
 }
 
+// Z (n x (n - k), row-major, leading dimension ldz) <- the last n - k columns of Q = H_0 H_1 ... H_{k-1} (the orthonormal basis of the null space of
+// the factored matrix' row space complement).  One lane per column: the reflectors are applied right to left to the unit vectors e_{k+c}.
+__device__ __forceinline__ void w_form_q_tail(const double* W, int n, int k, int ld, const double* tau, double* Z, int ldz, int lane) {
+  const int nc = n - k;
+  if (lane < nc) {
+    double* col = Z + lane;
+    for (int i = 0; i < n; ++i) col[i * ldz] = (i == k + lane) ? 1.0 : 0.0;
+    for (int j = k - 1; j >= 0; --j) {
+      const double* v = W + j * ld; double w0 = col[j * ldz], w1 = 0.0; int i = j + 1;
+      for (; i + 1 < n; i += 2) { w0 = fma(v[i], col[i * ldz], w0); w1 = fma(v[i + 1], col[(i + 1) * ldz], w1); }
+      if (i < n) w0 = fma(v[i], col[i * ldz], w0);
+      const double w = (w0 + w1) * tau[j]; col[j * ldz] -= w; for (int i2 = j + 1; i2 < n; ++i2) col[i2 * ldz] = fma(-w, v[i2], col[i2 * ldz]);
+    }
+  }
+  __syncwarp();
+}
+
 // In-place Cholesky (lower) of the n x n symmetric matrix A (row-major, ld), n <= 32.  Returns false when a pivot <= 0.
 __device__ __forceinline__ bool w_cholesky(double* A, int n, int ld, int lane) {
   bool ok = true;
