@@ -224,6 +224,24 @@ int qmb200_measure_fp64_peak(qmb200_handle* h, double* tflops);
 
 /* diagnostics: the QP step (dx, du) of the last solve and per-robot scalars [armijo, baseline cost, dyn SSE, eq SSE, |dx|, |du|, -, -] */
 int qmb200_debug_get_step(qmb200_handle* h, double* dx /*[B][NMAX][30]*/, double* du /*[B][NMAX][30]*/, double* robot /*[B][8]*/);
+/* ---- multi-GPU: robots are independent, rank g owns a contiguous robot range, the only exchange per tick is ONE all-gather of the torque rows.
+ *      NCCL is driven from this library (opened with dlopen at the first call: no link-time dependency).  Bootstrap: rank 0 calls qmb200_comm_get_unique_id and
+ *      ships the 128 bytes to the other ranks by any means; every rank then calls qmb200_comm_init on its handle (collective, like ncclCommInitRank). */
+#define QMB200_COMM_ID_BYTES 128
+int qmb200_comm_get_unique_id(void* id128);
+int qmb200_comm_init(qmb200_handle* h, int32_t nranks, int32_t rank, const void* id128);
+int qmb200_comm_destroy(qmb200_handle* h);                                   /* also done by qmb200_destroy */
+int qmb200_comm_info(const qmb200_handle* h, int32_t* nranks, int32_t* rank, int32_t* nccl_version);
+/* torque_all[r * B + i][0:18] = torque rows (cmd[.][36:54]) of rank r's robot i, on every rank: one pack kernel + one ncclAllGather on `cuda_stream` (NULL: the
+ * handle's stream).  nccl_comm: an ncclComm_t of the caller, or NULL for the handle's communicator (no communicator at all: single rank, plain copy).
+ * perm (device, optional): the batch was submitted in gait-binned order, perm[p] = original local index of the robot at position p; the gathered buffer is in
+ * ORIGINAL order.  All ranks must hold the same batch size. */
+int qmb200_allgather_torque(qmb200_handle* h, void* nccl_comm, const double* cmd_local /*[B][54] device*/, const int32_t* perm /*[B] device or NULL*/,
+                            double* torque_all /*[nranks * B][18] device*/, void* cuda_stream);
+/* Host helper for mixed-gait batches (BASELINE configs[4]): permutation that sorts the robots by contact phase (stance code at t0, events in the window, time to the
+ * next event); perm[p] = original index of the robot at position p. */
+int qmb200_gait_bin_permutation(int32_t n, const double* t0, const int32_t* n_events, const double* event_times /*[n][EMAX]*/, const int32_t* modes /*[n][EMAX+1]*/, int32_t* perm /*[n]*/);
+
 /* Host-only (no CUDA device needed): run the constructor chain's parsers (QMInterface::setupModel / setupOptimalControlProblem inputs: task.info, robot.urdf,
  * reference.info, optional gains file — batch / device of cfg are ignored) and copy the resulting model + settings constants (the block replicated to every GPU)
  * into out.  Returns the block size in bytes (also when out is NULL or capacity is too small: nothing is copied then), negative on a parse error

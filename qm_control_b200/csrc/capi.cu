@@ -47,6 +47,7 @@ struct qmb200_handle {
   bool c_ready = false; double *c_tobs = nullptr, *c_xobs = nullptr, *c_jcmd = nullptr, *c_armpos = nullptr, *c_lasttime = nullptr, *c_cmd7 = nullptr, *c_ee = nullptr, *c_lastee = nullptr,
                                *c_jpos = nullptr, *c_jvel = nullptr, *c_effort = nullptr, *c_ttimes = nullptr, *c_tstates = nullptr; int32_t *c_status = nullptr, *c_ntarget = nullptr;
   double hw_delay = 0.0; double *hw_ring_cmd = nullptr, *hw_ring_stamp = nullptr; int32_t* hw_ring_state = nullptr;   // QMHWSim command-delay FIFO
+  void* comm = nullptr; int comm_ranks = 0, comm_rank = 0; double* d_send = nullptr;   // NCCL communicator of this handle (capi_comm.inc) and the packed torque rows
   int chunks = 1; cudaStream_t cs[MAX_CHUNKS] = {nullptr}; cudaEvent_t fork_ev = nullptr, join_ev[MAX_CHUNKS] = {nullptr};
 };
 
@@ -99,6 +100,7 @@ int qmb200_create(const qmb200_config* cfg, qmb200_handle** out) {
 void qmb200_destroy(qmb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  qmb200_comm_destroy(h);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   for (int c = 0; c < qmb200_handle::MAX_CHUNKS; ++c) { if (h->cs[c]) { cudaStreamSynchronize(h->cs[c]); cudaStreamDestroy(h->cs[c]); } if (h->join_ev[c]) cudaEventDestroy(h->join_ev[c]); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
@@ -203,3 +205,4 @@ int qmb200_wbc_set_iteration_caps(qmb200_handle* h, int32_t level0_passes, int32
 
 #include "capi_mpc.inc"
 #include "capi_ctrl.inc"
+#include "capi_comm.inc"

@@ -190,6 +190,32 @@ class Solver:
         keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
         self._chk(self.lib.qmb200_tick_dev(self.h, *[_p(prob_dev[k]) for k in keys], _p(t_eval), _p(rbd), _p(period), _p(cmd), _p(status), C.c_void_p(stream) if stream else None), "qmb200_tick_dev")
 
+    # ---------------- multi-GPU (include/qmb200.h: one NCCL all-gather of the torque rows per tick, driven from the C++ host) ----------------
+    def comm_unique_id(self):
+        """rank 0: the 128-byte ncclUniqueId to ship to the other ranks."""
+        buf = C.create_string_buffer(128)
+        if self.lib.qmb200_comm_get_unique_id(buf) != 0:
+            raise QmbError("qmb200_comm_get_unique_id: %s" % self.lib.qmb200_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        self._chk(self.lib.qmb200_comm_init(self.h, int(nranks), int(rank), C.c_char_p(bytes(unique_id))), "qmb200_comm_init")
+
+    def comm_info(self):
+        n, r, v = C.c_int32(), C.c_int32(), C.c_int32(); self.lib.qmb200_comm_info(self.h, C.byref(n), C.byref(r), C.byref(v)); return n.value, r.value, v.value
+
+    def allgather_torque(self, cmd_dev, torque_all_dev, perm_dev=None, stream=None):
+        """torque_all[r * B + i] = cmd[i, 36:54] of rank r (original robot order when perm_dev is given); device tensors."""
+        self._chk(self.lib.qmb200_allgather_torque(self.h, None, _p(cmd_dev), _p(perm_dev), _p(torque_all_dev), C.c_void_p(stream) if stream else None), "qmb200_allgather_torque")
+
+    def gait_bin_permutation(self, prob):
+        """Host: perm[p] = original index of the robot at position p after sorting by contact phase (qmb200_gait_bin_permutation)."""
+        n = len(prob["t0"]); perm = np.zeros(n, dtype=np.int32)
+        rc = self.lib.qmb200_gait_bin_permutation(n, _p(_f64(prob["t0"])), _p(_i32(prob["n_events"])), _p(_f64(prob["event_times"])), _p(_i32(prob["modes"])), _p(perm))
+        if rc != 0:
+            raise QmbError("qmb200_gait_bin_permutation failed")
+        return perm
+
     def set_pipeline(self, chunks):
         """Number of robot ranges the tick runs as concurrent stream chains (include/qmb200.h: qmb200_set_pipeline)."""
         self._chk(self.lib.qmb200_set_pipeline(self.h, int(chunks)), "qmb200_set_pipeline")

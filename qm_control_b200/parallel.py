@@ -51,3 +51,13 @@ def max_over_ranks(value, device):
     if dist.is_initialized():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def init_comm(solver, rank, world):
+    """Bootstrap of the library's own NCCL communicator (include/qmb200.h, qmb200_comm_*): rank 0 creates the ncclUniqueId, torch.distributed only carries the
+    128 bytes to the other ranks; every collective of the data path is then issued by the C++ host (qmb200_allgather_torque).  No-op for one rank."""
+    if world == 1:
+        return
+    ids = [solver.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    solver.comm_init(world, rank, ids[0])
