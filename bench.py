@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--batch", type=int, default=UNIT_BATCH); ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="tick", choices=["tick", "mpc", "wbc", "mixed"], help="tick = the BASELINE metric (default); mpc / wbc / mixed = configs[1] / [2] / [4] side lines on one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true"); ap.add_argument("--no-e2e", action="store_true"); ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and configs[4] records")
+    ap.add_argument("--solver", default="sqp", choices=["sqp", "ipm", "ddp"], help="MPC solver variant (qmb200_mpc_set_solver); the BASELINE metric is quoted on sqp, the controller's solver")
     ap.add_argument("--chunks", type=int, default=PIPELINE_CHUNKS, help="robot ranges run as concurrent stream chains inside one tick")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -302,6 +303,8 @@ def main():
         return
     B = args.batch; n_int = int(round(HORIZON / DT))
     loop = TickLoop(q, torch, dev, local, stream, B, np.arange(rank * B, (rank + 1) * B), CONFIG, world, rank, chunks=args.chunks); solver = loop.solver
+    if args.solver != "sqp":
+        solver.mpc_set_solver(args.solver)
     for _ in range(args.warmup):
         loop.step()
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.15)
@@ -409,7 +412,7 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "full MPC+WBC tick (BASELINE configs[3] shape): trot gait schedule, horizon 1.0 s / dt 0.01 (100 intervals + event nodes), 24-DoF quadruped-manipulator, one SQP iteration + 3-level HoQp",
-                          "batch_per_gpu": B, "pipeline_chunks": args.chunks, "global_batch": B * world, "robot_ticks_per_s": B * world / (ms * 1e-3),
+                          "batch_per_gpu": B, "mpc_solver": args.solver, "pipeline_chunks": args.chunks, "global_batch": B * world, "robot_ticks_per_s": B * world / (ms * 1e-3),
                           "parallelism": "dp%d (robots sharded, one NCCL all-gather of the torque rows per tick issued by the C++ host: qmb200_allgather_torque)" % world, "allgather_ms": ag_ms, "nccl_version": nccl_v,
                           "l2": "per-tick working set (LQ stage buffer %.1f GB) >> 126 MB L2; no flush needed" % (B * solver.nmax * 2084 * 8 / 1e9),
                           "robots_flagged": flagged, "robots_flagged_note": "mpc_neg_dt / mpc_not_pd: synthetic robot 1758's schedule puts an event 0.68 us after a grid node, which gives the interval a NEGATIVE duration in upstream's own time discretisation (weakEpsilon shift > gap > dt_min): a non-convex QP every exact solver rejects; root-caused in tests/test_neg_interval_cpu.py"},

@@ -224,6 +224,22 @@ int qmb200_measure_fp64_peak(qmb200_handle* h, double* tflops);
 
 /* diagnostics: the QP step (dx, du) of the last solve and per-robot scalars [armijo, baseline cost, dyn SSE, eq SSE, |dx|, |du|, -, -] */
 int qmb200_debug_get_step(qmb200_handle* h, double* dx /*[B][NMAX][30]*/, double* du /*[B][NMAX][30]*/, double* robot /*[B][8]*/);
+/* ---- solver variants.  QMInterface loads four solver blocks (QMInterface.cpp:69-73: ddp{}, sqp{}, ipm{}, rollout{}); QMController::setupMpc runs
+ *      SqpMpc (QMController.cpp:287-288), the handle's default.  The other two blocks select, on the same OCP, LQ model (K2) and backward pass (K3):
+ *      IPM  ocs2 IpmSolver with ipm{} (task.info:95-125).  The OCP of qm_interface has no inequality constraint terms (soft constraints + state-input
+ *           equalities only, QMInterface.cpp:79-142), so the interior-point iteration carries no barrier / slack / dual variables and its primal step is the
+ *           Newton step of the equality-constrained problem - the SQP step; what changes are the iteration count and the filter line-search thresholds
+ *           (ipmIteration, deltaTol, g_max = 10, g_min).
+ *      DDP  ocs2 GaussNewtonDDP with ddp{} (task.info:33-71) in its discrete-time form (ddp.algorithm ILQR; the file's SLQ integrates a continuous-time Riccati
+ *           equation and ODE45 rollouts, which cannot be pinned without a reference run): nominal single-shooting rollout from the measured state, LQ
+ *           approximation along it, the discrete Riccati backward pass, rollout line search of the affine controller on merit = cost + penalty * sqrt(ISE of
+ *           the state-input equalities) over step lengths maxStepLength * 0.5^j >= minStepLength. */
+#define QMB200_SOLVER_SQP 0
+#define QMB200_SOLVER_IPM 1
+#define QMB200_SOLVER_DDP 2
+int qmb200_mpc_set_solver(qmb200_handle* h, int32_t solver);
+int qmb200_mpc_get_solver(const qmb200_handle* h, int32_t* solver, int32_t* iterations, double* delta_tol, double* g_max, double* g_min);
+
 /* ---- multi-GPU: robots are independent, rank g owns a contiguous robot range, the only exchange per tick is ONE all-gather of the torque rows.
  *      NCCL is driven from this library (opened with dlopen at the first call: no link-time dependency).  Bootstrap: rank 0 calls qmb200_comm_get_unique_id and
  *      ships the 128 bytes to the other ranks by any means; every rank then calls qmb200_comm_init on its handle (collective, like ncclCommInitRank). */

@@ -256,6 +256,16 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
       bool fl[4]; mode_to_contact_flags(mode_at_time(sched, t), fl); Vec ui(NU); weight_compensating_input(m, fl, ui.data()); u.push_back(ui); x.push_back(x.back());
     } else { u.push_back(interpolate(t, ptimes, pu)); x.push_back(interpolate(tn, ptimes, prev->x)); }
   }
+  // ---- DDP (GaussNewtonDDP::runImpl [upstream ocs2_ddp, recalled]; ddp{} of task.info:33-71): the nominal trajectory is a ROLLOUT of the nominal inputs from the
+  //      measured state (single shooting: no dynamics defect).  Restated on the solver's own time grid with its RK2 step (the reference integrates with ODE45,
+  //      rollout{} task.info:128-136, and sweeps a continuous-time Riccati equation for algorithm SLQ; this is the discrete-time form, ddp.algorithm ILQR) ----
+  auto rollout_nominal = [&](std::vector<Vec>& xs, const std::vector<Vec>& us) {
+    xs.assign(N + 1, Vec(NX)); for (int i = 0; i < NX; ++i) xs[0][i] = x0[i];
+    for (int k = 0; k < N; ++k) {
+      if (grid[k].event == 1) { xs[k + 1] = xs[k]; continue; }
+      const double t = interval_start(grid[k]), dt = interval_end(grid[k + 1]) - t; (void)t; double xn[NX]; rk2_step<double>(m, s, xs[k].data(), us[k].data(), dt, xn); xs[k + 1].assign(xn, xn + NX); }
+  };
+  if (s.solver == 2) rollout_nominal(x, u);
   // ---- SqpSolver::runImpl [upstream ocs2_sqp, recalled]: for (iter < sqpIteration) { setupQuadraticSubproblem; getOCPSolution; takeStep; checkConvergence } ----
   for (int iteration = 0; iteration < s.sqp_iterations; ++iteration) {
   if (dbg) { dbg->A.clear(); dbg->B.clear(); dbg->b.clear(); dbg->Q.clear(); dbg->R.clear(); dbg->P.clear(); dbg->C.clear(); dbg->D.clear(); dbg->q.clear(); dbg->r.clear(); dbg->e.clear(); dbg->is_event.clear(); }
@@ -313,6 +323,31 @@ MpcSolution mpc_solve(const Model& m, const MpcSettings& s, double t0, const dou
     du[k] = S.Px * dx[k] + S.Pu * dut + S.Pe;
   }
   armijo += dot(qN.q, dx[N]);
+  if (s.solver == 2) {
+    // ---- DDP line search [upstream ocs2_ddp LineSearchStrategy, recalled]: step lengths maxStepLength * contraction^j >= minStepLength; the candidate is a ROLLOUT
+    //      of the updated affine controller  u = u_nom + alpha * du_ff + K (x - x_nom)  (full-space law of the constrained LQ problem: K = Px + Pu K~,
+    //      du_ff = Pu k~ + Pe); merit = cost + penalty * sqrt(equality-constraint SSE), accepted at the first sufficient decrease ----
+    const double merit0 = base.cost + s.ddp_penalty * std::sqrt(base.eq);
+    double alpha = s.ddp_max_step; bool accepted = false; Perf sp; int trials = 0; std::vector<Vec> xn(N + 1), un(N); double dxn = 0, dun = 0;
+    for (auto& v : dx) dxn += norm2(v); for (auto& v : du) dun += norm2(v); dxn = std::sqrt(dxn); dun = std::sqrt(dun);
+    while (alpha >= s.ddp_min_step) {
+      ++trials; xn[0].assign(x0, x0 + NX);
+      for (int k = 0; k < N; ++k) {
+        Stage& S = st[k];
+        if (S.event) { un[k] = Vec(NU, 0.0); xn[k + 1] = xn[k]; continue; }
+        Vec ddx = xn[k] - x[k]; Vec dut = K[k] * ddx + alpha * kff[k]; Vec d = S.Px * ddx + S.Pu * dut + alpha * S.Pe; un[k] = u[k] + d;
+        const double t = interval_start(grid[k]), dt = interval_end(grid[k + 1]) - t; (void)t; double xx[NX]; rk2_step<double>(m, s, xn[k].data(), un[k].data(), dt, xx); xn[k + 1].assign(xx, xx + NX);
+      }
+      sp = compute_performance(m, s, sched, tt, grid, x0, xn, un);
+      const double merit = sp.cost + s.ddp_penalty * std::sqrt(sp.eq);
+      if (merit < merit0 - s.ddp_armijo * alpha * std::fabs(merit0)) { accepted = true; break; }
+      alpha *= s.ddp_contraction;
+    }
+    if (accepted) { x = xn; u = un; } else alpha = 0.0;
+    if (dbg) { dbg->alpha = alpha; dbg->base_cost = base.cost; dbg->base_dyn_sse = base.dyn; dbg->base_eq_sse = base.eq; dbg->step_cost = sp.cost; dbg->step_dyn_sse = sp.dyn; dbg->step_eq_sse = sp.eq; dbg->armijo = armijo; dbg->trials = trials; dbg->dx = dx; dbg->du = du; dbg->iterations = iteration + 1; dbg->convergence = 0; }
+    if (iteration + 1 >= s.sqp_iterations || !accepted) break;
+    continue;
+  }
   // ---- takeStep: filter line search (ocs2 FilterLinesearch) [recalled] ----
   auto violation = [](const Perf& p) { return std::sqrt(p.dyn + p.eq); };
   double dxn = 0, dun = 0; for (auto& v : dx) dxn += norm2(v); for (auto& v : du) dun += norm2(v); dxn = std::sqrt(dxn); dun = std::sqrt(dun);

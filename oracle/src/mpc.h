@@ -19,6 +19,9 @@ struct MpcSettings {
   int sqp_iterations = 1; double cost_tol = 1e-4;   // sqp.sqpIteration (task.info:28), costTol [upstream ocs2_sqp default]: SqpSolver::runImpl loop + checkConvergence
   // RK2 form x+ = x + dt (w1 k1 + w2 k2), k2 = f(x + c dt k1): Heun (c=1,w=1/2,1/2) is OCS2's SensitivityIntegrator rk2 [recalled]
   double rk_c = 1.0, rk_w1 = 0.5, rk_w2 = 0.5;
+  // solver variant: 0 = multiple-shooting SQP (sqp{}), 1 = multiple-shooting IPM (ipm{}: no inequality rows in this OCP => the same Newton step, other tolerances),
+  // 2 = DDP (ddp{}): single-shooting rollouts, discrete Riccati backward pass, rollout line search on merit = cost + penalty * sqrt(equality SSE)
+  int solver = 0; double ddp_penalty = 20.0, ddp_min_step = 1e-2, ddp_max_step = 1.0, ddp_armijo = 1e-4, ddp_contraction = 0.5;
   // cost (task.info:192-287, QMInterface.cpp:274-319)
   Mat Q, R;
   double mu_ee_pos = 2000, mu_ee_ori = 1000, mu_final_ee_pos = 2000, mu_final_ee_ori = 1000;   // task.info:235-245

@@ -31,7 +31,7 @@ class WbcGains(C.Structure):
 # every symbol include/qmb200.h declares (checked by the CPU test-suite)
 SYMBOLS = ["qmb200_create", "qmb200_destroy", "qmb200_last_error", "qmb200_get_dims", "qmb200_get_model_info", "qmb200_get_joint_name",
            "qmb200_wbc_update", "qmb200_wbc_update_dev", "qmb200_wbc_set_input_last", "qmb200_wbc_get_input_last", "qmb200_wbc_get_gains", "qmb200_wbc_set_gains", "qmb200_wbc_get_diagnostics", "qmb200_wbc_set_iteration_caps",
-           "qmb200_mpc_solve", "qmb200_mpc_solve_dev", "qmb200_mpc_set_iterations", "qmb200_mpc_reset", "qmb200_mpc_set_solution", "qmb200_mpc_get_solution",
+           "qmb200_mpc_solve", "qmb200_mpc_solve_dev", "qmb200_mpc_set_iterations", "qmb200_mpc_set_solver", "qmb200_mpc_get_solver", "qmb200_mpc_reset", "qmb200_mpc_set_solution", "qmb200_mpc_get_solution",
            "qmb200_policy_eval", "qmb200_policy_eval_dev", "qmb200_tick", "qmb200_tick_dev", "qmb200_centroidal_state_from_rbd",
            "qmb200_gait_schedule", "qmb200_launch_count", "qmb200_stream", "qmb200_debug_get_step",
            "qmb200_gait_create", "qmb200_gait_destroy", "qmb200_gait_insert_template", "qmb200_gait_get_mode_schedule",

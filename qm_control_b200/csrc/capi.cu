@@ -30,7 +30,7 @@ struct qmb200_handle {
   DevModel* d_model = nullptr;
   int B = 0, nmax = 0, variant = 0, device = 0;
   cudaStream_t stream = nullptr;
-  std::string err;
+  std::string err, task_file;   // task_file: qmb200_mpc_set_solver re-reads the sqp{} / ipm{} / ddp{} block
   int64_t launches = 0;
   // staging for the host-pointer API
   double *d_xdes = nullptr, *d_udes = nullptr, *d_rbd = nullptr, *d_period = nullptr, *d_time = nullptr, *d_cmd = nullptr, *d_input_last = nullptr, *d_teval = nullptr;
@@ -78,6 +78,7 @@ int qmb200_create(const qmb200_config* cfg, qmb200_handle** out) {
   } catch (const std::exception& e) { g_create_error = e.what(); delete h; return -2; }
   if (cfg->time_horizon > 0) h->hm.dev.time_horizon = cfg->time_horizon;
   if (cfg->dt > 0) h->hm.dev.dt = cfg->dt;
+  h->task_file = cfg->task_file;
   h->B = cfg->batch; h->variant = cfg->wbc_variant; h->device = cfg->device; h->law_prm.variant = cfg->wbc_variant == QMB200_WBC_HIERARCHICAL_MPC ? 1 : 0;
   const int nint = (int)std::ceil(h->hm.dev.time_horizon / h->hm.dev.dt - 1e-9);
   h->nmax = cfg->max_nodes > 0 ? cfg->max_nodes : nint + 1 + 20;

@@ -51,6 +51,10 @@ struct DevModel {
   double lift_off_velocity, touch_down_velocity, swing_height, swing_time_scale, position_error_gain;
   double dt, time_horizon, delta_tol, g_max, g_min, alpha_decay, alpha_min, gamma_c, armijo_factor;
   double rk_c, rk_w1, rk_w2;
+  // solver variant (qmb200_mpc_set_solver): 0 = multiple-shooting SQP (sqp{}, what QMController runs), 1 = multiple-shooting IPM (ipm{}: this OCP has no
+  // inequality rows, so the interior-point step IS the equality-constrained Newton step; only the tolerances differ), 2 = DDP (ddp{}: single-shooting rollouts,
+  // discrete Riccati backward pass, rollout line search on the merit cost + penalty * sqrt(equality SSE))
+  int solver; double ddp_penalty, ddp_min_step, ddp_max_step, ddp_armijo, ddp_contraction;
   int wbc_iter_cap0, wbc_iter_cap;   // WBC iteration caps: level-0 semismooth passes (30) and active-set iterations per level (80); qmb200_wbc_set_iteration_caps (diagnostics / tests)
   double cost_tol; int sqp_iterations;   // sqp.sqpIteration (task.info:28) and costTol [upstream ocs2_sqp default 1e-4]: SqpSolver::runImpl loop + checkConvergence
 };

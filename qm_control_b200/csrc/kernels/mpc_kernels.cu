@@ -789,6 +789,116 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const 
     double* si = step_info + (size_t)b * 4; si[0] = alpha; si[1] = sc; si[2] = sd; si[3] = se; }
 }
 
+// =====================================================================================================
+// DDP variant (ddp{} of task.info:33-71, qmb200_mpc_set_solver): single-shooting rollouts.  One warp per robot, sequential in time.
+//   mode 0  nominal rollout: x_0 = measured state, x_{k+1} = RK2(x_k, u_nom,k) - the trajectory the LQ approximation is built along (no dynamics defect)
+//   mode 1  line search [upstream ocs2_ddp LineSearchStrategy, recalled]: for alpha = maxStep * contraction^j >= minStep roll out the updated affine controller
+//           u = u_nom + alpha du_ff + K (x - x_nom) - evaluated from the structured stage record and the projected gains exactly as K3's linear rollout does,
+//           du = Px dx + Pu (K~ dx + alpha k~) + alpha Pe - and accept the first alpha with merit = cost + penalty * sqrt(equality SSE) below the nominal merit.
+// The reference integrates these rollouts with ODE45 (rollout{}, task.info:128-136) and, for algorithm SLQ, sweeps a continuous-time Riccati equation; this is the
+// discrete-time form on the solver's own grid (ddp.algorithm ILQR): same LQ model, same backward pass as the SQP path (K2 / K3).
+constexpr int RO_WARPS = 4;
+struct RoSmem { PointWs pt; CostWs cost; ConWs con; double xa[NX + 2], dxv[NX + 2], dut[MU + 2], f1[NX]; double ev[EMAX]; unsigned char modes[EMAX + 8]; };
+
+__global__ void __launch_bounds__(32 * RO_WARPS, 4) mpc_rollout_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
+                                                                  double* __restrict__ xt, double* __restrict__ ut, const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int mode_ls, int iteration) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x * RO_WARPS + warp; if (b >= B) return;
+  if (status[b] & MST_CONVERGED) return;
+  RoSmem& sm = reinterpret_cast<RoSmem*>(smem_raw)[warp];
+  const int n = sol.n_nodes[b]; const int N = n - 1;
+  const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
+  double* gx = sol.x + (size_t)b * nmax * NX; double* gu = sol.u + (size_t)b * nmax * NU;
+  double* tx = xt + (size_t)b * nmax * NX; double* tu = ut + (size_t)b * nmax * NU;
+  const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
+  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
+  const int lfp = pack_leg_foot(mdl); const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, imass_unused = 0.0; (void)imass_unused;
+  const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
+  // one RK2 step from sm.xa with the input in sm.pt.u; returns the new state component of this lane (lane < 30)
+  auto rk2 = [&](double dt) -> double {
+    if (lane < NX) sm.pt.x[lane] = sm.xa[lane];
+    __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 3);
+    if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
+    __syncwarp();
+    if (lane < NX) sm.pt.x[lane] = sm.xa[lane] + mdl->rk_c * dt * sm.f1[lane];
+    __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 3);
+    const double xn = (lane < NX) ? sm.xa[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) : 0.0; __syncwarp(); return xn; };
+  if (!mode_ls) {
+    if (lane < NX + 2) sm.xa[lane] = (lane < NX) ? p.x0[(size_t)b * NX + lane] : 0.0;
+    __syncwarp(); if (lane < NX) gx[lane] = sm.xa[lane];
+    for (int k = 0; k < N; ++k) {
+      if (ge[k] != 1) { const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t;
+        if (lane < NU) sm.pt.u[lane] = gu[(size_t)k * NU + lane];
+        __syncwarp(); const double xn = rk2(dt); if (lane < NX) sm.xa[lane] = xn; __syncwarp(); }
+      if (lane < NX) gx[(size_t)(k + 1) * NX + lane] = sm.xa[lane];
+    }
+    return;
+  }
+  // ---- line search ----
+  const double* rb = robot + (size_t)b * ROBOT_DBL; const double base_cost = rb[1], base_eq = rb[3]; const double pen = mdl->ddp_penalty;
+  const double merit0 = base_cost + pen * sqrt(base_eq); const bool failed = (status[b] & MST_NOT_PD) != 0;
+  double alpha = mdl->ddp_max_step; bool accepted = false; double sc = base_cost, se = base_eq;
+  const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const double* gb = gains + (size_t)b * nmax * GAIN_DBL;
+  while (!failed && alpha >= mdl->ddp_min_step) {
+    double cost = 0.0, eq = 0.0;
+    if (lane < NX + 2) { sm.xa[lane] = (lane < NX) ? p.x0[(size_t)b * NX + lane] : 0.0; sm.dxv[lane] = 0.0; } if (lane < MU + 2) sm.dut[lane] = 0.0;
+    __syncwarp(); if (lane < NX) tx[lane] = sm.xa[lane];
+    for (int k = 0; k < N; ++k) {
+      if (ge[k] == 1) { if (lane < NU) tu[(size_t)k * NU + lane] = 0.0; if (lane < NX) tx[(size_t)(k + 1) * NX + lane] = sm.xa[lane]; continue; }
+      const double* tl = sgb + (size_t)k * STAGE_DBL + ST_TAIL; const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const double* Kg = gb + (size_t)k * GAIN_DBL;
+      const int ndep = si[SI_NDEP];
+      if (lane < NX) sm.dxv[lane] = sm.xa[lane] - gx[(size_t)k * NX + lane];
+      __syncwarp();
+      if (lane < MU) { const double* kr = Kg + lane * LDG; double s0 = 0.0, s1 = 0.0;   // du~ = K~ dx + alpha k~ (lane = row; rows of padded inputs are zero)
+#pragma unroll 5
+        for (int j = 0; j < NX; j += 2) { s0 = fma(kr[j], sm.dxv[j], s0); s1 = fma(kr[j + 1], sm.dxv[j + 1], s1); }
+        sm.dut[lane] = s0 + s1 + alpha * kr[NX]; }
+      __syncwarp();
+      double un = (lane < NU) ? gu[(size_t)k * NU + lane] : 0.0;   // u = u_nom + du: every lane < 30 finds its own input among the free / dependent lists
+      if (lane < NU) { double du = 0.0; bool found = false;
+        for (int a = 0; a < MU && !found; ++a) if (si[SI_FREE + a] == lane) { du = sm.dut[a]; found = true; }
+        for (int d = 0; d < ndep && !found; ++d) if (si[SI_DEP + d] == lane) { found = true; du = alpha * tl[T_PED + d];
+            if (lane >= 12) { const int j = lane - 12, lg = j / 3, first = 3 * lg; const double* px = tl + T_PXJ + j * 12;
+              for (int c = 0; c < 12; ++c) du = fma(px[c], sm.dxv[sup_col(c, first)], du);
+              const int foot = (lfp >> (2 * lg)) & 3; if (si[SI_PIV + foot] >= 0) for (int q2 = 0; q2 < 2; ++q2) { const int col = si[SI_PCOL + 2 * foot + q2]; if (col >= 0) du = fma(tl[T_PU2 + 2 * foot + q2], sm.dut[col], du); } } }
+        un += du; sm.pt.u[lane] = un; tu[(size_t)k * NU + lane] = un; }
+      __syncwarp();
+      const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; const int mode = mode_at_time(ev, modes, ne, t); const int fm = flag_mask(mode);
+      // performance of the node (cost, equality residuals) at (x, u) - computePerformance
+      if (lane < NX) sm.pt.x[lane] = sm.xa[lane];
+      __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 6);
+      { TargetRef ref = target_reference(tt, ts, nk, t, lane); cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, false, lane); }
+      foot_velocity<false>(mdl, &sm.pt, &sm.con, lane);
+      { double es = 0.0;
+        if (lane < 4) { const int i = lane; if ((fm >> i) & 1) { for (int a = 0; a < 3; ++a) es += sm.con.e[i][a] * sm.con.e[i][a]; }
+          else { double zp, zv; swing_reference(mdl, ev, modes, ne, i, t, zp, zv); double ez = sm.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp); es += ez * ez; for (int a = 0; a < 3; ++a) es += sm.pt.u[3 * i + a] * sm.pt.u[3 * i + a]; } }
+        eq += dt * warp_sum(es); }
+      // RK2 step (the first stage was just evaluated at (x, u): reuse it)
+      if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
+      __syncwarp();
+      if (lane < NX) sm.pt.x[lane] = sm.xa[lane] + mdl->rk_c * dt * sm.f1[lane];
+      __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 3);
+      const double xn = (lane < NX) ? sm.xa[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) : 0.0;
+      __syncwarp(); if (lane < NX) { sm.xa[lane] = xn; tx[(size_t)(k + 1) * NX + lane] = xn; }
+      __syncwarp();
+    }
+    { // final cost at x_N
+      const double t = interval_start(gt[N], ge[N]); if (lane < NX) { sm.pt.x[lane] = sm.xa[lane]; sm.pt.u[lane] = 0.0; }
+      __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 6);
+      TargetRef ref = target_reference(tt, ts, nk, t, lane); cost += stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, 0, true, lane); }
+    const double merit = cost + pen * sqrt(eq); sc = cost; se = eq;
+    if (merit < merit0 - mdl->ddp_armijo * alpha * fabs(merit0)) { accepted = true; break; }
+    alpha *= mdl->ddp_contraction;
+  }
+  if (accepted) { for (int e = lane; e < n * NX; e += 32) { gx[e] = tx[e]; if (e < N * NU) gu[e] = tu[e]; } }
+  else { alpha = 0.0; sc = base_cost; se = base_eq; }
+  __syncwarp();
+  // toPrimalSolution [upstream]: input at a pre-event node repeats the previous one; last input repeated
+  for (int k = 1; k < n; ++k) { const bool copy = (k == n - 1) || (ge[k] == 1); if (copy && lane < NU) gu[(size_t)k * NU + lane] = gu[(size_t)(k - 1) * NU + lane]; __syncwarp(); }
+  if (lane == 0) { int flags = accepted ? 0 : MST_NO_STEP; if (!accepted && iteration + 1 < mdl->sqp_iterations) flags |= MST_CONVERGED; if (flags) atomicOr(&status[b], flags);
+    double* si = step_info + (size_t)b * 4; si[0] = alpha; si[1] = sc; si[2] = 0.0; si[3] = se; }
+}
+
 __global__ void mpc_fixup_kernel(int B, int nmax, MpcSolutionDev sol) { const int b = blockIdx.x; if (b >= B) return; const int n = sol.n_nodes[b]; if (n >= 2) fixup_inputs(sol, b, nmax, n, threadIdx.x, blockDim.x); }
 
 // =====================================================================================================
@@ -818,6 +928,7 @@ int mpc_configure_device() {
   cudaError_t e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RoSmem) * RO_WARPS));
   return (int)e;
 }
 
@@ -828,6 +939,8 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, sizeof(double) * SETUP_WARPS * nmax, stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
   if (ev) cudaEventRecord(ev[1], stream);
   const long long nodes = (long long)nb * nmax; const int iters = hm.sqp_iterations < 1 ? 1 : hm.sqp_iterations; int launched = 1;
+  const bool ddp = hm.solver == 2; const int ro_grid = (nb + RO_WARPS - 1) / RO_WARPS;
+  if (ddp) { mpc_rollout_kernel<<<ro_grid, 32 * RO_WARPS, sizeof(RoSmem) * RO_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status, m.step_info, 0, 0); ++launched; }   // nominal rollout from the measured state
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
   // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
   for (int it = 0; it < iters; ++it) {
@@ -835,7 +948,8 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);
     mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[3], stream);
-    mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
+    if (ddp) mpc_rollout_kernel<<<ro_grid, 32 * RO_WARPS, sizeof(RoSmem) * RO_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status, m.step_info, 1, it);   // rollout line search (m.dx / m.du hold the trial trajectories)
+    else mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
     launched += 3;
   }
   if (ev) cudaEventRecord(ev[4], stream);

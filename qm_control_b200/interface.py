@@ -157,6 +157,17 @@ class Solver:
         keys = ("t0", "x0", "n_events", "event_times", "modes", "n_target", "target_times", "target_states")
         self._chk(self.lib.qmb200_mpc_solve_dev(self.h, *[_p(prob_dev[k]) for k in keys], C.c_void_p(stream) if stream else None), "qmb200_mpc_solve_dev")
 
+    SOLVERS = {"sqp": 0, "ipm": 1, "ddp": 2}
+
+    def mpc_set_solver(self, solver):
+        """'sqp' (SqpMpc, what QMController runs), 'ipm' (ipm{} block) or 'ddp' (ddp{} block, discrete-time form): include/qmb200.h."""
+        self._chk(self.lib.qmb200_mpc_set_solver(self.h, self.SOLVERS[solver] if isinstance(solver, str) else int(solver)), "qmb200_mpc_set_solver")
+
+    def mpc_get_solver(self):
+        s, it = C.c_int32(), C.c_int32(); dt, gx, gn = C.c_double(), C.c_double(), C.c_double()
+        self.lib.qmb200_mpc_get_solver(self.h, C.byref(s), C.byref(it), C.byref(dt), C.byref(gx), C.byref(gn))
+        return dict(solver=s.value, iterations=it.value, delta_tol=dt.value, g_max=gx.value, g_min=gn.value)
+
     def mpc_set_iterations(self, sqp_iterations=0, cost_tol=0.0):
         """sqp.sqpIteration / costTol (SqpSolver::runImpl loop bound and checkConvergence tolerance)."""
         self._chk(self.lib.qmb200_mpc_set_iterations(self.h, int(sqp_iterations), float(cost_tol)), "qmb200_mpc_set_iterations")

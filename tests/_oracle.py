@@ -118,6 +118,10 @@ class Oracle:
     def mpc_set_sqp(self, sqp_iterations=0, cost_tol=0.0):
         self.lib.orc_mpc_set_sqp(self.h, C.c_int(int(sqp_iterations)), C.c_double(float(cost_tol)))
 
+    def mpc_set_solver(self, solver=-1, iterations=0, delta_tol=0.0, g_max=0.0, g_min=0.0, ddp_penalty=0.0, ddp_min_step=0.0, ddp_max_step=0.0):
+        """solver: 0 SQP, 1 IPM, 2 DDP; tolerances <= 0 keep their value (the tests read the task file's block themselves)."""
+        self.lib.orc_mpc_set_solver(self.h, C.c_int(int(solver)), C.c_int(int(iterations)), *[C.c_double(float(v)) for v in (delta_tol, g_max, g_min, ddp_penalty, ddp_min_step, ddp_max_step)])
+
     def mpc_weights(self):
         Q = np.zeros((30, 30)); R = np.zeros((30, 30))
         self.lib.orc_mpc_get_weights(self.h, _d(Q), _d(R))

@@ -9,7 +9,7 @@ the hot path consumes:
         links (inertial only), joints (origin/axis/limit); visuals, collisions, gazebo and
         transmission blocks dropped.
   * assets/qm_task.info       <- qm_controllers/config/task.info        (comments stripped,
-        unused ddp/ipm/rollout blocks dropped)
+        the ddp / ipm / rollout blocks are kept for the solver variants)
   * assets/qm_reference.info  <- qm_controllers/config/reference.info   (comments stripped)
   * assets/qm_gait.info       <- qm_controllers/config/gait.info        (comments stripped)
   * assets/qm_wbc_gains.info  <- qm_wbc/cfg/wbcWigeht.cfg               (defaults -> INFO keys)
@@ -108,7 +108,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     minimise_urdf(os.path.join(REF, "qm_description/urdf/qudraputed_manipulator/robot.urdf"), os.path.join(OUT, "qm_robot.urdf"))
     cfg = os.path.join(REF, "qm_controllers/config")
-    strip_info(os.path.join(cfg, "task.info"), os.path.join(OUT, "qm_task.info"), drop_blocks=("ddp", "ipm", "rollout"))
+    strip_info(os.path.join(cfg, "task.info"), os.path.join(OUT, "qm_task.info"), drop_blocks=())   # ddp{} / ipm{} / rollout{} stay: qmb200_mpc_set_solver reads them
     strip_info(os.path.join(cfg, "reference.info"), os.path.join(OUT, "qm_reference.info"))
     strip_info(os.path.join(cfg, "gait.info"), os.path.join(OUT, "qm_gait.info"))
     wbc_gains(os.path.join(REF, "qm_wbc/cfg/wbcWigeht.cfg"), os.path.join(OUT, "qm_wbc_gains.info"))
