@@ -253,7 +253,7 @@ def side_workload(args, q, torch, dev, local, stream):
         for _ in range(args.steps):
             step()
         e1.record(); torch.cuda.synchronize(dev); ms = e0.elapsed_time(e1) / args.steps; launches = solver.launch_count - l0; ab = 15840 * n_int + 2328
-        out = {"workload": "configs[1]: batched MPC only (one SQP iteration), state 30 / input 30, horizon 100, stance", "batch": B, "l2": "stage buffer %.1f GB >> 126 MB L2" % (B * solver.nmax * 2084 * 8 / 1e9)}
+        out = {"workload": "configs[1]: batched MPC only (one SQP iteration), state 30 / input 30, horizon 100, stance", "batch": B, "l2": "stage buffer %.1f GB >> 126 MB L2" % (B * solver.nmax * 1484 * 8 / 1e9)}
     else:
         B = args.batch if args.batch != UNIT_BATCH else 4096; solver = q.Solver(batch=B, device=local)
         prob, wbc = synthetic.make_batch(np.arange(B), config=3); x_des, u_des, mode = synthetic.nominal_wbc_inputs(prob, solver.robot_mass)
@@ -414,7 +414,7 @@ def main():
                "config": {"workload": "full MPC+WBC tick (BASELINE configs[3] shape): trot gait schedule, horizon 1.0 s / dt 0.01 (100 intervals + event nodes), 24-DoF quadruped-manipulator, one SQP iteration + 3-level HoQp",
                           "batch_per_gpu": B, "mpc_solver": args.solver, "pipeline_chunks": args.chunks, "global_batch": B * world, "robot_ticks_per_s": B * world / (ms * 1e-3),
                           "parallelism": "dp%d (robots sharded, one NCCL all-gather of the torque rows per tick issued by the C++ host: qmb200_allgather_torque)" % world, "allgather_ms": ag_ms, "nccl_version": nccl_v,
-                          "l2": "per-tick working set (LQ stage buffer %.1f GB) >> 126 MB L2; no flush needed" % (B * solver.nmax * 2084 * 8 / 1e9),
+                          "l2": "per-tick working set (LQ stage buffer %.1f GB) >> 126 MB L2; no flush needed" % (B * solver.nmax * 1484 * 8 / 1e9),
                           "robots_flagged": flagged, "robots_flagged_note": "mpc_neg_dt / mpc_not_pd: synthetic robot 1758's schedule puts an event 0.68 us after a grid node, which gives the interval a NEGATIVE duration in upstream's own time discretisation (weakEpsilon shift > gap > dt_min): a non-convex QP every exact solver rejects; root-caused in tests/test_neg_interval_cpu.py"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
         out.update(extras)

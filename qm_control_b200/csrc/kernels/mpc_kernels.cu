@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   cost_val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, fm, terminal, lane);
   if (terminal) {   // setupTerminalNode: finalEndEffector soft constraint only (QMInterface.cpp:104)
     double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
-    for (int e = lane; e < NX * LDX; e += 32) { const int r = e / LDX, c = e - r * LDX; const int a = ee_pos(r), cc = (c < NX) ? ee_pos(c) : -1;
-      sg[ST_Q + e] = (c == NX) ? sm.quad.qf[r] : ((a >= 0 && cc >= 0) ? sm.quad.E[a * 12 + cc] : 0.0); }   // final cost: Hessian, gradient in column 30, zero padding
+    for (int r = 0; r < NX; ++r) { const int a = ee_pos(r); if (lane < q_row_padded(r)) { const int cc = (lane <= r) ? ee_pos(lane) : -1; sg[ST_Q + q_row_offset(r) + lane] = (a >= 0 && cc >= 0) ? sm.quad.E[a * 12 + cc] : 0.0; } }   // final cost: packed lower triangle
+    if (lane < NX) tl[T_q + lane] = sm.quad.qf[lane];                                                                                                       // and its gradient
     if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = cost_val; tl[T_MISC + 2] = 0.0; tl[T_MISC + 3] = 0.0; }
     return;
   }
@@ -332,13 +332,14 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
           for (int c = 0; c < 3; ++c) acc[12 + 3 * l + c] += blk[9 + c]; }
       }
     }
-    // Q~ is symmetric: lane r stores its row as COLUMN r, so every store instruction writes one contiguous 240-byte row; q~ in column 30 (and in the tail for the rollout)
-    double* Qcol = sg + ST_Q + r; const double dq = sm.quad.qdiag[r];
+    // Q~ is symmetric and leaves as its packed lower triangle: lane r holds row r = column r, so for every c the lanes r <= c store the run Q~[c][0..c] of
+    // packed row c - one contiguous piece per store instruction; q~ goes to the tail
+    const double dq = sm.quad.qdiag[r];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) Qcol[(size_t)c * LDX] = dt * (acc[c] + ((c == r) ? dq : 0.0));
-    sg[ST_Q + r * LDX + NX] = dt * qv; tl[T_q + r] = dt * qv;
+    for (int c = 0; c < NX; ++c) if (r <= c) sg[ST_Q + q_row_offset(c) + r] = dt * (acc[c] + ((c == r) ? dq : 0.0));
+    if (!(r & 1)) sg[ST_Q + q_row_offset(r) + r + 1] = 0.0;   // even rows carry one padding entry
+    tl[T_q + r] = dt * qv;
   }
-  for (int e = lane; e < NX * 5; e += 32) sg[ST_Q + (e / 5) * LDX + 31 + (e % 5)] = 0.0;   // padding columns 31..35
   LQ_LOCKSTEP();
   for (int e = lane; e < 8 * 12; e += 32) tl[T_SJ + e] = 0.0;
   __syncwarp();
@@ -495,8 +496,9 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
   auto issue_ab = [&](int k) { const double* sg = sgb + (size_t)k * STAGE_DBL; gAB.begin((9 * LDX + 9 * LDB) * 8, tid);
     gAB.copy(sm.A + 3 * LDX, sg + ST_AR, 9 * LDX * 8, tid); gAB.copy(sm.Bm + 3 * LDB, sg + ST_BR, 9 * LDB * 8, tid); };     // rows 3:12 of A~ (with b~ in column 30) and of B~
   auto issue_tail = [&](int k) { gT.begin(TAIL_DBL * 8, tid); gT.copy(sm.tail, sgb + (size_t)k * STAGE_DBL + ST_TAIL, TAIL_DBL * 8, tid); };
-  // Q~, q~ land in the (dead) P buffer as the C operand of phase 3; only the three helper warps of node k wait for them
-  auto issue_q = [&](int k) { gQ.begin(NX * LDX * 8, tid); gQ.copy(sm.P, sgb + (size_t)k * STAGE_DBL + ST_Q, NX * LDX * 8, tid); };
+  // Q~ (packed lower triangle, one 3.8 KB run) lands in the B~ buffer, which is idle between phase 2 and the next node's fetch; only the three helper warps of
+  // node k wait for it, and they have slack (the factorisation warp is the critical path of phase 3)
+  auto issue_q = [&](int k) { gQ.begin(Q_PACKED * 8, tid); gQ.copy(sm.Bm, sgb + (size_t)k * STAGE_DBL + ST_Q, Q_PACKED * 8, tid); };
   // rebuild the structured part of A~ / B~ of the node whose tail sits in sm.tail (all threads; A~ rows 3:12 and B~ rows 3:12 arrive by copy)
   auto expand = [&]() {
     const double* tl = sm.tail; const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const double dtw = tl[T_MISC];
@@ -518,7 +520,8 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       sm.srow[tid] = (signed char)slot; sm.sfirst[tid] = (signed char)first; }
   };
   // terminal value function and baseline performance
-  for (int e = tid; e < NX * LDX; e += RIC_THREADS) sm.P[e] = sgb[(size_t)N * STAGE_DBL + ST_Q + e];
+  for (int e = tid; e < NX * NX; e += RIC_THREADS) { const int r = e / NX, c = e - r * NX; sm.P[r * LDX + c] = sgb[(size_t)N * STAGE_DBL + ST_Q + q_row_offset(r > c ? r : c) + (r > c ? c : r)]; }
+  if (tid < NX) sm.P[tid * LDX + NX] = sgb[(size_t)N * STAGE_DBL + ST_TAIL + T_q + tid];
   double perf0 = 0, perf1 = 0, perf2 = 0;
   for (int k = tid; k < n; k += RIC_THREADS) { const double* pf = sgb + (size_t)k * STAGE_DBL + ST_TAIL + T_MISC + 1; perf0 += pf[0]; perf1 += pf[1]; perf2 += pf[2]; }
   if (tid < NX) { const double d = p.x0[(size_t)b * NX + tid] - sol.x[(size_t)b * nmax * NX + tid]; sm.dx[tid] = d; perf1 += d * d; }
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       double d[1][3][2] = {}; warp_mma<NX, 1, 3, false>(sm.P, LDX, 8 * warp, sm.Bm, LDB, 0, d, g, t);
       cfrag_store<1, 3>(sm.PB, LDB, 8 * warp, 0, NX, d, g, t); }
     __syncthreads();                                 // W, PB visible; P is dead until phase 3
-    issue_q(k);
+    if (tid < NX) sm.P[tid * LDX + NX] = sm.tail[T_q + tid];   // q~ waits in column 30 of the dead buffer (the tail is replaced after phase 2)
     // ---- phase 2: G = S~ + B~'W (24x32: warp = column tile; column 30: h = r~ + B~'(p + P b~)) ; H = R~ + B~'PB (24x24: warps 0-2).  S~, r~ and R~ are
     //      not stored densely: the C fragments are initialised from the structured entries of the tail ----
     { const double* tl = sm.tail; const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const int mm = si[SI_M];
@@ -575,6 +578,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
             d[mt][0][e] = v; } }
         warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.PB, LDB, 8 * warp, d, g, t); cfrag_store<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); } }
     __syncthreads();
+    issue_q(k);                                      // B~ is idle now: Q~ of this node streams into it
     if (k > 0) issue_tail(k - 1);                   // the tail buffer is free: next node's small pieces stream in during phase 3
     // ---- phase 3: one warp factors H and solves for Y and the gains ; the other three compute P <- Q~ + A~'W (column 30: q~ + A~'(p + P b~)).
     // The serial role rotates over the warps (= over the SM sub-partitions): co-resident CTAs would otherwise queue their serial sections on one scheduler.
@@ -614,10 +618,18 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
         for (int c = 0; c < a; ++c) y[c] = fma(-sm.Lt[c * MU + a], y[a], y[c]);
       }
     } else {
-      if (QMB_TMA) gQ.wait();                                                  // Q~ is in the P buffer
       const int hi = (warp - sw - 1) & 3;                                      // helper index 0..2: 8x8 tiles hi, hi+3, ... of the 4x4 tile grid
-      for (int tile = hi; tile < 16; tile += 3) { const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3);
-        double c[1][1][2]; cfrag_load<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); warp_mma<NX, 1, 1, false>(sm.A, LDX, i0, sm.W, LDX, j0, c, g, t); cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); }
+      // A~'W of all the helper's tiles first (accumulators in registers), THEN the wait for Q~: the copy was issued one barrier ago and lands behind this work
+      double acc[6][1][1][2];
+#pragma unroll
+      for (int q6 = 0; q6 < 6; ++q6) { const int tile = hi + 3 * q6; acc[q6][0][0][0] = 0.0; acc[q6][0][0][1] = 0.0;
+        if (tile < 16) warp_mma<NX, 1, 1, false>(sm.A, LDX, 8 * (tile >> 2), sm.W, LDX, 8 * (tile & 3), acc[q6], g, t); }
+      if (QMB_TMA) gQ.wait();                                                  // Q~ (packed lower triangle) is in the B~ buffer, q~ in column 30 of P
+#pragma unroll
+      for (int q6 = 0; q6 < 6; ++q6) { const int tile = hi + 3 * q6; if (tile >= 16) continue; const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3), ri = i0 + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { const int cj = j0 + 2 * t + e; acc[q6][0][0][e] += (ri < NX && cj <= NX) ? (cj == NX ? sm.P[ri * LDX + NX] : (cj <= ri ? sm.Bm[q_row_offset(ri) + cj] : sm.Bm[q_row_offset(cj) + ri])) : 0.0; }
+        cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, acc[q6], g, t); }
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; if (k > 0) gT.wait(); break; }            // (an in-flight copy must land before the CTA may exit)
@@ -680,7 +692,7 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
         s += __shfl_xor_sync(FULL, s, 1); s += __shfl_xor_sync(FULL, s, 2); if (rr < 9 && jb == 0) dxn[3 + rr] = s + tl[T_b + 3 + rr]; }
     }
     __syncthreads();
-    if (tid < NX) { const double dxi = ((N & 1) ? sm.tmp : sm.dx)[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_Q + tid * LDX + NX] * dxi; }
+    if (tid < NX) { const double dxi = ((N & 1) ? sm.tmp : sm.dx)[tid]; dxo[((size_t)b * nmax + N) * NX + tid] = dxi; duo[((size_t)b * nmax + N) * NU + tid] = 0.0; dxn2 += dxi * dxi; armijo += sgb[(size_t)N * STAGE_DBL + ST_TAIL + T_q + tid] * dxi; }
   }
   armijo = warp_sum(armijo); dxn2 = warp_sum(dxn2); dun2 = warp_sum(dun2);
   __syncthreads();
