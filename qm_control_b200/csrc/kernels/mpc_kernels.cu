@@ -618,18 +618,14 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
         for (int c = 0; c < a; ++c) y[c] = fma(-sm.Lt[c * MU + a], y[a], y[c]);
       }
     } else {
-      const int hi = (warp - sw - 1) & 3;                                      // helper index 0..2: 8x8 tiles hi, hi+3, ... of the 4x4 tile grid
-      // A~'W of all the helper's tiles first (accumulators in registers), THEN the wait for Q~: the copy was issued one barrier ago and lands behind this work
-      double acc[6][1][1][2];
-#pragma unroll
-      for (int q6 = 0; q6 < 6; ++q6) { const int tile = hi + 3 * q6; acc[q6][0][0][0] = 0.0; acc[q6][0][0][1] = 0.0;
-        if (tile < 16) warp_mma<NX, 1, 1, false>(sm.A, LDX, 8 * (tile >> 2), sm.W, LDX, 8 * (tile & 3), acc[q6], g, t); }
       if (QMB_TMA) gQ.wait();                                                  // Q~ (packed lower triangle) is in the B~ buffer, q~ in column 30 of P
+      const int hi = (warp - sw - 1) & 3;                                      // helper index 0..2: 8x8 tiles hi, hi+3, ... of the 4x4 tile grid
+      // (tried: all tiles' A~'W first and the wait for Q~ afterwards - 12 more live registers, 17.2 -> 17.7 ms, profiles/r02_ab_k3_rejected.json)
+      for (int tile = hi; tile < 16; tile += 3) { const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3);
+        double c[1][1][2]; const int ri = i0 + g;   // C operand = Q~ (packed lower triangle in the B~ buffer) | q~ (column 30 of P)
 #pragma unroll
-      for (int q6 = 0; q6 < 6; ++q6) { const int tile = hi + 3 * q6; if (tile >= 16) continue; const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3), ri = i0 + g;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) { const int cj = j0 + 2 * t + e; acc[q6][0][0][e] += (ri < NX && cj <= NX) ? (cj == NX ? sm.P[ri * LDX + NX] : (cj <= ri ? sm.Bm[q_row_offset(ri) + cj] : sm.Bm[q_row_offset(cj) + ri])) : 0.0; }
-        cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, acc[q6], g, t); }
+        for (int e = 0; e < 2; ++e) { const int cj = j0 + 2 * t + e; c[0][0][e] = (ri < NX && cj <= NX) ? (cj == NX ? sm.P[ri * LDX + NX] : (cj <= ri ? sm.Bm[q_row_offset(ri) + cj] : sm.Bm[q_row_offset(cj) + ri])) : 0.0; }
+        warp_mma<NX, 1, 1, false>(sm.A, LDX, i0, sm.W, LDX, j0, c, g, t); cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); }
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; if (k > 0) gT.wait(); break; }            // (an in-flight copy must land before the CTA may exit)
