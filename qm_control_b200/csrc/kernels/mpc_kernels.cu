@@ -29,47 +29,65 @@ __device__ __forceinline__ int flag_mask(int mode) { int m = 0; for (int i = 0; 
 
 // =====================================================================================================
 // K1: time grid + initial guess
+// per-warp shared-memory staging of K1 (nmax entries each): previous grid, new grid, and for every interval of the new grid where its values come from
+struct SetupIdx { int iu, ix; double au, ax; };
+__host__ __device__ inline size_t setup_smem_per_warp(int nmax) { return (size_t)nmax * (8 + 8 + 4 + sizeof(SetupIdx) + 4) + 8 * EMAX + 64; }
 __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev prev, MpcSolutionDev next, int32_t* __restrict__ status) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x * SETUP_WARPS + warp; if (b >= B) return;
-  const double t0 = p.t0[b], tf = t0 + mdl->time_horizon, dt = mdl->dt; const int ne = clamp_events(p.n_events[b]); const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
-  double* gt = next.t + (size_t)b * nmax; int32_t* ge = next.event + (size_t)b * nmax; int st = 0;
+  extern __shared__ __align__(16) unsigned char s_setup[];
+  unsigned char* base = s_setup + (size_t)warp * ((setup_smem_per_warp(nmax) + 15) & ~(size_t)15);
+  double* spt = reinterpret_cast<double*>(base); double* sgt = spt + nmax; SetupIdx* sidx = reinterpret_cast<SetupIdx*>(sgt + nmax); double* sev = reinterpret_cast<double*>(sidx + nmax);
+  int32_t* sge = reinterpret_cast<int32_t*>(sev + EMAX); int32_t* sflag = sge + nmax; unsigned char* smodes = reinterpret_cast<unsigned char*>(sflag + nmax);
+  const double t0 = p.t0[b], tf = t0 + mdl->time_horizon, dt = mdl->dt; const int ne = clamp_events(p.n_events[b]); int st = 0;
   if (ne != p.n_events[b] || clamp_targets(p.n_target[b]) != p.n_target[b]) st |= MST_OVERFLOW;
-  // ---- timeDiscretizationWithEvents [upstream ocs2_oc/oc_data/TimeDiscretization.cpp] ----
+  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sev[lane] = (lane < ne) ? gev[lane] : 0.0; smodes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) smodes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
+  __syncwarp();
+  const double* ev = sev; const unsigned char* modes = smodes;
+  // ---- timeDiscretizationWithEvents [upstream ocs2_oc/oc_data/TimeDiscretization.cpp]: sequential by nature, kept in registers / shared memory ----
   int n = 0;
   if (lane == 0) {
-    const double dt_min = 10.0 * 1e-9; /* 10 * ocs2 numeric_traits::limitEpsilon [upstream] */ gt[0] = t0; ge[0] = 0; n = 1; int next_ev = lower_bound_idx(ev, ne, t0);
-    while (gt[n - 1] < tf) {
-      double nt = gt[n - 1] + dt; int nev = 0; bool is_event = false;
+    const double dt_min = 10.0 * 1e-9; /* 10 * ocs2 numeric_traits::limitEpsilon [upstream] */ double last_t = t0; int last_e = 0; sgt[0] = t0; sge[0] = 0; n = 1; int next_ev = lower_bound_idx(ev, ne, t0);
+    while (last_t < tf) {
+      double nt = last_t + dt; int nev = 0; bool is_event = false;
       if (next_ev < ne && nt >= ev[next_ev]) { nt = ev[next_ev]; is_event = true; nev = 1; ++next_ev; }
       if (nt >= tf) { is_event = false; nt = tf; nev = 0; }
-      if (nt > gt[n - 1] + dt_min) { if (n >= nmax) { st |= MST_OVERFLOW; break; } gt[n] = nt; ge[n] = nev; ++n; } else if (ge[n - 1] != 2) { gt[n - 1] = nt; ge[n - 1] = nev; } else if (nt >= tf) break;
-      if (is_event) { if (n >= nmax) { st |= MST_OVERFLOW; break; } gt[n] = nt; ge[n] = 2; ++n; }
+      if (nt > last_t + dt_min) { if (n >= nmax) { st |= MST_OVERFLOW; break; } sgt[n] = nt; sge[n] = nev; ++n; last_t = nt; last_e = nev; } else if (last_e != 2) { sgt[n - 1] = nt; sge[n - 1] = nev; last_t = nt; last_e = nev; } else if (nt >= tf) break;
+      if (is_event) { if (n >= nmax) { st |= MST_OVERFLOW; break; } sgt[n] = nt; sge[n] = 2; ++n; last_t = nt; last_e = 2; }
     }
     next.n_nodes[b] = n;
   }
   n = __shfl_sync(FULL, n, 0); st |= __shfl_sync(FULL, st, 0);
   __syncwarp();
+  double* gt = next.t + (size_t)b * nmax; int32_t* ge = next.event + (size_t)b * nmax;
+  for (int i = lane; i < n; i += 32) { gt[i] = sgt[i]; ge[i] = sge[i]; }
   // ---- initializeStateInputTrajectories [upstream ocs2_oc/multiple_shooting/Initialization.cpp] ----
   const int np = prev.n_nodes ? prev.n_nodes[b] : 0; const bool has_prev = np >= 2;
-  // the previous grid is staged in shared memory: every interpolation below starts with a binary search over it (7 dependent loads)
-  extern __shared__ double s_prev_t[]; double* spt = s_prev_t + (size_t)warp * nmax;
   { const double* gpt = prev.t + (size_t)b * nmax; for (int i = lane; i < np && i < nmax; i += 32) spt[i] = gpt[i]; __syncwarp(); }
-  const double* pt = spt; const double* px = prev.x + (size_t)b * nmax * NX; const double* pu = prev.u + (size_t)b * nmax * NU;
+  const double* pt = spt; const double* __restrict__ px = prev.x + (size_t)b * nmax * NX; const double* __restrict__ pu = prev.u + (size_t)b * nmax * NU;
   const double state_till = has_prev ? pt[np - 1] : t0, input_till = has_prev ? pt[np - 2] : t0;
-  double* gx = next.x + (size_t)b * nmax * NX; double* gu = next.u + (size_t)b * nmax * NU;
-  auto interp = [&](const double* traj, double t) { int idx; double a; time_segment(pt, np, t, idx, a); return (lane < NX) ? a * traj[(size_t)idx * NX + lane] + (1.0 - a) * traj[(size_t)(idx + 1 < np ? idx + 1 : idx) * NX + lane] : 0.0; };
-  double xk;
-  { const double ti = interval_start(gt[0], ge[0]); xk = (has_prev && ti < state_till) ? interp(px, ti) : (lane < NX ? p.x0[(size_t)b * NX + lane] : 0.0); }
-  if (lane < NX) gx[lane] = xk;
-  for (int k = 0; k < n - 1; ++k) {
-    double uk = 0.0;
-    if (ge[k] != 1) {
-      const double t = interval_start(gt[k], ge[k]), tn = interval_end(gt[k + 1], ge[k + 1]);
-      if (!has_prev || t > input_till || tn > state_till) {   // QMInitializer::compute: weight-compensating input, state held
-        const int mode = mode_at_time(ev, modes, ne, t); int nst = 0; for (int i = 0; i < 4; ++i) nst += contact_flag(mode, i);
-        if (lane < 12 && (lane % 3) == 2 && contact_flag(mode, lane / 3)) uk = mdl->total_mass * 9.81 / nst;
-      } else { uk = interp(pu, t); xk = interp(px, tn); }
+  double* __restrict__ gx = next.x + (size_t)b * nmax * NX; double* __restrict__ gu = next.u + (size_t)b * nmax * NU;
+  // where every interval takes its values from (lane = interval: the binary searches over the previous grid run 32 at a time):
+  //   flag 2 pre-event node (no input, state carried), 1 warm start (interpolation of the previous solution), 0 QMInitializer (weight-compensating input, state held)
+  for (int k = lane; k < n - 1; k += 32) {
+    int flag = 2; SetupIdx ix{0, 0, 1.0, 1.0};
+    if (sge[k] != 1) {
+      const double t = interval_start(sgt[k], sge[k]), tn = interval_end(sgt[k + 1], sge[k + 1]);
+      if (!has_prev || t > input_till || tn > state_till) { flag = 0; ix.iu = mode_at_time(ev, modes, ne, t); }   // QMInitializer::compute: the mode selects the weight-compensating input
+      else { flag = 1; time_segment(pt, np, t, ix.iu, ix.au); time_segment(pt, np, tn, ix.ix, ix.ax); }
     }
+    sflag[k] = flag; sidx[k] = ix;
+  }
+  __syncwarp();
+  auto lerp = [&](const double* __restrict__ traj, int idx, double a) { return (lane < NX) ? a * traj[(size_t)idx * NX + lane] + (1.0 - a) * traj[(size_t)(idx + 1 < np ? idx + 1 : idx) * NX + lane] : 0.0; };
+  double xk;
+  { const double ti = interval_start(sgt[0], sge[0]); if (has_prev && ti < state_till) { int idx; double a; time_segment(pt, np, ti, idx, a); xk = lerp(px, idx, a); } else xk = (lane < NX ? p.x0[(size_t)b * NX + lane] : 0.0); }
+  if (lane < NX) gx[lane] = xk;
+  // sequential only through the carried state; the loads of an interval do not depend on the previous one, so four intervals are in flight
+#pragma unroll 4
+  for (int k = 0; k < n - 1; ++k) {
+    const int flag = sflag[k]; const SetupIdx ix = sidx[k]; double uk = 0.0;
+    if (flag == 1) { uk = lerp(pu, ix.iu, ix.au); xk = lerp(px, ix.ix, ix.ax); }
+    else if (flag == 0) { const int mode = ix.iu; int nst = 0; for (int i = 0; i < 4; ++i) nst += contact_flag(mode, i); if (lane < 12 && (lane % 3) == 2 && contact_flag(mode, lane / 3)) uk = mdl->total_mass * 9.81 / nst; }
     if (lane < NX) { gu[(size_t)k * NU + lane] = uk; gx[(size_t)(k + 1) * NX + lane] = xk; }
   }
   if (lane < NX && n >= 1) gu[(size_t)(n - 1) * NU + lane] = 0.0;
@@ -924,6 +942,7 @@ __global__ void mpc_policy_eval_kernel(int b0, int B, int nmax, MpcSolutionDev s
 // =====================================================================================================
 bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<void*>& allocs, cudaStream_t stream) {
   m.B = B; m.nmax = nmax; m.cur = 0;
+  if (SETUP_WARPS * ((setup_smem_per_warp(nmax) + 15) & ~(size_t)15) > 200 * 1024) { err = "max_nodes too large for the grid staging of the setup kernel (limit ~1000 nodes)"; return false; }
   auto A = [&](auto** p, size_t count) { void* q = nullptr; const size_t bytes = count * sizeof(**p); cudaError_t e = cudaMalloc(&q, bytes); if (e != cudaSuccess) { err = std::string("cudaMalloc (MPC buffers) failed: ") + cudaGetErrorString(e); return false; } cudaMemsetAsync(q, 0, bytes, stream); allocs.push_back(q); *p = static_cast<std::remove_reference_t<decltype(**p)>*>(q); return true; };
   const size_t Bn = (size_t)B * nmax;
   bool ok = A(&m.t0, B) && A(&m.x0, (size_t)B * NX) && A(&m.n_events, B) && A(&m.event_times, (size_t)B * EMAX) && A(&m.modes, (size_t)B * (EMAX + 1)) && A(&m.n_target, B) && A(&m.target_times, (size_t)B * KMAX) && A(&m.target_states, (size_t)B * KMAX * TARGET_DIM);
@@ -933,7 +952,8 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
 }
 
 int mpc_configure_device() {
-  cudaError_t e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
+  cudaError_t e = cudaFuncSetAttribute(mpc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // 48 B per node and warp: opt-in beyond nmax ~ 250
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RoSmem) * RO_WARPS));
@@ -944,7 +964,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   const int nb = b1 - b0, nmax = m.nmax; if (nb <= 0) return 0;
   MpcSolutionDev prev = m.sol[m.cur], next = m.sol[1 - m.cur];   // the caller flips m.cur once all ranges are queued
   if (ev) cudaEventRecord(ev[0], stream);
-  mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, sizeof(double) * SETUP_WARPS * nmax, stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
+  mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, SETUP_WARPS * ((setup_smem_per_warp(nmax) + 15) & ~(size_t)15), stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
   if (ev) cudaEventRecord(ev[1], stream);
   const long long nodes = (long long)nb * nmax; const int iters = hm.sqp_iterations < 1 ? 1 : hm.sqp_iterations; int launched = 1;
   const bool ddp = hm.solver == 2; const int ro_grid = (nb + RO_WARPS - 1) / RO_WARPS;
