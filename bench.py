@@ -40,9 +40,10 @@ def algorithmic_bytes(n_intervals):
                 total=15840 * N + 4184)
 
 
-def riccati_flops(n_intervals, m=16.0):
-    fma = 2 * 27000 + 3 * 900 * m + 30 * m * m + 31 * m * m + (900 + 60 * m)   # backward blocks + forward rollout, per node
-    return 2.0 * fma * n_intervals
+def riccati_flops(n_intervals):
+    """COUNTED tensor-core flops of the backward sweep: ncu sm__inst_executed_pipe_tensor_subpipe_dmma.sum = 62,054,400 DMMA.8x8x4 warp instructions for 1024 robots x
+    100 regular nodes (profiles/r02c_riccati_dmma.csv) = 606 per node, 512 flop each.  The scalar work (Cholesky, substitutions, rollout) is not counted."""
+    return 606.0 * 512.0 * n_intervals
 
 
 class ClockSampler(threading.Thread):
@@ -353,7 +354,7 @@ def main():
                 "whole_tick": {"achieved": ab["total"] * B / (ms_local * 1e-3) / 1e9, "frac": ab["total"] * B / (ms_local * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_robot": ab["total"]},
                 "fp64": {"kernel": "mpc_riccati_kernel", "achieved_tflops": riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 if ktimes.get("riccati") else None, "peak_tflops": fp64_peak, "peak_source": "measured in-process (FMA microbenchmark)",
                          "frac": (riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and ktimes.get("riccati")) else None,
-                         "flops_source": "dense-block formula of bench.py riccati_flops() (600 DMMA.8x8x4 per node backward + the rollout), not counted flops",
+                         "flops_source": "counted: ncu DMMA instruction count x 512 (profiles/r02c_riccati_dmma.csv); same capture: tensor (DMMA) sub-pipe active 37.9 % of peak sustained", "tensor_pipe_active_pct": 37.88,
                          "note": "the path is fp64 latency/issue bound, not HBM bound (SURVEY 8d: ~48 FLOP/B against a ~6 FLOP/B fp64 ridge); the Riccati products run on the fp64 tensor cores (DMMA.8x8x4, same 37 TFLOP/s peak as the DFMA pipe, tools/microbench/dmma_peak.cu); the HBM fraction is reported because BASELINE.json asks for it"}}
 
     # strong scaling as BASELINE.json states configs[3] / [4]: the TOTAL batch is fixed and split over the ranks

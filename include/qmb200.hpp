@@ -112,6 +112,8 @@ class SqpMpc {
  public:
   explicit SqpMpc(std::shared_ptr<Solver> solver) : solver_(std::move(solver)) { if (solver_->batch() != 1) throw std::runtime_error("SqpMpc: the single-robot mirror needs a batch-1 handle"); }
   void reset() { solver_->check(qmb200_mpc_reset(solver_->get()), "SqpMpc::reset"); }
+  // the other solver blocks QMInterface loads (QMInterface.cpp:69-73): ocs2::IpmMpc with ipm{} / ocs2::GaussNewtonDDP_MPC with ddp{} on the same OCP (qmb200.h: QMB200_SOLVER_*)
+  void setSolver(int32_t solver) { solver_->check(qmb200_mpc_set_solver(solver_->get(), solver), "SqpMpc::setSolver"); }
   PrimalSolution run(scalar_t initTime, const vector_t& initState, const ModeSchedule& modeSchedule, const TargetTrajectories& targets) {
     if (initState.size() != QMB200_NX) throw std::runtime_error("SqpMpc::run: wrong state size");
     const int32_t ne = static_cast<int32_t>(modeSchedule.eventTimes.size()), nk = static_cast<int32_t>(targets.timeTrajectory.size());

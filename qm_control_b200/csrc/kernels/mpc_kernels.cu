@@ -726,7 +726,10 @@ __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax
   for (int k = 1; k < n; ++k) { const bool copy = (k == n - 1) || (ge[k] == 1); if (copy) { for (int i = tid; i < NU; i += nthreads) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i]; } __syncthreads(); }
 }
 
-__global__ void __launch_bounds__(32 * LS_WARPS, 4) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
+#ifndef QMB_LS_MINB
+#define QMB_LS_MINB 4
+#endif
+__global__ void __launch_bounds__(32 * LS_WARPS, QMB_LS_MINB) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
                                                                      const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int iteration) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[LS_WARPS][3]; __shared__ int decision;

@@ -18,4 +18,11 @@ for tick in range(2):
     cmd, status = s.tick(p, p["t0"] + 0.002, wbc["rbd"], wbc["period"])
     cmd2, status2 = ctrl.update(wbc["rbd"], 0.002)
     eff, st = s.hw_write(ctrl.t_obs, np.full(B, 0.002), ctrl.joint_cmd, wbc["rbd"][:, 6:24], wbc["rbd"][:, 30:48])
-print("sanitize_small ok", status, status2)
+# solver variants (IPM thresholds; DDP: rollout kernels) and the multi-GPU pack path on one rank
+import torch  # noqa: E402
+for name in ("ipm", "ddp", "sqp"):
+    s.mpc_set_solver(name); out = s.mpc_solve(prob)
+dev = torch.device("cuda", 0); cmd_d = torch.from_numpy(cmd).to(dev); all_d = torch.zeros((B, 18), dtype=torch.float64, device=dev)
+perm = s.gait_bin_permutation(prob); s.allgather_torque(cmd_d, all_d, torch.from_numpy(perm).to(dev)); torch.cuda.synchronize()
+s1 = q.Solver(batch=B, dt=0.015, wbc_variant=1); c1, st1 = s1.tick(prob, prob["t0"] + 0.002, wbc["rbd"], wbc["period"])
+print("sanitize_small ok", status, status2, out["status"], st1)
