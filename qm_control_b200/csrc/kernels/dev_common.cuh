@@ -82,6 +82,17 @@ __device__ __forceinline__ void warp_argmax(double& v, int& idx) {
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
 }
+// argmax over the ACTIVE lanes of non-negative values (ties -> lowest lane; v = -1 when no lane is active): a non-negative double orders like its bit
+// pattern, so two 32-bit REDUX maxima (high word, then low word among the lanes holding the high maximum) and a ballot replace five shuffle rounds
+__device__ __forceinline__ void warp_argmax_nonneg(double& v, int& idx, bool active) {
+  const unsigned long long b = active ? (unsigned long long)__double_as_longlong(v) : 0ull;
+  const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+  const unsigned mh = __reduce_max_sync(FULL, hi);
+  const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+  const unsigned m = __ballot_sync(FULL, active && hi == mh && lo == ml);
+  if (m == 0u) { v = -1.0; idx = 0; return; }
+  idx = __ffs(m) - 1; v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
 __device__ __forceinline__ void warp_argmin(double& v, int& idx) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -5,7 +5,14 @@
 #pragma once
 #include "dev_common.cuh"
 
+// column norms of the pivot search in w_qrcp: 0 = re-summed in every step, 1 = LAPACK-style downdating, 2 = re-summed for free inside the trailing update (default;
+// measured on B200 at 8192 robots: profiles/r02_ab_wbc.jsonl)
+#ifndef QMB_QRCP_NORMS
+#define QMB_QRCP_NORMS 2
+#endif
+
 namespace qmb {
+
 
 // QR with column pivoting of W (n x r, column-major, leading dimension ld, r <= 32).
 // On exit: R in the upper triangle, Householder vectors below the diagonal (unit leading entry implied),
@@ -13,23 +20,40 @@ namespace qmb {
 // (columns whose remaining norm is <= tol_rel * largest initial column norm are treated as zero).
 __device__ __forceinline__ int w_qrcp(double* W, int n, int r, int ld, double* tau, int* perm, double tol_rel, int lane) {
   if (lane < r) perm[lane] = lane;
-  double n0 = 0.0;
-  if (lane < r) for (int i = 0; i < n; ++i) { const double x = W[i + lane * ld]; n0 += x * x; }
-  const double thresh = tol_rel * tol_rel * warp_max(n0);
+  // vn = squared norm of the not yet factored part of this lane's column.  Mode 1 DOWNDATES it after every reflector (vn -= R[j][c]^2) with vref = its value
+  // at the last exact evaluation and the safeguard of LAPACK's dgeqp3: once cancellation has eaten half of the digits (vn <= sqrt(eps) * vref) the lane re-sums
+  // its column, so every rank decision (columns near zero) is taken on an exact value.  Mode 2 forms the exact sum inside the trailing update.
+  double vn = 0.0;
+  if (lane < r) for (int i = 0; i < n; ++i) { const double x = W[i + lane * ld]; vn += x * x; }
+  double vref = vn;
+  const double thresh = tol_rel * tol_rel * warp_max(vn);
   const int kmax = n < r ? n : r; int rank = kmax;
   __syncwarp();
   for (int j = 0; j < kmax; ++j) {
-    double nr = -1.0; int pc = lane;
-    if (lane >= j && lane < r) { nr = 0.0; for (int i = j; i < n; ++i) { const double x = W[i + lane * ld]; nr += x * x; } }
-    warp_argmax(nr, pc);
+#if QMB_QRCP_NORMS == 0
+    if (lane >= j && lane < r) { vn = 0.0; for (int i = j; i < n; ++i) { const double x = W[i + lane * ld]; vn += x * x; } }
+#endif
+    double nr = vn; int pc = lane;
+    warp_argmax_nonneg(nr, pc, lane >= j && lane < r);
     if (!(nr > thresh)) { rank = j; break; }
     if (pc != j) {
       for (int i = lane; i < n; i += 32) { const double t = W[i + j * ld]; W[i + j * ld] = W[i + pc * ld]; W[i + pc * ld] = t; }
       if (lane == 0) { const int t = perm[j]; perm[j] = perm[pc]; perm[pc] = t; }
+      const double vj = __shfl_sync(FULL, vn, j), rj = __shfl_sync(FULL, vref, j);
+      if (lane == pc) { vn = vj; vref = rj; }
     }
     __syncwarp();
+#if QMB_QRCP_NORMS == 1
+    { // exact norm of the pivot column (the reflector must annihilate it to rounding): rows over lanes
+      double part = 0.0; for (int i = j + lane; i < n; i += 32) { const double x = W[i + j * ld]; part += x * x; }
+      nr = warp_sum(part);
+      if (!(nr > thresh)) { rank = j; break; }
+    }
+#endif
+    // one reciprocal for both tau = (beta - x0) / beta and the scale 1 / (x0 - beta) of the reflector's tail
     const double x0 = W[j + j * ld]; const double beta = (x0 >= 0.0) ? -sqrt(nr) : sqrt(nr);
-    const double tj = (beta - x0) / beta; const double scal = 1.0 / (x0 - beta);
+    const double d = x0 - beta, inv = 1.0 / (beta * d);
+    const double tj = -d * d * inv; const double scal = beta * inv;
     __syncwarp();
     for (int i = j + 1 + lane; i < n; i += 32) W[i + j * ld] *= scal;
     if (lane == 0) { W[j + j * ld] = beta; tau[j] = tj; }
@@ -37,7 +61,21 @@ __device__ __forceinline__ int w_qrcp(double* W, int n, int r, int ld, double* t
     if (lane > j && lane < r) {
       double* col = W + lane * ld; const double* v = W + j * ld;
       double w = col[j]; for (int i = j + 1; i < n; ++i) w += v[i] * col[i];
-      w *= tj; col[j] -= w; for (int i = j + 1; i < n; ++i) col[i] -= w * v[i];
+      w *= tj; const double cj = col[j] - w; col[j] = cj;
+#if QMB_QRCP_NORMS == 2
+      double nn = 0.0; for (int i = j + 1; i < n; ++i) { const double c = fma(-w, v[i], col[i]); col[i] = c; nn = fma(c, c, nn); }
+      vn = nn;   // the exact squared norm of what is left of this column, formed for free
+#else
+      for (int i = j + 1; i < n; ++i) col[i] -= w * v[i];
+#endif
+#if QMB_QRCP_NORMS == 1
+      vn = fmax(vn - cj * cj, 0.0);
+      if (vref > 0.0 && vn <= 1.4901161193847656e-8 * vref) {
+        vn = 0.0; for (int i = j + 1; i < n; ++i) { const double x = col[i]; vn += x * x; }
+        if (!(vn > thresh)) vn = 0.0;   // the remainder of a column only shrinks: below the rank threshold once = never a pivot, never re-summed again
+        vref = vn;
+      }
+#endif
     }
     __syncwarp();
   }
