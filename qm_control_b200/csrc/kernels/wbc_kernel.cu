@@ -27,9 +27,10 @@ constexpr int LDM = 25;   // leading dimension of 24-column matrices (odd → co
 constexpr int LDZ = 37;   // leading dimension of 36-column / 36-row matrices
 constexpr int LZ = 19;    // leading dimension of matrices in null-space coordinates (at most 18 columns: level 0 always has 18 independent rows)
 constexpr int MAXR = 24;  // max rows of one level's equality task (22 in flight mode) or 18 + violated rows at level 0
+constexpr int LJC = 9;    // pitch of a compact foot-Jacobian row
 constexpr int MAXW = 20;  // max size of the inequality working set
 #ifndef QMB_WBC_WARPS
-#define QMB_WBC_WARPS 7
+#define QMB_WBC_WARPS 8
 #endif
 constexpr int WBC_WARPS = QMB_WBC_WARPS;   // robots (= warps) per CTA, one CTA per SM: the kernel is latency bound, its speed is the number of warps an SM holds
 
@@ -37,7 +38,7 @@ enum { ST_OK = 0, ST_ITER_CAP = 1, ST_TOO_MANY_ROWS = 2, ST_NAN = 4 };
 
 // end-effector quantities: produced by the rigid-body passes, consumed when the level-1 rows are built - they live where the projected rows go afterwards
 struct EeWs { double Jee[6 * LDM], djv_ee[6], ee_m_pos[3], ee_m_vel[3], ee_m_rot[9], ee_m_w[3], ee_d_pos[3], ee_d_vel[3], ee_d_rot[9]; };
-// QP workspace, 22 KB per robot (round 1: 44 KB, which capped the SM at four warps):
+// QP workspace, 20 KB per robot (round 1: 44 KB, which capped the SM at four warps; the whole per-robot block is now 28 KB = eight warps per SM):
 //   * the null-space basis is kept in null-space width (36 x <= 18) instead of 36 x 36,
 //   * the level-0 factorisation runs in place on the task rows (row i of the task IS column i of the column-major QR workspace),
 //   * levels >= 1 iterate in null-space coordinates on the projected rows A_p Z (<= 22 x 18), so the 36-wide rows are only a build area that the
@@ -50,7 +51,7 @@ struct QpWs {
              __device__ ZA() {} } za;
   union AH { double Ah[MAXR * LZ];                // projected task rows A_p Z (rows x nz, pitch LZ) = column-major nz x rows for the null-space QR of the level
              EeWs ee; __device__ AH() {} } ah;
-  double G[18 * 19];                              // normal equations of an overdetermined / rank-deficient step (k <= 18 at levels >= 1; level 0 borrows Z)
+  double G[18 * 19 / 2 + 1];                      // normal equations (packed lower triangle) of an overdetermined / rank-deficient step (k <= 18 at levels >= 1; level 0 borrows Z)
   double tau[MAXR], tauc[MAXW];
   double xbar[36], dx[36], g[36], y[36], s[36], zac[LZ + 1], rhs[MAXR], bp[MAXR], bh[MAXR], lam[MAXW], t18[MAXR];
   int perm[MAXR], permc[MAXW], wset[MAXW];
@@ -61,8 +62,9 @@ static_assert(sizeof(RbdWs) <= sizeof(double) * (36 * LZ + MAXR * LDZ), "rigid-b
 struct WbcSmem {
   double q[NQ], v[NQ], qd[NQ], vd[NQ];
   double M[NQ * LDM], nle[NQ];
-  double Jf[12 * LDM], djv_f[12], fpos_m[12], fvel_m[12], fpos_d[12], fvel_d[12];
-  double Tm[9], wdot_base[3], base_acc[6], xdes[NX], udes[NU], lim[NJ], vstar[56];
+  // foot Jacobians in their sparsity: row 3 f + a = [6 base columns | the 3 columns of the foot's own leg] (the other 15 of the 24 columns are structurally zero)
+  double Jc[12 * LJC], djv_f[12], fpos_m[12], fvel_m[12], fpos_d[12], fvel_d[12];
+  double Tm[9], wdot_base[3], base_acc[6], fdes[12], lim[NJ], vstar[56];   // fdes: the MPC's contact forces (the rest of x_des / u_des is read from HBM once)
   QpWs qp;
 };
 
@@ -71,7 +73,14 @@ struct WbcSmem {
 // [36, 36+5*nc): friction pyramid of the stance feet (WbcBase.cpp:360-383, 407-437).  The trailing all-zero
 // rows the reference appends (WbcBase.cpp:426-427) can never be active and are skipped.
 // value(i, x) = D_i x - f_i
-struct IneqCtx { const WbcSmem* sm; int mode; int nc; double mu; };
+struct IneqCtx { const WbcSmem* sm; int mode; int nc; double mu; int lfp, ffp; };   // lfp: leg -> foot, two bits per leg; ffp: foot -> first joint of its leg, four bits per foot
+__device__ __forceinline__ int foot_first(int ffp, int f) { return (ffp >> (4 * f)) & 15; }
+// (J_f^T F)[6 + jn]: the only contact forces that load joint jn are those of the joint's own foot
+__device__ __forceinline__ double jt_force(const WbcSmem* sm, int lfp, int jn, const double* F) {
+  if (jn >= 12) return 0.0;
+  const int lg = jn / 3, f = (lfp >> (2 * lg)) & 3, d = jn - 3 * lg; const double* J = sm->Jc + 3 * f * LJC + 6 + d;
+  return J[0] * F[3 * f] + J[LJC] * F[3 * f + 1] + J[2 * LJC] * F[3 * f + 2];
+}
 
 __device__ __forceinline__ int stance_foot_by_rank(int mode, int rank) { int k = 0; for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { if (k == rank) return f; ++k; } return -1; }
 
@@ -79,7 +88,7 @@ __device__ __forceinline__ double ineq_row_dot(const IneqCtx& c, int i, const do
   if (i < 36) {
     const int jn = i < 18 ? i : i - 18; const double* Mr = c.sm->M + (6 + jn) * LDM; double s = 0.0;
     for (int k = 0; k < NQ; ++k) s += Mr[k] * x[k];
-    for (int k = 0; k < 12; ++k) s -= c.sm->Jf[k * LDM + 6 + jn] * x[NQ + k];
+    s -= jt_force(c.sm, c.lfp, jn, x + NQ);
     return i < 18 ? s : -s;
   }
   const int r = i - 36; const int foot = stance_foot_by_rank(c.mode, r / 5); const int t = r % 5; const double* F = x + NQ + 3 * foot;
@@ -95,7 +104,8 @@ __device__ __forceinline__ double ineq_rhs(const IneqCtx& c, int i) {   // f_i +
   return f + c.sm->vstar[i];
 }
 __device__ __forceinline__ double ineq_row_elem(const IneqCtx& c, int i, int k) {   // D_i[k]
-  if (i < 36) { const int jn = i < 18 ? i : i - 18; const double sgn = i < 18 ? 1.0 : -1.0; return sgn * (k < NQ ? c.sm->M[(6 + jn) * LDM + k] : -c.sm->Jf[(k - NQ) * LDM + 6 + jn]); }
+  if (i < 36) { const int jn = i < 18 ? i : i - 18; const double sgn = i < 18 ? 1.0 : -1.0; if (k < NQ) return sgn * c.sm->M[(6 + jn) * LDM + k];
+    const int r = k - NQ, d = jn - foot_first(c.ffp, r / 3); return (d >= 0 && d < 3) ? -sgn * c.sm->Jc[r * LJC + 6 + d] : 0.0; }
   const int r = i - 36; const int foot = stance_foot_by_rank(c.mode, r / 5); const int t = r % 5; const int kk = k - NQ - 3 * foot;
   if (kk < 0 || kk > 2) return 0.0;
   if (kk == 2) return t == 0 ? -1.0 : -c.mu;
@@ -105,8 +115,8 @@ __device__ __forceinline__ double ineq_row_elem(const IneqCtx& c, int i, int k) 
 
 // ---------------------------------------------------------------------------------------------------------
 // Minimum-norm least squares  min || Abar y - rhs ||  with Abar^T stored column-wise in W (n x r, leading dimension ldw): COD.
-// On exit y[0..n) holds the solution in the coordinates of W's rows; returns rank.  Uses qp.tau/perm/t18 and the k x k scratch G (leading dimension ldg).
-__device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, int ldw, const double* rhs, double* y, double* G, int ldg, int lane) {
+// On exit y[0..n) holds the solution in the coordinates of W's rows; returns rank.  Uses qp.tau/perm/t18 and the scratch G (k(k+1)/2 doubles).
+__device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, int ldw, const double* rhs, double* y, double* G, int lane) {
   const int k = w_qrcp(W, n, r, ldw, qp.tau, qp.perm, 1e-11, lane);
   // Abar = P R^T Q^T  →  residual_c = sum_{i<=min(c,k-1)} R[i][c] y_i - rhs[perm[c]]
   for (int i = lane; i < n; i += 32) y[i] = 0.0;
@@ -119,12 +129,14 @@ __device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, int ldw, const doubl
       if (lane == 0) y[c] = (rhs[qp.perm[c]] - s) / W[c + c * ldw];
       __syncwarp();
     }
-  } else {        // overdetermined / rank deficient: normal equations on the k x k triangular factor
-    for (int e = lane; e < k * k; e += 32) { const int a = e / k, b = e % k; double s = 0.0; for (int c = (a > b ? a : b); c < r; ++c) s += W[a + c * ldw] * W[b + c * ldw]; G[a * ldg + b] = s; }
+  } else {        // overdetermined / rank deficient: normal equations on the k x k triangular factor, G = R R^T as a packed lower triangle
+    { int a = 0, b = lane; while (b > a) { b -= a + 1; ++a; }   // entry number `lane` of the packed triangle; the lane then strides by 32 entries
+      while (a < k) { double s = 0.0; for (int c = a; c < r; ++c) s += W[a + c * ldw] * W[b + c * ldw]; G[tri(a) + b] = s;
+        b += 32; while (b > a) { b -= a + 1; ++a; } } }
     if (lane < k) { double s = 0.0; for (int c = lane; c < r; ++c) s += W[lane + c * ldw] * rhs[qp.perm[c]]; qp.t18[lane] = s; }
     __syncwarp();
-    w_cholesky(G, k, ldg, lane);
-    w_chol_solve(G, k, ldg, qp.t18, lane);
+    w_cholesky(G, k, lane);
+    w_chol_solve(G, k, qp.t18, lane);
     if (lane < k) y[lane] = qp.t18[lane];
     __syncwarp();
   }
@@ -137,7 +149,7 @@ __device__ int cod_lstsq(QpWs& qp, double* W, int n, int r, int ldw, const doubl
 //   level 1: HierarchicalWbc: height, base angular, EE linear, EE angular, 100*swing (t>=10) | arm joint tracking (t<10)
 //            HierarchicalMpcWbc: height, base angular, base linear, 100*swing
 //   level 2: contact force + base linear | contact force
-__device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int level, int mode, int variant, bool init_phase, int lane) {
+__device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int level, int mode, int variant, bool init_phase, int ffp, int lane) {
   QpWs& qp = sm.qp; double* Ap = qp.za.q.AR; const EeWs& ee = qp.ah.ee; int nc = 0; for (int f = 0; f < 4; ++f) nc += contact_flag(mode, f);
   int rows = 0;
   if (level == 0) rows = 18;
@@ -146,10 +158,10 @@ __device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int le
   for (int e = lane; e < rows * LDZ; e += 32) Ap[e] = 0.0;
   __syncwarp();
   if (level == 0) {
-    for (int e = lane; e < 6 * 36; e += 32) { const int r = e / 36, k = e % 36; Ap[r * LDZ + k] = (k < NQ) ? sm.M[r * LDM + k] : -sm.Jf[(k - NQ) * LDM + r]; }
+    for (int e = lane; e < 6 * 36; e += 32) { const int r = e / 36, k = e % 36; Ap[r * LDZ + k] = (k < NQ) ? sm.M[r * LDM + k] : -sm.Jc[(k - NQ) * LJC + r]; }
     if (lane < 6) qp.bp[lane] = -sm.nle[lane];
     int row = 6;
-    for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; Ap[(row + a) * LDZ + k] = sm.Jf[(3 * f + a) * LDM + k]; } if (lane < 3) qp.bp[row + lane] = -sm.djv_f[3 * f + lane]; row += 3; }
+    for (int f = 0; f < 4; ++f) if (contact_flag(mode, f)) { if (lane < 27) { const int a = lane / 9, c = lane - 9 * a; Ap[(row + a) * LDZ + (c < 6 ? c : foot_first(ffp, f) + c)] = sm.Jc[(3 * f + a) * LJC + c]; } if (lane < 3) qp.bp[row + lane] = -sm.djv_f[3 * f + lane]; row += 3; }
     for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) { if (lane < 3) { Ap[(row + lane) * LDZ + NQ + 3 * f + lane] = 1.0; qp.bp[row + lane] = 0.0; } row += 3; }
   } else if (level == 1) {
     int row = 0;
@@ -184,14 +196,14 @@ __device__ int build_level(WbcSmem& sm, const DevModel* __restrict__ mdl, int le
       }
       // formulateSwingLegTask * 100 (WbcBase.cpp:311-334, HierarchicalWbc.cpp:29)
       for (int f = 0; f < 4; ++f) if (!contact_flag(mode, f)) {
-        for (int e = lane; e < 3 * NQ; e += 32) { const int a = e / NQ, k = e % NQ; Ap[(row + a) * LDZ + k] = 100.0 * sm.Jf[(3 * f + a) * LDM + k]; }
+        if (lane < 27) { const int a = lane / 9, c = lane - 9 * a; Ap[(row + a) * LDZ + (c < 6 ? c : foot_first(ffp, f) + c)] = 100.0 * sm.Jc[(3 * f + a) * LJC + c]; }
         if (lane < 3) { const int i = 3 * f + lane; qp.bp[row + lane] = 100.0 * (mdl->kp_swing * (sm.fpos_d[i] - sm.fpos_m[i]) + mdl->kd_swing * (sm.fvel_d[i] - sm.fvel_m[i]) - sm.djv_f[i]); }
         row += 3;
       }
     }
   } else {
     // formulateContactForceTask (WbcBase.cpp:534-546)
-    if (lane < 12) { Ap[lane * LDZ + NQ + lane] = 1.0; qp.bp[lane] = sm.udes[lane]; }
+    if (lane < 12) { Ap[lane * LDZ + NQ + lane] = 1.0; qp.bp[lane] = sm.fdes[lane]; }
     if (variant == 0 && lane < 2) { Ap[(12 + lane) * LDZ + lane] = 1.0; qp.bp[12 + lane] = sm.base_acc[lane] + mdl->base_linear_kp * (sm.qd[lane] - sm.q[lane]) + mdl->base_linear_kd * (sm.vd[lane] - sm.v[lane]); }
   }
   __syncwarp();
@@ -245,7 +257,7 @@ __device__ int solve_level(WbcSmem& sm, const IneqCtx& ic, int rows, int off, in
     const int nfree = nz - kc;
     for (int i = lane; i < nz; i += 32) qp.s[i] = 0.0;
     __syncwarp();
-    if (nfree > 0) cod_lstsq(qp, W1 + kc, nfree, rows, LZ, qp.rhs, qp.s + kc, qp.G, 19, lane);
+    if (nfree > 0) cod_lstsq(qp, W1 + kc, nfree, rows, LZ, qp.rhs, qp.s + kc, qp.G, lane);
     if (kc > 0) w_apply_q(Wc, nz, kc, LZ, qp.tauc, qp.s, lane);
     for (int i = lane; i < 36; i += 32) { double d = 0.0; for (int c = 0; c < nz; ++c) d = fma(Z[i * LZ + off + c], qp.s[c], d); qp.dx[i] = d; }
     __syncwarp();
@@ -305,7 +317,10 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   int nc = 0; for (int f = 0; f < 4; ++f) nc += contact_flag(mode, f);
 
   // ---- load the robot's inputs (coalesced, one 240-B / 440-B record each) ----
-  if (lane < NX) { sm.xdes[lane] = x_des[(size_t)b * NX + lane]; sm.udes[lane] = u_des[(size_t)b * NU + lane]; }
+  const double* xdes = x_des + (size_t)b * NX; const double* udes = u_des + (size_t)b * NU;
+  if (lane < 12) sm.fdes[lane] = udes[lane];
+  const int lfp = mdl->leg_foot[0] | (mdl->leg_foot[1] << 2) | (mdl->leg_foot[2] << 4) | (mdl->leg_foot[3] << 6);
+  const int ffp = mdl->foot_leg[0] | (mdl->foot_leg[1] << 4) | (mdl->foot_leg[2] << 8) | (mdl->foot_leg[3] << 12);
   const double* rb = rbd_meas + (size_t)b * 55;
   // updateMeasured (WbcBase.cpp:138-144): rbd = [zyx(3), pos(3), joints(18), w_world(3), v_lin(3), joint vel(18), ...]
   if (lane < 3) { sm.q[lane] = rb[3 + lane]; sm.q[3 + lane] = rb[lane]; sm.v[lane] = rb[NQ + 3 + lane]; }
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   for (int i = lane; i < 56; i += 32) sm.vstar[i] = 0.0;
   __syncwarp();
   if (lane == 0) { euler_rate_map(sm.q[3], sm.q[4], sm.Tm); double Ti[9]; inv3(sm.Tm, Ti); const double w[3] = {rb[NQ], rb[NQ + 1], rb[NQ + 2]}; matvec3(Ti, w, sm.v + 3); }
-  if (lane < NQ) sm.qd[lane] = sm.xdes[6 + lane];
+  if (lane < NQ) sm.qd[lane] = xdes[6 + lane];
   __syncwarp();
 
   // ---- measured side: M, nle, foot/EE Jacobians and bias accelerations ----
@@ -325,7 +340,8 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   for (int f = 0; f < 4; ++f) {
     const int body = mdl->foot_body[f]; double pl[3] = {mdl->foot_p[f][0], mdl->foot_p[f][1], mdl->foot_p[f][2]}, pw[3]; matvec3(ws->R[body], pl, pw);
     pw[0] += ws->p[body][0]; pw[1] += ws->p[body][1]; pw[2] += ws->p[body][2];
-    const int first = mdl->foot_leg[f]; point_jacobian(ws, pw, first, first + 2, sm.Jf + 3 * f * LDM, LDM, lane);
+    if (lane < 9) { const double* S = ws->S[lane < 6 ? lane : foot_first(ffp, f) + lane]; double col[3]; cross3(S, pw, col);   // = point_jacobian restricted to the non-zero columns
+      for (int a = 0; a < 3; ++a) sm.Jc[(3 * f + a) * LJC + lane] = col[a] + S[3 + a]; }
     if (lane == 0) { double vel[3], acc[3]; point_vel_acc(ws, body, pw, vel, acc); for (int a = 0; a < 3; ++a) { sm.fpos_m[3 * f + a] = pw[a]; sm.fvel_m[3 * f + a] = vel[a]; sm.djv_f[3 * f + a] = acc[a]; } }
   }
   {
@@ -341,18 +357,18 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   // ---- desired side (WbcBase.cpp:193-226) ----
   // vDesired = [A_b^{-1}(qD) m h ; u joints]  (SRBD mapping); jointAccel = (u - inputLast)/period; inputLast <- u
   double jacc = 0.0;
-  if (lane < NJ) { jacc = (sm.udes[12 + lane] - input_last[(size_t)b * NU + 12 + lane]) / period; sm.vd[6 + lane] = sm.udes[12 + lane]; }
+  if (lane < NJ) { const double uj = udes[12 + lane]; jacc = (uj - input_last[(size_t)b * NU + 12 + lane]) / period; sm.vd[6 + lane] = uj; }
   __syncwarp();
-  if (lane < NU) input_last[(size_t)b * NU + lane] = sm.udes[lane];
+  if (lane < NU) input_last[(size_t)b * NU + lane] = udes[lane];
   double A22inv[9], A12[9];   // SRBD blocks at qDesired (kept in lane 0's registers; bound BEFORE dccrba in the reference)
   if (lane == 0) {
     double R[9], T[9]; rot_zyx(sm.qd[3], sm.qd[4], sm.qd[5], R); euler_rate_map(sm.qd[3], sm.qd[4], T);
     double c[3]; matvec3(R, mdl->c_nom, c);
     double RI[9], RIRt[9], A22[9]; matmul3(R, mdl->I_nom, RI); matmul3_nt(RI, R, RIRt); matmul3(RIRt, T, A22); inv3(A22, A22inv);
     const double Sx[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0}; double ST[9]; matmul3(Sx, T, ST); for (int i = 0; i < 9; ++i) A12[i] = mdl->total_mass * ST[i];
-    double ha[3] = {mdl->total_mass * sm.xdes[3], mdl->total_mass * sm.xdes[4], mdl->total_mass * sm.xdes[5]}, ed[3]; matvec3(A22inv, ha, ed);
+    double ha[3] = {mdl->total_mass * xdes[3], mdl->total_mass * xdes[4], mdl->total_mass * xdes[5]}, ed[3]; matvec3(A22inv, ha, ed);
     double t[3]; matvec3(A12, ed, t);
-    for (int a = 0; a < 3; ++a) { sm.vd[a] = sm.xdes[a] - t[a] / mdl->total_mass; sm.vd[3 + a] = ed[a]; }
+    for (int a = 0; a < 3; ++a) { sm.vd[a] = xdes[a] - t[a] / mdl->total_mass; sm.vd[3 + a] = ed[a]; }
   }
   __syncwarp();
   rbd_kinematics<true>(mdl, sm.qd, sm.vd, ws, lane);
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
     // centroidalMomentumRate = m*getNormalizedCentroidalMomentumRate(u) [true COM] - dAg v - Aj qdd_j ; baseAcc = AbInv(SRBD) * that
     const double mt = ws->Ic[0][0]; const double com[3] = {ws->Ic[0][1] / mt, ws->Ic[0][2] / mt, ws->Ic[0][3] / mt};
     double lin[3] = {0, 0, -9.81 * mdl->total_mass}, ang[3] = {0, 0, 0};
-    for (int f = 0; f < 4; ++f) { const double* F = sm.udes + 3 * f; const double r[3] = {sm.fpos_d[3 * f] - com[0], sm.fpos_d[3 * f + 1] - com[1], sm.fpos_d[3 * f + 2] - com[2]}; lin[0] += F[0]; lin[1] += F[1]; lin[2] += F[2]; cross3_add(r, F, ang); }
+    for (int f = 0; f < 4; ++f) { const double* F = sm.fdes + 3 * f; const double r[3] = {sm.fpos_d[3 * f] - com[0], sm.fpos_d[3 * f + 1] - com[1], sm.fpos_d[3 * f + 2] - com[2]}; lin[0] += F[0]; lin[1] += F[1]; lin[2] += F[2]; cross3_add(r, F, ang); }
     // spatial force about the origin → about the COM: n_com = nO - com x f
     const double* Fb = ws->F[0]; double cf[3]; cross3(com, Fb + 3, cf);
     double cp[3]; cross3(com, Phi + 3, cp);
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   __syncwarp();
 
   // ---- hierarchy ----
-  QpWs& qp = sm.qp; IneqCtx ic{&sm, mode, nc, mdl->wbc_friction}; int status = 0;
+  QpWs& qp = sm.qp; IneqCtx ic{&sm, mode, nc, mdl->wbc_friction, lfp, ffp}; int status = 0;
   const bool init_phase = time < 10.0;   // HierarchicalWbc.cpp:32
   double* AR = qp.za.q.AR; double* Z = qp.za.q.Z;
   for (int i = lane; i < 36; i += 32) qp.xbar[i] = 0.0;
@@ -397,12 +413,12 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   unsigned vmask0 = 0, vmask1 = 0;   // violated set, bit per inequality (lane-uniform)
   int k0 = 0;
   for (int it = 0; it < cap0; ++it) {
-    int r = build_level(sm, mdl, 0, mode, variant, init_phase, lane); it0 = it + 1;
+    int r = build_level(sm, mdl, 0, mode, variant, init_phase, ffp, lane); it0 = it + 1;
     // append violated rows
     for (int i = 0; i < nineq; ++i) { const bool in = (i < 32) ? ((vmask0 >> i) & 1u) : ((vmask1 >> (i - 32)) & 1u); if (in) { if (r >= MAXR) { status |= ST_TOO_MANY_ROWS; break; }
         for (int k = lane; k < 36; k += 32) AR[r * LDZ + k] = ineq_row_elem(ic, i, k); if (lane == 0) qp.bp[r] = ineq_rhs(ic, i); ++r; } }
     __syncwarp();
-    k0 = cod_lstsq(qp, AR, 36, r, LDZ, qp.bp, qp.xbar, Z, MAXR + 1, lane);   // Z is not in use yet: scratch of the rank-deficient branch
+    k0 = cod_lstsq(qp, AR, 36, r, LDZ, qp.bp, qp.xbar, Z, lane);   // Z is not in use yet: scratch of the rank-deficient branch
     __syncwarp();
     unsigned n0 = 0, n1 = 0;   // next violated set: strictly violated rows, plus rows of V sitting on their boundary
     for (int i = lane; i < nineq; i += 32) { const double val = ineq_row_dot(ic, i, qp.xbar) - ineq_rhs(ic, i); const double sc = 1e-9 * (1.0 + fabs(ineq_rhs(ic, i)));
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   int off = 0, nzc = 0, nw = 0, it1 = 0, it2 = 0;
   {
     if (vmask0 | vmask1) {   // the last factorisation contains violated rows: factor A0 alone (otherwise the one in AR already is the QR of A0')
-      const int rows0 = build_level(sm, mdl, 0, mode, variant, init_phase, lane);
+      const int rows0 = build_level(sm, mdl, 0, mode, variant, init_phase, ffp, lane);
       k0 = w_qrcp(AR, 36, rows0, LDZ, qp.tau, qp.perm, 1e-11, lane);
     }
     nzc = 36 - k0;
@@ -428,7 +444,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   }
   // levels 1 and 2
   for (int level = 1; level <= 2 && nzc > 0; ++level) {
-    const int rows = build_level(sm, mdl, level, mode, variant, init_phase, lane);
+    const int rows = build_level(sm, mdl, level, mode, variant, init_phase, ffp, lane);
     const int nz = nzc - off;
     if (nz <= 0) break;                                   // trivial kernel (the reference keeps one zero column, HoQp.cpp:129)
     project_task(qp, rows, off, nz, lane);
@@ -443,7 +459,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
   double* out = cmd_out + (size_t)b * 54;
   for (int i = lane; i < 36; i += 32) out[i] = qp.xbar[i];
   bool bad = false;
-  if (lane < NJ) { const double* Mr = sm.M + (6 + lane) * LDM; double s = sm.nle[6 + lane]; for (int k = 0; k < NQ; ++k) s += Mr[k] * qp.xbar[k]; for (int k = 0; k < 12; ++k) s -= sm.Jf[k * LDM + 6 + lane] * qp.xbar[NQ + k]; out[36 + lane] = s; bad = !isfinite(s); }
+  if (lane < NJ) { const double* Mr = sm.M + (6 + lane) * LDM; double s = sm.nle[6 + lane]; for (int k = 0; k < NQ; ++k) s += Mr[k] * qp.xbar[k]; s -= jt_force(&sm, lfp, lane, qp.xbar + NQ); out[36 + lane] = s; bad = !isfinite(s); }
   if (__any_sync(FULL, bad)) status |= ST_NAN;
   // status word: WBC flags only, in the low byte (bits 8..15 carry the MPC flags after qmb200_tick's merge, bit 16 = QMB200_ST_SAFETY: include/qmb200.h);
   // iteration counts / working-set size go to the separate diagnostics word: it0 | it1 << 8 | it2 << 16 | nw << 24

@@ -142,34 +142,39 @@ __device__ __forceinline__ void w_form_q_tail(const double* W, int n, int k, int
   __syncwarp();
 }
 
-// In-place Cholesky (lower) of the n x n symmetric matrix A (row-major, ld), n <= 32.  Returns false when a pivot <= 0.
-__device__ __forceinline__ bool w_cholesky(double* A, int n, int ld, int lane) {
+// Packed lower triangle: entry (a, b <= a) of a symmetric matrix sits at a(a+1)/2 + b.  Half the storage of a square scratch, half the entries to form,
+// and the triangular row offsets are distinct mod 16, so a lane = row walk down a column is bank-conflict free.
+__device__ __forceinline__ int tri(int a) { return (a * (a + 1)) >> 1; }
+// In-place Cholesky (lower, packed) of the n x n symmetric matrix A, n <= 32.  Returns false when a pivot <= 0.
+__device__ __forceinline__ bool w_cholesky(double* A, int n, int lane) {
   bool ok = true;
   for (int j = 0; j < n; ++j) {
-    const double d = A[j * ld + j];
+    const double d = A[tri(j) + j];
     if (!(d > 0.0)) { ok = false; break; }
     const double s = sqrt(d);
     __syncwarp();
-    if (lane == j) A[j * ld + j] = s;
-    if (lane > j && lane < n) A[lane * ld + j] /= s;
+    double* row = A + tri(lane);
+    if (lane == j) row[j] = s;
+    if (lane > j && lane < n) row[j] /= s;
     __syncwarp();
-    if (lane > j && lane < n) { const double lij = A[lane * ld + j]; for (int c = j + 1; c <= lane; ++c) A[lane * ld + c] -= lij * A[c * ld + j]; }
+    if (lane > j && lane < n) { const double lij = row[j]; int oc = tri(j + 1) + j; for (int c = j + 1; c <= lane; ++c) { row[c] -= lij * A[oc]; oc += c + 1; } }
     __syncwarp();
   }
   return ok;
 }
-// Solve L L^T x = b in place (b in shared memory, n <= 32); L lower from w_cholesky.
-__device__ __forceinline__ void w_chol_solve(const double* L, int n, int ld, double* b, int lane) {
+// Solve L L^T x = b in place (b in shared memory, n <= 32); L lower packed from w_cholesky.
+__device__ __forceinline__ void w_chol_solve(const double* L, int n, double* b, int lane) {
+  const double* row = L + tri(lane);
   for (int j = 0; j < n; ++j) {   // forward
-    if (lane == j) b[j] /= L[j * ld + j];
+    if (lane == j) b[j] /= row[j];
     __syncwarp();
-    if (lane > j && lane < n) b[lane] -= L[lane * ld + j] * b[j];
+    if (lane > j && lane < n) b[lane] -= row[j] * b[j];
     __syncwarp();
   }
   for (int j = n - 1; j >= 0; --j) {   // backward with L^T
-    if (lane == j) b[j] /= L[j * ld + j];
+    if (lane == j) b[j] /= row[j];
     __syncwarp();
-    if (lane < j) b[lane] -= L[j * ld + lane] * b[j];
+    if (lane < j) b[lane] -= L[tri(j) + lane] * b[j];
     __syncwarp();
   }
 }
