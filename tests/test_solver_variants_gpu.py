@@ -56,7 +56,7 @@ def test_ddp_variant_matches_the_oracle_and_descends(oracle):
         for tick, (out, ref) in enumerate(res):
             assert np.all((out["status"] & ~16) == 0), np.unique(out["status"])
             np.testing.assert_array_equal(out["step_info"][:, 0], ref["dbg"][:, 0])                    # accepted step length
-            assert_traj(out, ref, 100 * MPC_TOL, tag="ddp tick %d" % tick)                             # 100 sequential nonlinear RK2 steps amplify the 1e-12 of the gains
+            assert_traj(out, ref, MPC_TOL, tag="ddp tick %d" % tick)                                   # observed 1e-12 on B200 (profiles/r02d_parity_levels.txt)
             acc = ref["dbg"][:, 0] > 0; assert acc.all()
             np.testing.assert_allclose(out["step_info"][acc, 1], ref["dbg"][acc, 4], rtol=1e-8, atol=1e-9)   # cost of the accepted rollout
             assert np.all(out["step_info"][:, 2] == 0.0)                                               # single shooting: the accepted trajectory is a rollout, no dynamics defect
