@@ -220,6 +220,8 @@ int qmb200_set_pipeline(qmb200_handle* h, int chunks);
 int qmb200_set_profiling(qmb200_handle* h, int on);
 int qmb200_collect_kernel_times(qmb200_handle* h);
 int qmb200_get_kernel_times(qmb200_handle* h, double* ms6);
+/* the part of ms6[1] (LQ approximation) spent in the thread-per-node flow kernel (kinematics, flow maps, constraint rows); the rest is the warp-per-node projection kernel */
+int qmb200_get_flow_kernel_time(qmb200_handle* h, double* ms);
 int qmb200_measure_fp64_peak(qmb200_handle* h, double* tflops);
 
 /* diagnostics: the QP step (dx, du) of the last solve and per-robot scalars [armijo, baseline cost, dyn SSE, eq SSE, |dx|, |du|, -, -] */

@@ -37,8 +37,8 @@ struct qmb200_handle {
   int32_t *d_mode = nullptr, *d_status = nullptr, *d_wbc_diag = nullptr;   // d_wbc_diag: per-robot WBC iteration counts (qmb200_wbc_get_diagnostics), kept out of the status word
   MpcBuffers mpc;   // device buffers of the MPC path (kernels/mpc_api.cuh)
   std::vector<void*> allocs;
-  bool profiling = false; cudaEvent_t ev[8] = {nullptr};   // [0..4] MPC kernels, [5..7] policy / wbc brackets
-  double kernel_ms[6] = {0, 0, 0, 0, 0, 0}; int64_t kernel_calls = 0; bool ev_pending = false;
+  bool profiling = false; cudaEvent_t ev[8] = {nullptr};   // [0..4] MPC kernels, [5..6] policy / wbc brackets, [7] flow kernel | LQ kernel
+  double kernel_ms[7] = {0, 0, 0, 0, 0, 0, 0}; int64_t kernel_calls = 0; bool ev_pending = false;   // kernel_ms[6]: the flow kernel's share of [1]
   // tick pipeline: the batch is cut into `chunks` robot ranges, each running its MPC → policy → WBC chain on its own stream, so that
   // kernels with different bottlenecks (LQ: instruction latency, Riccati: shared-memory bandwidth, WBC) share the SMs
   static constexpr int MAX_CHUNKS = 8;

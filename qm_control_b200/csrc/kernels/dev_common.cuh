@@ -3,7 +3,16 @@
 // shared memory or registers, HBM is touched only for the batch I/O buffers.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+
+// Scalar helpers are host + device: tests/nodeeval_host.cpp compiles the one-thread-per-node evaluator (node_eval.cuh) with g++ and checks it against the
+// oracle on the CPU.  Everything that needs warp intrinsics stays inside #ifdef __CUDACC__.
+#ifdef __CUDACC__
+#define QMB_HD __host__ __device__ __forceinline__
+#else
+#define QMB_HD inline
+#endif
 
 namespace qmb {
 
@@ -59,6 +68,7 @@ struct DevModel {
   double cost_tol; int sqp_iterations;   // sqp.sqpIteration (task.info:28) and costTol [upstream ocs2_sqp default 1e-4]: SqpSolver::runImpl loop + checkConvergence
 };
 
+#ifdef __CUDACC__
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -101,47 +111,49 @@ __device__ __forceinline__ void warp_argmin(double& v, int& idx) {
   }
 }
 
+#endif  // __CUDACC__
+
 // ---- tiny 3-vector / 3x3 helpers on plain arrays ----
-__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+QMB_HD void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
 }
-__device__ __forceinline__ void cross3_add(const double* a, const double* b, double* c) {
+QMB_HD void cross3_add(const double* a, const double* b, double* c) {
   c[0] += a[1] * b[2] - a[2] * b[1]; c[1] += a[2] * b[0] - a[0] * b[2]; c[2] += a[0] * b[1] - a[1] * b[0];
 }
-__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-__device__ __forceinline__ void matvec3(const double* M, const double* v, double* o) {
+QMB_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+QMB_HD void matvec3(const double* M, const double* v, double* o) {
   o[0] = M[0] * v[0] + M[1] * v[1] + M[2] * v[2]; o[1] = M[3] * v[0] + M[4] * v[1] + M[5] * v[2]; o[2] = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
 }
-__device__ __forceinline__ void matTvec3(const double* M, const double* v, double* o) {
+QMB_HD void matTvec3(const double* M, const double* v, double* o) {
   o[0] = M[0] * v[0] + M[3] * v[1] + M[6] * v[2]; o[1] = M[1] * v[0] + M[4] * v[1] + M[7] * v[2]; o[2] = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
 }
-__device__ __forceinline__ void matmul3(const double* A, const double* B, double* C) {
+QMB_HD void matmul3(const double* A, const double* B, double* C) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 // C = A * B^T
-__device__ __forceinline__ void matmul3_nt(const double* A, const double* B, double* C) {
+QMB_HD void matmul3_nt(const double* A, const double* B, double* C) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
 }
 // R = Rz(z) Ry(y) Rx(x)   (ocs2 getRotationMatrixFromZyxEulerAngles)
-__device__ __forceinline__ void rot_zyx(double z, double y, double x, double* R) {
+QMB_HD void rot_zyx(double z, double y, double x, double* R) {
   double sz, cz, sy, cy, sx, cx; sincos(z, &sz, &cz); sincos(y, &sy, &cy); sincos(x, &sx, &cx);
   R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
   R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
   R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
 }
 // T: euler-ZYX rates → world angular velocity (ocs2 getMappingFromEulerAnglesZyxDerivativeToGlobalAngularVelocity)
-__device__ __forceinline__ void euler_rate_map(double z, double y, double* T) {
+QMB_HD void euler_rate_map(double z, double y, double* T) {
   double sz, cz, sy, cy; sincos(z, &sz, &cz); sincos(y, &sy, &cy);
   T[0] = 0; T[1] = -sz; T[2] = cy * cz; T[3] = 0; T[4] = cz; T[5] = cy * sz; T[6] = 1; T[7] = 0; T[8] = -sy;
 }
 // Tdot * ed  (time derivative of T along euler rates ed=(zd,yd,xd), applied to ed)
-__device__ __forceinline__ void euler_rate_map_dot_times(double z, double y, const double* ed, double* o) {
+QMB_HD void euler_rate_map_dot_times(double z, double y, const double* ed, double* o) {
   double sz, cz, sy, cy; sincos(z, &sz, &cz); sincos(y, &sy, &cy);
   const double zd = ed[0], yd = ed[1];
   // d/dt of columns: col1 = (-sz, cz, 0) → (-cz zd, -sz zd, 0); col2 = (cy cz, cy sz, -sy) → (-sy yd cz - cy sz zd, -sy yd sz + cy cz zd, -cy yd)
@@ -150,23 +162,23 @@ __device__ __forceinline__ void euler_rate_map_dot_times(double z, double y, con
   o[2] = (-cy * yd) * ed[2];
 }
 // Variants taking precomputed trig values tr = {sin z, cos z, sin y, cos y, sin x, cos x} (one warp-wide sincos pass serves all users)
-__device__ __forceinline__ void rot_zyx_sc(const double* tr, double* R) {
+QMB_HD void rot_zyx_sc(const double* tr, double* R) {
   const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3], sx = tr[4], cx = tr[5];
   R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
   R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
   R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
 }
-__device__ __forceinline__ void euler_rate_map_sc(const double* tr, double* T) {
+QMB_HD void euler_rate_map_sc(const double* tr, double* T) {
   const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3];
   T[0] = 0; T[1] = -sz; T[2] = cy * cz; T[3] = 0; T[4] = cz; T[5] = cy * sz; T[6] = 1; T[7] = 0; T[8] = -sy;
 }
-__device__ __forceinline__ void euler_rate_map_dot_times_sc(const double* tr, const double* ed, double* o) {
+QMB_HD void euler_rate_map_dot_times_sc(const double* tr, const double* ed, double* o) {
   const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3]; const double zd = ed[0], yd = ed[1];
   o[0] = (-cz * zd) * ed[1] + (-sy * yd * cz - cy * sz * zd) * ed[2];
   o[1] = (-sz * zd) * ed[1] + (-sy * yd * sz + cy * cz * zd) * ed[2];
   o[2] = (-cy * yd) * ed[2];
 }
-__device__ __forceinline__ void inv3(const double* m, double* o) {
+QMB_HD void inv3(const double* m, double* o) {
   const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
   const double id = 1.0 / (m[0] * c00 + m[1] * c01 + m[2] * c02);
   o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
@@ -174,7 +186,7 @@ __device__ __forceinline__ void inv3(const double* m, double* o) {
   o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
 }
 // rotation vector of E = L * R^T  (ocs2 rotationErrorInWorld)
-__device__ __forceinline__ void rotation_error_world(const double* L, const double* Rr, double* e) {
+QMB_HD void rotation_error_world(const double* L, const double* Rr, double* e) {
   double E[9]; matmul3_nt(L, Rr, E);
   const double w[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
   const double c = 0.5 * (E[0] + E[4] + E[8] - 1.0), s = 0.5 * sqrt(dot3(w, w));
@@ -182,6 +194,6 @@ __device__ __forceinline__ void rotation_error_world(const double* L, const doub
   const double k = atan2(s, c) / (2.0 * s); e[0] = k * w[0]; e[1] = k * w[1]; e[2] = k * w[2];
 }
 // modeNumber2StanceLeg: bit3 LF, bit2 RF, bit1 LH, bit0 RH (contact order LF,RF,LH,RH)
-__device__ __forceinline__ bool contact_flag(int mode, int foot) { return (mode >> (3 - foot)) & 1; }
+QMB_HD bool contact_flag(int mode, int foot) { return (mode >> (3 - foot)) & 1; }
 
 }  // namespace qmb

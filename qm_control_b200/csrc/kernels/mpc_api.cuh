@@ -49,6 +49,7 @@ struct MpcBuffers {
   double *t0 = nullptr, *x0 = nullptr, *event_times = nullptr, *target_times = nullptr, *target_states = nullptr;
   int32_t *n_events = nullptr, *modes = nullptr, *n_target = nullptr;
   MpcSolutionDev sol[2];
+  double *node_rec = nullptr;   // K2a -> K2b: per node the flow-map / constraint / end-effector record (ne::NodeRec, 492 doubles)
   double *stage = nullptr, *gains = nullptr, *dx = nullptr, *du = nullptr, *robot = nullptr, *step_info = nullptr;
   int32_t *stage_i = nullptr, *status = nullptr;
 };
@@ -59,7 +60,7 @@ struct MpcProblemDev { const double* t0; const double* x0; const int32_t* n_even
 
 // One SQP iteration for robots [b0, b1) (4 kernels on `stream`): reads m.sol[m.cur], writes m.sol[1 - m.cur]; the caller
 // flips m.cur after queueing every range.  Returns the number of kernels launched.
-// `ev` (optional, 5 events): recorded before K1 and after each of K1..K4 for per-kernel timing.
+// `ev` (optional, 8 events): [0..4] recorded before K1 and after each of K1, K2 (flow + LQ), K3, K4 for per-kernel timing; [7] between the flow kernel and the LQ kernel.
 int mpc_solve_launch(const DevModel* mdl, const DevModel& host_mdl, MpcBuffers& m, const MpcProblemDev& p, int b0, int b1, cudaStream_t stream, cudaEvent_t* ev = nullptr);
 // fp64 FMA throughput microbenchmark (roofline denominator for the compute-bound kernels); returns TFLOP/s
 double measure_fp64_peak(cudaStream_t stream);

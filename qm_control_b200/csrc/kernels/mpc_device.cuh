@@ -11,12 +11,10 @@
 #pragma once
 #include "dev_common.cuh"
 #include "rbd.cuh"
+#include "mpc_scalar.cuh"
 
 namespace qmb {
 
-constexpr int MU = 18;      // max projected input dimension (30 - 12 equality rows in stance)
-constexpr int MAXDEP = 16;  // max dependent inputs (fly: 4 x (3 forces + 1 joint))
-constexpr double WEAK_EPS = 1e-6;   // ocs2 numeric_traits::weakEpsilon: interval start/end shift at event nodes [upstream]
 
 struct PointWs {
   KinWs kin;
@@ -28,10 +26,6 @@ struct PointWs {
   double pf[4][3], d[4][3], Jl[4][9], al[4][9];   // Jl[i][3*j + a]: component a of leg-Jacobian column j of foot i
 };
 
-// leg (joint order LF, LH, RF, RH) → foot (contact order) map packed two bits per leg: loaded once per kernel, every lookup is then pure ALU
-// (the map sits in front of shared-memory indexing in the flat stage-record sweeps, so a global load per lookup is a dependent chain)
-__device__ __forceinline__ int pack_leg_foot(const DevModel* __restrict__ mdl) { return mdl->leg_foot[0] | (mdl->leg_foot[1] << 2) | (mdl->leg_foot[2] << 4) | (mdl->leg_foot[3] << 6); }
-__device__ __forceinline__ int foot_of_leg_joint(int lfp, int j) { return (lfp >> (2 * (j / 3))) & 3; }
 
 // Evaluate the flow map (and its Jacobian rows if with_jac) at (ws->x, ws->u).
 // max_depth: 6 = whole tree, 3 = base + legs (the flow map does not see the arm links; only the end-effector cost does).
@@ -118,43 +112,17 @@ __device__ __forceinline__ void point_eval(const DevModel* __restrict__ mdl, Poi
   }
 }
 
-// ---- reference signals -------------------------------------------------------------------------------
-// ocs2::lookup::findIndexInTimeArray (std::lower_bound)
-__device__ __forceinline__ int lower_bound_idx(const double* a, int n, double t) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < t) lo = mid + 1; else hi = mid; } return lo; }
-template <class MT> __device__ __forceinline__ int mode_at_time(const double* ev, const MT* modes, int ne, double t) { return modes[lower_bound_idx(ev, ne, t)]; }
-// ocs2::LinearInterpolation::timeSegment
-__device__ __forceinline__ void time_segment(const double* times, int n, double t, int& index, double& alpha) {
-  if (n <= 1) { index = 0; alpha = 1.0; return; }
-  const int part = lower_bound_idx(times, n, t); int idx = (part != 0 || t != times[0]) ? part - 1 : 0; const int last = n - 1;
-  if (idx >= 0) {
-    if (idx < last) { const double len = times[idx + 1] - times[idx], till = times[idx + 1] - t; index = idx; alpha = (len > 2.0 * 2.220446049250313e-16) ? till / len : (till > 0.5 * len ? 1.0 : 0.0); return; }
-    index = (last - 1 > 0) ? last - 1 : 0; alpha = 0.0; return;
-  }
-  index = 0; alpha = 1.0;
-}
-// SwingTrajectoryPlanner::getZvelocityConstraint / getZpositionConstraint [upstream]: status=false when the swing phase is not enclosed
-template <class MT> __device__ __forceinline__ bool swing_reference(const DevModel* __restrict__ mdl, const double* ev, const MT* modes, int ne, int leg, double t, double& zp, double& zv) {
-  const int np = ne + 1; const int p = lower_bound_idx(ev, ne, t); zp = 0.0; zv = 0.0;
-  if (contact_flag(modes[p], leg)) return true;
-  int start = -1; for (int ip = p - 1; ip >= 0; --ip) if (contact_flag(modes[ip], leg)) { start = ip; break; }
-  int fin = np - 1; for (int ip = p + 1; ip < np; ++ip) if (contact_flag(modes[ip], leg)) { fin = ip - 1; break; }
-  if (start < 0 || fin >= np - 1) return false;
-  const double t0 = ev[start], t1 = ev[fin]; const double scaling = fmin(1.0, (t1 - t0) / mdl->swing_time_scale); const double tm = 0.5 * (t0 + t1), zm = scaling * mdl->swing_height;
-  double ta, pa, va, tb, pb, vb;
-  if (t < tm) { ta = t0; pa = 0.0; va = scaling * mdl->lift_off_velocity; tb = tm; pb = zm; vb = 0.0; } else { ta = tm; pa = zm; va = 0.0; tb = t1; pb = 0.0; vb = scaling * mdl->touch_down_velocity; }
-  const double dtt = tb - ta, dp = pb - pa, dv = vb - va; const double c0 = pa, c1 = va * dtt, c2 = -(3.0 * va + dv) * dtt + 3.0 * dp, c3 = (2.0 * va + dv) * dtt - 2.0 * dp; const double idt = 1.0 / dtt, tn = (t - ta) * idt;
-  zp = ((c3 * tn + c2) * tn + c1) * tn + c0; zv = ((3.0 * c3 * tn + 2.0 * c2) * tn + c1) * idt; return true;
-}
-// ocs2 RelaxedBarrierPenalty [upstream]
-__device__ __forceinline__ void relaxed_barrier(double mu, double delta, double h, double& p0, double& p1, double& p2) {
-  if (h > delta) { const double ih = 1.0 / h; p0 = -mu * log(h); p1 = -mu * ih; p2 = mu * ih * ih; }
-  else { const double t = (h - 2.0 * delta) / delta; p0 = mu * (-log(delta) + 0.5 * t * t - 0.5); p1 = mu * (h - 2.0 * delta) / (delta * delta); p2 = mu / (delta * delta); }
-}
-
 // Target trajectory references at time t: xnom[30] (TargetTrajectories::getDesiredState().head(30)), EE pose reference
 // (EndEffectorConstraint::interpolateEndEffectorPose, EndEffectorConstraint.cpp:82-113; Eigen slerp semantics).  All lanes compute the same
 // scalars; lane < 30 returns its own xnom component.
 struct TargetRef { double xnom; double pref[3]; double qref[4]; };
+// state reference of this lane only (the end-effector pose reference is consumed by the flow kernel)
+__device__ __forceinline__ double target_xnom(const double* tt, const double* ts /*[K][37]*/, int nk, double t, int lane) {
+  int idx; double a; time_segment(tt, nk, t, idx, a);
+  const double* l = ts + (size_t)idx * 37; const double* rr = ts + (size_t)((nk > 1) ? idx + 1 : idx) * 37;
+  if (nk <= 1) a = 1.0;
+  return (lane < NX) ? a * l[lane] + (1.0 - a) * rr[lane] : 0.0;
+}
 __device__ __forceinline__ TargetRef target_reference(const double* tt, const double* ts /*[K][37]*/, int nk, double t, int lane) {
   TargetRef r; int idx; double a; time_segment(tt, nk, t, idx, a);
   const double* l = ts + (size_t)idx * 37; const double* rr = ts + (size_t)((nk > 1) ? idx + 1 : idx) * 37;
@@ -175,7 +143,6 @@ __device__ __forceinline__ TargetRef target_reference(const double* tt, const do
 // only what depends on (x,u) is stored:  Qf = Q + diag(qdiag) + scatter(E on the 12 end-effector columns),
 // Rf = R + diag(rdiag) + blockdiag(fric[foot]) on the 12 force inputs.
 struct QuadWs { double E[144], fric[36], qdiag[NX], rdiag[NU], qf[NX], rf[NU]; };
-__device__ __forceinline__ int ee_pos(int c) { return (c >= 6 && c < 12) ? c - 6 : (c >= 24 ? c - 18 : -1); }
 __device__ __forceinline__ double quad_Q(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
   double v = mdl->Q[i * NX + j]; if (i == j) v += q->qdiag[i]; const int a = ee_pos(i), b = ee_pos(j); if (a >= 0 && b >= 0) v += q->E[a * 12 + b]; return v; }
 __device__ __forceinline__ double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
@@ -183,7 +150,6 @@ __device__ __forceinline__ double quad_R(const DevModel* __restrict__ mdl, const
   const int bi = i / 3; if (bi != j / 3) return 0.0;
   double v = mdl->Rblk[bi][(i - 3 * bi) * 3 + (j - 3 * bi)]; if (i == j) v += q->rdiag[i]; if (i < 12) v += q->fric[bi * 9 + (i - 3 * bi) * 3 + (j - 3 * bi)]; return v; }
 struct CostWs { double Je[6 * 12], e[6], quat[4], pee[3]; };
-__device__ __forceinline__ int ee_col(int i) { return i < 6 ? 6 + i : 18 + i; }   // 12 state columns the EE pose depends on: p(6:9), theta(9:12), arm(24:30)
 
 // End-effector error e = [p_ee - p_ref; quaternionDistance(q_ee, q_ref)] and (optionally) its Jacobian columns.  ws must hold the kinematics at x.
 template <bool with_jac>
@@ -220,8 +186,9 @@ __device__ __forceinline__ void ee_error(const DevModel* __restrict__ mdl, const
 
 // Intermediate (or terminal) cost value; when with_quad also the quadratic model in cw (NOT scaled by dt).  `flags` = contact flags bitmask (bit i = foot i).
 // Returns the cost value (lane-uniform).
-template <bool with_quad>
-__device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, const PointWs* ws, CostWs* cw, QuadWs* qw, const TargetRef& ref, int flagmask, bool terminal, int lane) {
+// EE_PRE: the end-effector error (cw->e) and its Jacobian (cw->Je) were produced by the thread-per-node flow kernel (node_eval.cuh); WS then only needs x / u.
+template <bool with_quad, bool EE_PRE = false, class WS = PointWs, class CW = CostWs>
+__device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, const WS* ws, CW* cw, QuadWs* qw, const TargetRef& ref, int flagmask, bool terminal, int lane) {
   double value = 0.0;
   if (with_quad) { for (int e = lane; e < 144; e += 32) qw->E[e] = 0.0; for (int e = lane; e < 36; e += 32) qw->fric[e] = 0.0; if (lane < NX) { qw->qdiag[lane] = 0.0; qw->rdiag[lane] = 0.0; qw->qf[lane] = 0.0; qw->rf[lane] = 0.0; } __syncwarp(); }
   int nst = 0; for (int i = 0; i < 4; ++i) nst += (flagmask >> i) & 1;
@@ -243,7 +210,7 @@ __device__ __forceinline__ double stage_cost(const DevModel* __restrict__ mdl, c
     __syncwarp();
   }
   // end-effector soft constraint (quadratic penalty, Gauss-Newton)
-  ee_error<with_quad>(mdl, ws, cw, ref, lane);
+  if constexpr (!EE_PRE) ee_error<with_quad>(mdl, ws, cw, ref, lane);
   {
     const double mup = terminal ? mdl->mu_final_ee_pos : mdl->mu_ee_pos, muo = terminal ? mdl->mu_final_ee_ori : mdl->mu_ee_ori;
     double v = 0.0; for (int r = 0; r < 6; ++r) v += 0.5 * (r < 3 ? mup : muo) * cw->e[r] * cw->e[r]; value += v;
@@ -291,8 +258,6 @@ struct ConWs {
   double C[4][3][12];   // dg/dx rows of foot i on its support columns (stance: 3 rows; swing: row 2 only)
   double e[4][3];       // constraint values (stance: foot velocity; swing: e[i][2] = v_z - zdot_ref)
 };
-// state column of support position `pos` (0..11) for the leg whose first joint is `first`
-__device__ __forceinline__ int sup_col(int pos, int first) { return pos < 6 ? pos : (pos < 9 ? pos + 3 : 12 + first + pos - 9); }
 // foot velocity v = h_lin + omega x d + sum_j Jl_j qd_j and (optionally) its state Jacobian; lanes 0..3 (one per foot)
 template <bool with_jac>
 __device__ __forceinline__ void foot_velocity(const DevModel* __restrict__ mdl, const PointWs* ws, ConWs* cn, int lane) {

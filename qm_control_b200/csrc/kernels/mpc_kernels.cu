@@ -10,12 +10,16 @@
 #include <cstdlib>
 #include "mpc_api.cuh"
 #include "mpc_device.cuh"
+#include "node_eval.cuh"
 #include "wlinalg.cuh"
 
 namespace qmb {
 
 #ifndef QMB_LQ_WARPS
 #define QMB_LQ_WARPS 6
+#endif
+#ifndef QMB_LQ_MINB
+#define QMB_LQ_MINB 2
 #endif
 constexpr int LQ_WARPS = QMB_LQ_WARPS, LS_WARPS = 4, SETUP_WARPS = 4;
 enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16, MST_CONVERGED = 32, MST_NEG_DT = 64 };   // NEG_DT: an interval with non-positive duration (include/qmb200.h)   // CONVERGED: checkConvergence stopped the SQP loop before sqpIteration
@@ -109,20 +113,75 @@ struct LegWs {
   int dep[3];           // is joint j of this leg dependent
   int pivot, stance, first, free_col[3];   // projected-input column of each free joint (-1 if dependent)
 };
-struct LqEarly { CostWs cost; ConWs con; };                                   // live until the per-leg projection blocks are built
-struct LqLate { double BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX]; };                // produced after the second flow evaluation
-struct LqSmem {
-  PointWs pt; QuadWs quad; LegWs leg[4];
-  union EL { LqEarly e; LqLate l; __device__ EL() {} } el;
-  double xs[NX], xnext[NX], f1[NX], A1r[9 * NX], B1h[36];             // A1r becomes A_d - I (rows 3:12) in place
+struct LqLate { double BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX]; };                // produced by the RK2 combination, after the cost / projection blocks have consumed rec.foot and rec.ee
+struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp's slice starts 16-byte aligned
+  ne::NodeRec rec;                                                             // the node's record from the flow kernel (K2a); LqLate overlays rec.foot / rec.ee once they are dead
+  QuadWs quad; LegWs leg[4];
+  double x[NX], u[NU], xnext[NX];                                              // (x, u) of the node in the layout stage_cost reads (x then u), next node's state for the defect
+  double A1r[9 * NX], Ar[9 * NX], B1h[36], Bh[36];                             // rows 3:12 of df/dx and rows 3:6, columns 0:12 of df/du at the two RK2 stages; A1r becomes A_d - I in place
   double Pe_full[NU], rs[NU];
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
   double ev[EMAX]; unsigned char modes[EMAX + 8];   // the robot's mode schedule, staged once per node: the binary searches and the swing-interval scans then hit shared memory
 };
+static_assert(sizeof(LqLate) <= sizeof(ne::FootRec) + sizeof(ne::EeRec) && offsetof(ne::NodeRec, ee) == offsetof(ne::NodeRec, foot) + sizeof(ne::FootRec), "LqLate overlays rec.foot + rec.ee");
+static_assert(sizeof(LqSmem) % 16 == 0 && offsetof(LqSmem, rec) == 0, "aligned record slice");
 static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep two CTAs per SM");
 
-// The LQ kernel is ~220 KB of straight-line code executed once per node: warps of a CTA are re-aligned at a few phase
-// boundaries so that they share instruction-cache lines (exited warps - event / terminal / padding nodes - no longer take part).
+// =====================================================================================================
+// K2a: flow kernel - one THREAD per node (node_eval.cuh).  Kinematics of the five chains, both RK2 stages of the flow map with their Jacobian blocks, the
+// foot-velocity rows with their Jacobians and the end-effector error with its Jacobian: 492 doubles per node, handed to K2b through HBM (written once, read once,
+// both fully coalesced: the warp transposes 32 thread-private records through shared memory, K2b's warp reads its node's record as one contiguous run).
+#ifndef QMB_FL_MINB
+#define QMB_FL_MINB 3
+#endif
+constexpr int FL_WARPS = 4;
+__global__ void __launch_bounds__(32 * FL_WARPS, QMB_FL_MINB) mpc_flow_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ rec, const int32_t* __restrict__ status) {
+  __shared__ double tile[FL_WARPS][32][33];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const long long gid = (long long)blockIdx.x * (32 * FL_WARPS) + tid;
+  const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax);
+  const int n = (b < B) ? sol.n_nodes[b] : 0;
+  bool work = b < B && k < n && !(status[b] & MST_CONVERGED);
+  const bool terminal = work && (k == n - 1);
+  if (work && !terminal && sol.event[(size_t)b * nmax + k] == 1) work = false;   // event node: identity jump map, nothing to evaluate
+  ne::NodeRec r;
+  if (work) {
+    const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
+    const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
+    double x[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { x[i] = xk[i]; u[i] = terminal ? 0.0 : uk[i]; }
+    const double t = interval_start(gt[k], ge[k]); const double dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
+    ne::BaseKin bk; double al[4][9];
+    ne::base_eval<true>(mdl, x, bk); ne::flow_eval<true>(mdl, x, u, bk, r.s1, r.foot.Jl, r.foot.pf, al);
+    if (!terminal) { for (int i = 0; i < 4; ++i) ne::foot_velocity_1<true>(mdl, x, u, bk, i, r.s1.d[i], r.foot.Jl[i], al[i], r.foot.e[i], r.foot.C[i]); }
+    { const int nk = clamp_targets(p.n_target[b]); double pref[3], qref[4]; ne::target_reference_full(p.target_times + (size_t)b * KMAX, p.target_states + (size_t)b * KMAX * TARGET_DIM, nk, t, nullptr, pref, qref);
+      ne::ee_eval<true>(mdl, x, bk, pref, qref, r.ee.e, r.ee.Je); }
+    if (!terminal) {   // second RK2 stage at x + c dt k1 (rows 12:30 of the flow map are the joint-velocity inputs)
+      const double cdt = mdl->rk_c * dt;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] += cdt * (i < 12 ? r.s1.f[i < 12 ? i : 0] : u[i]);
+      ne::base_eval<true>(mdl, x, bk); ne::flow_eval<true>(mdl, x, u, bk, r.s2, nullptr, nullptr, nullptr);
+    }
+  }
+  // transposed write-out: 32 doubles of each lane's record per round through the warp's tile, then one 256-byte run per node and instruction
+  const unsigned active = __ballot_sync(FULL, work); if (!active) return;
+  const double* rr = reinterpret_cast<const double*>(&r); double* gbase = rec + ((size_t)b0 * nmax + (size_t)(gid - lane)) * ne::NODE_REC_DBL;   // node index = robot * nmax + k, as K2b reads it
+  for (int c0 = 0; c0 < ne::NODE_REC_DBL; c0 += 32) {
+    const int cnt = (ne::NODE_REC_DBL - c0 < 32) ? ne::NODE_REC_DBL - c0 : 32;
+    if (work) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < cnt) tile[warp][lane][j] = rr[c0 + j]; }
+    __syncwarp();
+    if (lane < cnt) {
+#pragma unroll 8
+      for (int rw = 0; rw < 32; ++rw) if ((active >> rw) & 1u) gbase[(size_t)rw * ne::NODE_REC_DBL + c0 + lane] = tile[warp][rw][lane]; }
+    __syncwarp();
+  }
+}
+
+// =====================================================================================================
+// K2b: cost quadratic model, equality constraints, projection, RK2 sensitivities and the structured stage record of one node (one warp per node), on the
+// record of the flow kernel.
 // Optional re-alignment of a CTA's warps at phase boundaries (instruction-cache sharing).  Measured on B200 with the structured record (profiles/r02_ab_k3.jsonl):
 // 21.88 ms with, 21.42 ms without - the kernel is no longer fetch bound, so it is OFF.  When enabled the barrier is taken only by CTAs whose six warps all hold
 // regular (intermediate) nodes - a CTA-uniform predicate established before any warp can exit - so no warp ever waits for one that has returned.
@@ -130,51 +189,65 @@ static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep t
 #define QMB_LQ_LOCKSTEP 0
 #endif
 #define LQ_LOCKSTEP() do { if (QMB_LQ_LOCKSTEP && lockstep) __syncthreads(); } while (0)
-__global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ stage, int32_t* __restrict__ status) {
+// rows 3:12 of df/dx (9 x 30, two thirds zeros) and the force block of rows 3:6 of df/du from the Jacobian blocks of a flow record: fill, then lane = column writes
+// its own non-zeros (the fill and the column writes are separated by a warp barrier)
+__device__ __forceinline__ void expand_flow(const ne::FlowRec& fr, double* Ar, double* Bh, double im, int lane) {
+  for (int e = lane; e < 9 * NX; e += 32) Ar[e] = 0.0;
+  for (int e = lane; e < 36; e += 32) { const int r = e / 12, c = e - 12 * r, i = c / 3, a = c - 3 * i; const double* d = fr.d[i];   // cross(d_i, e_a)[r] / m
+    Bh[e] = ((r == a) ? 0.0 : (((a - r + 3) % 3 == 1) ? -d[3 - r - a] : d[3 - r - a])) * im; }
+  __syncwarp();
+  if (lane < 24) {
+    const int col = lane;
+    if (col < 3) Ar[(3 + col) * NX + col] = 1.0;                                                         // d pdot / d h_lin = I
+    else if (col < 6) { for (int a = 0; a < 3; ++a) { Ar[(3 + a) * NX + col] = fr.Mpc[3 * a + col - 3]; Ar[(6 + a) * NX + col] = fr.Mtw[3 * a + col - 3]; } }   // d / d h_ang
+    else if (col >= 9 && col < 12) { for (int a = 0; a < 3; ++a) { Ar[a * NX + col] = fr.hth[col - 9][a]; Ar[(3 + a) * NX + col] = fr.vp[col - 9][a]; Ar[(6 + a) * NX + col] = fr.vt[col - 9][a]; } }   // d / d theta
+    else if (col >= 12) { for (int a = 0; a < 3; ++a) Ar[a * NX + col] = fr.JxF[col - 12][a]; }          // d hdot_ang / d q_leg = (J_j x F) / m
+  }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ rec, double* __restrict__ stage, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
   const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax);
   const int n = (b < B) ? sol.n_nodes[b] : 0;
   const bool work = b < B && k < n && !(status[b] & MST_CONVERGED);   // MST_CONVERGED: SqpSolver::runImpl left the iteration loop for this robot
   const bool regular = work && k < n - 1 && sol.event[(size_t)b * nmax + k] != 1;
-  const bool lockstep = __syncthreads_and(regular) != 0;                // every thread of the CTA is still here: the early exits come after this point
-  (void)lockstep;
+  const bool lockstep = QMB_LQ_LOCKSTEP ? (__syncthreads_and(regular) != 0) : false;   // every thread of the CTA is still here: the early exits come after this point
+  (void)lockstep; (void)regular;
   if (!work) return;
-  LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp];
+  LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp]; LqLate& lt = *reinterpret_cast<LqLate*>(&sm.rec.foot);
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL;
   const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
-  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
-  const int lfp = pack_leg_foot(mdl);
-  const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
   const bool terminal = (k == n - 1);
-  if (lane < NX) { sm.xs[lane] = xk[lane]; sm.pt.u[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
+  if (lane < NX) { sm.x[lane] = xk[lane]; sm.u[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
   __syncwarp();
   if (!terminal && ge[k] == 1) {   // event node: identity jump map, no input, no cost (setupEventNode)
     double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
-    double d = 0.0; if (lane < NX) { d = sm.xs[lane] - sm.xnext[lane]; tl[T_b + lane] = d; }
+    double d = 0.0; if (lane < NX) { d = sm.x[lane] - sm.xnext[lane]; tl[T_b + lane] = d; }
     const double ss = warp_sum(d * d);
     if (lane == 0) { si[SI_TYPE] = 1; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = 0.0; tl[T_MISC + 2] = ss; tl[T_MISC + 3] = 0.0; }
     return;
   }
-  const double t = interval_start(gt[k], ge[k]);
-  if (lane < NX) sm.pt.x[lane] = sm.xs[lane];
+  { // the node's record (K2a): one contiguous 3.9 KB run, 16 bytes per lane and load
+    const double2* rg = reinterpret_cast<const double2*>(rec + ((size_t)b * nmax + k) * ne::NODE_REC_DBL); double2* rs = reinterpret_cast<double2*>(&sm.rec);
+    const int cnt2 = terminal ? (int)((offsetof(ne::NodeRec, s2) + 15) / 16) : ne::NODE_REC_DBL / 2;   // terminal node: no second stage
+    for (int e = lane; e < cnt2; e += 32) rs[e] = __ldg(rg + e);
+    const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
   __syncwarp();
+  const int lfp = pack_leg_foot(mdl);
+  const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
+  const double t = interval_start(gt[k], ge[k]);
   const double dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
   const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
   if (!terminal && !(dt > 0.0) && lane == 0) atomicOr(&status[b], MST_NEG_DT);   // getIntervalDuration <= 0: an event within weakEpsilon of a grid node (QMB200_ST_NEG_DT)
   double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0;
-  // One inlined copy of the flow-map evaluation serves both RK2 stages (and the terminal node): the kernel is
-  // instruction-fetch sensitive (straight-line code of several hundred KB), so the pass loop is deliberately not unrolled.
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-  point_eval<true>(mdl, &sm.pt, lane, lfp, pass == 0 ? 6 : 3);   // the second RK2 stage needs the flow map only: no arm links
-  LQ_LOCKSTEP();
-  if (pass == 1) break;
-  // ---- first flow evaluation at (x,u): dynamics Jacobians, cost, constraints ----
-  TargetRef ref = target_reference(tt, ts, nk, t, lane);
-  cost_val = stage_cost<true>(mdl, &sm.pt, &sm.el.e.cost, &sm.quad, ref, fm, terminal, lane);
+  {
+  // ---- cost quadratic model at (x, u) (the end-effector error and its Jacobian come with the record) ----
+  TargetRef ref; ref.xnom = target_xnom(tt, ts, nk, t, lane);
+  struct XU { double x[NX], u[NU]; }; static_assert(offsetof(LqSmem, u) == offsetof(LqSmem, x) + NX * 8, "x then u");
+  cost_val = stage_cost<true, true>(mdl, reinterpret_cast<const XU*>(sm.x), &sm.rec.ee, &sm.quad, ref, fm, terminal, lane);
   if (terminal) {   // setupTerminalNode: finalEndEffector soft constraint only (QMInterface.cpp:104)
     double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
     for (int r = 0; r < NX; ++r) { const int a = ee_pos(r); if (lane < q_row_padded(r)) { const int cc = (lane <= r) ? ee_pos(lane) : -1; sg[ST_Q + q_row_offset(r) + lane] = (a >= 0 && cc >= 0) ? sm.quad.E[a * 12 + cc] : 0.0; } }   // final cost: packed lower triangle
@@ -182,7 +255,6 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = cost_val; tl[T_MISC + 2] = 0.0; tl[T_MISC + 3] = 0.0; }
     return;
   }
-  foot_velocity<true>(mdl, &sm.pt, &sm.el.e.con, lane);
   LQ_LOCKSTEP();
   int nd_before = 0; for (int i = 0; i < 4; ++i) if (i < lane) nd_before += ((fm >> i) & 1) ? 3 : 4;
   ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
@@ -191,14 +263,14 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   bool swing_ok = true; int pivot = -1;
   if (lane < 4) {   // lane = foot (contact order); its leg's first joint = foot_leg
     const int i = lane; const int first = mdl->foot_leg[i]; LegWs& L = sm.leg[i]; L.first = first; L.stance = (fm >> i) & 1;
-    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.el.e.con.e[i][a] * sm.el.e.con.e[i][a]; }
+    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.rec.foot.e[i][a] * sm.rec.foot.e[i][a]; }
     else {
       double zp, zv; swing_ok = swing_reference(mdl, ev, modes, ne, i, t, zp, zv);
-      double ez = sm.el.e.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp);
-      sm.el.e.con.e[i][2] = ez;
-      for (int a = 0; a < 3; ++a) { sm.dep_idx[nd_before + a] = 3 * i + a; eq_ss += sm.pt.u[3 * i + a] * sm.pt.u[3 * i + a]; }
+      double ez = sm.rec.foot.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.rec.foot.pf[i][2] - zp);
+      sm.rec.foot.e[i][2] = ez;
+      for (int a = 0; a < 3; ++a) { sm.dep_idx[nd_before + a] = 3 * i + a; eq_ss += sm.u[3 * i + a] * sm.u[3 * i + a]; }
       eq_ss += ez * ez;
-      double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.pt.Jl[i][3 * j + 2]); if (a > best) { best = a; pivot = j; } }   // pivot: largest |d v_z / d qdot_j|
+      double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.rec.foot.Jl[i][3 * j + 2]); if (a > best) { best = a; pivot = j; } }   // pivot: largest |d v_z / d qdot_j|
       sm.dep_idx[nd_before + 3] = 12 + first + pivot; L.pivot = pivot; for (int j = 0; j < 3; ++j) L.dep[j] = (j == pivot);
     }
   }
@@ -217,15 +289,15 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     for (int j = 0; j < 3; ++j) { L.free_col[j] = sm.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) { L.Px[j][c] = 0.0; L.U[j][c] = 0.0; } }
     L.Pu2[0] = L.Pu2[1] = 0.0;
     if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  →  dqd = -Jl^{-1} (C dx + e)
-      double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.pt.Jl[i][3 * j + a]; inv3(Jm, Ji);
-      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.el.e.con.e[i][a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
-        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.el.e.con.C[i][a][c]; L.Px[j][c] = sv; } }
+      double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.rec.foot.Jl[i][3 * j + a]; inv3(Jm, Ji);
+      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.rec.foot.e[i][a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
+        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.rec.foot.C[i][a][c]; L.Px[j][c] = sv; } }
     } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
-      for (int a = 0; a < 3; ++a) sm.Pe_full[3 * i + a] = -sm.pt.u[3 * i + a];
-      const double piv = sm.pt.Jl[i][3 * pivot + 2], nip = -1.0 / piv;
-      L.Pe[pivot] = sm.el.e.con.e[i][2] * nip; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
-      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = sm.el.e.con.C[i][2][c] * nip;
-      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = sm.pt.Jl[i][3 * j + 2] * nip;
+      for (int a = 0; a < 3; ++a) sm.Pe_full[3 * i + a] = -sm.u[3 * i + a];
+      const double piv = sm.rec.foot.Jl[i][3 * pivot + 2], nip = -1.0 / piv;
+      L.Pe[pivot] = sm.rec.foot.e[i][2] * nip; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
+      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = sm.rec.foot.C[i][2][c] * nip;
+      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = sm.rec.foot.Jl[i][3 * j + 2] * nip;
     }
     // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
     for (int a = 0; a < 3; ++a) { double sv = sm.quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
@@ -240,16 +312,13 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
     sm.rs[lane] = sv;
   }
   LQ_LOCKSTEP();
-  // keep k1 data, then second flow evaluation at x + c dt k1
-  if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
-  for (int e = lane; e < 9 * NX; e += 32) sm.A1r[e] = sm.pt.Ar[e];
-  for (int e = lane; e < 36; e += 32) sm.B1h[e] = sm.pt.Bh[e];
-  __syncwarp();
-  if (lane < NX) sm.pt.x[lane] = sm.xs[lane] + mdl->rk_c * dt * sm.f1[lane];
-  __syncwarp();
+  // continuous-time Jacobians of the two RK2 stages from the record's blocks
+  const double imr = 1.0 / mdl->total_mass;
+  expand_flow(sm.rec.s1, sm.A1r, sm.B1h, imr, lane); expand_flow(sm.rec.s2, sm.Ar, sm.Bh, imr, lane);
   }
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2), imass = 1.0 / mass;
-  double bb = 0.0; if (lane < NX) { bb = sm.xs[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xnext[lane]; sm.el.l.bvec[lane] = bb; }   // defect
+  double bb = 0.0; if (lane < NX) { const double fa = lane < 12 ? sm.rec.s1.f[lane < 12 ? lane : 0] : sm.u[lane], fb = lane < 12 ? sm.rec.s2.f[lane < 12 ? lane : 0] : sm.u[lane];   // rows 12:30 of the flow map: the joint-velocity inputs
+    bb = sm.x[lane] + dt * (w1 * fa + w2 * fb) - sm.xnext[lane]; lt.bvec[lane] = bb; }   // defect
   const double dyn_ss = warp_sum(bb * bb);
   // A_d - I (rows 3:12) = dt (w1 A1 + w2 (A2 + c dt A2 A1)) ; B_d rows 3:12 = dt (w1 B1 + w2 (B2 + c dt A2 B1)): force columns (9x12), joint columns only in the h_ang rows (3x18)
   if (lane < NX) {   // lane = column c: needs column c of A1 only, so A1r can be overwritten in place
@@ -257,12 +326,12 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
 #pragma unroll
     for (int q = 0; q < 9; ++q) a1[q] = sm.A1r[q * NX + c];
 #pragma unroll
-    for (int r = 0; r < 9; ++r) { const double* a2 = sm.pt.Ar + r * NX; double aa = 0.0;
+    for (int r = 0; r < 9; ++r) { const double* a2 = sm.Ar + r * NX; double aa = 0.0;
 #pragma unroll
       for (int q = 0; q < 9; ++q) aa = fma(a2[3 + q], a1[q], aa);
       out[r] = dt * (w1 * a1[r] + w2 * (a2[c] + cdt * aa));
-      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.pt.Bh[r * 12 + c]; } double ab = a2[c % 3] * imass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; sm.el.l.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
-      else if (r < 3) sm.el.l.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c]; }
+      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.Bh[r * 12 + c]; } double ab = a2[c % 3] * imass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; lt.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
+      else if (r < 3) lt.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c]; }
 #pragma unroll
     for (int r = 0; r < 9; ++r) sm.A1r[r * NX + c] = out[r];
   }
@@ -271,14 +340,14 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   // ---- projected dynamics: b~ = b + B_d Pe (lane = state row) ; rows 3:12 of A~ = A_d + B_d Px (the h_ang rows pick up the dependent joint velocities) ----
   double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
   if (lane < NX) {
-    const int r = lane; double bt = sm.el.l.bvec[r];
+    const int r = lane; double bt = lt.bvec[r];
     if (r >= 3 && r < 6) {       // + sum_legs BrdJ[r][joint] * Px_joint (accumulated in the shared-memory row, own thread)
       double* arow = sm.A1r + (r - 3) * NX; double acc[12];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const LegWs& L = sm.leg[i];
 #pragma unroll
         for (int c = 0; c < 12; ++c) acc[c] = 0.0;
-        for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double coef = sm.el.l.BrdJ[(r - 3) * NJ + L.first + j]; bt += coef * L.Pe[j];
+        for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double coef = lt.BrdJ[(r - 3) * NJ + L.first + j]; bt += coef * L.Pe[j];
 #pragma unroll
           for (int c = 0; c < 12; ++c) acc[c] = fma(coef, L.Px[j][c], acc[c]); }
 #pragma unroll
@@ -290,7 +359,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
       if (L.dep[j]) bt += dtw * L.Pe[j];
     }
     if (r < 3) for (int f = 0; f < 4; ++f) bt += (dtw * imass) * sm.Pe_full[3 * f + r];
-    if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += sm.el.l.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
+    if (r >= 3 && r < 12) for (int f = 0; f < 4; ++f) if (!sm.leg[f].stance) for (int a = 0; a < 3; ++a) bt += lt.BrdF[(r - 3) * 12 + 3 * f + a] * sm.Pe_full[3 * f + a];
     tl[T_b + r] = bt;
     if (r >= 3 && r < 12) sg[ST_AR + (r - 3) * LDX + NX] = bt;   // b~[3:12] also rides in column 30 of the dense A~ rows (K3's vector recursion)
   }
@@ -306,9 +375,9 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, 12 / LQ_WARPS) mpc_lq_kernel(co
   for (int e = lane; e < 9 * LDB; e += 32) {
     const int rr = e / LDB, a = e - rr * LDB; const int r = 3 + rr; double v = 0.0;
     if (a < m) { const int fa = sm.free_idx[a];
-      if (fa < 12) v = sm.el.l.BrdF[rr * 12 + fa];
-      else if (r < 6) { v = sm.el.l.BrdJ[rr * NJ + fa - 12];
-        if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += sm.el.l.BrdJ[rr * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
+      if (fa < 12) v = lt.BrdF[rr * 12 + fa];
+      else if (r < 6) { v = lt.BrdJ[rr * NJ + fa - 12];
+        if (fa < 24) { const LegWs& L = sm.leg[foot_of_leg_joint(lfp, fa - 12)]; if (!L.stance) { const int jf = (fa - 12) % 3; v += lt.BrdJ[rr * NJ + L.first + L.pivot] * L.Pu2[jf > L.pivot ? jf - 1 : jf]; } } }
     }
     sg[ST_BR + e] = v;
   }
@@ -718,8 +787,8 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
 
 // =====================================================================================================
 // K4: filter line search (one CTA per robot; warps stride over nodes) + trajectory update + input fix-up
-struct LsSmem { PointWs pt; CostWs cost; ConWs con; double xa[NX], ua[NU], xna[NX], f1[NX]; double ev[EMAX]; unsigned char modes[EMAX + 8]; };   // ev / modes: the robot's mode schedule (one copy per warp)
-
+// One THREAD per node (node_eval.cuh): the trial point's kinematics, flow maps, cost and constraint residuals are chains of scalar work with 3..9 useful lanes in
+// the warp-per-node form (7.2 ms at 8192 robots); here every lane carries a node, nothing lives in shared memory, and the per-robot sums are a block reduction.
 __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax, int n, int tid, int nthreads) {
   // toPrimalSolution [upstream]: input at a pre-event node repeats the previous one; last input repeated
   const int32_t* ge = sol.event + (size_t)b * nmax; double* gu = sol.u + (size_t)b * nmax * NU;
@@ -731,17 +800,15 @@ __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax
 #endif
 __global__ void __launch_bounds__(32 * LS_WARPS, QMB_LS_MINB) mpc_linesearch_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ dxo, const double* __restrict__ duo,
                                                                      const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int iteration) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double red[LS_WARPS][3]; __shared__ int decision;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x; if (b >= B) return;
+  __shared__ double red[LS_WARPS][3]; __shared__ int decision; __shared__ double s_ev[EMAX]; __shared__ unsigned char s_modes[EMAX + 8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const int b = b0 + blockIdx.x; if (b >= B) return;
   if (status[b] & MST_CONVERGED) return;
-  LsSmem& sm = reinterpret_cast<LsSmem*>(smem_raw)[warp];
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* gx = sol.x + (size_t)b * nmax * NX; double* gu = sol.u + (size_t)b * nmax * NU; const double* gdx = dxo + (size_t)b * nmax * NX; const double* gdu = duo + (size_t)b * nmax * NU;
-  const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
-  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
-  const int lfp = pack_leg_foot(mdl);
+  const int ne = clamp_events(p.n_events[b]); const double* ev = s_ev; const unsigned char* modes = s_modes;
+  if (tid < 32) { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); s_ev[lane] = (lane < ne) ? gev[lane] : 0.0; s_modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) s_modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
+  __syncthreads();
   const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
   const double* rb = robot + (size_t)b * ROBOT_DBL; const double armijo = rb[0], base_cost = rb[1], base_viol = sqrt(rb[2] + rb[3]), dxn = rb[4], dun = rb[5];
   const bool failed = (status[b] & MST_NOT_PD) != 0;
@@ -749,38 +816,34 @@ __global__ void __launch_bounds__(32 * LS_WARPS, QMB_LS_MINB) mpc_linesearch_ker
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2;
   while (!failed) {
     double cost = 0.0, dyn = 0.0, eq = 0.0;
-    for (int k = warp; k <= N; k += LS_WARPS) {
-      if (lane < NX) { sm.xa[lane] = gx[(size_t)k * NX + lane] + alpha * gdx[(size_t)k * NX + lane]; if (k < N) { sm.ua[lane] = gu[(size_t)k * NU + lane] + alpha * gdu[(size_t)k * NU + lane]; sm.xna[lane] = gx[(size_t)(k + 1) * NX + lane] + alpha * gdx[(size_t)(k + 1) * NX + lane]; } else sm.ua[lane] = 0.0; }
-      __syncwarp();
-      if (k == 0) { double d = (lane < NX) ? p.x0[(size_t)b * NX + lane] - sm.xa[lane] : 0.0; dyn += warp_sum(d * d); }
-      if (k < N && ge[k] == 1) { double d = (lane < NX) ? sm.xa[lane] - sm.xna[lane] : 0.0; dyn += warp_sum(d * d); __syncwarp(); continue; }
+    for (int k = tid; k <= N; k += 32 * LS_WARPS) {
+      double xa[NX], ua[NU]; const bool terminal = (k == N);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { xa[i] = gx[(size_t)k * NX + i] + alpha * gdx[(size_t)k * NX + i]; ua[i] = terminal ? 0.0 : gu[(size_t)k * NU + i] + alpha * gdu[(size_t)k * NU + i]; }
+      if (k == 0) { double s = 0.0; for (int i = 0; i < NX; ++i) { const double d = p.x0[(size_t)b * NX + i] - xa[i]; s = fma(d, d, s); } dyn += s; }
+      if (!terminal && ge[k] == 1) { double s = 0.0; for (int i = 0; i < NX; ++i) { const double d = xa[i] - (gx[(size_t)(k + 1) * NX + i] + alpha * gdx[(size_t)(k + 1) * NX + i]); s = fma(d, d, s); } dyn += s; continue; }
       const double t = interval_start(gt[k], ge[k]);
-      if (lane < NX) { sm.pt.x[lane] = sm.xa[lane]; sm.pt.u[lane] = sm.ua[lane]; }
-      __syncwarp();
-      const bool terminal = (k == N);
       const double dt = terminal ? 1.0 : interval_end(gt[k + 1], ge[k + 1]) - t; const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
-      bool done = false;
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {   // one inlined copy of the flow map for both RK2 stages (instruction-fetch footprint)
-        point_eval<false>(mdl, &sm.pt, lane, lfp, pass == 0 ? 6 : 3);
-        if (pass == 1) break;
-        TargetRef ref = target_reference(tt, ts, nk, t, lane);
-        cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, terminal, lane);
-        if (terminal) { done = true; break; }
-        foot_velocity<false>(mdl, &sm.pt, &sm.con, lane);
-        double es = 0.0;
-      if (lane < 4) { const int i = lane; if ((fm >> i) & 1) { for (int a = 0; a < 3; ++a) es += sm.con.e[i][a] * sm.con.e[i][a]; }
-        else { double zp, zv; swing_reference(mdl, ev, modes, ne, i, t, zp, zv); double ez = sm.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp); es += ez * ez; for (int a = 0; a < 3; ++a) es += sm.ua[3 * i + a] * sm.ua[3 * i + a]; } }
-      eq += dt * warp_sum(es);
-      if (lane < NX) { sm.f1[lane] = sm.pt.f[lane]; }
-      __syncwarp();
-      if (lane < NX) sm.pt.x[lane] = sm.xa[lane] + mdl->rk_c * dt * sm.f1[lane];
-      __syncwarp();
-      }
-      if (done) { __syncwarp(); continue; }
-      double d = (lane < NX) ? sm.xa[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) - sm.xna[lane] : 0.0; dyn += dt * warp_sum(d * d);
-      __syncwarp();
+      ne::BaseKin bk; ne::FlowRec fr; double Jl[4][9], pf[4][3];
+      ne::base_eval<false>(mdl, xa, bk); ne::flow_eval<false>(mdl, xa, ua, bk, fr, Jl, pf, nullptr);
+      { double xnom[NX], pref[3], qref[4], ee[6]; ne::target_reference_full(tt, ts, nk, t, xnom, pref, qref); ne::ee_eval<false>(mdl, xa, bk, pref, qref, ee, nullptr);
+        cost += dt * ne::cost_value(mdl, xa, ua, xnom, ee, fm, terminal); }
+      if (terminal) continue;
+      { double fe[4][3]; for (int i = 0; i < 4; ++i) ne::foot_velocity_1<false>(mdl, xa, ua, bk, i, fr.d[i], Jl[i], nullptr, fe[i], nullptr);
+        eq += dt * ne::equality_ss(mdl, ua, fe, pf, fm, ev, modes, ne, t, nullptr); }
+      double f1[12], x2[NX]; const double cdt = mdl->rk_c * dt;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { f1[i] = fr.f[i]; x2[i] = xa[i] + cdt * f1[i]; }
+#pragma unroll
+      for (int i = 12; i < NX; ++i) x2[i] = xa[i] + cdt * ua[i];
+      ne::base_eval<false>(mdl, x2, bk); ne::flow_eval<false>(mdl, x2, ua, bk, fr, nullptr, nullptr, nullptr);
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { const double fa = (i < 12) ? f1[i < 12 ? i : 0] : ua[i], fb = (i < 12) ? fr.f[i < 12 ? i : 0] : ua[i];   // rows 12:30 of the flow map are the joint-velocity inputs
+        const double d = xa[i] + dt * (w1 * fa + w2 * fb) - (gx[(size_t)(k + 1) * NX + i] + alpha * gdx[(size_t)(k + 1) * NX + i]); s = fma(d, d, s); }
+      dyn += dt * s;
     }
+    cost = warp_sum(cost); dyn = warp_sum(dyn); eq = warp_sum(eq);
     if (lane == 0) { red[warp][0] = cost; red[warp][1] = dyn; red[warp][2] = eq; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -950,7 +1013,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
   const size_t Bn = (size_t)B * nmax;
   bool ok = A(&m.t0, B) && A(&m.x0, (size_t)B * NX) && A(&m.n_events, B) && A(&m.event_times, (size_t)B * EMAX) && A(&m.modes, (size_t)B * (EMAX + 1)) && A(&m.n_target, B) && A(&m.target_times, (size_t)B * KMAX) && A(&m.target_states, (size_t)B * KMAX * TARGET_DIM);
   for (int s = 0; s < 2 && ok; ++s) ok = A(&m.sol[s].n_nodes, B) && A(&m.sol[s].t, Bn) && A(&m.sol[s].event, Bn) && A(&m.sol[s].x, Bn * NX) && A(&m.sol[s].u, Bn * NU);
-  ok = ok && A(&m.stage, Bn * STAGE_DBL) && A(&m.gains, Bn * GAIN_DBL) && A(&m.dx, Bn * NX) && A(&m.du, Bn * NU) && A(&m.robot, (size_t)B * ROBOT_DBL) && A(&m.status, B) && A(&m.step_info, (size_t)B * 4);
+  ok = ok && A(&m.stage, Bn * STAGE_DBL) && A(&m.gains, Bn * GAIN_DBL) && A(&m.dx, Bn * NX) && A(&m.du, Bn * NU) && A(&m.node_rec, Bn * ne::NODE_REC_DBL) && A(&m.robot, (size_t)B * ROBOT_DBL) && A(&m.status, B) && A(&m.step_info, (size_t)B * 4);
   return ok;
 }
 
@@ -958,7 +1021,6 @@ int mpc_configure_device() {
   cudaError_t e = cudaFuncSetAttribute(mpc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // 48 B per node and warp: opt-in beyond nmax ~ 250
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LsSmem) * LS_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RoSmem) * RO_WARPS));
   return (int)e;
 }
@@ -975,13 +1037,15 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
   // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
   for (int it = 0; it < iters; ++it) {
-    mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.status);
+    mpc_flow_kernel<<<(unsigned)((nodes + 32 * FL_WARPS - 1) / (32 * FL_WARPS)), 32 * FL_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.node_rec, m.status);
+    if (ev && it == iters - 1) cudaEventRecord(ev[7], stream);
+    mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.node_rec, m.stage, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);
     mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[3], stream);
     if (ddp) mpc_rollout_kernel<<<ro_grid, 32 * RO_WARPS, sizeof(RoSmem) * RO_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status, m.step_info, 1, it);   // rollout line search (m.dx / m.du hold the trial trajectories)
-    else mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, sizeof(LsSmem) * LS_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
-    launched += 3;
+    else mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
+    launched += 4;
   }
   if (ev) cudaEventRecord(ev[4], stream);
   return launched;

@@ -239,7 +239,9 @@ class Solver:
 
     def kernel_times(self):
         ms = np.zeros(6); self._chk(self.lib.qmb200_get_kernel_times(self.h, _p(ms)), "qmb200_get_kernel_times")
-        return dict(zip(("setup", "lq", "riccati", "linesearch", "policy_eval", "wbc"), ms.tolist()))
+        d = dict(zip(("setup", "lq", "riccati", "linesearch", "policy_eval", "wbc"), ms.tolist()))
+        v = C.c_double(); self._chk(self.lib.qmb200_get_flow_kernel_time(self.h, C.byref(v)), "qmb200_get_flow_kernel_time"); d["lq_flow"] = v.value   # part of "lq"
+        return d
 
     def measure_fp64_peak(self):
         v = C.c_double(); self._chk(self.lib.qmb200_measure_fp64_peak(self.h, C.byref(v)), "qmb200_measure_fp64_peak"); return v.value

@@ -5,7 +5,7 @@ out=gpurun_out/ab_$tag.jsonl; : > $out
 libs="$@"; [ -z "$libs" ] && libs=qm_control_b200/libqmb200.so
 for lib in $libs; do
   echo "{\"lib\": \"$lib\"}" >> $out
-  QMB200_LIB=$PWD/$lib timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e >> $out 2>> gpurun_out/ab_$tag.err
+  QMB200_LIB=$PWD/$lib timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-extras >> $out 2>> gpurun_out/ab_$tag.err
 done
 python - "$out" <<'PY'
 import json, sys
