@@ -139,16 +139,6 @@ __device__ __forceinline__ TargetRef target_reference(const double* tt, const do
 }
 
 // ---- cost --------------------------------------------------------------------------------------------
-// Quadratic model of the intermediate cost (unscaled by dt) in COMPACT form: the constant weights stay in DevModel (L1/L2 resident),
-// only what depends on (x,u) is stored:  Qf = Q + diag(qdiag) + scatter(E on the 12 end-effector columns),
-// Rf = R + diag(rdiag) + blockdiag(fric[foot]) on the 12 force inputs.
-struct QuadWs { double E[144], fric[36], qdiag[NX], rdiag[NU], qf[NX], rf[NU]; };
-__device__ __forceinline__ double quad_Q(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
-  double v = mdl->Q[i * NX + j]; if (i == j) v += q->qdiag[i]; const int a = ee_pos(i), b = ee_pos(j); if (a >= 0 && b >= 0) v += q->E[a * 12 + b]; return v; }
-__device__ __forceinline__ double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
-  if (i >= 24 || j >= 24) return (i == j) ? mdl->Rarm[i - 24] + q->rdiag[i] : 0.0;
-  const int bi = i / 3; if (bi != j / 3) return 0.0;
-  double v = mdl->Rblk[bi][(i - 3 * bi) * 3 + (j - 3 * bi)]; if (i == j) v += q->rdiag[i]; if (i < 12) v += q->fric[bi * 9 + (i - 3 * bi) * 3 + (j - 3 * bi)]; return v; }
 struct CostWs { double Je[6 * 12], e[6], quat[4], pee[3]; };
 
 // End-effector error e = [p_ee - p_ref; quaternionDistance(q_ee, q_ref)] and (optionally) its Jacobian columns.  ws must hold the kinematics at x.

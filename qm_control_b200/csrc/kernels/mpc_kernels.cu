@@ -16,7 +16,7 @@
 namespace qmb {
 
 #ifndef QMB_LQ_WARPS
-#define QMB_LQ_WARPS 6
+#define QMB_LQ_WARPS 7
 #endif
 #ifndef QMB_LQ_MINB
 #define QMB_LQ_MINB 2
@@ -104,18 +104,9 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mpc_setup_kernel(const DevMo
 // constraint of a foot touches 12 state columns (h, euler angles, own leg joints) and its own 3 joint-velocity inputs,
 // the input weight couples joint velocities only inside a leg.  The projection is therefore assembled per leg
 // (3x12 blocks) and written straight into the dense stage record the Riccati kernel consumes.
-struct LegWs {
-  double Px[3][12];     // rows of P_x of the dependent joint-velocity inputs of this leg on the support columns (stance: 3 rows; swing: pivot row only)
-  double U[3][12];      // R_leg * Px
-  double Rl[9];         // 3x3 input-weight block of the leg (incl. diagonal additions)
-  double Pe[3], rs[3];  // P_e of the dependent joints ; r + R P_e on the leg's joint inputs
-  double Pu2[2];        // swing: coupling of the pivot joint to the two free joints
-  int dep[3];           // is joint j of this leg dependent
-  int pivot, stance, first, free_col[3];   // projected-input column of each free joint (-1 if dependent)
-};
 struct LqLate { double BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX]; };                // produced by the RK2 combination, after the cost / projection blocks have consumed rec.foot and rec.ee
 struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp's slice starts 16-byte aligned
-  ne::NodeRec rec;                                                             // the node's record from the flow kernel (K2a); LqLate overlays rec.foot / rec.ee once they are dead
+  ne::NodeRec rec;                                                             // the node's record from the flow kernel (K2a); LqLate overlays rec.foot[] once the cost / projection / Jacobian expansion have consumed it
   QuadWs quad; LegWs leg[4];
   double x[NX], u[NU], xnext[NX];                                              // (x, u) of the node in the layout stage_cost reads (x then u), next node's state for the defect
   double A1r[9 * NX], Ar[9 * NX], B1h[36], Bh[36];                             // rows 3:12 of df/dx and rows 3:6, columns 0:12 of df/du at the two RK2 stages; A1r becomes A_d - I in place
@@ -123,7 +114,7 @@ struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp'
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
   double ev[EMAX]; unsigned char modes[EMAX + 8];   // the robot's mode schedule, staged once per node: the binary searches and the swing-interval scans then hit shared memory
 };
-static_assert(sizeof(LqLate) <= sizeof(ne::FootRec) + sizeof(ne::EeRec) && offsetof(ne::NodeRec, ee) == offsetof(ne::NodeRec, foot) + sizeof(ne::FootRec), "LqLate overlays rec.foot + rec.ee");
+static_assert(sizeof(LqLate) <= 4 * sizeof(ne::FootBlk) && offsetof(ne::NodeRec, foot) == 0, "LqLate overlays the foot blocks of the record");
 static_assert(sizeof(LqSmem) % 16 == 0 && offsetof(LqSmem, rec) == 0, "aligned record slice");
 static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep two CTAs per SM");
 
@@ -134,49 +125,68 @@ static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep t
 #ifndef QMB_FL_MINB
 #define QMB_FL_MINB 3
 #endif
-constexpr int FL_WARPS = 4;
+constexpr int FL_WARPS = 4, FL_TILE = 64;   // widest block of the record: a foot (63 doubles)
+constexpr int FL_SMEM = FL_WARPS * 32 * (FL_TILE + 1) * 8;
 __global__ void __launch_bounds__(32 * FL_WARPS, QMB_FL_MINB) mpc_flow_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, double* __restrict__ rec, const int32_t* __restrict__ status) {
-  __shared__ double tile[FL_WARPS][32][33];
+  // Each block of the record is produced straight into the lane's row of the warp's transposition tile (shared memory: the record never lives in thread-local
+  // memory - with 57 k resident threads a 4 KB stack frame is 230 MB, more than the L2) and leaves as one contiguous run per node and store instruction.
+  extern __shared__ __align__(16) unsigned char smem_raw[]; double (*tile)[32][FL_TILE + 1] = reinterpret_cast<double (*)[32][FL_TILE + 1]>(smem_raw);   // [FL_WARPS][32][FL_TILE + 1]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const long long gid = (long long)blockIdx.x * (32 * FL_WARPS) + tid;
   const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax);
   const int n = (b < B) ? sol.n_nodes[b] : 0;
   bool work = b < B && k < n && !(status[b] & MST_CONVERGED);
   const bool terminal = work && (k == n - 1);
   if (work && !terminal && sol.event[(size_t)b * nmax + k] == 1) work = false;   // event node: identity jump map, nothing to evaluate
-  ne::NodeRec r;
+  const unsigned active = __ballot_sync(FULL, work); if (!active) return;
+  double* row = &tile[warp][lane][0]; double* gbase = rec + ((size_t)b0 * nmax + (size_t)(gid - lane)) * ne::NODE_REC_DBL;   // node index = robot * nmax + k, as K2b reads it
+  auto flush = [&](int off, int cnt) {   // rows of the tile -> records: 32 (or 64) consecutive doubles of one node per store instruction
+    __syncwarp();
+#pragma unroll 4
+    for (int rw = 0; rw < 32; ++rw) if ((active >> rw) & 1u) { double* g = gbase + (size_t)rw * ne::NODE_REC_DBL + off; if (lane < cnt) g[lane] = tile[warp][rw][lane]; if (lane + 32 < cnt) g[lane + 32] = tile[warp][rw][lane + 32]; }
+    __syncwarp(); };
+  double x[NX], u[NU]; ne::BaseKin bk; ne::FlowAcc acc; double t = 0.0, dt = 0.0;
   if (work) {
     const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
     const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
-    double x[NX], u[NU];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { x[i] = xk[i]; u[i] = terminal ? 0.0 : uk[i]; }
-    const double t = interval_start(gt[k], ge[k]); const double dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
-    ne::BaseKin bk; double al[4][9];
-    ne::base_eval<true>(mdl, x, bk); ne::flow_eval<true>(mdl, x, u, bk, r.s1, r.foot.Jl, r.foot.pf, al);
-    if (!terminal) { for (int i = 0; i < 4; ++i) ne::foot_velocity_1<true>(mdl, x, u, bk, i, r.s1.d[i], r.foot.Jl[i], al[i], r.foot.e[i], r.foot.C[i]); }
-    { const int nk = clamp_targets(p.n_target[b]); double pref[3], qref[4]; ne::target_reference_full(p.target_times + (size_t)b * KMAX, p.target_states + (size_t)b * KMAX * TARGET_DIM, nk, t, nullptr, pref, qref);
-      ne::ee_eval<true>(mdl, x, bk, pref, qref, r.ee.e, r.ee.Je); }
-    if (!terminal) {   // second RK2 stage at x + c dt k1 (rows 12:30 of the flow map are the joint-velocity inputs)
-      const double cdt = mdl->rk_c * dt;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] += cdt * (i < 12 ? r.s1.f[i < 12 ? i : 0] : u[i]);
-      ne::base_eval<true>(mdl, x, bk); ne::flow_eval<true>(mdl, x, u, bk, r.s2, nullptr, nullptr, nullptr);
-    }
+    t = interval_start(gt[k], ge[k]); dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
+    ne::base_eval<true>(mdl, x, bk); ne::flow_acc_init(acc);
   }
-  // transposed write-out: 32 doubles of each lane's record per round through the warp's tile, then one 256-byte run per node and instruction
-  const unsigned active = __ballot_sync(FULL, work); if (!active) return;
-  const double* rr = reinterpret_cast<const double*>(&r); double* gbase = rec + ((size_t)b0 * nmax + (size_t)(gid - lane)) * ne::NODE_REC_DBL;   // node index = robot * nmax + k, as K2b reads it
-  for (int c0 = 0; c0 < ne::NODE_REC_DBL; c0 += 32) {
-    const int cnt = (ne::NODE_REC_DBL - c0 < 32) ? ne::NODE_REC_DBL - c0 : 32;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {   // foot blocks: kinematics of the leg, foot-velocity rows
+    if (work) { ne::FootBlk* fb = reinterpret_cast<ne::FootBlk*>(row); double al[9];
+      ne::foot_eval<true>(mdl, x, u, bk, i, acc, fb->d, fb->pf, fb->Jl, al, fb->JxF);
+      if (!terminal) ne::foot_velocity_1<true>(mdl, x, u, bk, i, fb->d, fb->Jl, al, fb->e, fb->C); }
+    flush(i * ne::FOOT_DBL, ne::FOOT_DBL);
+  }
+  double f1[12];
+  if (work) { ne::FlowBlk* fl = reinterpret_cast<ne::FlowBlk*>(row); ne::flow_finish<true>(mdl, x, bk, acc, fl->f, fl);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) f1[i] = fl->f[i]; }
+  flush(4 * ne::FOOT_DBL, ne::FLOW_DBL);
+  { ne::EeRec ee;   // end-effector error and its Jacobian: 78 doubles, two flushes
+    if (work) { const int nk = clamp_targets(p.n_target[b]); const ne::TargetSeg sg = ne::target_segment(p.target_times + (size_t)b * KMAX, p.target_states + (size_t)b * KMAX * TARGET_DIM, nk, t);
+      double pref[3], qref[4]; ne::target_pose(sg, nk, pref, qref); ne::ee_eval<true>(mdl, x, bk, pref, qref, ee.e, ee.Je);
+#pragma unroll
+      for (int j = 0; j < 39; ++j) row[j] = reinterpret_cast<const double*>(&ee)[j]; }
+    flush(4 * ne::FOOT_DBL + ne::FLOW_DBL, 39);
     if (work) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < cnt) tile[warp][lane][j] = rr[c0 + j]; }
-    __syncwarp();
-    if (lane < cnt) {
-#pragma unroll 8
-      for (int rw = 0; rw < 32; ++rw) if ((active >> rw) & 1u) gbase[(size_t)rw * ne::NODE_REC_DBL + c0 + lane] = tile[warp][rw][lane]; }
-    __syncwarp();
+      for (int j = 0; j < 39; ++j) row[j] = reinterpret_cast<const double*>(&ee)[39 + j]; }
+    flush(4 * ne::FOOT_DBL + ne::FLOW_DBL + 39, 39); }
+  const bool stage2 = work && !terminal;
+  if (stage2) {   // second RK2 stage at x + c dt k1 (rows 12:30 of the flow map are the joint-velocity inputs)
+    const double cdt = mdl->rk_c * dt;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] += cdt * (i < 12 ? f1[i < 12 ? i : 0] : u[i]);
+    ne::base_eval<true>(mdl, x, bk); ne::flow_acc_init(acc);
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) { ne::Foot2Blk* f2 = reinterpret_cast<ne::Foot2Blk*>(row) + i; ne::foot_eval<true>(mdl, x, u, bk, i, acc, f2->d, nullptr, nullptr, nullptr, f2->JxF); }
   }
+  flush(4 * ne::FOOT_DBL + ne::FLOW_DBL + ne::EE_DBL, 4 * ne::FOOT2_DBL);
+  if (stage2) { ne::FlowBlk* fl = reinterpret_cast<ne::FlowBlk*>(row); ne::flow_finish<true>(mdl, x, bk, acc, fl->f, fl); }
+  flush(4 * ne::FOOT_DBL + ne::FLOW_DBL + ne::EE_DBL + 4 * ne::FOOT2_DBL, ne::FLOW_DBL);
 }
 
 // =====================================================================================================
@@ -191,17 +201,17 @@ __global__ void __launch_bounds__(32 * FL_WARPS, QMB_FL_MINB) mpc_flow_kernel(co
 #define LQ_LOCKSTEP() do { if (QMB_LQ_LOCKSTEP && lockstep) __syncthreads(); } while (0)
 // rows 3:12 of df/dx (9 x 30, two thirds zeros) and the force block of rows 3:6 of df/du from the Jacobian blocks of a flow record: fill, then lane = column writes
 // its own non-zeros (the fill and the column writes are separated by a warp barrier)
-__device__ __forceinline__ void expand_flow(const ne::FlowRec& fr, double* Ar, double* Bh, double im, int lane) {
+__device__ __forceinline__ void expand_flow(const ne::FlowBlk& fb, const double* d0, const double* jxf0, int fstride /*doubles between two feet*/, double* Ar, double* Bh, double im, int lfp, int lane) {
   for (int e = lane; e < 9 * NX; e += 32) Ar[e] = 0.0;
-  for (int e = lane; e < 36; e += 32) { const int r = e / 12, c = e - 12 * r, i = c / 3, a = c - 3 * i; const double* d = fr.d[i];   // cross(d_i, e_a)[r] / m
+  for (int e = lane; e < 36; e += 32) { const int r = e / 12, c = e - 12 * r, i = c / 3, a = c - 3 * i; const double* d = d0 + i * fstride;   // cross(d_i, e_a)[r] / m
     Bh[e] = ((r == a) ? 0.0 : (((a - r + 3) % 3 == 1) ? -d[3 - r - a] : d[3 - r - a])) * im; }
   __syncwarp();
   if (lane < 24) {
     const int col = lane;
     if (col < 3) Ar[(3 + col) * NX + col] = 1.0;                                                         // d pdot / d h_lin = I
-    else if (col < 6) { for (int a = 0; a < 3; ++a) { Ar[(3 + a) * NX + col] = fr.Mpc[3 * a + col - 3]; Ar[(6 + a) * NX + col] = fr.Mtw[3 * a + col - 3]; } }   // d / d h_ang
-    else if (col >= 9 && col < 12) { for (int a = 0; a < 3; ++a) { Ar[a * NX + col] = fr.hth[col - 9][a]; Ar[(3 + a) * NX + col] = fr.vp[col - 9][a]; Ar[(6 + a) * NX + col] = fr.vt[col - 9][a]; } }   // d / d theta
-    else if (col >= 12) { for (int a = 0; a < 3; ++a) Ar[a * NX + col] = fr.JxF[col - 12][a]; }          // d hdot_ang / d q_leg = (J_j x F) / m
+    else if (col < 6) { for (int a = 0; a < 3; ++a) { Ar[(3 + a) * NX + col] = fb.Mpc[3 * a + col - 3]; Ar[(6 + a) * NX + col] = fb.Mtw[3 * a + col - 3]; } }   // d / d h_ang
+    else if (col >= 9 && col < 12) { for (int a = 0; a < 3; ++a) { Ar[a * NX + col] = fb.hth[col - 9][a]; Ar[(3 + a) * NX + col] = fb.vp[col - 9][a]; Ar[(6 + a) * NX + col] = fb.vt[col - 9][a]; } }   // d / d theta
+    else if (col >= 12) { const int j12 = col - 12; const double* jf = jxf0 + foot_of_leg_joint(lfp, j12) * fstride + 3 * (j12 % 3); for (int a = 0; a < 3; ++a) Ar[a * NX + col] = jf[a]; }   // d hdot_ang / d q_leg = (J_j x F) / m
   }
   __syncwarp();
 }
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   const bool lockstep = QMB_LQ_LOCKSTEP ? (__syncthreads_and(regular) != 0) : false;   // every thread of the CTA is still here: the early exits come after this point
   (void)lockstep; (void)regular;
   if (!work) return;
-  LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp]; LqLate& lt = *reinterpret_cast<LqLate*>(&sm.rec.foot);
+  LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp]; LqLate& lt = *reinterpret_cast<LqLate*>(&sm.rec.foot[0]);
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL;
   const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   }
   { // the node's record (K2a): one contiguous 3.9 KB run, 16 bytes per lane and load
     const double2* rg = reinterpret_cast<const double2*>(rec + ((size_t)b * nmax + k) * ne::NODE_REC_DBL); double2* rs = reinterpret_cast<double2*>(&sm.rec);
-    const int cnt2 = terminal ? (int)((offsetof(ne::NodeRec, s2) + 15) / 16) : ne::NODE_REC_DBL / 2;   // terminal node: no second stage
+    const int cnt2 = terminal ? (int)((offsetof(ne::NodeRec, foot2) + 15) / 16) : ne::NODE_REC_DBL / 2;   // terminal node: no second stage
     for (int e = lane; e < cnt2; e += 32) rs[e] = __ldg(rg + e);
     const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
   __syncwarp();
@@ -263,14 +273,14 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   bool swing_ok = true; int pivot = -1;
   if (lane < 4) {   // lane = foot (contact order); its leg's first joint = foot_leg
     const int i = lane; const int first = mdl->foot_leg[i]; LegWs& L = sm.leg[i]; L.first = first; L.stance = (fm >> i) & 1;
-    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.rec.foot.e[i][a] * sm.rec.foot.e[i][a]; }
+    if (L.stance) { for (int j = 0; j < 3; ++j) { sm.dep_idx[nd_before + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; for (int a = 0; a < 3; ++a) eq_ss += sm.rec.foot[i].e[a] * sm.rec.foot[i].e[a]; }
     else {
       double zp, zv; swing_ok = swing_reference(mdl, ev, modes, ne, i, t, zp, zv);
-      double ez = sm.rec.foot.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.rec.foot.pf[i][2] - zp);
-      sm.rec.foot.e[i][2] = ez;
+      double ez = sm.rec.foot[i].e[2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.rec.foot[i].pf[2] - zp);
+      sm.rec.foot[i].e[2] = ez;
       for (int a = 0; a < 3; ++a) { sm.dep_idx[nd_before + a] = 3 * i + a; eq_ss += sm.u[3 * i + a] * sm.u[3 * i + a]; }
       eq_ss += ez * ez;
-      double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.rec.foot.Jl[i][3 * j + 2]); if (a > best) { best = a; pivot = j; } }   // pivot: largest |d v_z / d qdot_j|
+      double best = -1.0; for (int j = 0; j < 3; ++j) { const double a = fabs(sm.rec.foot[i].Jl[3 * j + 2]); if (a > best) { best = a; pivot = j; } }   // pivot: largest |d v_z / d qdot_j|
       sm.dep_idx[nd_before + 3] = 12 + first + pivot; L.pivot = pivot; for (int j = 0; j < 3; ++j) L.dep[j] = (j == pivot);
     }
   }
@@ -289,15 +299,15 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
     for (int j = 0; j < 3; ++j) { L.free_col[j] = sm.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) { L.Px[j][c] = 0.0; L.U[j][c] = 0.0; } }
     L.Pu2[0] = L.Pu2[1] = 0.0;
     if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  →  dqd = -Jl^{-1} (C dx + e)
-      double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.rec.foot.Jl[i][3 * j + a]; inv3(Jm, Ji);
-      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.rec.foot.e[i][a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
-        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.rec.foot.C[i][a][c]; L.Px[j][c] = sv; } }
+      double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.rec.foot[i].Jl[3 * j + a]; inv3(Jm, Ji);
+      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * sm.rec.foot[i].e[a]; L.Pe[j] = pe; sm.Pe_full[12 + first + j] = pe;
+        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * sm.rec.foot[i].C[a][c]; L.Px[j][c] = sv; } }
     } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
       for (int a = 0; a < 3; ++a) sm.Pe_full[3 * i + a] = -sm.u[3 * i + a];
-      const double piv = sm.rec.foot.Jl[i][3 * pivot + 2], nip = -1.0 / piv;
-      L.Pe[pivot] = sm.rec.foot.e[i][2] * nip; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
-      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = sm.rec.foot.C[i][2][c] * nip;
-      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = sm.rec.foot.Jl[i][3 * j + 2] * nip;
+      const double piv = sm.rec.foot[i].Jl[3 * pivot + 2], nip = -1.0 / piv;
+      L.Pe[pivot] = sm.rec.foot[i].e[2] * nip; sm.Pe_full[12 + first + pivot] = L.Pe[pivot];
+      for (int c = 0; c < 12; ++c) L.Px[pivot][c] = sm.rec.foot[i].C[2][c] * nip;
+      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = sm.rec.foot[i].Jl[3 * j + 2] * nip;
     }
     // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
     for (int a = 0; a < 3; ++a) { double sv = sm.quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   LQ_LOCKSTEP();
   // continuous-time Jacobians of the two RK2 stages from the record's blocks
   const double imr = 1.0 / mdl->total_mass;
-  expand_flow(sm.rec.s1, sm.A1r, sm.B1h, imr, lane); expand_flow(sm.rec.s2, sm.Ar, sm.Bh, imr, lane);
+  expand_flow(sm.rec.s1, sm.rec.foot[0].d, sm.rec.foot[0].JxF, ne::FOOT_DBL, sm.A1r, sm.B1h, imr, lfp, lane); expand_flow(sm.rec.s2, sm.rec.foot2[0].d, sm.rec.foot2[0].JxF, ne::FOOT2_DBL, sm.Ar, sm.Bh, imr, lfp, lane);
   }
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2), imass = 1.0 / mass;
   double bb = 0.0; if (lane < NX) { const double fa = lane < 12 ? sm.rec.s1.f[lane < 12 ? lane : 0] : sm.u[lane], fb = lane < 12 ? sm.rec.s2.f[lane < 12 ? lane : 0] : sm.u[lane];   // rows 12:30 of the flow map: the joint-velocity inputs
@@ -824,23 +834,28 @@ __global__ void __launch_bounds__(32 * LS_WARPS, QMB_LS_MINB) mpc_linesearch_ker
       if (!terminal && ge[k] == 1) { double s = 0.0; for (int i = 0; i < NX; ++i) { const double d = xa[i] - (gx[(size_t)(k + 1) * NX + i] + alpha * gdx[(size_t)(k + 1) * NX + i]); s = fma(d, d, s); } dyn += s; continue; }
       const double t = interval_start(gt[k], ge[k]);
       const double dt = terminal ? 1.0 : interval_end(gt[k + 1], ge[k + 1]) - t; const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
-      ne::BaseKin bk; ne::FlowRec fr; double Jl[4][9], pf[4][3];
-      ne::base_eval<false>(mdl, xa, bk); ne::flow_eval<false>(mdl, xa, ua, bk, fr, Jl, pf, nullptr);
-      { double xnom[NX], pref[3], qref[4], ee[6]; ne::target_reference_full(tt, ts, nk, t, xnom, pref, qref); ne::ee_eval<false>(mdl, xa, bk, pref, qref, ee, nullptr);
-        cost += dt * ne::cost_value(mdl, xa, ua, xnom, ee, fm, terminal); }
+      ne::BaseKin bk; ne::FlowAcc acc; double f1[12];
+      ne::base_eval<false>(mdl, xa, bk); ne::flow_acc_init(acc);
+      { double fe[4][3], pf[4][3];
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) { double d[3], Jl[9]; ne::foot_eval<false>(mdl, xa, ua, bk, i, acc, d, pf[i], Jl, nullptr, nullptr); if (!terminal) ne::foot_velocity_1<false>(mdl, xa, ua, bk, i, d, Jl, nullptr, fe[i], nullptr); }
+        if (!terminal) eq += dt * ne::equality_ss(mdl, ua, fe, pf, fm, ev, modes, ne, t, nullptr); }
+      ne::flow_finish<false>(mdl, xa, bk, acc, f1, nullptr);
+      { const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4], ee[6]; ne::target_pose(sg, nk, pref, qref); ne::ee_eval<false>(mdl, xa, bk, pref, qref, ee, nullptr);
+        cost += dt * ne::cost_value(mdl, xa, ua, sg, ee, fm, terminal); }
       if (terminal) continue;
-      { double fe[4][3]; for (int i = 0; i < 4; ++i) ne::foot_velocity_1<false>(mdl, xa, ua, bk, i, fr.d[i], Jl[i], nullptr, fe[i], nullptr);
-        eq += dt * ne::equality_ss(mdl, ua, fe, pf, fm, ev, modes, ne, t, nullptr); }
-      double f1[12], x2[NX]; const double cdt = mdl->rk_c * dt;
+      const double cdt = mdl->rk_c * dt;   // second stage in place (the trial state is re-read from L2 for the defect)
 #pragma unroll
-      for (int i = 0; i < 12; ++i) { f1[i] = fr.f[i]; x2[i] = xa[i] + cdt * f1[i]; }
-#pragma unroll
-      for (int i = 12; i < NX; ++i) x2[i] = xa[i] + cdt * ua[i];
-      ne::base_eval<false>(mdl, x2, bk); ne::flow_eval<false>(mdl, x2, ua, bk, fr, nullptr, nullptr, nullptr);
+      for (int i = 0; i < NX; ++i) xa[i] += cdt * (i < 12 ? f1[i < 12 ? i : 0] : ua[i]);
+      double f2[12]; ne::base_eval<false>(mdl, xa, bk); ne::flow_acc_init(acc);
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) { double d[3]; ne::foot_eval<false>(mdl, xa, ua, bk, i, acc, d, nullptr, nullptr, nullptr, nullptr); }
+      ne::flow_finish<false>(mdl, xa, bk, acc, f2, nullptr);
       double s = 0.0;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { const double fa = (i < 12) ? f1[i < 12 ? i : 0] : ua[i], fb = (i < 12) ? fr.f[i < 12 ? i : 0] : ua[i];   // rows 12:30 of the flow map are the joint-velocity inputs
-        const double d = xa[i] + dt * (w1 * fa + w2 * fb) - (gx[(size_t)(k + 1) * NX + i] + alpha * gdx[(size_t)(k + 1) * NX + i]); s = fma(d, d, s); }
+      for (int i = 0; i < NX; ++i) { const double fa = (i < 12) ? f1[i < 12 ? i : 0] : ua[i], fb = (i < 12) ? f2[i < 12 ? i : 0] : ua[i];   // rows 12:30 of the flow map are the joint-velocity inputs
+        const double x0i = gx[(size_t)k * NX + i] + alpha * gdx[(size_t)k * NX + i];
+        const double d = x0i + dt * (w1 * fa + w2 * fb) - (gx[(size_t)(k + 1) * NX + i] + alpha * gdx[(size_t)(k + 1) * NX + i]); s = fma(d, d, s); }
       dyn += dt * s;
     }
     cost = warp_sum(cost); dyn = warp_sum(dyn); eq = warp_sum(eq);
@@ -1019,6 +1034,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
 
 int mpc_configure_device() {
   cudaError_t e = cudaFuncSetAttribute(mpc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // 48 B per node and warp: opt-in beyond nmax ~ 250
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RoSmem) * RO_WARPS));
@@ -1037,7 +1053,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
   // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
   for (int it = 0; it < iters; ++it) {
-    mpc_flow_kernel<<<(unsigned)((nodes + 32 * FL_WARPS - 1) / (32 * FL_WARPS)), 32 * FL_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.node_rec, m.status);
+    mpc_flow_kernel<<<(unsigned)((nodes + 32 * FL_WARPS - 1) / (32 * FL_WARPS)), 32 * FL_WARPS, FL_SMEM, stream>>>(mdl, b0, b1, nmax, p, next, m.node_rec, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[7], stream);
     mpc_lq_kernel<<<(unsigned)((nodes + LQ_WARPS - 1) / LQ_WARPS), 32 * LQ_WARPS, sizeof(LqSmem) * LQ_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.node_rec, m.stage, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);

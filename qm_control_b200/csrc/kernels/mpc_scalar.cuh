@@ -50,4 +50,26 @@ QMB_HD int ee_col(int i) { return i < 6 ? 6 + i : 18 + i; }   // 12 state column
 // state column of support position `pos` (0..11) for the leg whose first joint is `first`
 QMB_HD int sup_col(int pos, int first) { return pos < 6 ? pos : (pos < 9 ? pos + 3 : 12 + first + pos - 9); }
 
+// Quadratic model of the intermediate cost (unscaled by dt) in COMPACT form: the constant weights stay in DevModel (L1/L2 resident),
+// only what depends on (x,u) is stored:  Qf = Q + diag(qdiag) + scatter(E on the 12 end-effector columns),
+// Rf = R + diag(rdiag) + blockdiag(fric[foot]) on the 12 force inputs.
+struct QuadWs { double E[144], fric[36], qdiag[NX], rdiag[NU], qf[NX], rf[NU]; };
+QMB_HD double quad_Q(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
+  double v = mdl->Q[i * NX + j]; if (i == j) v += q->qdiag[i]; const int a = ee_pos(i), b = ee_pos(j); if (a >= 0 && b >= 0) v += q->E[a * 12 + b]; return v; }
+QMB_HD double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
+  if (i >= 24 || j >= 24) return (i == j) ? mdl->Rarm[i - 24] + q->rdiag[i] : 0.0;
+  const int bi = i / 3; if (bi != j / 3) return 0.0;
+  double v = mdl->Rblk[bi][(i - 3 * bi) * 3 + (j - 3 * bi)]; if (i == j) v += q->rdiag[i]; if (i < 12) v += q->fric[bi * 9 + (i - 3 * bi) * 3 + (j - 3 * bi)]; return v; }
+// per-leg blocks of the structured projection (K2): the velocity constraint of a foot touches 12 state columns (h, euler angles, own leg joints) and its own 3
+// joint-velocity inputs, the input weight couples joint velocities only inside a leg
+struct LegWs {
+  double Px[3][12];     // rows of P_x of the dependent joint-velocity inputs of this leg on the support columns (stance: 3 rows; swing: pivot row only)
+  double U[3][12];      // R_leg * Px
+  double Rl[9];         // 3x3 input-weight block of the leg (incl. diagonal additions)
+  double Pe[3], rs[3];  // P_e of the dependent joints ; r + R P_e on the leg's joint inputs
+  double Pu2[2];        // swing: coupling of the pivot joint to the two free joints
+  int dep[3];           // is joint j of this leg dependent
+  int pivot, stance, first, free_col[3];   // projected-input column of each free joint (-1 if dependent)
+};
+
 }  // namespace qmb

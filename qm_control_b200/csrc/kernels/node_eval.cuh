@@ -15,27 +15,25 @@
 namespace qmb {
 namespace ne {
 
-// Jacobian blocks of the flow map: rows 3:12 of df/dx are [d hdot_ang; d pdot; d thetadot] and only these blocks are non-trivial (mpc_device.cuh point_eval)
-struct FlowRec {
-  double f[12];        // rows 0:12 of the flow map (rows 12:30 are the joint-velocity inputs)
-  double d[4][3];      // foot - com (the force columns of df/du are cross(d_i, e_a) / m)
-  double Mpc[9], Mtw[9];             // d pdot / d h_ang ; d thetadot / d h_ang
+// ---- the record K2a hands to K2b per node, in the order the flow kernel produces it (one flush of its transposition tile per block) ----
+struct FootBlk { double d[3], pf[3], Jl[9], JxF[9], e[3], C[3][12]; };   // foot - com, foot position, leg Jacobian Jl[3 * j + a], (J_j x F_i) / m, foot velocity residual and its rows on the 12 support columns
+struct FlowBlk {                      // rows 3:12 of df/dx are [d hdot_ang; d pdot; d thetadot] and only these blocks (+ the feet's JxF, d) are non-trivial (mpc_device.cuh point_eval)
+  double f[12];                       // rows 0:12 of the flow map (rows 12:30 are the joint-velocity inputs)
+  double Mpc[9], Mtw[9];              // d pdot / d h_ang ; d thetadot / d h_ang
   double hth[3][3], vp[3][3], vt[3][3];   // columns theta_k of hdot_ang, pdot, thetadot  ([k][a])
-  double JxF[12][3];   // d hdot_ang / d q_leg, joint order: (J_j x F_i) / m
 };
-constexpr int FLOW_DBL = 12 + 12 + 18 + 27 + 36;   // 105
-static_assert(sizeof(FlowRec) == FLOW_DBL * 8, "FlowRec is a flat array of doubles");
-
-// what the constraint / cost side needs from the kinematics at the node's (x, u)
-struct FootRec { double Jl[4][9]; double pf[4][3]; double C[4][3][12]; double e[4][3]; };   // Jl[i][3 * j + a]; C / e as ConWs of mpc_device.cuh
 struct EeRec { double Je[6 * 12]; double e[6]; };
-// the record K2a hands to K2b per node
-struct NodeRec { FlowRec s1; FootRec foot; EeRec ee; FlowRec s2; };
-constexpr int NODE_REC_DBL = (int)(sizeof(NodeRec) / 8);
+struct Foot2Blk { double d[3], JxF[9]; };                                // second RK2 stage: what the flow Jacobian needs from a foot
+struct NodeRec { FootBlk foot[4]; FlowBlk s1; EeRec ee; Foot2Blk foot2[4]; FlowBlk s2; };
+constexpr int FOOT_DBL = 63, FLOW_DBL = 57, EE_DBL = 78, FOOT2_DBL = 12;
+constexpr int NODE_REC_DBL = 4 * FOOT_DBL + FLOW_DBL + EE_DBL + 4 * FOOT2_DBL + FLOW_DBL;   // 492
+static_assert(sizeof(FootBlk) == FOOT_DBL * 8 && sizeof(FlowBlk) == FLOW_DBL * 8 && sizeof(EeRec) == EE_DBL * 8 && sizeof(Foot2Blk) == FOOT2_DBL * 8 && sizeof(NodeRec) == NODE_REC_DBL * 8, "the record is a flat array of doubles");
 static_assert(sizeof(NodeRec) % 16 == 0, "records stay 16-byte aligned");
 
 // base-frame quantities shared by the pieces below
 struct BaseKin { double tr[6], R0[9], T[9], Tinv[9], W[9], c[3], rcom[3], omega[3], thd[3], dom[3][3]; };
+// sums over the feet that the flow map needs
+struct FlowAcc { double fsum[3], hang[3], hth[3][3]; };
 
 // one serial chain from the base: joints first .. first + NJC - 1; returns the last body's frame, every joint's origin and axis (world)
 template <int NJC>
@@ -85,30 +83,32 @@ QMB_HD void base_eval(const DevModel* __restrict__ mdl, const double* x, BaseKin
       cross3(Tk, bk.omega, t1); cross3(Tk, ha, t2); matvec3(bk.W, t2, t3); for (int a = 0; a < 3; ++a) bk.dom[k][a] = t1[a] - t3[a]; } }   // d omega / d theta_k
 }
 
-// Flow map at (x, u) (+ Jacobian blocks); also returns the leg Jacobians / foot positions for the constraint rows when `foot` is given.
-// Leg Jacobian columns al (joint axes) are returned through `al` when non-null (foot-velocity Jacobian).
+QMB_HD void flow_acc_init(FlowAcc& acc) { for (int a = 0; a < 3; ++a) { acc.fsum[a] = 0.0; acc.hang[a] = 0.0; for (int k = 0; k < 3; ++k) acc.hth[k][a] = 0.0; } }
+
+// One foot (contact order i; its leg's joints foot_leg[i] .. + 2): chain kinematics, foot - com, leg Jacobian columns Jl[3 * j + a] (+ joint axes al, same layout),
+// the foot's share of the flow map (accumulated in acc) and, with JAC, (J_j x F_i) / m.  Jl / al / pf / JxF may be null.
 template <bool JAC>
-QMB_HD void flow_eval(const DevModel* __restrict__ mdl, const double* x, const double* u, const BaseKin& bk, FlowRec& fr, double (*Jl)[9], double (*pf)[3], double (*al)[9]) {
-  const double m = mdl->total_mass, im = 1.0 / m; const double* ha = x + 3; const double* om = bk.omega; const double* c = bk.c;
-  double hang[3] = {0, 0, 0}, fsum[3] = {0, 0, 0};
-  if (JAC) for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) fr.hth[k][a] = 0.0;
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {   // foot i (contact order); its leg's joints first .. first + 2
-    const int first = mdl->foot_leg[i]; double Rl[9], pl[3], org[3][3], axs[3][3];
-    chain_fk<3>(mdl, bk.R0, x + 6, x + 12, first, Rl, pl, org, axs);
-    double pw[3]; matvec3(Rl, mdl->foot_p[i], pw); double d[3];
-    for (int a = 0; a < 3; ++a) { pw[a] += pl[a]; d[a] = pw[a] - bk.rcom[a]; fr.d[i][a] = d[a]; if (pf) pf[i][a] = pw[a]; }
-    const double* F = u + 3 * i;
-    for (int a = 0; a < 3; ++a) fsum[a] += F[a];
-    cross3_add(d, F, hang);
-    for (int j = 0; j < 3; ++j) { const double r[3] = {pw[0] - org[j][0], pw[1] - org[j][1], pw[2] - org[j][2]}; double col[3]; cross3(axs[j], r, col);
-      if (Jl) for (int a = 0; a < 3; ++a) Jl[i][3 * j + a] = col[a];
-      if (al) for (int a = 0; a < 3; ++a) al[i][3 * j + a] = axs[j][a];
-      if (JAC) { double jf[3]; cross3(col, F, jf); for (int a = 0; a < 3; ++a) fr.JxF[first + j][a] = jf[a] * im; } }
-    if (JAC) for (int k = 0; k < 3; ++k) { const double Tk[3] = {bk.T[k], bk.T[3 + k], bk.T[6 + k]}; double t[3]; cross3(Tk, d, t); cross3_add(t, F, fr.hth[k]); }
-  }
-  for (int a = 0; a < 3; ++a) { fr.f[a] = fsum[a] * im + (a == 2 ? -9.81 : 0.0); fr.f[3 + a] = hang[a] * im; fr.f[9 + a] = bk.thd[a]; }
-  { double oc[3]; cross3(om, c, oc); for (int a = 0; a < 3; ++a) fr.f[6 + a] = x[a] + oc[a]; }
+QMB_HD void foot_eval(const DevModel* __restrict__ mdl, const double* x, const double* u, const BaseKin& bk, int i, FlowAcc& acc, double* d, double* pf, double* Jl, double* al, double* JxF) {
+  const int first = mdl->foot_leg[i]; double Rl[9], pl[3], org[3][3], axs[3][3];
+  chain_fk<3>(mdl, bk.R0, x + 6, x + 12, first, Rl, pl, org, axs);
+  double pw[3]; matvec3(Rl, mdl->foot_p[i], pw);
+  for (int a = 0; a < 3; ++a) { pw[a] += pl[a]; d[a] = pw[a] - bk.rcom[a]; if (pf) pf[a] = pw[a]; }
+  const double* F = u + 3 * i; const double im = 1.0 / mdl->total_mass;
+  for (int a = 0; a < 3; ++a) acc.fsum[a] += F[a];
+  cross3_add(d, F, acc.hang);
+  for (int j = 0; j < 3; ++j) { const double r[3] = {pw[0] - org[j][0], pw[1] - org[j][1], pw[2] - org[j][2]}; double col[3]; cross3(axs[j], r, col);
+    if (Jl) for (int a = 0; a < 3; ++a) Jl[3 * j + a] = col[a];
+    if (al) for (int a = 0; a < 3; ++a) al[3 * j + a] = axs[j][a];
+    if (JAC) { double jf[3]; cross3(col, F, jf); for (int a = 0; a < 3; ++a) JxF[3 * j + a] = jf[a] * im; } }
+  if (JAC) for (int k = 0; k < 3; ++k) { const double Tk[3] = {bk.T[k], bk.T[3 + k], bk.T[6 + k]}; double t[3]; cross3(Tk, d, t); cross3_add(t, F, acc.hth[k]); }
+}
+
+// rows 0:12 of the flow map from the accumulated foot terms (+ the base-frame Jacobian blocks)
+template <bool JAC>
+QMB_HD void flow_finish(const DevModel* __restrict__ mdl, const double* x, const BaseKin& bk, const FlowAcc& acc, double* f, FlowBlk* fb) {
+  const double im = 1.0 / mdl->total_mass; const double* om = bk.omega; const double* c = bk.c;
+  for (int a = 0; a < 3; ++a) { f[a] = acc.fsum[a] * im + (a == 2 ? -9.81 : 0.0); f[3 + a] = acc.hang[a] * im; f[9 + a] = bk.thd[a]; }
+  { double oc[3]; cross3(om, c, oc); for (int a = 0; a < 3; ++a) f[6 + a] = x[a] + oc[a]; }
   if (JAC) {
     const double* tr = bk.tr; const double sz = tr[0], cz = tr[1], sy = tr[2], cy = tr[3]; const double th1 = bk.thd[1], th2 = bk.thd[2];
     for (int k = 0; k < 3; ++k) {
@@ -118,16 +118,15 @@ QMB_HD void flow_eval(const DevModel* __restrict__ mdl, const double* x, const d
       else { dT[0] = 0.0; dT[1] = 0.0; dT[2] = 0.0; }
       const double Tk[3] = {bk.T[k], bk.T[3 + k], bk.T[6 + k]}; const double* domk = bk.dom[k];
       double tc[3], vpk[3]; cross3(Tk, c, tc); cross3(domk, c, vpk); cross3_add(om, tc, vpk);           // d(omega x c)/d theta_k
-      for (int a = 0; a < 3; ++a) { fr.vp[k][a] = vpk[a]; fr.hth[k][a] *= im; }
-      const double tmp[3] = {domk[0] - dT[0], domk[1] - dT[1], domk[2] - dT[2]}; matvec3(bk.Tinv, tmp, fr.vt[k]);
+      for (int a = 0; a < 3; ++a) { fb->vp[k][a] = vpk[a]; fb->hth[k][a] = acc.hth[k][a] * im; }
+      const double tmp[3] = {domk[0] - dT[0], domk[1] - dT[1], domk[2] - dT[2]}; matvec3(bk.Tinv, tmp, fb->vt[k]);
     }
     const double* W = bk.W;
     for (int i = 0; i < 3; ++i) for (int jj = 0; jj < 3; ++jj) {   // Mpc = -S(c) W ; Mtw = Tinv W
       const double s0 = (i == 0) ? 0.0 : (i == 1 ? c[2] : -c[1]), s1 = (i == 0) ? -c[2] : (i == 1 ? 0.0 : c[0]), s2 = (i == 0) ? c[1] : (i == 1 ? -c[0] : 0.0);
-      fr.Mpc[3 * i + jj] = -(s0 * W[jj] + s1 * W[3 + jj] + s2 * W[6 + jj]);
-      fr.Mtw[3 * i + jj] = bk.Tinv[3 * i] * W[jj] + bk.Tinv[3 * i + 1] * W[3 + jj] + bk.Tinv[3 * i + 2] * W[6 + jj]; }
+      fb->Mpc[3 * i + jj] = -(s0 * W[jj] + s1 * W[3 + jj] + s2 * W[6 + jj]);
+      fb->Mtw[3 * i + jj] = bk.Tinv[3 * i] * W[jj] + bk.Tinv[3 * i + 1] * W[3 + jj] + bk.Tinv[3 * i + 2] * W[6 + jj]; }
   }
-  (void)ha;
 }
 
 // foot velocity v_i = h_lin + omega x d_i + sum_j Jl_j qd_j (+ its state Jacobian on the 12 support columns), foot_velocity<> of mpc_device.cuh for one foot
@@ -151,18 +150,21 @@ QMB_HD void foot_velocity_1(const DevModel* __restrict__ mdl, const double* x, c
   }
 }
 
-// Target trajectory references at time t (target_reference of mpc_device.cuh, all 30 state references at once)
-QMB_HD void target_reference_full(const double* tt, const double* ts /*[K][37]*/, int nk, double t, double* xnom, double* pref, double* qref) {
-  int idx; double a; time_segment(tt, nk, t, idx, a);
-  const double* l = ts + (size_t)idx * 37; const double* rr = ts + (size_t)((nk > 1) ? idx + 1 : idx) * 37;
-  if (nk <= 1) a = 1.0;
-  if (xnom) for (int i = 0; i < NX; ++i) xnom[i] = a * l[i] + (1.0 - a) * rr[i];
+// Target trajectory references at time t (target_reference of mpc_device.cuh): the two knots and the interpolation weight of the state reference
+// (xnom_i = a * l[i] + (1 - a) * rr[i]) and the end-effector pose reference (EndEffectorConstraint::interpolateEndEffectorPose, Eigen slerp semantics)
+struct TargetSeg { const double* l; const double* rr; double a; };
+QMB_HD TargetSeg target_segment(const double* tt, const double* ts /*[K][37]*/, int nk, double t) {
+  int idx; double a; time_segment(tt, nk, t, idx, a); TargetSeg sg; sg.l = ts + (size_t)idx * 37; sg.rr = ts + (size_t)((nk > 1) ? idx + 1 : idx) * 37; sg.a = (nk <= 1) ? 1.0 : a; return sg;
+}
+QMB_HD void target_pose(const TargetSeg& sg, int nk, double* pref, double* qref) {
+  const double* l = sg.l; const double* rr = sg.rr; const double a = sg.a;
   for (int i = 0; i < 3; ++i) pref[i] = a * l[30 + i] + (1.0 - a) * rr[30 + i];
   if (nk > 1) {
     const double* ql = l + 33; const double* qr = rr + 33; const double tq = 1.0 - a; double d = 0.0; for (int i = 0; i < 4; ++i) d += ql[i] * qr[i];
     const double ad = fabs(d); double s0, s1;
     if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - tq; s1 = tq; } else { const double th = acos(ad), st = sin(th); const double ist = 1.0 / st; s0 = sin((1.0 - tq) * th) * ist; s1 = sin(tq * th) * ist; }
-    if (d < 0.0) s1 = -s1; for (int i = 0; i < 4; ++i) qref[i] = s0 * ql[i] + s1 * qr[i];
+    if (d < 0.0) s1 = -s1;
+    for (int i = 0; i < 4; ++i) qref[i] = s0 * ql[i] + s1 * qr[i];
   } else { for (int i = 0; i < 4; ++i) qref[i] = l[33 + i]; }
 }
 
@@ -194,12 +196,12 @@ QMB_HD void ee_eval(const DevModel* __restrict__ mdl, const double* x, const Bas
 }
 
 // Intermediate (or terminal) cost VALUE at (x, u) given the end-effector error (stage_cost<false> of mpc_device.cuh; unscaled by dt)
-QMB_HD double cost_value(const DevModel* __restrict__ mdl, const double* x, const double* u, const double* xnom, const double* ee, int flagmask, bool terminal) {
+QMB_HD double cost_value(const DevModel* __restrict__ mdl, const double* x, const double* u, const TargetSeg& sg, const double* ee, int flagmask, bool terminal) {
   double value = 0.0;
   if (!terminal) {
     int nst = 0; for (int i = 0; i < 4; ++i) nst += (flagmask >> i) & 1;
     double dx[NX], du[NU];
-    for (int i = 0; i < NX; ++i) { dx[i] = x[i] - xnom[i]; double un = 0.0; if (i < 12 && (i % 3) == 2 && ((flagmask >> (i / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du[i] = u[i] - un; }
+    for (int i = 0; i < NX; ++i) { dx[i] = x[i] - (sg.a * sg.l[i] + (1.0 - sg.a) * sg.rr[i]); double un = 0.0; if (i < 12 && (i % 3) == 2 && ((flagmask >> (i / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du[i] = u[i] - un; }
     double acc = 0.0;
     if (mdl->q_is_diag) { for (int i = 0; i < NX; ++i) acc = fma(dx[i] * mdl->Qdiag[i], dx[i], acc); }
     else { for (int i = 0; i < NX; ++i) { double qd = 0.0; for (int j = 0; j < NX; ++j) qd = fma(mdl->Q[i * NX + j], dx[j], qd); acc = fma(dx[i], qd, acc); } }
@@ -223,6 +225,100 @@ QMB_HD double cost_value(const DevModel* __restrict__ mdl, const double* x, cons
     value += bv;
   }
   return value;
+}
+
+// Quadratic model of the intermediate (or terminal) cost at (x, u) in the compact form of QuadWs (NOT scaled by dt) and the cost value: stage_cost<true> of
+// mpc_device.cuh for one thread.  ee / Je: end-effector error and its Jacobian on the 12 columns p, theta, arm (ee_eval).
+QMB_HD double cost_quad(const DevModel* __restrict__ mdl, const double* x, const double* u, const TargetSeg& sg, const double* ee, const double* Je, int flagmask, bool terminal, QuadWs& q) {
+  double value = 0.0;
+  for (int e = 0; e < 36; ++e) q.fric[e] = 0.0;
+  for (int i = 0; i < NX; ++i) { q.qdiag[i] = 0.0; q.rdiag[i] = 0.0; q.qf[i] = 0.0; q.rf[i] = 0.0; }
+  if (!terminal) {   // tracking cost: 1/2 dx'Q dx + 1/2 du'R du, u_nom = weightCompensatingInput(contact flags)
+    int nst = 0; for (int i = 0; i < 4; ++i) nst += (flagmask >> i) & 1;
+    double dx[NX], du[NU], acc = 0.0;
+    for (int i = 0; i < NX; ++i) { dx[i] = x[i] - (sg.a * sg.l[i] + (1.0 - sg.a) * sg.rr[i]); double un = 0.0; if (i < 12 && (i % 3) == 2 && ((flagmask >> (i / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du[i] = u[i] - un; }
+    if (mdl->q_is_diag) { for (int i = 0; i < NX; ++i) { const double qd = mdl->Qdiag[i] * dx[i]; q.qf[i] = qd; acc = fma(dx[i], qd, acc); } }
+    else { for (int i = 0; i < NX; ++i) { double qd = 0.0; for (int j = 0; j < NX; ++j) qd = fma(mdl->Q[i * NX + j], dx[j], qd); q.qf[i] = qd; acc = fma(dx[i], qd, acc); } }
+    for (int blk = 0; blk < 8; ++blk) { const double* Rb = mdl->Rblk[blk]; const double* d3 = du + 3 * blk;
+      for (int r = 0; r < 3; ++r) { const double rd = fma(Rb[3 * r], d3[0], fma(Rb[3 * r + 1], d3[1], Rb[3 * r + 2] * d3[2])); q.rf[3 * blk + r] = rd; acc = fma(d3[r], rd, acc); } }
+    for (int i = 0; i < 6; ++i) { const double rd = mdl->Rarm[i] * du[24 + i]; q.rf[24 + i] = rd; acc = fma(du[24 + i], rd, acc); }
+    value += 0.5 * acc;
+  }
+  { // end-effector soft constraint (quadratic penalty, Gauss-Newton)
+    const double mup = terminal ? mdl->mu_final_ee_pos : mdl->mu_ee_pos, muo = terminal ? mdl->mu_final_ee_ori : mdl->mu_ee_ori;
+    double v = 0.0; for (int r = 0; r < 6; ++r) v += 0.5 * (r < 3 ? mup : muo) * ee[r] * ee[r]; value += v;
+    for (int i = 0; i < 12; ++i) { for (int j = 0; j <= i; ++j) { double sv = 0.0; for (int r = 0; r < 6; ++r) sv += (r < 3 ? mup : muo) * Je[r * 12 + i] * Je[r * 12 + j]; q.E[i * 12 + j] = sv; q.E[j * 12 + i] = sv; }
+      double sv = 0.0; for (int r = 0; r < 6; ++r) sv += (r < 3 ? mup : muo) * ee[r] * Je[r * 12 + i]; q.qf[ee_col(i)] += sv; }
+  }
+  if (!terminal) {
+    double bv = 0.0, shift = 0.0;
+    for (int l = 0; l < 12; ++l) {   // arm joint position (state 24:30) and velocity (input 24:30) soft box, relaxed log barrier
+      const int i = l % 6; const bool pos = l < 6; const double val = pos ? x[24 + i] : u[24 + i];
+      const double lo = pos ? mdl->arm_pos_lower[i] : mdl->arm_vel_lower[i], hi = pos ? mdl->arm_pos_upper[i] : mdl->arm_vel_upper[i];
+      const double mu = pos ? mdl->pos_limit_mu : mdl->vel_limit_mu, de = pos ? mdl->pos_limit_delta : mdl->vel_limit_delta;
+      double a0, a1, a2, b0, b1, b2; relaxed_barrier(mu, de, val - lo, a0, a1, a2); relaxed_barrier(mu, de, hi - val, b0, b1, b2); bv += a0 + b0;
+      if (pos) { q.qf[24 + i] += a1 - b1; q.qdiag[24 + i] += a2 + b2; } else { q.rf[24 + i] += a1 - b1; q.rdiag[24 + i] += a2 + b2; } }
+    for (int i = 0; i < 4; ++i) if ((flagmask >> i) & 1) {   // friction cone soft constraints of the stance feet; hessianDiagonalShift acts on every state and input diagonal [upstream FrictionConeConstraint]
+      const double Fx = u[3 * i], Fy = u[3 * i + 1], Fz = u[3 * i + 2]; const double n2 = Fx * Fx + Fy * Fy + mdl->friction_reg, n = sqrt(n2), in = 1.0 / n, in32 = in * in * in;
+      double p0, p1, p2; relaxed_barrier(mdl->friction_barrier_mu, mdl->friction_barrier_delta, mdl->friction_mu * Fz - n, p0, p1, p2); bv += p0;
+      const double g[3] = {-Fx * in, -Fy * in, mdl->friction_mu}; const double H2[9] = {-(Fy * Fy + mdl->friction_reg) * in32, Fx * Fy * in32, 0, Fx * Fy * in32, -(Fx * Fx + mdl->friction_reg) * in32, 0, 0, 0, 0};
+      for (int a = 0; a < 3; ++a) { q.rf[3 * i + a] += p1 * g[a]; for (int bb = 0; bb < 3; ++bb) q.fric[i * 9 + 3 * a + bb] = p2 * g[a] * g[bb] + p1 * H2[3 * a + bb]; }
+      shift += -p1 * mdl->friction_hess_shift; }
+    value += bv;
+    for (int i = 0; i < NX; ++i) { q.qdiag[i] += shift; q.rdiag[i] += shift; }
+  }
+  return value;
+}
+
+// free / dependent partition of the 30 inputs and the structured projection du = Px dx + Pu du~ + Pe of the node's equality constraints, per leg (K2 of mpc_kernels.cu):
+// stance foot: zero velocity, Jl dqd = -(C dx + e): the three joint velocities of the leg are dependent; swing foot: zero force (dF = -F) and normal velocity with the
+// joint of largest |d v_z / d qd_j| eliminated.  e[i][2] of a swing foot must already hold v_z - zdot_ref (+ gain * (z - z_ref)).
+struct ProjRec {
+  LegWs leg[4]; double Pe_full[NU], rs[NU];
+  int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU]; int ndep, m;
+};
+QMB_HD void project_node(const DevModel* __restrict__ mdl, const QuadWs& quad, const double* u, const FootBlk* foot, int fm, int lfp, ProjRec& pr) {
+  int ndep = 0; int pivot[4];
+  for (int i = 0; i < NU; ++i) pr.Pe_full[i] = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    const int first = mdl->foot_leg[i]; LegWs& L = pr.leg[i]; L.first = first; L.stance = (fm >> i) & 1; pivot[i] = -1;
+    if (L.stance) { for (int j = 0; j < 3; ++j) { pr.dep_idx[ndep + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; ndep += 3; }
+    else { double best = -1.0; int pv = 0; for (int j = 0; j < 3; ++j) { const double a = fabs(foot[i].Jl[3 * j + 2]); if (a > best) { best = a; pv = j; } }   // pivot: largest |d v_z / d qdot_j|
+      for (int a = 0; a < 3; ++a) pr.dep_idx[ndep + a] = 3 * i + a;
+      pr.dep_idx[ndep + 3] = 12 + first + pv; L.pivot = pv; pivot[i] = pv; for (int j = 0; j < 3; ++j) L.dep[j] = (j == pv); ndep += 4; }
+  }
+  for (int d = ndep; d < MAXDEP; ++d) pr.dep_idx[d] = -1;
+  pr.ndep = ndep; pr.m = NU - ndep;
+  { int rank = 0; for (int c = 0; c < NU; ++c) { bool is_dep = false; for (int d = 0; d < ndep; ++d) is_dep |= (pr.dep_idx[d] == c); pr.col_of_input[c] = is_dep ? -1 : rank; if (!is_dep) pr.free_idx[rank++] = c; }
+    for (; rank < MU; ++rank) pr.free_idx[rank] = -1; }
+  for (int i = 0; i < 4; ++i) {
+    LegWs& L = pr.leg[i]; const int first = L.first; const FootBlk& fb = foot[i];
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) L.Rl[3 * a + c] = quad_R(mdl, &quad, 12 + first + a, 12 + first + c);
+    for (int j = 0; j < 3; ++j) { L.free_col[j] = pr.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) { L.Px[j][c] = 0.0; L.U[j][c] = 0.0; } }
+    L.Pu2[0] = L.Pu2[1] = 0.0;
+    if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  ->  dqd = -Jl^{-1} (C dx + e)
+      double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = fb.Jl[3 * j + a]; inv3(Jm, Ji);
+      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * fb.e[a]; L.Pe[j] = pe; pr.Pe_full[12 + first + j] = pe;
+        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * fb.C[a][c]; L.Px[j][c] = sv; } }
+    } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
+      const int pv = pivot[i];
+      for (int a = 0; a < 3; ++a) pr.Pe_full[3 * i + a] = -u[3 * i + a];
+      const double piv = fb.Jl[3 * pv + 2], nip = -1.0 / piv;
+      L.Pe[pv] = fb.e[2] * nip; pr.Pe_full[12 + first + pv] = L.Pe[pv];
+      for (int c = 0; c < 12; ++c) L.Px[pv][c] = fb.C[2][c] * nip;
+      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pv) L.Pu2[nf++] = fb.Jl[3 * j + 2] * nip;
+    }
+    // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
+    for (int a = 0; a < 3; ++a) { double sv = quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Px[j][c]; L.U[a][c] = sv; }
+  }
+  // rs of every input: r + R Pe (R couples joint velocities only inside a leg; forces and arm inputs only with themselves)
+  for (int c = 0; c < NU; ++c) {
+    double sv = quad.rf[c];
+    if (c < 12) { const int f = c / 3; for (int a = 0; a < 3; ++a) sv += quad_R(mdl, &quad, c, 3 * f + a) * pr.Pe_full[3 * f + a]; }
+    else if (c < 24) { const int i = foot_of_leg_joint(lfp, c - 12); sv = pr.leg[i].rs[(c - 12) % 3]; }
+    pr.rs[c] = sv;
+  }
 }
 
 // squared equality-constraint residual of a node (ZeroVelocity on stance feet; ZeroForce + NormalVelocity on swing feet); swing_ok reports an unenclosed swing phase

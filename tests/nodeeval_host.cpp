@@ -17,20 +17,21 @@ void nev_destroy(void* h) { delete static_cast<HostModel*>(h); }
 
 // flow map with dense Jacobians assembled from the blocks (the way K2b expands them)
 void nev_flow(void* h, const double* x, const double* u, double* f, double* A, double* B) {
-  const DevModel* mdl = &static_cast<HostModel*>(h)->dev; ne::BaseKin bk; ne::FlowRec fr;
-  ne::base_eval<true>(mdl, x, bk); ne::flow_eval<true>(mdl, x, u, bk, fr, nullptr, nullptr, nullptr);
-  for (int i = 0; i < 12; ++i) f[i] = fr.f[i];
+  const DevModel* mdl = &static_cast<HostModel*>(h)->dev; ne::BaseKin bk; ne::FlowBlk fb; ne::FlowAcc acc; double d[4][3], JxF[4][9];
+  ne::base_eval<true>(mdl, x, bk); ne::flow_acc_init(acc);
+  for (int i = 0; i < 4; ++i) ne::foot_eval<true>(mdl, x, u, bk, i, acc, d[i], nullptr, nullptr, nullptr, JxF[i]);
+  ne::flow_finish<true>(mdl, x, bk, acc, fb.f, &fb);
+  for (int i = 0; i < 12; ++i) f[i] = fb.f[i];
   for (int i = 12; i < 30; ++i) f[i] = u[i];
   std::memset(A, 0, 900 * sizeof(double)); std::memset(B, 0, 900 * sizeof(double));
   const double im = 1.0 / mdl->total_mass;
   for (int a = 0; a < 3; ++a) {
     A[(6 + a) * 30 + a] = 1.0;
-    for (int c = 0; c < 3; ++c) { A[(6 + a) * 30 + 3 + c] = fr.Mpc[3 * a + c]; A[(9 + a) * 30 + 3 + c] = fr.Mtw[3 * a + c];
-      A[(3 + a) * 30 + 9 + c] = fr.hth[c][a]; A[(6 + a) * 30 + 9 + c] = fr.vp[c][a]; A[(9 + a) * 30 + 9 + c] = fr.vt[c][a]; }
-    for (int j = 0; j < 12; ++j) A[(3 + a) * 30 + 12 + j] = fr.JxF[j][a];
-    for (int i = 0; i < 4; ++i) B[a * 30 + 3 * i + a] = im;
+    for (int c = 0; c < 3; ++c) { A[(6 + a) * 30 + 3 + c] = fb.Mpc[3 * a + c]; A[(9 + a) * 30 + 3 + c] = fb.Mtw[3 * a + c];
+      A[(3 + a) * 30 + 9 + c] = fb.hth[c][a]; A[(6 + a) * 30 + 9 + c] = fb.vp[c][a]; A[(9 + a) * 30 + 9 + c] = fb.vt[c][a]; }
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 3; ++j) A[(3 + a) * 30 + 12 + mdl->foot_leg[i] + j] = JxF[i][3 * j + a]; B[a * 30 + 3 * i + a] = im; }
   }
-  for (int i = 0; i < 4; ++i) for (int a = 0; a < 3; ++a) { double ea[3] = {0, 0, 0}; ea[a] = 1.0; double col[3]; cross3(fr.d[i], ea, col); for (int r = 0; r < 3; ++r) B[(3 + r) * 30 + 3 * i + a] = col[r] * im; }
+  for (int i = 0; i < 4; ++i) for (int a = 0; a < 3; ++a) { double ea[3] = {0, 0, 0}; ea[a] = 1.0; double col[3]; cross3(d[i], ea, col); for (int r = 0; r < 3; ++r) B[(3 + r) * 30 + 3 * i + a] = col[r] * im; }
   for (int j = 12; j < 30; ++j) B[j * 30 + j] = 1.0;
 }
 
@@ -38,15 +39,40 @@ void nev_flow(void* h, const double* x, const double* u, double* f, double* A, d
 // C [4][3][12] and Je [6][12] at one node
 int nev_stage(void* h, int ne_, const double* ev, const int* modes, int nk, const double* tt, const double* ts, double t, const double* x, const double* u, int terminal,
               double* cost, double* eq_ss, double* foot_e /*12*/, double* ee_e /*6*/, double* C /*144*/, double* Je /*72*/) {
-  const DevModel* mdl = &static_cast<HostModel*>(h)->dev; ne::BaseKin bk; ne::FlowRec fr; ne::FootRec ft; double al[4][9];
-  ne::base_eval<true>(mdl, x, bk); ne::flow_eval<true>(mdl, x, u, bk, fr, ft.Jl, ft.pf, al);
+  const DevModel* mdl = &static_cast<HostModel*>(h)->dev; ne::BaseKin bk; ne::FlowAcc acc; ne::FootBlk fb[4]; double al[9], fe[4][3], pf[4][3];
+  ne::base_eval<true>(mdl, x, bk); ne::flow_acc_init(acc);
   const int mode = mode_at_time(ev, modes, ne_, t); int fm = 0; for (int i = 0; i < 4; ++i) if (contact_flag(mode, i)) fm |= 1 << i; if (terminal) fm = 0;
-  for (int i = 0; i < 4; ++i) ne::foot_velocity_1<true>(mdl, x, u, bk, i, fr.d[i], ft.Jl[i], al[i], ft.e[i], ft.C[i]);
-  double xnom[30], pref[3], qref[4]; ne::target_reference_full(tt, ts, nk, t, xnom, pref, qref);
+  for (int i = 0; i < 4; ++i) { ne::foot_eval<true>(mdl, x, u, bk, i, acc, fb[i].d, fb[i].pf, fb[i].Jl, al, fb[i].JxF); ne::foot_velocity_1<true>(mdl, x, u, bk, i, fb[i].d, fb[i].Jl, al, fb[i].e, fb[i].C);
+    for (int a = 0; a < 3; ++a) { fe[i][a] = fb[i].e[a]; pf[i][a] = fb[i].pf[a]; } std::memcpy(C + 36 * i, fb[i].C, sizeof(fb[i].C)); }
+  const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4]; ne::target_pose(sg, nk, pref, qref);
   ne::EeRec ee; ne::ee_eval<true>(mdl, x, bk, pref, qref, ee.e, ee.Je);
-  *cost = ne::cost_value(mdl, x, u, xnom, ee.e, fm, terminal != 0);
-  bool ok = true; *eq_ss = terminal ? 0.0 : ne::equality_ss(mdl, u, ft.e, ft.pf, fm, ev, modes, ne_, t, &ok);
-  std::memcpy(foot_e, ft.e, sizeof(ft.e)); std::memcpy(ee_e, ee.e, sizeof(ee.e)); std::memcpy(C, ft.C, sizeof(ft.C)); std::memcpy(Je, ee.Je, sizeof(ee.Je));
+  *cost = ne::cost_value(mdl, x, u, sg, ee.e, fm, terminal != 0);
+  bool ok = true; *eq_ss = terminal ? 0.0 : ne::equality_ss(mdl, u, fe, pf, fm, ev, modes, ne_, t, &ok);
+  std::memcpy(foot_e, fe, sizeof(fe)); std::memcpy(ee_e, ee.e, sizeof(ee.e)); std::memcpy(Je, ee.Je, sizeof(ee.Je));
+  return ok ? 0 : 1;
+}
+
+// quadratic cost model (dense, NOT scaled by dt) and the structured projection du = Px dx + Pu du~ + Pe (dense) of one intermediate node
+int nev_quad(void* h, int ne_, const double* ev, const int* modes, int nk, const double* tt, const double* ts, double t, const double* x, const double* u,
+             double* cost, double* Qd /*900*/, double* Rd /*900*/, double* q /*30*/, double* r /*30*/, double* Pxd /*900*/, double* Pud /*30x18*/, double* Ped /*30*/, int* m_out) {
+  const DevModel* mdl = &static_cast<HostModel*>(h)->dev; ne::BaseKin bk; ne::FlowAcc acc; ne::FootBlk fb[4]; double al[9];
+  ne::base_eval<true>(mdl, x, bk); ne::flow_acc_init(acc);
+  const int mode = mode_at_time(ev, modes, ne_, t); int fm = 0; for (int i = 0; i < 4; ++i) if (contact_flag(mode, i)) fm |= 1 << i;
+  bool ok = true;
+  for (int i = 0; i < 4; ++i) { ne::foot_eval<true>(mdl, x, u, bk, i, acc, fb[i].d, fb[i].pf, fb[i].Jl, al, fb[i].JxF); ne::foot_velocity_1<true>(mdl, x, u, bk, i, fb[i].d, fb[i].Jl, al, fb[i].e, fb[i].C);
+    if (!((fm >> i) & 1)) { double zp, zv; ok &= swing_reference(mdl, ev, modes, ne_, i, t, zp, zv); double ez = fb[i].e[2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (fb[i].pf[2] - zp); fb[i].e[2] = ez; } }
+  const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4]; ne::target_pose(sg, nk, pref, qref);
+  ne::EeRec ee; ne::ee_eval<true>(mdl, x, bk, pref, qref, ee.e, ee.Je);
+  QuadWs quad; *cost = ne::cost_quad(mdl, x, u, sg, ee.e, ee.Je, fm, false, quad);
+  for (int i = 0; i < 30; ++i) { q[i] = quad.qf[i]; r[i] = quad.rf[i]; for (int j = 0; j < 30; ++j) { Qd[i * 30 + j] = quad_Q(mdl, &quad, i, j); Rd[i * 30 + j] = quad_R(mdl, &quad, i, j); } }
+  ne::ProjRec pr; const int lfp = pack_leg_foot(mdl); ne::project_node(mdl, quad, u, fb, fm, lfp, pr);
+  std::memset(Pxd, 0, 900 * sizeof(double)); std::memset(Pud, 0, 30 * 18 * sizeof(double)); std::memset(Ped, 0, 30 * sizeof(double));
+  for (int a = 0; a < pr.m; ++a) Pud[pr.free_idx[a] * 18 + a] = 1.0;
+  for (int c = 0; c < 30; ++c) Ped[c] = pr.Pe_full[c];
+  for (int i = 0; i < 4; ++i) { const LegWs& L = pr.leg[i];
+    for (int j = 0; j < 3; ++j) if (L.dep[j]) { for (int c = 0; c < 12; ++c) Pxd[(12 + L.first + j) * 30 + sup_col(c, L.first)] = L.Px[j][c]; }
+    if (!L.stance) { int nf = 0; for (int j = 0; j < 3; ++j) if (j != L.pivot) { Pud[(12 + L.first + L.pivot) * 18 + L.free_col[j]] = L.Pu2[nf++]; } } }
+  *m_out = pr.m;
   return ok ? 0 : 1;
 }
 

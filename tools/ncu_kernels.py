@@ -10,7 +10,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
-NAMES = {"mpc_lq_kernel": "lq", "mpc_riccati_kernel": "riccati", "mpc_linesearch_kernel": "linesearch", "wbc_update_kernel": "wbc"}
+NAMES = {"mpc_flow_kernel": "flow", "mpc_lq_kernel": "lq", "mpc_riccati_kernel": "riccati", "mpc_linesearch_kernel": "linesearch", "wbc_update_kernel": "wbc"}
 txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt))); hdr, units = rows[0], rows[1]; summary = {}
 for r in rows[2:]:
