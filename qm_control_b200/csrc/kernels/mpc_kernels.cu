@@ -123,7 +123,7 @@ static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep t
 // foot-velocity rows with their Jacobians and the end-effector error with its Jacobian: 492 doubles per node, handed to K2b through HBM (written once, read once,
 // both fully coalesced: the warp transposes 32 thread-private records through shared memory, K2b's warp reads its node's record as one contiguous run).
 #ifndef QMB_FL_MINB
-#define QMB_FL_MINB 3
+#define QMB_FL_MINB 2
 #endif
 constexpr int FL_WARPS = 4, FL_TILE = 64;   // widest block of the record: a foot (63 doubles)
 constexpr int FL_SMEM = FL_WARPS * 32 * (FL_TILE + 1) * 8;
@@ -643,13 +643,28 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
     }
     gAB.wait(); if (QMB_TMA) __syncthreads();     // rows 3:12 of A~, B~ have landed; the rebuilt rows and P of node k+1 are visible to everybody
     // ---- phase 1: W = P'A (32x32: warp = 16x16 block; column 30: p + P b~) ; PB = P'B~ (32x24: warp = row tile) ----
+    // Rows 24:30 of A~ (arm joint positions) are identity rows with b~ in column 30, rows 24:30 of B~ carry dtw at the arm's own projected columns (the last six
+    // free inputs): their contributions to every product of the sweep are copies / scaled copies of rows of P, W, PB and enter through the C fragments, so the
+    // tensor-core contraction runs over k = 0..23 only (6 instead of 8 k-steps in phases 1-3: 130 of 606 DMMA per node less).
+    const double dtw_k = sm.tail[T_MISC]; const int acol0 = reinterpret_cast<const int32_t*>(sm.tail + T_INT)[SI_M] - 6;   // projected column of arm joint 24
     { const int i0 = 16 * (warp >> 1), j0 = 16 * (warp & 1);
-      double c[2][2][2] = {}; warp_mma<NX, 2, 2, false>(sm.P, LDX, i0, sm.A, LDX, j0, c, g, t);
-      if ((warp & 1) && t == 3) {   // C element (row, column 30) lives in n-tile 1 of the right-hand block, lane t = 3, slot 0
+      double c[2][2][2] = {};
+      if (warp & 1) {   // right-hand block: n-tile 1 holds columns 24..31; lane t owns columns 24 + 2t, 25 + 2t (t = 3: column 30 = p + P b~, column 31 = padding)
 #pragma unroll
-        for (int m = 0; m < 2; ++m) { const int ri = i0 + 8 * m + g; if (ri < NX) c[m][1][0] += sm.P[ri * LDX + NX]; } }
+        for (int m = 0; m < 2; ++m) { const int ri = i0 + 8 * m + g; if (ri < NX) {
+            if (t < 3) { c[m][1][0] = sm.P[(24 + 2 * t) * LDX + ri]; c[m][1][1] = sm.P[(25 + 2 * t) * LDX + ri]; }
+            else { double sv = sm.P[ri * LDX + NX];
+#pragma unroll
+              for (int kk = 24; kk < NX; ++kk) sv = fma(sm.P[kk * LDX + ri], sm.A[kk * LDX + NX], sv);
+              c[m][1][0] = sv; } } } }
+      warp_mma<24, 2, 2, false>(sm.P, LDX, i0, sm.A, LDX, j0, c, g, t);
       cfrag_store<2, 2>(sm.W, LDX, i0, j0, NX, c, g, t);
-      double d[1][3][2] = {}; warp_mma<NX, 1, 3, false>(sm.P, LDX, 8 * warp, sm.Bm, LDB, 0, d, g, t);
+      double d[1][3][2];
+#pragma unroll
+      for (int nn = 0; nn < 3; ++nn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { const int a = 8 * nn + 2 * t + e - acol0, ri = 8 * warp + g; d[0][nn][e] = ((unsigned)a < 6u && ri < NX) ? dtw_k * sm.P[(24 + a) * LDX + ri] : 0.0; }
+      warp_mma<24, 1, 3, false>(sm.P, LDX, 8 * warp, sm.Bm, LDB, 0, d, g, t);
       cfrag_store<1, 3>(sm.PB, LDB, 8 * warp, 0, NX, d, g, t); }
     __syncthreads();                                 // W, PB visible; P is dead until phase 3
     if (tid < NX) sm.P[tid * LDX + NX] = sm.tail[T_q + tid];   // q~ waits in column 30 of the dead buffer (the tail is replaced after phase 2)
@@ -661,9 +676,10 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       for (int mt = 0; mt < 3; ++mt) { const int a = 8 * mt + g; const bool rowok = a < MU; const int slot = rowok ? sm.srow[a] : -1, first = rowok ? sm.sfirst[a] : 0;
 #pragma unroll
         for (int e = 0; e < 2; ++e) { const int j = 8 * warp + 2 * t + e; double v = 0.0;
-          if (rowok) { if (j == NX) v = tl[T_r + a]; else if (slot >= 0 && j < NX) { const int ps = sup_pos(j, first); if (ps >= 0) v = tl[T_SJ + slot * 12 + ps]; } }
+          if (rowok) { if (j == NX) v = tl[T_r + a]; else if (slot >= 0 && j < NX) { const int ps = sup_pos(j, first); if (ps >= 0) v = tl[T_SJ + slot * 12 + ps]; }
+            if ((unsigned)(a - acol0) < 6u) v = fma(dtw_k, sm.W[(24 + a - acol0) * LDX + j], v); }   // arm rows of B~: dtw * W[24 + ., :]
           c[mt][0][e] = v; } }
-      warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.W, LDX, 8 * warp, c, g, t); cfrag_store<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t);
+      warp_mma<24, 3, 1, false>(sm.Bm, LDB, 0, sm.W, LDX, 8 * warp, c, g, t); cfrag_store<3, 1>(sm.G, LDG, 0, 8 * warp, MU, c, g, t);
       if (warp < 3) { double d[3][1][2];
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt) { const int a = 8 * mt + g; const int fa = (a < MU) ? si[SI_FREE + a] : -1;
@@ -671,9 +687,10 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
           for (int e = 0; e < 2; ++e) { const int cc = 8 * warp + 2 * t + e; double v = 0.0;
             if (a < MU && cc < MU) { if (a >= mm) v = (a == cc) ? 1.0 : 0.0;                                  // identity padding of the projected input
               else if (fa >= 24) v = (a == cc) ? tl[T_RT + 3 * a] : 0.0;                                      // arm: diagonal
-              else { const int fc = si[SI_FREE + cc]; if (fc >= 0 && fc / 3 == fa / 3) v = tl[T_RT + 3 * a + fc - 3 * (fc / 3)]; } }   // own input triple
+              else { const int fc = si[SI_FREE + cc]; if (fc >= 0 && fc / 3 == fa / 3) v = tl[T_RT + 3 * a + fc - 3 * (fc / 3)]; }   // own input triple
+              if ((unsigned)(a - acol0) < 6u) v = fma(dtw_k, sm.PB[(24 + a - acol0) * LDB + cc], v); }                                 // arm rows of B~: dtw * PB[24 + ., :]
             d[mt][0][e] = v; } }
-        warp_mma<NX, 3, 1, false>(sm.Bm, LDB, 0, sm.PB, LDB, 8 * warp, d, g, t); cfrag_store<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); } }
+        warp_mma<24, 3, 1, false>(sm.Bm, LDB, 0, sm.PB, LDB, 8 * warp, d, g, t); cfrag_store<3, 1>(sm.H, LDH, 0, 8 * warp, MU, d, g, t); } }
     __syncthreads();
     issue_q(k);                                      // B~ is idle now: Q~ of this node streams into it
     if (k > 0) issue_tail(k - 1);                   // the tail buffer is free: next node's small pieces stream in during phase 3
@@ -721,8 +738,10 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
       for (int tile = hi; tile < 16; tile += 3) { const int i0 = 8 * (tile >> 2), j0 = 8 * (tile & 3);
         double c[1][1][2]; const int ri = i0 + g;   // C operand = Q~ (packed lower triangle in the B~ buffer) | q~ (column 30 of P)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) { const int cj = j0 + 2 * t + e; c[0][0][e] = (ri < NX && cj <= NX) ? (cj == NX ? sm.P[ri * LDX + NX] : (cj <= ri ? sm.Bm[q_row_offset(ri) + cj] : sm.Bm[q_row_offset(cj) + ri])) : 0.0; }
-        warp_mma<NX, 1, 1, false>(sm.A, LDX, i0, sm.W, LDX, j0, c, g, t); cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); }
+        for (int e = 0; e < 2; ++e) { const int cj = j0 + 2 * t + e; double v = (ri < NX && cj <= NX) ? (cj == NX ? sm.P[ri * LDX + NX] : (cj <= ri ? sm.Bm[q_row_offset(ri) + cj] : sm.Bm[q_row_offset(cj) + ri])) : 0.0;
+          if (ri >= 24 && ri < NX && cj <= NX) v += sm.W[ri * LDX + cj];   // identity rows 24:30 of A~: row ri of A~'W is row ri of W
+          c[0][0][e] = v; }
+        warp_mma<24, 1, 1, false>(sm.A, LDX, i0, sm.W, LDX, j0, c, g, t); cfrag_store<1, 1>(sm.P, LDX, i0, j0, NX, c, g, t); }
     }
     __syncthreads();
     if (sm.flag) { st |= MST_NOT_PD; if (k > 0) gT.wait(); break; }            // (an in-flight copy must land before the CTA may exit)
@@ -802,7 +821,8 @@ __global__ void __launch_bounds__(RIC_THREADS, 4) mpc_riccati_kernel(const DevMo
 __device__ __forceinline__ void fixup_inputs(MpcSolutionDev sol, int b, int nmax, int n, int tid, int nthreads) {
   // toPrimalSolution [upstream]: input at a pre-event node repeats the previous one; last input repeated
   const int32_t* ge = sol.event + (size_t)b * nmax; double* gu = sol.u + (size_t)b * nmax * NU;
-  for (int k = 1; k < n; ++k) { const bool copy = (k == n - 1) || (ge[k] == 1); if (copy) { for (int i = tid; i < NU; i += nthreads) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i]; } __syncthreads(); }
+  // thread i owns component i at every node: the copies chain through k inside one thread, so no barrier is needed (the caller synchronises before the call)
+  for (int i = tid; i < NU; i += nthreads) for (int k = 1; k < n; ++k) if ((k == n - 1) || (ge[k] == 1)) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i];
 }
 
 #ifndef QMB_LS_MINB
@@ -880,7 +900,15 @@ __global__ void __launch_bounds__(32 * LS_WARPS, QMB_LS_MINB) mpc_linesearch_ker
     alpha *= mdl->alpha_decay;
   }
   if (accepted) {
-    for (int e = threadIdx.x; e < n * NX; e += blockDim.x) { gx[e] += alpha * gdx[e]; if (e < N * NU) gu[e] += alpha * gdu[e]; }
+    // x += alpha dx, u += alpha du: four independent elements per thread and round (the loads of a round are issued before its stores)
+    const int tot = n * NX, totu = N * NU, nt = blockDim.x;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * nt) {
+      double vx[4], vu[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int e = e0 + q * nt; vx[q] = (e < tot) ? gx[e] + alpha * gdx[e] : 0.0; vu[q] = (e < totu) ? gu[e] + alpha * gdu[e] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int e = e0 + q * nt; if (e < tot) gx[e] = vx[q]; if (e < totu) gu[e] = vu[q]; }
+    }
   } else { alpha = 0.0; sc = base_cost; sd = rb[2]; se = rb[3]; }
   __syncthreads();
   fixup_inputs(sol, b, nmax, n, threadIdx.x, blockDim.x);

@@ -213,112 +213,22 @@ QMB_HD double cost_value(const DevModel* __restrict__ mdl, const double* x, cons
   { const double mup = terminal ? mdl->mu_final_ee_pos : mdl->mu_ee_pos, muo = terminal ? mdl->mu_final_ee_ori : mdl->mu_ee_ori;
     double v = 0.0; for (int r = 0; r < 6; ++r) v += 0.5 * (r < 3 ? mup : muo) * ee[r] * ee[r]; value += v; }
   if (!terminal) {
+    // relaxed log barriers: sum_i -mu log(h_i) = -mu log(prod_i h_i) over the entries in the logarithmic branch (24 + 4 fp64 logarithms become 3); the
+    // quadratic extension (h <= delta) is summed as it is
     double bv = 0.0;
-    for (int l = 0; l < 12; ++l) {   // arm joint position (state 24:30) and velocity (input 24:30) soft box, relaxed log barrier
-      const int i = l % 6; const bool pos = l < 6; const double val = pos ? x[24 + i] : u[24 + i];
-      const double lo = pos ? mdl->arm_pos_lower[i] : mdl->arm_vel_lower[i], hi = pos ? mdl->arm_pos_upper[i] : mdl->arm_vel_upper[i];
-      const double mu = pos ? mdl->pos_limit_mu : mdl->vel_limit_mu, de = pos ? mdl->pos_limit_delta : mdl->vel_limit_delta;
-      double a0, a1, a2, b0, b1, b2; relaxed_barrier(mu, de, val - lo, a0, a1, a2); relaxed_barrier(mu, de, hi - val, b0, b1, b2); bv += a0 + b0; }
-    for (int i = 0; i < 4; ++i) if ((flagmask >> i) & 1) {   // friction cone soft constraints of the stance feet
-      const double Fx = u[3 * i], Fy = u[3 * i + 1], Fz = u[3 * i + 2]; const double n = sqrt(Fx * Fx + Fy * Fy + mdl->friction_reg);
-      double p0, p1, p2; relaxed_barrier(mdl->friction_barrier_mu, mdl->friction_barrier_delta, mdl->friction_mu * Fz - n, p0, p1, p2); bv += p0; }
+    for (int grp = 0; grp < 2; ++grp) {   // arm joint position (state 24:30) and velocity (input 24:30) soft box
+      const bool pos = grp == 0; const double mu = pos ? mdl->pos_limit_mu : mdl->vel_limit_mu, de = pos ? mdl->pos_limit_delta : mdl->vel_limit_delta; double prod = 1.0;
+      for (int i = 0; i < 6; ++i) { const double val = pos ? x[24 + i] : u[24 + i]; const double lo = pos ? mdl->arm_pos_lower[i] : mdl->arm_vel_lower[i], hi = pos ? mdl->arm_pos_upper[i] : mdl->arm_vel_upper[i];
+        const double h2[2] = {val - lo, hi - val};
+        for (int sd = 0; sd < 2; ++sd) { const double h = h2[sd]; if (h > de) prod *= h; else { const double tq = (h - 2.0 * de) / de; bv += mu * (-log(de) + 0.5 * tq * tq - 0.5); } } }
+      bv -= mu * log(prod); }
+    { double prod = 1.0; const double mu = mdl->friction_barrier_mu, de = mdl->friction_barrier_delta;   // friction cone soft constraints of the stance feet
+      for (int i = 0; i < 4; ++i) if ((flagmask >> i) & 1) { const double Fx = u[3 * i], Fy = u[3 * i + 1], Fz = u[3 * i + 2]; const double h = mdl->friction_mu * Fz - sqrt(Fx * Fx + Fy * Fy + mdl->friction_reg);
+        if (h > de) prod *= h; else { const double tq = (h - 2.0 * de) / de; bv += mu * (-log(de) + 0.5 * tq * tq - 0.5); } }
+      bv -= mu * log(prod); }
     value += bv;
   }
   return value;
-}
-
-// Quadratic model of the intermediate (or terminal) cost at (x, u) in the compact form of QuadWs (NOT scaled by dt) and the cost value: stage_cost<true> of
-// mpc_device.cuh for one thread.  ee / Je: end-effector error and its Jacobian on the 12 columns p, theta, arm (ee_eval).
-QMB_HD double cost_quad(const DevModel* __restrict__ mdl, const double* x, const double* u, const TargetSeg& sg, const double* ee, const double* Je, int flagmask, bool terminal, QuadWs& q) {
-  double value = 0.0;
-  for (int e = 0; e < 36; ++e) q.fric[e] = 0.0;
-  for (int i = 0; i < NX; ++i) { q.qdiag[i] = 0.0; q.rdiag[i] = 0.0; q.qf[i] = 0.0; q.rf[i] = 0.0; }
-  if (!terminal) {   // tracking cost: 1/2 dx'Q dx + 1/2 du'R du, u_nom = weightCompensatingInput(contact flags)
-    int nst = 0; for (int i = 0; i < 4; ++i) nst += (flagmask >> i) & 1;
-    double dx[NX], du[NU], acc = 0.0;
-    for (int i = 0; i < NX; ++i) { dx[i] = x[i] - (sg.a * sg.l[i] + (1.0 - sg.a) * sg.rr[i]); double un = 0.0; if (i < 12 && (i % 3) == 2 && ((flagmask >> (i / 3)) & 1)) un = mdl->total_mass * 9.81 / nst; du[i] = u[i] - un; }
-    if (mdl->q_is_diag) { for (int i = 0; i < NX; ++i) { const double qd = mdl->Qdiag[i] * dx[i]; q.qf[i] = qd; acc = fma(dx[i], qd, acc); } }
-    else { for (int i = 0; i < NX; ++i) { double qd = 0.0; for (int j = 0; j < NX; ++j) qd = fma(mdl->Q[i * NX + j], dx[j], qd); q.qf[i] = qd; acc = fma(dx[i], qd, acc); } }
-    for (int blk = 0; blk < 8; ++blk) { const double* Rb = mdl->Rblk[blk]; const double* d3 = du + 3 * blk;
-      for (int r = 0; r < 3; ++r) { const double rd = fma(Rb[3 * r], d3[0], fma(Rb[3 * r + 1], d3[1], Rb[3 * r + 2] * d3[2])); q.rf[3 * blk + r] = rd; acc = fma(d3[r], rd, acc); } }
-    for (int i = 0; i < 6; ++i) { const double rd = mdl->Rarm[i] * du[24 + i]; q.rf[24 + i] = rd; acc = fma(du[24 + i], rd, acc); }
-    value += 0.5 * acc;
-  }
-  { // end-effector soft constraint (quadratic penalty, Gauss-Newton)
-    const double mup = terminal ? mdl->mu_final_ee_pos : mdl->mu_ee_pos, muo = terminal ? mdl->mu_final_ee_ori : mdl->mu_ee_ori;
-    double v = 0.0; for (int r = 0; r < 6; ++r) v += 0.5 * (r < 3 ? mup : muo) * ee[r] * ee[r]; value += v;
-    for (int i = 0; i < 12; ++i) { for (int j = 0; j <= i; ++j) { double sv = 0.0; for (int r = 0; r < 6; ++r) sv += (r < 3 ? mup : muo) * Je[r * 12 + i] * Je[r * 12 + j]; q.E[i * 12 + j] = sv; q.E[j * 12 + i] = sv; }
-      double sv = 0.0; for (int r = 0; r < 6; ++r) sv += (r < 3 ? mup : muo) * ee[r] * Je[r * 12 + i]; q.qf[ee_col(i)] += sv; }
-  }
-  if (!terminal) {
-    double bv = 0.0, shift = 0.0;
-    for (int l = 0; l < 12; ++l) {   // arm joint position (state 24:30) and velocity (input 24:30) soft box, relaxed log barrier
-      const int i = l % 6; const bool pos = l < 6; const double val = pos ? x[24 + i] : u[24 + i];
-      const double lo = pos ? mdl->arm_pos_lower[i] : mdl->arm_vel_lower[i], hi = pos ? mdl->arm_pos_upper[i] : mdl->arm_vel_upper[i];
-      const double mu = pos ? mdl->pos_limit_mu : mdl->vel_limit_mu, de = pos ? mdl->pos_limit_delta : mdl->vel_limit_delta;
-      double a0, a1, a2, b0, b1, b2; relaxed_barrier(mu, de, val - lo, a0, a1, a2); relaxed_barrier(mu, de, hi - val, b0, b1, b2); bv += a0 + b0;
-      if (pos) { q.qf[24 + i] += a1 - b1; q.qdiag[24 + i] += a2 + b2; } else { q.rf[24 + i] += a1 - b1; q.rdiag[24 + i] += a2 + b2; } }
-    for (int i = 0; i < 4; ++i) if ((flagmask >> i) & 1) {   // friction cone soft constraints of the stance feet; hessianDiagonalShift acts on every state and input diagonal [upstream FrictionConeConstraint]
-      const double Fx = u[3 * i], Fy = u[3 * i + 1], Fz = u[3 * i + 2]; const double n2 = Fx * Fx + Fy * Fy + mdl->friction_reg, n = sqrt(n2), in = 1.0 / n, in32 = in * in * in;
-      double p0, p1, p2; relaxed_barrier(mdl->friction_barrier_mu, mdl->friction_barrier_delta, mdl->friction_mu * Fz - n, p0, p1, p2); bv += p0;
-      const double g[3] = {-Fx * in, -Fy * in, mdl->friction_mu}; const double H2[9] = {-(Fy * Fy + mdl->friction_reg) * in32, Fx * Fy * in32, 0, Fx * Fy * in32, -(Fx * Fx + mdl->friction_reg) * in32, 0, 0, 0, 0};
-      for (int a = 0; a < 3; ++a) { q.rf[3 * i + a] += p1 * g[a]; for (int bb = 0; bb < 3; ++bb) q.fric[i * 9 + 3 * a + bb] = p2 * g[a] * g[bb] + p1 * H2[3 * a + bb]; }
-      shift += -p1 * mdl->friction_hess_shift; }
-    value += bv;
-    for (int i = 0; i < NX; ++i) { q.qdiag[i] += shift; q.rdiag[i] += shift; }
-  }
-  return value;
-}
-
-// free / dependent partition of the 30 inputs and the structured projection du = Px dx + Pu du~ + Pe of the node's equality constraints, per leg (K2 of mpc_kernels.cu):
-// stance foot: zero velocity, Jl dqd = -(C dx + e): the three joint velocities of the leg are dependent; swing foot: zero force (dF = -F) and normal velocity with the
-// joint of largest |d v_z / d qd_j| eliminated.  e[i][2] of a swing foot must already hold v_z - zdot_ref (+ gain * (z - z_ref)).
-struct ProjRec {
-  LegWs leg[4]; double Pe_full[NU], rs[NU];
-  int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU]; int ndep, m;
-};
-QMB_HD void project_node(const DevModel* __restrict__ mdl, const QuadWs& quad, const double* u, const FootBlk* foot, int fm, int lfp, ProjRec& pr) {
-  int ndep = 0; int pivot[4];
-  for (int i = 0; i < NU; ++i) pr.Pe_full[i] = 0.0;
-  for (int i = 0; i < 4; ++i) {
-    const int first = mdl->foot_leg[i]; LegWs& L = pr.leg[i]; L.first = first; L.stance = (fm >> i) & 1; pivot[i] = -1;
-    if (L.stance) { for (int j = 0; j < 3; ++j) { pr.dep_idx[ndep + j] = 12 + first + j; L.dep[j] = 1; } L.pivot = -1; ndep += 3; }
-    else { double best = -1.0; int pv = 0; for (int j = 0; j < 3; ++j) { const double a = fabs(foot[i].Jl[3 * j + 2]); if (a > best) { best = a; pv = j; } }   // pivot: largest |d v_z / d qdot_j|
-      for (int a = 0; a < 3; ++a) pr.dep_idx[ndep + a] = 3 * i + a;
-      pr.dep_idx[ndep + 3] = 12 + first + pv; L.pivot = pv; pivot[i] = pv; for (int j = 0; j < 3; ++j) L.dep[j] = (j == pv); ndep += 4; }
-  }
-  for (int d = ndep; d < MAXDEP; ++d) pr.dep_idx[d] = -1;
-  pr.ndep = ndep; pr.m = NU - ndep;
-  { int rank = 0; for (int c = 0; c < NU; ++c) { bool is_dep = false; for (int d = 0; d < ndep; ++d) is_dep |= (pr.dep_idx[d] == c); pr.col_of_input[c] = is_dep ? -1 : rank; if (!is_dep) pr.free_idx[rank++] = c; }
-    for (; rank < MU; ++rank) pr.free_idx[rank] = -1; }
-  for (int i = 0; i < 4; ++i) {
-    LegWs& L = pr.leg[i]; const int first = L.first; const FootBlk& fb = foot[i];
-    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) L.Rl[3 * a + c] = quad_R(mdl, &quad, 12 + first + a, 12 + first + c);
-    for (int j = 0; j < 3; ++j) { L.free_col[j] = pr.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) { L.Px[j][c] = 0.0; L.U[j][c] = 0.0; } }
-    L.Pu2[0] = L.Pu2[1] = 0.0;
-    if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  ->  dqd = -Jl^{-1} (C dx + e)
-      double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = fb.Jl[3 * j + a]; inv3(Jm, Ji);
-      for (int j = 0; j < 3; ++j) { double pe = 0.0; for (int a = 0; a < 3; ++a) pe -= Ji[3 * j + a] * fb.e[a]; L.Pe[j] = pe; pr.Pe_full[12 + first + j] = pe;
-        for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int a = 0; a < 3; ++a) sv -= Ji[3 * j + a] * fb.C[a][c]; L.Px[j][c] = sv; } }
-    } else {          // zero force: dF = -F ; normal velocity: pivot joint eliminated
-      const int pv = pivot[i];
-      for (int a = 0; a < 3; ++a) pr.Pe_full[3 * i + a] = -u[3 * i + a];
-      const double piv = fb.Jl[3 * pv + 2], nip = -1.0 / piv;
-      L.Pe[pv] = fb.e[2] * nip; pr.Pe_full[12 + first + pv] = L.Pe[pv];
-      for (int c = 0; c < 12; ++c) L.Px[pv][c] = fb.C[2][c] * nip;
-      int nf = 0; for (int j = 0; j < 3; ++j) if (j != pv) L.Pu2[nf++] = fb.Jl[3 * j + 2] * nip;
-    }
-    // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
-    for (int a = 0; a < 3; ++a) { double sv = quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
-    for (int a = 0; a < 3; ++a) for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Px[j][c]; L.U[a][c] = sv; }
-  }
-  // rs of every input: r + R Pe (R couples joint velocities only inside a leg; forces and arm inputs only with themselves)
-  for (int c = 0; c < NU; ++c) {
-    double sv = quad.rf[c];
-    if (c < 12) { const int f = c / 3; for (int a = 0; a < 3; ++a) sv += quad_R(mdl, &quad, c, 3 * f + a) * pr.Pe_full[3 * f + a]; }
-    else if (c < 24) { const int i = foot_of_leg_joint(lfp, c - 12); sv = pr.leg[i].rs[(c - 12) % 3]; }
-    pr.rs[c] = sv;
-  }
 }
 
 // squared equality-constraint residual of a node (ZeroVelocity on stance feet; ZeroForce + NormalVelocity on swing feet); swing_ok reports an unenclosed swing phase

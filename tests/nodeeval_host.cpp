@@ -52,28 +52,4 @@ int nev_stage(void* h, int ne_, const double* ev, const int* modes, int nk, cons
   return ok ? 0 : 1;
 }
 
-// quadratic cost model (dense, NOT scaled by dt) and the structured projection du = Px dx + Pu du~ + Pe (dense) of one intermediate node
-int nev_quad(void* h, int ne_, const double* ev, const int* modes, int nk, const double* tt, const double* ts, double t, const double* x, const double* u,
-             double* cost, double* Qd /*900*/, double* Rd /*900*/, double* q /*30*/, double* r /*30*/, double* Pxd /*900*/, double* Pud /*30x18*/, double* Ped /*30*/, int* m_out) {
-  const DevModel* mdl = &static_cast<HostModel*>(h)->dev; ne::BaseKin bk; ne::FlowAcc acc; ne::FootBlk fb[4]; double al[9];
-  ne::base_eval<true>(mdl, x, bk); ne::flow_acc_init(acc);
-  const int mode = mode_at_time(ev, modes, ne_, t); int fm = 0; for (int i = 0; i < 4; ++i) if (contact_flag(mode, i)) fm |= 1 << i;
-  bool ok = true;
-  for (int i = 0; i < 4; ++i) { ne::foot_eval<true>(mdl, x, u, bk, i, acc, fb[i].d, fb[i].pf, fb[i].Jl, al, fb[i].JxF); ne::foot_velocity_1<true>(mdl, x, u, bk, i, fb[i].d, fb[i].Jl, al, fb[i].e, fb[i].C);
-    if (!((fm >> i) & 1)) { double zp, zv; ok &= swing_reference(mdl, ev, modes, ne_, i, t, zp, zv); double ez = fb[i].e[2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (fb[i].pf[2] - zp); fb[i].e[2] = ez; } }
-  const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4]; ne::target_pose(sg, nk, pref, qref);
-  ne::EeRec ee; ne::ee_eval<true>(mdl, x, bk, pref, qref, ee.e, ee.Je);
-  QuadWs quad; *cost = ne::cost_quad(mdl, x, u, sg, ee.e, ee.Je, fm, false, quad);
-  for (int i = 0; i < 30; ++i) { q[i] = quad.qf[i]; r[i] = quad.rf[i]; for (int j = 0; j < 30; ++j) { Qd[i * 30 + j] = quad_Q(mdl, &quad, i, j); Rd[i * 30 + j] = quad_R(mdl, &quad, i, j); } }
-  ne::ProjRec pr; const int lfp = pack_leg_foot(mdl); ne::project_node(mdl, quad, u, fb, fm, lfp, pr);
-  std::memset(Pxd, 0, 900 * sizeof(double)); std::memset(Pud, 0, 30 * 18 * sizeof(double)); std::memset(Ped, 0, 30 * sizeof(double));
-  for (int a = 0; a < pr.m; ++a) Pud[pr.free_idx[a] * 18 + a] = 1.0;
-  for (int c = 0; c < 30; ++c) Ped[c] = pr.Pe_full[c];
-  for (int i = 0; i < 4; ++i) { const LegWs& L = pr.leg[i];
-    for (int j = 0; j < 3; ++j) if (L.dep[j]) { for (int c = 0; c < 12; ++c) Pxd[(12 + L.first + j) * 30 + sup_col(c, L.first)] = L.Px[j][c]; }
-    if (!L.stance) { int nf = 0; for (int j = 0; j < 3; ++j) if (j != L.pivot) { Pud[(12 + L.first + L.pivot) * 18 + L.free_col[j]] = L.Pu2[nf++]; } } }
-  *m_out = pr.m;
-  return ok ? 0 : 1;
-}
-
 }  // extern "C"

@@ -92,31 +92,3 @@ def test_constraint_and_end_effector_jacobians_by_central_differences(nev, oracl
         c = 6 + pos if pos < 6 else 18 + pos; d = np.zeros(30); d[c] = h
         fd = (_stage(nev, et, md, tt, ts, t, x + d, u)["ee"] - _stage(nev, et, md, tt, ts, t, x - d, u)["ee"]) / (2 * h)
         np.testing.assert_allclose(r0["Je"][:, pos], fd, atol=2e-7 * (1.0 + np.max(np.abs(r0["Je"]))))
-
-
-def test_cost_quadratic_model_and_projection_against_the_oracle_qp(nev, oracle):
-    """Thread-per-node cost model (cost_quad) against the oracle's unprojected QP blocks, and the structured projection du = Px dx + Pu du~ + Pe against the
-    oracle's own constraint linearisation: C + D Px = 0, D Pu = 0, D Pe + e = 0 (any particular solution + null-space basis is a valid projection)."""
-    lib, h = nev
-    oracle.mpc_set(dt=0.015, horizon=1.0); prob, _ = synthetic.make_batch(np.array([2]), config=5)      # flying trot: swing and stance legs
-    qp = oracle.mpc_qp(prob, NMAX); sol = oracle.mpc_solve_batch(prob, NMAX, nthreads=1); n = int(sol["n_nodes"][0]); t = sol["t"][0, :n]; ev = sol["event"][0, :n]
-    ne = int(prob["n_events"][0]); et = f64(prob["event_times"][0, :ne]); md = i32(prob["modes"][0, :ne + 1]); nk = int(prob["n_target"][0]); tt = f64(prob["target_times"][0, :nk]); ts = f64(prob["target_states"][0, :nk])
-    mass = oracle.model_info()["mass"]; x = f64(prob["x0"][0]); checked = 0; seen_m = set()
-    for k in range(1, n - 2, 4):
-        if ev[k] != 0 or ev[k + 1] != 0 or qp["is_event"][k]:
-            continue
-        dt = t[k + 1] - t[k]; mode = md[int(np.searchsorted(et, t[k], side="left"))]; flags = [(mode >> (3 - f)) & 1 for f in range(4)]; nc = sum(flags)
-        u = np.zeros(30)
-        for f in range(4):
-            if flags[f]:
-                u[3 * f + 2] = mass * 9.81 / nc
-        cost = C.c_double(); Qd = np.zeros((30, 30)); Rd = np.zeros((30, 30)); q = np.zeros(30); r = np.zeros(30); Px = np.zeros((30, 30)); Pu = np.zeros((30, 18)); Pe = np.zeros(30); m = C.c_int()
-        rc = lib.nev_quad(h, C.c_int(ne), _d(et), _i(md), C.c_int(nk), _d(tt), _d(ts), C.c_double(float(t[k])), _d(x), _d(u), C.byref(cost), _d(Qd), _d(Rd), _d(q), _d(r), _d(Px), _d(Pu), _d(Pe), C.byref(m)); assert rc == 0
-        for mine, ref in ((dt * Qd, qp["Q"][k]), (dt * Rd, qp["R"][k]), (dt * q, qp["q"][k]), (dt * r, qp["r"][k])):
-            np.testing.assert_allclose(mine, ref, rtol=0, atol=1e-10 * max(1.0, np.max(np.abs(ref))))
-        ng = int(qp["ng"][k]); Cc = qp["C"][k, :ng]; D = qp["D"][k, :ng]; e = qp["e"][k, :ng]; assert m.value == 30 - ng
-        sc = 1.0 + np.max(np.abs(Cc)) + np.max(np.abs(D))
-        assert np.max(np.abs(Cc + D @ Px)) < 1e-10 * sc and np.max(np.abs(D @ Pu[:, :m.value])) < 1e-10 * sc and np.max(np.abs(D @ Pe + e)) < 1e-10 * max(1.0, np.max(np.abs(e)))
-        assert np.linalg.matrix_rank(Pu[:, :m.value]) == m.value
-        checked += 1; seen_m.add(m.value)
-    assert checked >= 8 and len(seen_m) >= 2, (checked, seen_m)
