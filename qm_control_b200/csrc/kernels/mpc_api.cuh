@@ -49,6 +49,7 @@ struct MpcBuffers {
   double *t0 = nullptr, *x0 = nullptr, *event_times = nullptr, *target_times = nullptr, *target_states = nullptr;
   int32_t *n_events = nullptr, *modes = nullptr, *n_target = nullptr;
   MpcSolutionDev sol[2];
+  double *ddp_trial = nullptr;  // DDP line search: cost and equality SSE of every step length, [B][32][2]
   double *node_rec = nullptr;   // K2a -> K2b: per node the flow-map / constraint / end-effector record (ne::NodeRec, 492 doubles)
   double *stage = nullptr, *gains = nullptr, *dx = nullptr, *du = nullptr, *robot = nullptr, *step_info = nullptr;
   int32_t *stage_i = nullptr, *status = nullptr;

@@ -192,13 +192,7 @@ __global__ void __launch_bounds__(32 * FL_WARPS, QMB_FL_MINB) mpc_flow_kernel(co
 // =====================================================================================================
 // K2b: cost quadratic model, equality constraints, projection, RK2 sensitivities and the structured stage record of one node (one warp per node), on the
 // record of the flow kernel.
-// Optional re-alignment of a CTA's warps at phase boundaries (instruction-cache sharing).  Measured on B200 with the structured record (profiles/r02_ab_k3.jsonl):
-// 21.88 ms with, 21.42 ms without - the kernel is no longer fetch bound, so it is OFF.  When enabled the barrier is taken only by CTAs whose six warps all hold
-// regular (intermediate) nodes - a CTA-uniform predicate established before any warp can exit - so no warp ever waits for one that has returned.
-#ifndef QMB_LQ_LOCKSTEP
-#define QMB_LQ_LOCKSTEP 0
-#endif
-#define LQ_LOCKSTEP() do { if (QMB_LQ_LOCKSTEP && lockstep) __syncthreads(); } while (0)
+// (A CTA-wide re-alignment of the warps at phase boundaries - instruction-cache sharing - was measured and dropped: 21.88 ms with, 21.42 ms without, profiles/r02_ab_k3.jsonl.)
 // rows 3:12 of df/dx (9 x 30, two thirds zeros) and the force block of rows 3:6 of df/du from the Jacobian blocks of a flow record: fill, then lane = column writes
 // its own non-zeros (the fill and the column writes are separated by a warp barrier)
 __device__ __forceinline__ void expand_flow(const ne::FlowBlk& fb, const double* d0, const double* jxf0, int fstride /*doubles between two feet*/, double* Ar, double* Bh, double im, int lfp, int lane) {
@@ -219,37 +213,43 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const long long gid = (long long)blockIdx.x * LQ_WARPS + warp;
   const int b = b0 + (int)(gid / nmax), k = (int)(gid % nmax);
-  const int n = (b < B) ? sol.n_nodes[b] : 0;
-  const bool work = b < B && k < n && !(status[b] & MST_CONVERGED);   // MST_CONVERGED: SqpSolver::runImpl left the iteration loop for this robot
-  const bool regular = work && k < n - 1 && sol.event[(size_t)b * nmax + k] != 1;
-  const bool lockstep = QMB_LQ_LOCKSTEP ? (__syncthreads_and(regular) != 0) : false;   // every thread of the CTA is still here: the early exits come after this point
-  (void)lockstep; (void)regular;
-  if (!work) return;
+  if (b >= B) return;
+  // Everything the node needs from HBM is requested up front and independently (addresses depend on (b, k) only; every buffer covers all B * nmax nodes): the
+  // record of the flow kernel, (x, u, x_next), the grid entries.  Only then is the node classified - a padding node wastes a few sectors, a regular node sees
+  // one memory round trip instead of four dependent ones (node count -> event flag -> state -> record).
   LqSmem& sm = reinterpret_cast<LqSmem*>(smem_raw)[warp]; LqLate& lt = *reinterpret_cast<LqLate*>(&sm.rec.foot[0]);
+  const size_t node = (size_t)b * nmax + k; const bool has_next = k + 1 < nmax;
+  const double2* rg = reinterpret_cast<const double2*>(rec + node * ne::NODE_REC_DBL); double2 rr[(ne::NODE_REC_DBL / 2 + 31) / 32];
+#pragma unroll
+  for (int q = 0; q < (ne::NODE_REC_DBL / 2 + 31) / 32; ++q) { const int e = lane + 32 * q; rr[q] = (e < ne::NODE_REC_DBL / 2) ? __ldg(rg + e) : make_double2(0.0, 0.0); }
+  const double* xk = sol.x + node * NX; const double* uk = sol.u + node * NU;
+  const double xv = (lane < NX) ? xk[lane] : 0.0, uv = (lane < NU) ? uk[lane] : 0.0, xnv = (lane < NX && has_next) ? xk[NX + lane] : 0.0;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
-  double* sg = stage + ((size_t)b * nmax + k) * STAGE_DBL;
+  const double tk = gt[k], tk1 = has_next ? gt[k + 1] : 0.0; const int ek = ge[k], ek1 = has_next ? ge[k + 1] : 0;
   const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
-  const double* xk = sol.x + ((size_t)b * nmax + k) * NX; const double* uk = sol.u + ((size_t)b * nmax + k) * NU;
+  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
+  const int n = sol.n_nodes[b];
+  const bool work = k < n && !(status[b] & MST_CONVERGED);   // MST_CONVERGED: SqpSolver::runImpl left the iteration loop for this robot
+  if (!work) return;
+  double* sg = stage + node * STAGE_DBL;
   const bool terminal = (k == n - 1);
-  if (lane < NX) { sm.x[lane] = xk[lane]; sm.u[lane] = terminal ? 0.0 : uk[lane]; sm.xnext[lane] = terminal ? 0.0 : xk[NX + lane]; }
+  if (lane < NX) { sm.x[lane] = xv; sm.u[lane] = terminal ? 0.0 : uv; sm.xnext[lane] = terminal ? 0.0 : xnv; }
   __syncwarp();
-  if (!terminal && ge[k] == 1) {   // event node: identity jump map, no input, no cost (setupEventNode)
+  if (!terminal && ek == 1) {   // event node: identity jump map, no input, no cost (setupEventNode)
     double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
     double d = 0.0; if (lane < NX) { d = sm.x[lane] - sm.xnext[lane]; tl[T_b + lane] = d; }
     const double ss = warp_sum(d * d);
     if (lane == 0) { si[SI_TYPE] = 1; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = 0.0; tl[T_MISC + 2] = ss; tl[T_MISC + 3] = 0.0; }
     return;
   }
-  { // the node's record (K2a): one contiguous 3.9 KB run, 16 bytes per lane and load
-    const double2* rg = reinterpret_cast<const double2*>(rec + ((size_t)b * nmax + k) * ne::NODE_REC_DBL); double2* rs = reinterpret_cast<double2*>(&sm.rec);
-    const int cnt2 = terminal ? (int)((offsetof(ne::NodeRec, foot2) + 15) / 16) : ne::NODE_REC_DBL / 2;   // terminal node: no second stage
-    for (int e = lane; e < cnt2; e += 32) rs[e] = __ldg(rg + e);
-    const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
+  { double2* rs = reinterpret_cast<double2*>(&sm.rec);   // the node's record: one contiguous 3.9 KB run, 16 bytes per lane and load
+#pragma unroll
+    for (int q = 0; q < (ne::NODE_REC_DBL / 2 + 31) / 32; ++q) { const int e = lane + 32 * q; if (e < ne::NODE_REC_DBL / 2) rs[e] = rr[q]; } }
   __syncwarp();
   const int lfp = pack_leg_foot(mdl);
   const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
-  const double t = interval_start(gt[k], ge[k]);
-  const double dt = terminal ? 0.0 : interval_end(gt[k + 1], ge[k + 1]) - t;
+  const double t = interval_start(tk, ek);
+  const double dt = terminal ? 0.0 : interval_end(tk1, ek1) - t;
   const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
   if (!terminal && !(dt > 0.0) && lane == 0) atomicOr(&status[b], MST_NEG_DT);   // getIntervalDuration <= 0: an event within weakEpsilon of a grid node (QMB200_ST_NEG_DT)
   double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0;
@@ -265,7 +265,6 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
     if (lane == 0) { si[SI_TYPE] = 2; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = cost_val; tl[T_MISC + 2] = 0.0; tl[T_MISC + 3] = 0.0; }
     return;
   }
-  LQ_LOCKSTEP();
   int nd_before = 0; for (int i = 0; i < 4; ++i) if (i < lane) nd_before += ((fm >> i) & 1) ? 3 : 4;
   ndep = 0; for (int i = 0; i < 4; ++i) ndep += ((fm >> i) & 1) ? 3 : 4;
   m = NU - ndep;
@@ -321,7 +320,6 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
     else if (lane < 24) { const int i = foot_of_leg_joint(lfp, lane - 12); sv = sm.leg[i].rs[(lane - 12) % 3]; }
     sm.rs[lane] = sv;
   }
-  LQ_LOCKSTEP();
   // continuous-time Jacobians of the two RK2 stages from the record's blocks
   const double imr = 1.0 / mdl->total_mass;
   expand_flow(sm.rec.s1, sm.rec.foot[0].d, sm.rec.foot[0].JxF, ne::FOOT_DBL, sm.A1r, sm.B1h, imr, lfp, lane); expand_flow(sm.rec.s2, sm.rec.foot2[0].d, sm.rec.foot2[0].JxF, ne::FOOT2_DBL, sm.Ar, sm.Bh, imr, lfp, lane);
@@ -346,7 +344,6 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
     for (int r = 0; r < 9; ++r) sm.A1r[r * NX + c] = out[r];
   }
   __syncwarp();
-  LQ_LOCKSTEP();
   // ---- projected dynamics: b~ = b + B_d Pe (lane = state row) ; rows 3:12 of A~ = A_d + B_d Px (the h_ang rows pick up the dependent joint velocities) ----
   double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
   if (lane < NX) {
@@ -391,7 +388,6 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
     }
     sg[ST_BR + e] = v;
   }
-  LQ_LOCKSTEP();
   // ---- projected cost (changeOfInputVariables [upstream]); quadratic model scaled by dt ----
   if (lane < NX) {   // q~ = q + Px' rs ; Q~ = Q + Px' R Px : per leg a 12x12 block on its support columns
     const int r = lane; double acc[NX];
@@ -437,7 +433,6 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
     if (!(r & 1)) sg[ST_Q + q_row_offset(r) + r + 1] = 0.0;   // even rows carry one padding entry
     tl[T_q + r] = dt * qv;
   }
-  LQ_LOCKSTEP();
   for (int e = lane; e < 8 * 12; e += 32) tl[T_SJ + e] = 0.0;
   __syncwarp();
   if (lane < MU) {   // r~ = Pu' rs ; S~ = Pu' (R Px) (non-zero only for the free joints of swing legs) ; R~ = Pu' R Pu (block diagonal over the input triples)
@@ -932,105 +927,119 @@ __global__ void __launch_bounds__(32 * LS_WARPS, QMB_LS_MINB) mpc_linesearch_ker
 //           du = Px dx + Pu (K~ dx + alpha k~) + alpha Pe - and accept the first alpha with merit = cost + penalty * sqrt(equality SSE) below the nominal merit.
 // The reference integrates these rollouts with ODE45 (rollout{}, task.info:128-136) and, for algorithm SLQ, sweeps a continuous-time Riccati equation; this is the
 // discrete-time form on the solver's own grid (ddp.algorithm ILQR): same LQ model, same backward pass as the SQP path (K2 / K3).
-constexpr int RO_WARPS = 4;
-struct RoSmem { PointWs pt; CostWs cost; ConWs con; double xa[NX + 2], dxv[NX + 2], dut[MU + 2], f1[NX]; double ev[EMAX]; unsigned char modes[EMAX + 8]; };
-
-__global__ void __launch_bounds__(32 * RO_WARPS, 4) mpc_rollout_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
-                                                                  double* __restrict__ xt, double* __restrict__ ut, const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int mode_ls, int iteration) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; const int b = b0 + blockIdx.x * RO_WARPS + warp; if (b >= B) return;
+// Thread-parallel form (node_eval.cuh): a rollout is sequential in time, so one THREAD carries one rollout - the nominal rollout one per robot, the line search
+// one per (robot, step length): all step lengths of ddp.lineSearch run side by side (what OCS2 does with its thread pool) and the first accepted one in descending
+// order wins, so the result is the sequential search's.  The accepted step is then re-rolled in place by one thread per robot (mode 2).
+constexpr int RO_THREADS = 128, RO_MAXTRIALS = 32;
+// one RK2 step of the flow map from (x, u); with PERF also the node's cost (unscaled by dt) and equality SSE at (x, u).  x is replaced by the next state.
+template <bool PERF, class MT>
+__device__ __forceinline__ void rollout_step(const DevModel* __restrict__ mdl, double* x, const double* u, double t, double dt, int fm, const double* ev, const MT* modes, int ne, const double* tt, const double* ts, int nk, double& cost, double& eq) {
+  ne::BaseKin bk; ne::FlowAcc acc; double f1[12], x2[NX]; ne::base_eval<false>(mdl, x, bk); ne::flow_acc_init(acc);
+  if (PERF) { double fe[4][3], pf[4][3];
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) { double d[3], Jl[9]; ne::foot_eval<false>(mdl, x, u, bk, i, acc, d, pf[i], Jl, nullptr, nullptr); ne::foot_velocity_1<false>(mdl, x, u, bk, i, d, Jl, nullptr, fe[i], nullptr); }
+    eq += dt * ne::equality_ss(mdl, u, fe, pf, fm, ev, modes, ne, t, nullptr);
+    const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4], ee[6]; ne::target_pose(sg, nk, pref, qref); ne::ee_eval<false>(mdl, x, bk, pref, qref, ee, nullptr);
+    cost += dt * ne::cost_value(mdl, x, u, sg, ee, fm, false);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) { double d[3]; ne::foot_eval<false>(mdl, x, u, bk, i, acc, d, nullptr, nullptr, nullptr, nullptr); } }
+  ne::flow_finish<false>(mdl, x, bk, acc, f1, nullptr);
+  const double cdt = mdl->rk_c * dt, w1 = mdl->rk_w1, w2 = mdl->rk_w2;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x2[i] = x[i] + cdt * (i < 12 ? f1[i < 12 ? i : 0] : u[i]);
+  double f2[12]; ne::base_eval<false>(mdl, x2, bk); ne::flow_acc_init(acc);
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) { double d[3]; ne::foot_eval<false>(mdl, x2, u, bk, i, acc, d, nullptr, nullptr, nullptr, nullptr); }
+  ne::flow_finish<false>(mdl, x2, bk, acc, f2, nullptr);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] += dt * (w1 * (i < 12 ? f1[i < 12 ? i : 0] : u[i]) + w2 * (i < 12 ? f2[i < 12 ? i : 0] : u[i]));
+}
+// input of the updated affine controller at node k: u = u_nom + Px dx + Pu (K~ dx + alpha k~) + alpha Pe, from the structured stage record and the projected gains
+__device__ __forceinline__ void rollout_input(const double* __restrict__ tl, const double* __restrict__ Kg, const double* __restrict__ unom, const double* dxv, double alpha, int lfp, double* un) {
+  const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const int ndep = si[SI_NDEP]; double dut[MU];
+  for (int a = 0; a < MU; ++a) { const double* kr = Kg + a * LDG; double s0 = 0.0, s1 = 0.0;   // du~ = K~ dx + alpha k~ (rows of padded inputs are zero)
+#pragma unroll 5
+    for (int j = 0; j < NX; j += 2) { s0 = fma(kr[j], dxv[j], s0); s1 = fma(kr[j + 1], dxv[j + 1], s1); }
+    dut[a] = s0 + s1 + alpha * kr[NX]; }
+  for (int c = 0; c < NU; ++c) un[c] = unom[c];
+  for (int a = 0; a < MU; ++a) { const int fa = si[SI_FREE + a]; if (fa >= 0) un[fa] += dut[a]; }
+  for (int d = 0; d < ndep; ++d) { const int di = si[SI_DEP + d]; double du = alpha * tl[T_PED + d];
+    if (di >= 12) { const int j = di - 12, lg = j / 3, first = 3 * lg; const double* px = tl + T_PXJ + j * 12;
+      for (int c = 0; c < 12; ++c) du = fma(px[c], dxv[sup_col(c, first)], du);
+      const int foot = (lfp >> (2 * lg)) & 3; if (si[SI_PIV + foot] >= 0) for (int q2 = 0; q2 < 2; ++q2) { const int col = si[SI_PCOL + 2 * foot + q2]; if (col >= 0) du = fma(tl[T_PU2 + 2 * foot + q2], dut[col], du); } }
+    un[di] += du; }
+}
+// mode 0: nominal rollout (thread = robot).  mode 1: trial rollouts (thread = (robot, trial), trial = fastest index): cost and equality SSE of every step length
+// into `trial` [B][RO_MAXTRIALS][2].  mode 2: decision + in-place rollout of the accepted step (thread = robot).
+__global__ void __launch_bounds__(RO_THREADS, 2) mpc_rollout_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
+                                                                   double* __restrict__ trial, const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int mode_ls, int n_trials, int tr_pitch, int iteration) {
+  const long long gid = (long long)blockIdx.x * RO_THREADS + threadIdx.x;
+  const int b = b0 + (int)(mode_ls == 1 ? gid / tr_pitch : gid), tr = mode_ls == 1 ? (int)(gid % tr_pitch) : 0; if (b >= B || tr >= n_trials) return;
   if (status[b] & MST_CONVERGED) return;
-  RoSmem& sm = reinterpret_cast<RoSmem*>(smem_raw)[warp];
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   double* gx = sol.x + (size_t)b * nmax * NX; double* gu = sol.u + (size_t)b * nmax * NU;
-  double* tx = xt + (size_t)b * nmax * NX; double* tu = ut + (size_t)b * nmax * NU;
-  const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
-  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); __syncwarp(); }
-  const int lfp = pack_leg_foot(mdl); const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, imass_unused = 0.0; (void)imass_unused;
+  const int ne = clamp_events(p.n_events[b]); const double* ev = p.event_times + (size_t)b * EMAX; const int32_t* modes = p.modes + (size_t)b * (EMAX + 1);
+  const int lfp = pack_leg_foot(mdl);
   const int nk = clamp_targets(p.n_target[b]); const double* tt = p.target_times + (size_t)b * KMAX; const double* ts = p.target_states + (size_t)b * KMAX * TARGET_DIM;
-  // one RK2 step from sm.xa with the input in sm.pt.u; returns the new state component of this lane (lane < 30)
-  auto rk2 = [&](double dt) -> double {
-    if (lane < NX) sm.pt.x[lane] = sm.xa[lane];
-    __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 3);
-    if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
-    __syncwarp();
-    if (lane < NX) sm.pt.x[lane] = sm.xa[lane] + mdl->rk_c * dt * sm.f1[lane];
-    __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 3);
-    const double xn = (lane < NX) ? sm.xa[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) : 0.0; __syncwarp(); return xn; };
-  if (!mode_ls) {
-    if (lane < NX + 2) sm.xa[lane] = (lane < NX) ? p.x0[(size_t)b * NX + lane] : 0.0;
-    __syncwarp(); if (lane < NX) gx[lane] = sm.xa[lane];
+  double xa[NX], cost = 0.0, eq = 0.0;
+  if (mode_ls == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { xa[i] = p.x0[(size_t)b * NX + i]; gx[i] = xa[i]; }
     for (int k = 0; k < N; ++k) {
-      if (ge[k] != 1) { const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t;
-        if (lane < NU) sm.pt.u[lane] = gu[(size_t)k * NU + lane];
-        __syncwarp(); const double xn = rk2(dt); if (lane < NX) sm.xa[lane] = xn; __syncwarp(); }
-      if (lane < NX) gx[(size_t)(k + 1) * NX + lane] = sm.xa[lane];
+      if (ge[k] != 1) { const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; double u[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = gu[(size_t)k * NU + i];
+        rollout_step<false>(mdl, xa, u, t, dt, 0, ev, modes, ne, tt, ts, nk, cost, eq); }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) gx[(size_t)(k + 1) * NX + i] = xa[i];
     }
     return;
   }
-  // ---- line search ----
   const double* rb = robot + (size_t)b * ROBOT_DBL; const double base_cost = rb[1], base_eq = rb[3]; const double pen = mdl->ddp_penalty;
   const double merit0 = base_cost + pen * sqrt(base_eq); const bool failed = (status[b] & MST_NOT_PD) != 0;
+  double* tb = trial + (size_t)b * RO_MAXTRIALS * 2;
   double alpha = mdl->ddp_max_step; bool accepted = false; double sc = base_cost, se = base_eq;
-  const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const double* gb = gains + (size_t)b * nmax * GAIN_DBL;
-  while (!failed && alpha >= mdl->ddp_min_step) {
-    double cost = 0.0, eq = 0.0;
-    if (lane < NX + 2) { sm.xa[lane] = (lane < NX) ? p.x0[(size_t)b * NX + lane] : 0.0; sm.dxv[lane] = 0.0; } if (lane < MU + 2) sm.dut[lane] = 0.0;
-    __syncwarp(); if (lane < NX) tx[lane] = sm.xa[lane];
-    for (int k = 0; k < N; ++k) {
-      if (ge[k] == 1) { if (lane < NU) tu[(size_t)k * NU + lane] = 0.0; if (lane < NX) tx[(size_t)(k + 1) * NX + lane] = sm.xa[lane]; continue; }
-      const double* tl = sgb + (size_t)k * STAGE_DBL + ST_TAIL; const int32_t* si = reinterpret_cast<const int32_t*>(tl + T_INT); const double* Kg = gb + (size_t)k * GAIN_DBL;
-      const int ndep = si[SI_NDEP];
-      if (lane < NX) sm.dxv[lane] = sm.xa[lane] - gx[(size_t)k * NX + lane];
-      __syncwarp();
-      if (lane < MU) { const double* kr = Kg + lane * LDG; double s0 = 0.0, s1 = 0.0;   // du~ = K~ dx + alpha k~ (lane = row; rows of padded inputs are zero)
-#pragma unroll 5
-        for (int j = 0; j < NX; j += 2) { s0 = fma(kr[j], sm.dxv[j], s0); s1 = fma(kr[j + 1], sm.dxv[j + 1], s1); }
-        sm.dut[lane] = s0 + s1 + alpha * kr[NX]; }
-      __syncwarp();
-      double un = (lane < NU) ? gu[(size_t)k * NU + lane] : 0.0;   // u = u_nom + du: every lane < 30 finds its own input among the free / dependent lists
-      if (lane < NU) { double du = 0.0; bool found = false;
-        for (int a = 0; a < MU && !found; ++a) if (si[SI_FREE + a] == lane) { du = sm.dut[a]; found = true; }
-        for (int d = 0; d < ndep && !found; ++d) if (si[SI_DEP + d] == lane) { found = true; du = alpha * tl[T_PED + d];
-            if (lane >= 12) { const int j = lane - 12, lg = j / 3, first = 3 * lg; const double* px = tl + T_PXJ + j * 12;
-              for (int c = 0; c < 12; ++c) du = fma(px[c], sm.dxv[sup_col(c, first)], du);
-              const int foot = (lfp >> (2 * lg)) & 3; if (si[SI_PIV + foot] >= 0) for (int q2 = 0; q2 < 2; ++q2) { const int col = si[SI_PCOL + 2 * foot + q2]; if (col >= 0) du = fma(tl[T_PU2 + 2 * foot + q2], sm.dut[col], du); } } }
-        un += du; sm.pt.u[lane] = un; tu[(size_t)k * NU + lane] = un; }
-      __syncwarp();
-      const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; const int mode = mode_at_time(ev, modes, ne, t); const int fm = flag_mask(mode);
-      // performance of the node (cost, equality residuals) at (x, u) - computePerformance
-      if (lane < NX) sm.pt.x[lane] = sm.xa[lane];
-      __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 6);
-      { TargetRef ref = target_reference(tt, ts, nk, t, lane); cost += dt * stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, fm, false, lane); }
-      foot_velocity<false>(mdl, &sm.pt, &sm.con, lane);
-      { double es = 0.0;
-        if (lane < 4) { const int i = lane; if ((fm >> i) & 1) { for (int a = 0; a < 3; ++a) es += sm.con.e[i][a] * sm.con.e[i][a]; }
-          else { double zp, zv; swing_reference(mdl, ev, modes, ne, i, t, zp, zv); double ez = sm.con.e[i][2] - zv; if (mdl->position_error_gain != 0.0) ez += mdl->position_error_gain * (sm.pt.pf[i][2] - zp); es += ez * ez; for (int a = 0; a < 3; ++a) es += sm.pt.u[3 * i + a] * sm.pt.u[3 * i + a]; } }
-        eq += dt * warp_sum(es); }
-      // RK2 step (the first stage was just evaluated at (x, u): reuse it)
-      if (lane < NX) sm.f1[lane] = sm.pt.f[lane];
-      __syncwarp();
-      if (lane < NX) sm.pt.x[lane] = sm.xa[lane] + mdl->rk_c * dt * sm.f1[lane];
-      __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 3);
-      const double xn = (lane < NX) ? sm.xa[lane] + dt * (w1 * sm.f1[lane] + w2 * sm.pt.f[lane]) : 0.0;
-      __syncwarp(); if (lane < NX) { sm.xa[lane] = xn; tx[(size_t)(k + 1) * NX + lane] = xn; }
-      __syncwarp();
-    }
-    { // final cost at x_N
-      const double t = interval_start(gt[N], ge[N]); if (lane < NX) { sm.pt.x[lane] = sm.xa[lane]; sm.pt.u[lane] = 0.0; }
-      __syncwarp(); point_eval<false>(mdl, &sm.pt, lane, lfp, 6);
-      TargetRef ref = target_reference(tt, ts, nk, t, lane); cost += stage_cost<false>(mdl, &sm.pt, &sm.cost, (QuadWs*)nullptr, ref, 0, true, lane); }
-    const double merit = cost + pen * sqrt(eq); sc = cost; se = eq;
-    if (merit < merit0 - mdl->ddp_armijo * alpha * fabs(merit0)) { accepted = true; break; }
-    alpha *= mdl->ddp_contraction;
+  if (mode_ls == 1) { for (int j = 0; j < tr; ++j) alpha *= mdl->ddp_contraction; if (failed) return; }
+  else {   // mode 2: the first step length (descending) whose merit passes the armijo test [upstream ocs2_ddp LineSearchStrategy, recalled]
+    if (!failed) for (int j = 0; j < n_trials; ++j) { const double c = tb[2 * j], e = tb[2 * j + 1], merit = c + pen * sqrt(e);
+        if (merit < merit0 - mdl->ddp_armijo * alpha * fabs(merit0)) { accepted = true; sc = c; se = e; break; } alpha *= mdl->ddp_contraction; }
   }
-  if (accepted) { for (int e = lane; e < n * NX; e += 32) { gx[e] = tx[e]; if (e < N * NU) gu[e] = tu[e]; } }
-  else { alpha = 0.0; sc = base_cost; se = base_eq; }
-  __syncwarp();
+  if (mode_ls == 1 || accepted) {
+    const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const double* gb = gains + (size_t)b * nmax * GAIN_DBL; const bool write = mode_ls == 2;
+    double xnom[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { xa[i] = p.x0[(size_t)b * NX + i]; xnom[i] = gx[i]; }
+    if (write) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) gx[i] = xa[i]; }
+    for (int k = 0; k < N; ++k) {
+      if (ge[k] == 1) {   // event node: identity jump map, no input
+        if (write) { for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = 0.0; }
+      } else {
+        const double* tl = sgb + (size_t)k * STAGE_DBL + ST_TAIL; double dxv[NX], un[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dxv[i] = xa[i] - xnom[i];
+        rollout_input(tl, gb + (size_t)k * GAIN_DBL, gu + (size_t)k * NU, dxv, alpha, lfp, un);
+        if (write) { for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = un[i]; }
+        const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; const int fm = flag_mask(mode_at_time(ev, modes, ne, t));
+        if (write) rollout_step<false>(mdl, xa, un, t, dt, fm, ev, modes, ne, tt, ts, nk, cost, eq); else rollout_step<true>(mdl, xa, un, t, dt, fm, ev, modes, ne, tt, ts, nk, cost, eq);
+      }
+      // the nominal state of the next node is read before the new one replaces it (in-place commit)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { xnom[i] = gx[(size_t)(k + 1) * NX + i]; if (write) gx[(size_t)(k + 1) * NX + i] = xa[i]; }
+    }
+    if (!write) {   // final cost at x_N
+      const double t = interval_start(gt[N], ge[N]); ne::BaseKin bk; ne::base_eval<false>(mdl, xa, bk); double u0[NU]; for (int i = 0; i < NU; ++i) u0[i] = 0.0;
+      const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4], ee[6]; ne::target_pose(sg, nk, pref, qref); ne::ee_eval<false>(mdl, xa, bk, pref, qref, ee, nullptr);
+      cost += ne::cost_value(mdl, xa, u0, sg, ee, 0, true);
+      tb[2 * tr] = cost; tb[2 * tr + 1] = eq; return; }
+  }
+  if (!accepted) { alpha = 0.0; sc = base_cost; se = base_eq; }
   // toPrimalSolution [upstream]: input at a pre-event node repeats the previous one; last input repeated
-  for (int k = 1; k < n; ++k) { const bool copy = (k == n - 1) || (ge[k] == 1); if (copy && lane < NU) gu[(size_t)k * NU + lane] = gu[(size_t)(k - 1) * NU + lane]; __syncwarp(); }
-  if (lane == 0) { int flags = accepted ? 0 : MST_NO_STEP; if (!accepted && iteration + 1 < mdl->sqp_iterations) flags |= MST_CONVERGED; if (flags) atomicOr(&status[b], flags);
+  for (int k = 1; k < n; ++k) { if ((k == n - 1) || (ge[k] == 1)) for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i]; }
+  { int flags = accepted ? 0 : MST_NO_STEP; if (!accepted && iteration + 1 < mdl->sqp_iterations) flags |= MST_CONVERGED; if (flags) atomicOr(&status[b], flags);
     double* si = step_info + (size_t)b * 4; si[0] = alpha; si[1] = sc; si[2] = 0.0; si[3] = se; }
 }
 
@@ -1056,7 +1065,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
   const size_t Bn = (size_t)B * nmax;
   bool ok = A(&m.t0, B) && A(&m.x0, (size_t)B * NX) && A(&m.n_events, B) && A(&m.event_times, (size_t)B * EMAX) && A(&m.modes, (size_t)B * (EMAX + 1)) && A(&m.n_target, B) && A(&m.target_times, (size_t)B * KMAX) && A(&m.target_states, (size_t)B * KMAX * TARGET_DIM);
   for (int s = 0; s < 2 && ok; ++s) ok = A(&m.sol[s].n_nodes, B) && A(&m.sol[s].t, Bn) && A(&m.sol[s].event, Bn) && A(&m.sol[s].x, Bn * NX) && A(&m.sol[s].u, Bn * NU);
-  ok = ok && A(&m.stage, Bn * STAGE_DBL) && A(&m.gains, Bn * GAIN_DBL) && A(&m.dx, Bn * NX) && A(&m.du, Bn * NU) && A(&m.node_rec, Bn * ne::NODE_REC_DBL) && A(&m.robot, (size_t)B * ROBOT_DBL) && A(&m.status, B) && A(&m.step_info, (size_t)B * 4);
+  ok = ok && A(&m.stage, Bn * STAGE_DBL) && A(&m.gains, Bn * GAIN_DBL) && A(&m.dx, Bn * NX) && A(&m.du, Bn * NU) && A(&m.node_rec, Bn * ne::NODE_REC_DBL) && A(&m.ddp_trial, (size_t)B * RO_MAXTRIALS * 2) && A(&m.robot, (size_t)B * ROBOT_DBL) && A(&m.status, B) && A(&m.step_info, (size_t)B * 4);
   return ok;
 }
 
@@ -1065,7 +1074,6 @@ int mpc_configure_device() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RoSmem) * RO_WARPS));
   return (int)e;
 }
 
@@ -1076,8 +1084,10 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   mpc_setup_kernel<<<(nb + SETUP_WARPS - 1) / SETUP_WARPS, 32 * SETUP_WARPS, SETUP_WARPS * ((setup_smem_per_warp(nmax) + 15) & ~(size_t)15), stream>>>(mdl, b0, b1, nmax, p, prev, next, m.status);
   if (ev) cudaEventRecord(ev[1], stream);
   const long long nodes = (long long)nb * nmax; const int iters = hm.sqp_iterations < 1 ? 1 : hm.sqp_iterations; int launched = 1;
-  const bool ddp = hm.solver == 2; const int ro_grid = (nb + RO_WARPS - 1) / RO_WARPS;
-  if (ddp) { mpc_rollout_kernel<<<ro_grid, 32 * RO_WARPS, sizeof(RoSmem) * RO_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status, m.step_info, 0, 0); ++launched; }   // nominal rollout from the measured state
+  const bool ddp = hm.solver == 2; int n_trials = 0, tr_pitch = 1;
+  if (ddp) { for (double a = hm.ddp_max_step; a >= hm.ddp_min_step && n_trials < RO_MAXTRIALS; a *= hm.ddp_contraction) ++n_trials; while (tr_pitch < n_trials) tr_pitch *= 2; }   // step lengths of ddp.lineSearch; lanes of a warp: trials of the same robot side by side
+  const int ro_grid = (nb + RO_THREADS - 1) / RO_THREADS, ro_grid_tr = (int)(((long long)nb * tr_pitch + RO_THREADS - 1) / RO_THREADS);
+  if (ddp) { mpc_rollout_kernel<<<ro_grid, RO_THREADS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, m.step_info, 0, 1, 1, 0); ++launched; }   // nominal rollout from the measured state
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
   // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
   for (int it = 0; it < iters; ++it) {
@@ -1087,7 +1097,8 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);
     mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[3], stream);
-    if (ddp) mpc_rollout_kernel<<<ro_grid, 32 * RO_WARPS, sizeof(RoSmem) * RO_WARPS, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status, m.step_info, 1, it);   // rollout line search (m.dx / m.du hold the trial trajectories)
+    if (ddp) { mpc_rollout_kernel<<<ro_grid_tr, RO_THREADS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, m.step_info, 1, n_trials, tr_pitch, it);   // all step lengths side by side
+      mpc_rollout_kernel<<<ro_grid, RO_THREADS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, m.step_info, 2, n_trials, tr_pitch, it); ++launched; }   // decision + in-place rollout of the accepted step
     else mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
     launched += 4;
   }
