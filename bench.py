@@ -40,10 +40,21 @@ def algorithmic_bytes(n_intervals):
                 total=15840 * N + 4184)
 
 
+def riccati_counted():
+    """COUNTED tensor-core work of the backward sweep: ncu sm__inst_executed_pipe_tensor_subpipe_dmma.sum of one capture at 1024 robots x 100 regular nodes, and the
+    tensor sub-pipe activity of the same capture (profiles/r03_riccati_dmma.json, written by tools/dmma_json.py from the ncu csv; round 2: 606 DMMA per node, 37.9 %)."""
+    path = os.path.join(ROOT, "profiles", "r03_riccati_dmma.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return {"dmma_per_node": 606.0, "tensor_pipe_active_pct": 37.88, "source": "profiles/r02c_riccati_dmma.csv"}
+
+
 def riccati_flops(n_intervals):
-    """COUNTED tensor-core flops of the backward sweep: ncu sm__inst_executed_pipe_tensor_subpipe_dmma.sum = 62,054,400 DMMA.8x8x4 warp instructions for 1024 robots x
-    100 regular nodes (profiles/r02c_riccati_dmma.csv) = 606 per node, 512 flop each.  The scalar work (Cholesky, substitutions, rollout) is not counted."""
-    return 606.0 * 512.0 * n_intervals
+    """DMMA.8x8x4 warp instructions per node x 512 flop.  The scalar work (Cholesky, substitutions, rollout) is not counted."""
+    return riccati_counted()["dmma_per_node"] * 512.0 * n_intervals
 
 
 class ClockSampler(threading.Thread):
@@ -337,7 +348,7 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per kernel (profiles/traffic_r02.json, bytes per robot at the
         # captured batch; every kernel's traffic is linear in the batch), scaled to this launch
         per_kernel = {}; tj = {}
-        for name in ("traffic_r02.json", "traffic_r01.json"):
+        for name in ("traffic_r03.json", "traffic_r02.json", "traffic_r01.json"):
             tpath = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tpath):
                 try:
@@ -354,7 +365,7 @@ def main():
                 "whole_tick": {"achieved": ab["total"] * B / (ms_local * 1e-3) / 1e9, "frac": ab["total"] * B / (ms_local * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_robot": ab["total"]},
                 "fp64": {"kernel": "mpc_riccati_kernel", "achieved_tflops": riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 if ktimes.get("riccati") else None, "peak_tflops": fp64_peak, "peak_source": "measured in-process (FMA microbenchmark)",
                          "frac": (riccati_flops(n_int) * B / (ktimes["riccati"] * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and ktimes.get("riccati")) else None,
-                         "flops_source": "counted: ncu DMMA instruction count x 512 (profiles/r02c_riccati_dmma.csv); same capture: tensor (DMMA) sub-pipe active 37.9 % of peak sustained", "tensor_pipe_active_pct": 37.88,
+                         "flops_source": "counted: ncu DMMA instruction count x 512 (%s); tensor (DMMA) sub-pipe activity of the same capture" % riccati_counted().get("source"), "tensor_pipe_active_pct": riccati_counted().get("tensor_pipe_active_pct"), "dmma_per_node": riccati_counted().get("dmma_per_node"),
                          "note": "the path is fp64 latency/issue bound, not HBM bound (SURVEY 8d: ~48 FLOP/B against a ~6 FLOP/B fp64 ridge); the Riccati products run on the fp64 tensor cores (DMMA.8x8x4, same 37 TFLOP/s peak as the DFMA pipe, tools/microbench/dmma_peak.cu); the HBM fraction is reported because BASELINE.json asks for it"}}
 
     # strong scaling as BASELINE.json states configs[3] / [4]: the TOTAL batch is fixed and split over the ranks
@@ -365,7 +376,7 @@ def main():
             if sl is not None:
                 sm_, _, sag = sl.timed(max(3, args.steps // 2), 2, dev, dist); sm_ = parallel.max_over_ranks(sm_, dev); sag = parallel.max_over_ranks(sag, dev)
                 extras["strong_config3"] = {"global_batch": UNIT_BATCH, "batch_per_gpu": Bs, "ms_per_step": sm_, "value": 1.0 / (sm_ * 1e-3), "unit": UNIT, "allgather_ms": sag,
-                                            "waves": {"riccati_ctas_per_sm_slot": Bs / (148 * 4.0), "wbc_ctas_per_sm": -(-Bs // 7) / 148.0}}
+                                            "waves": {"riccati_ctas_per_sm_slot": Bs / (148 * 4.0), "wbc_ctas_per_sm": -(-Bs // 8) / 148.0}}
                 del sl
             else:
                 extras["strong_config3"] = {"global_batch": UNIT_BATCH, "batch_per_gpu": UNIT_BATCH, "ms_per_step": ms, "value": value, "unit": UNIT, "allgather_ms": ag_ms, "note": "one GPU: identical to the main line"} if B == UNIT_BATCH else None
