@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(32 * WBC_WARPS) wbc_update_kernel(const DevMod
                                                                    double* __restrict__ cmd_out, int32_t* __restrict__ status_out, int32_t* __restrict__ diag_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = b0 + blockIdx.x * WBC_WARPS + warp;
+  const int b = b0 + blockIdx.x * (int)(blockDim.x >> 5) + warp;   // robots per CTA = warps per CTA, chosen at launch (the warps of a CTA never synchronise with each other)
   if (b >= B) return;
   WbcSmem& sm = reinterpret_cast<WbcSmem*>(smem_raw)[warp];
   const int mode = mode_in[b]; const double period = period_in[b]; const double time = time_in[b];
@@ -471,10 +471,13 @@ size_t wbc_smem_bytes() { return sizeof(WbcSmem) * WBC_WARPS; }
 
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
                        double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0, int b1, int32_t* diag) {
-  const size_t smem = wbc_smem_bytes();
   if (b1 < 0) b1 = B; if (b1 <= b0) return;
-  const int grid = (b1 - b0 + WBC_WARPS - 1) / WBC_WARPS;
-  wbc_update_kernel<<<grid, 32 * WBC_WARPS, smem, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status, diag);
+  // Large batches: eight robots per CTA, one CTA per SM (eight resident warps, many waves).  A batch that fits one wave (a GPU's share of a strong-scaled job: 1024 robots on 148 SMs)
+  // is spread as one-robot CTAs - seven fit an SM by shared memory - so that every SM gets 6..7 robots instead of 128 SMs getting eight and 20 none.
+  int sms = 148; { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int nb = b1 - b0; const int wpc = (nb <= sms * 7) ? 1 : WBC_WARPS;
+  const int grid = (nb + wpc - 1) / wpc;
+  wbc_update_kernel<<<grid, 32 * wpc, sizeof(WbcSmem) * wpc, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status, diag);
 }
 
 // cudaFuncSetAttribute is per device: called from qmb200_create after cudaSetDevice (one handle per GPU, several handles / devices per process allowed)
