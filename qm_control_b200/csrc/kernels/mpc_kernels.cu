@@ -16,10 +16,10 @@
 namespace qmb {
 
 #ifndef QMB_LQ_WARPS
-#define QMB_LQ_WARPS 7
+#define QMB_LQ_WARPS 5
 #endif
 #ifndef QMB_LQ_MINB
-#define QMB_LQ_MINB 2
+#define QMB_LQ_MINB 3
 #endif
 constexpr int LQ_WARPS = QMB_LQ_WARPS, LS_WARPS = 4, SETUP_WARPS = 4;
 enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16, MST_CONVERGED = 32, MST_NEG_DT = 64 };   // NEG_DT: an interval with non-positive duration (include/qmb200.h)   // CONVERGED: checkConvergence stopped the SQP loop before sqpIteration
@@ -109,14 +109,14 @@ struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp'
   ne::NodeRec rec;                                                             // the node's record from the flow kernel (K2a); LqLate overlays rec.foot[] once the cost / projection / Jacobian expansion have consumed it
   QuadWs quad; LegWs leg[4];
   double x[NX], u[NU], xnext[NX];                                              // (x, u) of the node in the layout stage_cost reads (x then u), next node's state for the defect
-  double A1r[9 * NX], Ar[9 * NX], B1h[36], Bh[36];                             // rows 3:12 of df/dx and rows 3:6, columns 0:12 of df/du at the two RK2 stages; A1r becomes A_d - I in place
+  double A1r[9 * NX], Ar[9 * NX];                                              // rows 3:12 of df/dx at the two RK2 stages; A1r becomes A_d - I in place.  Until expand_flow fills it, Ar holds the robot's mode schedule
   double Pe_full[NU], rs[NU];
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
-  double ev[EMAX]; unsigned char modes[EMAX + 8];   // the robot's mode schedule, staged once per node: the binary searches and the swing-interval scans then hit shared memory
 };
+static_assert(9 * NX * 8 >= EMAX * 8 + EMAX + 8, "the mode schedule (event times + modes) is staged in the Ar buffer until the flow Jacobians are expanded");
 static_assert(sizeof(LqLate) <= 4 * sizeof(ne::FootBlk) && offsetof(ne::NodeRec, foot) == 0, "LqLate overlays the foot blocks of the record");
 static_assert(sizeof(LqSmem) % 16 == 0 && offsetof(LqSmem, rec) == 0, "aligned record slice");
-static_assert(sizeof(LqSmem) * LQ_WARPS + 1024 <= 116736, "LQ kernel must keep two CTAs per SM");
+static_assert((sizeof(LqSmem) * LQ_WARPS + 1024) * QMB_LQ_MINB <= 232448, "projection kernel: QMB_LQ_MINB CTAs of LQ_WARPS warps per SM (15.1 KB per node: three CTAs of five warps = 15 nodes in flight)");
 
 // =====================================================================================================
 // K2a: flow kernel - one THREAD per node (node_eval.cuh).  Kinematics of the five chains, both RK2 stages of the flow map with their Jacobian blocks, the
@@ -193,12 +193,10 @@ __global__ void __launch_bounds__(32 * FL_WARPS, QMB_FL_MINB) mpc_flow_kernel(co
 // K2b: cost quadratic model, equality constraints, projection, RK2 sensitivities and the structured stage record of one node (one warp per node), on the
 // record of the flow kernel.
 // (A CTA-wide re-alignment of the warps at phase boundaries - instruction-cache sharing - was measured and dropped: 21.88 ms with, 21.42 ms without, profiles/r02_ab_k3.jsonl.)
-// rows 3:12 of df/dx (9 x 30, two thirds zeros) and the force block of rows 3:6 of df/du from the Jacobian blocks of a flow record: fill, then lane = column writes
+// rows 3:12 of df/dx (9 x 30, two thirds zeros) from the Jacobian blocks of a flow record: fill, then lane = column writes
 // its own non-zeros (the fill and the column writes are separated by a warp barrier)
-__device__ __forceinline__ void expand_flow(const ne::FlowBlk& fb, const double* d0, const double* jxf0, int fstride /*doubles between two feet*/, double* Ar, double* Bh, double im, int lfp, int lane) {
+__device__ __forceinline__ void expand_flow(const ne::FlowBlk& fb, const double* jxf0, int fstride /*doubles between two feet*/, double* Ar, int lfp, int lane) {
   for (int e = lane; e < 9 * NX; e += 32) Ar[e] = 0.0;
-  for (int e = lane; e < 36; e += 32) { const int r = e / 12, c = e - 12 * r, i = c / 3, a = c - 3 * i; const double* d = d0 + i * fstride;   // cross(d_i, e_a)[r] / m
-    Bh[e] = ((r == a) ? 0.0 : (((a - r + 3) % 3 == 1) ? -d[3 - r - a] : d[3 - r - a])) * im; }
   __syncwarp();
   if (lane < 24) {
     const int col = lane;
@@ -226,8 +224,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   const double xv = (lane < NX) ? xk[lane] : 0.0, uv = (lane < NU) ? uk[lane] : 0.0, xnv = (lane < NX && has_next) ? xk[NX + lane] : 0.0;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
   const double tk = gt[k], tk1 = has_next ? gt[k + 1] : 0.0; const int ek = ge[k], ek1 = has_next ? ge[k + 1] : 0;
-  const int ne = clamp_events(p.n_events[b]); const double* ev = sm.ev; const unsigned char* modes = sm.modes;
-  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); sm.ev[lane] = (lane < ne) ? gev[lane] : 0.0; sm.modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) sm.modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
+  const int ne = clamp_events(p.n_events[b]); double* s_ev = sm.Ar; unsigned char* s_modes = reinterpret_cast<unsigned char*>(sm.Ar + EMAX); const double* ev = s_ev; const unsigned char* modes = s_modes;   // staged once per node: the binary searches and the swing-interval scans hit shared memory
+  { const double* gev = p.event_times + (size_t)b * EMAX; const int32_t* gmodes = p.modes + (size_t)b * (EMAX + 1); s_ev[lane] = (lane < ne) ? gev[lane] : 0.0; s_modes[lane] = (unsigned char)((lane <= ne) ? gmodes[lane] : 15); if (lane == 0) s_modes[EMAX] = (unsigned char)((EMAX <= ne) ? gmodes[EMAX] : 15); }
   const int n = sol.n_nodes[b];
   const bool work = k < n && !(status[b] & MST_CONVERGED);   // MST_CONVERGED: SqpSolver::runImpl left the iteration loop for this robot
   if (!work) return;
@@ -252,7 +250,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   const double dt = terminal ? 0.0 : interval_end(tk1, ek1) - t;
   const int mode = mode_at_time(ev, modes, ne, t); const int fm = terminal ? 0 : flag_mask(mode);
   if (!terminal && !(dt > 0.0) && lane == 0) atomicOr(&status[b], MST_NEG_DT);   // getIntervalDuration <= 0: an event within weakEpsilon of a grid node (QMB200_ST_NEG_DT)
-  double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0;
+  double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0; double b1v[3] = {0.0, 0.0, 0.0}, b2v[3] = {0.0, 0.0, 0.0};
   {
   // ---- cost quadratic model at (x, u) (the end-effector error and its Jacobian come with the record) ----
   TargetRef ref; ref.xnom = target_xnom(tt, ts, nk, t, lane);
@@ -322,7 +320,13 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   }
   // continuous-time Jacobians of the two RK2 stages from the record's blocks
   const double imr = 1.0 / mdl->total_mass;
-  expand_flow(sm.rec.s1, sm.rec.foot[0].d, sm.rec.foot[0].JxF, ne::FOOT_DBL, sm.A1r, sm.B1h, imr, lfp, lane); expand_flow(sm.rec.s2, sm.rec.foot2[0].d, sm.rec.foot2[0].JxF, ne::FOOT2_DBL, sm.Ar, sm.Bh, imr, lfp, lane);
+  expand_flow(sm.rec.s1, sm.rec.foot[0].JxF, ne::FOOT_DBL, sm.A1r, lfp, lane); expand_flow(sm.rec.s2, sm.rec.foot2[0].JxF, ne::FOOT2_DBL, sm.Ar, lfp, lane);
+  // force block of rows 3:6 of df/du at both stages, column c = lane < 12 (foot i = c / 3, axis a = c % 3): cross(d_i, e_a)[r] / m - three entries per stage, kept in registers
+  // (the foot blocks of the record are about to be overlaid by the RK2 combination's outputs)
+  if (lane < 12) { const int i = lane / 3, a = lane - 3 * i; const double* d1 = sm.rec.foot[i].d; const double* d2 = sm.rec.foot2[i].d;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) if (r != a) { const double sgn = ((a - r + 3) % 3 == 1) ? -imr : imr; b1v[r] = sgn * d1[3 - r - a]; b2v[r] = sgn * d2[3 - r - a]; } }
+  __syncwarp();
   }
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2), imass = 1.0 / mass;
   double bb = 0.0; if (lane < NX) { const double fa = lane < 12 ? sm.rec.s1.f[lane < 12 ? lane : 0] : sm.u[lane], fb = lane < 12 ? sm.rec.s2.f[lane < 12 ? lane : 0] : sm.u[lane];   // rows 12:30 of the flow map: the joint-velocity inputs
@@ -338,7 +342,9 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
 #pragma unroll
       for (int q = 0; q < 9; ++q) aa = fma(a2[3 + q], a1[q], aa);
       out[r] = dt * (w1 * a1[r] + w2 * (a2[c] + cdt * aa));
-      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = sm.B1h[r * 12 + c]; b2 = sm.Bh[r * 12 + c]; } double ab = a2[c % 3] * imass; for (int q = 0; q < 3; ++q) ab += a2[3 + q] * sm.B1h[q * 12 + c]; lt.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
+      if (c < 12) { double b1 = 0.0, b2 = 0.0; if (r < 3) { b1 = b1v[r < 3 ? r : 0]; b2 = b2v[r < 3 ? r : 0]; } double ab = a2[c % 3] * imass;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ab += a2[3 + q] * b1v[q]; lt.BrdF[r * 12 + c] = dt * (w1 * b1 + w2 * (b2 + cdt * ab)); }
       else if (r < 3) lt.BrdJ[r * NJ + c - 12] = dt * w2 * cdt * a2[c]; }
 #pragma unroll
     for (int r = 0; r < 9; ++r) sm.A1r[r * NX + c] = out[r];
