@@ -16,10 +16,10 @@
 namespace qmb {
 
 #ifndef QMB_LQ_WARPS
-#define QMB_LQ_WARPS 5
+#define QMB_LQ_WARPS 4
 #endif
 #ifndef QMB_LQ_MINB
-#define QMB_LQ_MINB 3
+#define QMB_LQ_MINB 4
 #endif
 constexpr int LQ_WARPS = QMB_LQ_WARPS, LS_WARPS = 4, SETUP_WARPS = 4;
 enum { MST_ITER_CAP = 1, MST_OVERFLOW = 2, MST_NAN = 4, MST_NOT_PD = 8, MST_NO_STEP = 16, MST_CONVERGED = 32, MST_NEG_DT = 64 };   // NEG_DT: an interval with non-positive duration (include/qmb200.h)   // CONVERGED: checkConvergence stopped the SQP loop before sqpIteration
@@ -108,7 +108,7 @@ struct LqLate { double BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX]; };                /
 struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp's slice starts 16-byte aligned
   ne::NodeRec rec;                                                             // the node's record from the flow kernel (K2a); LqLate overlays rec.foot[] once the cost / projection / Jacobian expansion have consumed it
   QuadWs quad; LegWs leg[4];
-  double x[NX], u[NU], xnext[NX];                                              // (x, u) of the node in the layout stage_cost reads (x then u), next node's state for the defect
+  double x[NX], u[NU];                                                         // (x, u) of the node in the layout stage_cost reads (x then u)
   double A1r[9 * NX], Ar[9 * NX];                                              // rows 3:12 of df/dx at the two RK2 stages; A1r becomes A_d - I in place.  Until expand_flow fills it, Ar holds the robot's mode schedule
   double Pe_full[NU], rs[NU];
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
@@ -116,7 +116,7 @@ struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp'
 static_assert(9 * NX * 8 >= EMAX * 8 + EMAX + 8, "the mode schedule (event times + modes) is staged in the Ar buffer until the flow Jacobians are expanded");
 static_assert(sizeof(LqLate) <= 4 * sizeof(ne::FootBlk) && offsetof(ne::NodeRec, foot) == 0, "LqLate overlays the foot blocks of the record");
 static_assert(sizeof(LqSmem) % 16 == 0 && offsetof(LqSmem, rec) == 0, "aligned record slice");
-static_assert((sizeof(LqSmem) * LQ_WARPS + 1024) * QMB_LQ_MINB <= 232448, "projection kernel: QMB_LQ_MINB CTAs of LQ_WARPS warps per SM (15.1 KB per node: three CTAs of five warps = 15 nodes in flight)");
+static_assert((sizeof(LqSmem) * LQ_WARPS + 1024) * QMB_LQ_MINB <= 232448, "projection kernel: QMB_LQ_MINB CTAs of LQ_WARPS warps per SM (13.8 KB per node: four CTAs of four warps = 16 nodes in flight)");
 
 // =====================================================================================================
 // K2a: flow kernel - one THREAD per node (node_eval.cuh).  Kinematics of the five chains, both RK2 stages of the flow map with their Jacobian blocks, the
@@ -231,11 +231,11 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   if (!work) return;
   double* sg = stage + node * STAGE_DBL;
   const bool terminal = (k == n - 1);
-  if (lane < NX) { sm.x[lane] = xv; sm.u[lane] = terminal ? 0.0 : uv; sm.xnext[lane] = terminal ? 0.0 : xnv; }
+  if (lane < NX) { sm.x[lane] = xv; sm.u[lane] = terminal ? 0.0 : uv; }   // the next node's state (defect) stays in the lane's register
   __syncwarp();
   if (!terminal && ek == 1) {   // event node: identity jump map, no input, no cost (setupEventNode)
     double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
-    double d = 0.0; if (lane < NX) { d = sm.x[lane] - sm.xnext[lane]; tl[T_b + lane] = d; }
+    double d = 0.0; if (lane < NX) { d = xv - xnv; tl[T_b + lane] = d; }
     const double ss = warp_sum(d * d);
     if (lane == 0) { si[SI_TYPE] = 1; si[SI_M] = 0; si[SI_NDEP] = 0; tl[T_MISC] = 0.0; tl[T_MISC + 1] = 0.0; tl[T_MISC + 2] = ss; tl[T_MISC + 3] = 0.0; }
     return;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   if (lane < 4) {
     const int i = lane; LegWs& L = sm.leg[i]; const int first = L.first;
     for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) L.Rl[3 * a + c] = quad_R(mdl, &sm.quad, 12 + first + a, 12 + first + c);
-    for (int j = 0; j < 3; ++j) { L.free_col[j] = sm.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) { L.Px[j][c] = 0.0; L.U[j][c] = 0.0; } }
+    for (int j = 0; j < 3; ++j) { L.free_col[j] = sm.col_of_input[12 + first + j]; L.Pe[j] = 0.0; for (int c = 0; c < 12; ++c) L.Px[j][c] = 0.0; }
     L.Pu2[0] = L.Pu2[1] = 0.0;
     if (L.stance) {   // zero velocity: Jl dqd = -(C dx + e)  →  dqd = -Jl^{-1} (C dx + e)
       double Jm[9], Ji[9]; for (int a = 0; a < 3; ++a) for (int j = 0; j < 3; ++j) Jm[3 * a + j] = sm.rec.foot[i].Jl[3 * j + a]; inv3(Jm, Ji);
@@ -306,9 +306,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
       for (int c = 0; c < 12; ++c) L.Px[pivot][c] = sm.rec.foot[i].C[2][c] * nip;
       int nf = 0; for (int j = 0; j < 3; ++j) if (j != pivot) L.Pu2[nf++] = sm.rec.foot[i].Jl[3 * j + 2] * nip;
     }
-    // rs = r + R Pe on the leg's joint inputs ; U = Rl Px
+    // rs = r + R Pe on the leg's joint inputs (the product Rl Px is formed where it is used: Q~ needs Px' (Rl Px), one 3-vector per row)
     for (int a = 0; a < 3; ++a) { double sv = sm.quad.rf[12 + first + a]; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Pe[j]; L.rs[a] = sv; }
-    for (int a = 0; a < 3; ++a) for (int c = 0; c < 12; ++c) { double sv = 0.0; for (int j = 0; j < 3; ++j) sv += L.Rl[3 * a + j] * L.Px[j][c]; L.U[a][c] = sv; }
   }
   __syncwarp();
   // rs of every input: r + R Pe (R couples joint velocities only inside a leg; forces and arm inputs only with themselves)
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   }
   const double w1 = mdl->rk_w1, w2 = mdl->rk_w2, cdt = mdl->rk_c * dt, mass = mdl->total_mass, dtw = dt * (w1 + w2), imass = 1.0 / mass;
   double bb = 0.0; if (lane < NX) { const double fa = lane < 12 ? sm.rec.s1.f[lane < 12 ? lane : 0] : sm.u[lane], fb = lane < 12 ? sm.rec.s2.f[lane < 12 ? lane : 0] : sm.u[lane];   // rows 12:30 of the flow map: the joint-velocity inputs
-    bb = sm.x[lane] + dt * (w1 * fa + w2 * fb) - sm.xnext[lane]; lt.bvec[lane] = bb; }   // defect
+    bb = xv + dt * (w1 * fa + w2 * fb) - xnv; lt.bvec[lane] = bb; }   // defect
   const double dyn_ss = warp_sum(bb * bb);
   // A_d - I (rows 3:12) = dt (w1 A1 + w2 (A2 + c dt A2 A1)) ; B_d rows 3:12 = dt (w1 B1 + w2 (B2 + c dt A2 B1)): force columns (9x12), joint columns only in the h_ang rows (3x18)
   if (lane < NX) {   // lane = column c: needs column c of A1 only, so A1r can be overwritten in place
@@ -417,9 +416,13 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
         double blk[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) blk[c] = 0.0;
+        double w3[3] = {0.0, 0.0, 0.0};   // row pr of Px' Rl ; then blk = w3' Px  (= row pr of Px' Rl Px)
         for (int j = 0; j < 3; ++j) if (L.dep[j]) { const double pj = L.Px[j][pr]; qv = fma(pj, L.rs[j], qv);
 #pragma unroll
-          for (int c = 0; c < 12; ++c) blk[c] = fma(pj, L.U[j][c], blk[c]); }
+          for (int a = 0; a < 3; ++a) w3[a] = fma(pj, L.Rl[3 * j + a], w3[a]); }
+        for (int a = 0; a < 3; ++a) if (L.dep[a]) { const double wa = w3[a];
+#pragma unroll
+          for (int c = 0; c < 12; ++c) blk[c] = fma(wa, L.Px[a][c], blk[c]); }
 #pragma unroll
         for (int c = 0; c < 6; ++c) acc[c] += blk[c];
 #pragma unroll
@@ -451,7 +454,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
         const LegWs& L = sm.leg[li]; const int pv = L.pivot; const int jfi = jf > pv ? jf - 1 : jf; const double pu = L.Pu2[jfi];
         rv += pu * L.rs[pv];
         const double coef = L.Rl[3 * jf + pv]; double* Srow = tl + T_SJ + (2 * li + jfi) * 12;
-        for (int c = 0; c < 12; ++c) Srow[c] = dt * (coef * L.Px[pv][c] + pu * L.U[pv][c]);
+        const double cf = dt * (coef + pu * L.Rl[3 * pv + pv]);   // only the pivot row of Px is non-zero in a swing leg: (Rl Px)[pv] = Rl[pv][pv] Px[pv]
+        for (int c = 0; c < 12; ++c) Srow[c] = cf * L.Px[pv][c];
       }
       rtil = dt * rv;
       // R is block diagonal (3x3 blocks over force / leg-joint triples, diagonal over the arm): only the free inputs of fa's own block contribute to row a

@@ -64,7 +64,6 @@ QMB_HD double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, i
 // joint-velocity inputs, the input weight couples joint velocities only inside a leg
 struct LegWs {
   double Px[3][12];     // rows of P_x of the dependent joint-velocity inputs of this leg on the support columns (stance: 3 rows; swing: pivot row only)
-  double U[3][12];      // R_leg * Px
   double Rl[9];         // 3x3 input-weight block of the leg (incl. diagonal additions)
   double Pe[3], rs[3];  // P_e of the dependent joints ; r + R P_e on the leg's joint inputs
   double Pu2[2];        // swing: coupling of the pivot joint to the two free joints
