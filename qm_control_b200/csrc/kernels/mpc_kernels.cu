@@ -2,11 +2,12 @@
 //   SqpSolver::runImpl as QMController configures it (qm_controllers/src/QMController.cpp:287-288, task.info:75-92)
 //   [upstream ocs2_sqp / ocs2_oc multiple_shooting, recalled — SURVEY.md App. A.5]:
 //     K1 mpc_setup_kernel      timeDiscretizationWithEvents + initializeStateInputTrajectories (QMInitializer.cpp:33-41 when cold)
-//     K2 mpc_lq_kernel         setupQuadraticSubproblem: RK2 sensitivities, cost quadratic model, equality constraints, projection
-//     K3 mpc_riccati_kernel    OCP-QP (HPIPM without inequality rows ≡ Riccati backward/forward sweep) + armijo metric
-//     K4 mpc_linesearch_kernel takeStep: filter line search, trajectory update
-// Parallelisation: K2 is node-parallel (one warp per (robot, node)); K3 is one warp per robot (the recursion is
-// sequential in time) with every 30x30 block in shared memory; K4 is one CTA per robot, warps striding over nodes.
+//     K2 setupQuadraticSubproblem in two kernels: mpc_flow_kernel (one THREAD per node: kinematics, both RK2 flow maps with Jacobian blocks, constraint rows,
+//        end-effector error) -> 3.9 KB node record -> mpc_lq_kernel (one warp per node: cost quadratic model, projection, RK2 sensitivities, structured stage record)
+//     K3 mpc_riccati_kernel    OCP-QP (HPIPM without inequality rows = Riccati backward/forward sweep) + armijo metric: one CTA per robot (the recursion is
+//        sequential in time), every 30x30 block in shared memory, products on fp64 tensor-core tiles, records fetched by TMA bulk copies
+//     K4 mpc_linesearch_kernel takeStep: filter line search, trajectory update: one CTA per robot, one thread per node
+//     mpc_rollout_kernel       DDP variant: single-shooting rollouts, one thread per robot (and step length)
 #include <cstdlib>
 #include "mpc_api.cuh"
 #include "mpc_device.cuh"
@@ -108,7 +109,7 @@ struct LqLate { double BrdF[9 * 12], BrdJ[3 * NJ], bvec[NX]; };                /
 struct alignas(16) LqSmem {   // 16-byte vector loads of the record: every warp's slice starts 16-byte aligned
   ne::NodeRec rec;                                                             // the node's record from the flow kernel (K2a); LqLate overlays rec.foot[] once the cost / projection / Jacobian expansion have consumed it
   QuadWs quad; LegWs leg[4];
-  double x[NX], u[NU];                                                         // (x, u) of the node in the layout stage_cost reads (x then u)
+  double x[NX], u[NU];                                                         // (x, u) of the node in the layout stage_cost_quad reads (x then u)
   double A1r[9 * NX], Ar[9 * NX];                                              // rows 3:12 of df/dx at the two RK2 stages; A1r becomes A_d - I in place.  Until expand_flow fills it, Ar holds the robot's mode schedule
   double Pe_full[NU], rs[NU];
   int dep_idx[MAXDEP], free_idx[MU], col_of_input[NU];
@@ -253,9 +254,8 @@ __global__ void __launch_bounds__(32 * LQ_WARPS, QMB_LQ_MINB) mpc_lq_kernel(cons
   double cost_val = 0.0, eq_ss = 0.0; int ndep = 0, m = 0; double b1v[3] = {0.0, 0.0, 0.0}, b2v[3] = {0.0, 0.0, 0.0};
   {
   // ---- cost quadratic model at (x, u) (the end-effector error and its Jacobian come with the record) ----
-  TargetRef ref; ref.xnom = target_xnom(tt, ts, nk, t, lane);
   struct XU { double x[NX], u[NU]; }; static_assert(offsetof(LqSmem, u) == offsetof(LqSmem, x) + NX * 8, "x then u");
-  cost_val = stage_cost<true, true>(mdl, reinterpret_cast<const XU*>(sm.x), &sm.rec.ee, &sm.quad, ref, fm, terminal, lane);
+  cost_val = stage_cost_quad(mdl, reinterpret_cast<const XU*>(sm.x), &sm.rec.ee, &sm.quad, target_xnom(tt, ts, nk, t, lane), fm, terminal, lane);
   if (terminal) {   // setupTerminalNode: finalEndEffector soft constraint only (QMInterface.cpp:104)
     double* tl = sg + ST_TAIL; int32_t* si = reinterpret_cast<int32_t*>(tl + T_INT);
     for (int r = 0; r < NX; ++r) { const int a = ee_pos(r); if (lane < q_row_padded(r)) { const int cc = (lane <= r) ? ee_pos(lane) : -1; sg[ST_Q + q_row_offset(r) + lane] = (a >= 0 && cc >= 0) ? sm.quad.E[a * 12 + cc] : 0.0; } }   // final cost: packed lower triangle

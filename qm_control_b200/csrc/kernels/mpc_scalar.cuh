@@ -54,8 +54,6 @@ QMB_HD int sup_col(int pos, int first) { return pos < 6 ? pos : (pos < 9 ? pos +
 // only what depends on (x,u) is stored:  Qf = Q + diag(qdiag) + scatter(E on the 12 end-effector columns),
 // Rf = R + diag(rdiag) + blockdiag(fric[foot]) on the 12 force inputs.
 struct QuadWs { double E[144], fric[36], qdiag[NX], rdiag[NU], qf[NX], rf[NU]; };
-QMB_HD double quad_Q(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
-  double v = mdl->Q[i * NX + j]; if (i == j) v += q->qdiag[i]; const int a = ee_pos(i), b = ee_pos(j); if (a >= 0 && b >= 0) v += q->E[a * 12 + b]; return v; }
 QMB_HD double quad_R(const DevModel* __restrict__ mdl, const QuadWs* q, int i, int j) {
   if (i >= 24 || j >= 24) return (i == j) ? mdl->Rarm[i - 24] + q->rdiag[i] : 0.0;
   const int bi = i / 3; if (bi != j / 3) return 0.0;

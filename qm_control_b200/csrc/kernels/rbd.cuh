@@ -112,9 +112,6 @@ __device__ __forceinline__ void rbd_kinematics(const DevModel* __restrict__ mdl,
   }
 }
 
-// positions-only workspace (MPC kernels)
-struct KinWs { double R[NB][9]; double p[NB][3]; double S[NQ][6]; double trig[6]; };
-
 // Pass 2: per-body world inertias; optionally RNEA body forces (gravity: +9.81 z base acceleration trick).
 // with_force: 0 none, 1 = F = I (A + Ag) + V x* I V with gravity, 2 = same without gravity (centroidal momentum rate bias)
 __device__ __forceinline__ void rbd_inertias(const DevModel* __restrict__ mdl, RbdWs* ws, int lane, int with_force) {
