@@ -982,7 +982,10 @@ __device__ __forceinline__ void rollout_input(const double* __restrict__ tl, con
 }
 // mode 0: nominal rollout (thread = robot).  mode 1: trial rollouts (thread = (robot, trial), trial = fastest index): cost and equality SSE of every step length
 // into `trial` [B][RO_MAXTRIALS][2].  mode 2: decision + in-place rollout of the accepted step (thread = robot).
-__global__ void __launch_bounds__(RO_THREADS, 2) mpc_rollout_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
+#ifndef QMB_RO_MINB
+#define QMB_RO_MINB 2
+#endif
+__global__ void __launch_bounds__(RO_THREADS, QMB_RO_MINB) mpc_rollout_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
                                                                    double* __restrict__ trial, const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int mode_ls, int n_trials, int tr_pitch, int iteration) {
   const long long gid = (long long)blockIdx.x * RO_THREADS + threadIdx.x;
   const int b = b0 + (int)(mode_ls == 1 ? gid / tr_pitch : gid), tr = mode_ls == 1 ? (int)(gid % tr_pitch) : 0; if (b >= B || tr >= n_trials) return;
