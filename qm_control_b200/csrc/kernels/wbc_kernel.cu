@@ -472,10 +472,10 @@ size_t wbc_smem_bytes() { return sizeof(WbcSmem) * WBC_WARPS; }
 void launch_wbc_update(const DevModel* mdl, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const double* period, const double* time,
                        double* input_last, int variant, double* cmd, int32_t* status, cudaStream_t stream, int b0, int b1, int32_t* diag) {
   if (b1 < 0) b1 = B; if (b1 <= b0) return;
-  // Large batches: eight robots per CTA, one CTA per SM (eight resident warps, many waves).  A batch that fits one wave (a GPU's share of a strong-scaled job: 1024 robots on 148 SMs)
-  // is spread as one-robot CTAs - seven fit an SM by shared memory - so that every SM gets 6..7 robots instead of 128 SMs getting eight and 20 none.
-  int sms = 148; { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int nb = b1 - b0; const int wpc = (nb <= sms * 7) ? 1 : WBC_WARPS;
+  // Eight robots per CTA, one CTA per SM.  Measured on B200 (profiles/r03_rejected.json): smaller CTAs LOSE although they would even out the per-CTA tail - four robots per CTA
+  // 5.98 -> 6.6 ms, one-robot CTAs 12.3 ms at 8192 robots: the kernel is ~24 k SASS instructions, warps of one CTA run in phase and share the instruction cache; a batch of one
+  // wave (1024 robots) takes the time of its slowest robot (1.23 ms) whatever the CTA shape.
+  const int nb = b1 - b0; const int wpc = WBC_WARPS;
   const int grid = (nb + wpc - 1) / wpc;
   wbc_update_kernel<<<grid, 32 * wpc, sizeof(WbcSmem) * wpc, stream>>>(mdl, b0, b1, x_des, u_des, rbd, mode, period, time, input_last, variant, cmd, status, diag);
 }
