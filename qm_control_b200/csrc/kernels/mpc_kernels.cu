@@ -980,15 +980,14 @@ __device__ __forceinline__ void rollout_input(const double* __restrict__ tl, con
       const int foot = (lfp >> (2 * lg)) & 3; if (si[SI_PIV + foot] >= 0) for (int q2 = 0; q2 < 2; ++q2) { const int col = si[SI_PCOL + 2 * foot + q2]; if (col >= 0) du = fma(tl[T_PU2 + 2 * foot + q2], dut[col], du); } }
     un[di] += du; }
 }
-// mode 0: nominal rollout (thread = robot).  mode 1: trial rollouts (thread = (robot, trial), trial = fastest index): cost and equality SSE of every step length
-// into `trial` [B][RO_MAXTRIALS][2].  mode 2: decision + in-place rollout of the accepted step (thread = robot).
+// mode 0: nominal rollout (thread = robot).  mode 2: decision on the trial merits + in-place rollout of the accepted step (thread = robot).
 #ifndef QMB_RO_MINB
 #define QMB_RO_MINB 2
 #endif
 __global__ void __launch_bounds__(RO_THREADS, QMB_RO_MINB) mpc_rollout_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
                                                                    double* __restrict__ trial, const double* __restrict__ robot, int32_t* __restrict__ status, double* __restrict__ step_info, int mode_ls, int n_trials, int tr_pitch, int iteration) {
   const long long gid = (long long)blockIdx.x * RO_THREADS + threadIdx.x;
-  const int b = b0 + (int)(mode_ls == 1 ? gid / tr_pitch : gid), tr = mode_ls == 1 ? (int)(gid % tr_pitch) : 0; if (b >= B || tr >= n_trials) return;
+  const int b = b0 + (int)gid; if (b >= B) return;
   if (status[b] & MST_CONVERGED) return;
   const int n = sol.n_nodes[b]; const int N = n - 1;
   const double* gt = sol.t + (size_t)b * nmax; const int32_t* ge = sol.event + (size_t)b * nmax;
@@ -1014,46 +1013,89 @@ __global__ void __launch_bounds__(RO_THREADS, QMB_RO_MINB) mpc_rollout_kernel(co
   const double merit0 = base_cost + pen * sqrt(base_eq); const bool failed = (status[b] & MST_NOT_PD) != 0;
   double* tb = trial + (size_t)b * RO_MAXTRIALS * 2;
   double alpha = mdl->ddp_max_step; bool accepted = false; double sc = base_cost, se = base_eq;
-  if (mode_ls == 1) { for (int j = 0; j < tr; ++j) alpha *= mdl->ddp_contraction; if (failed) return; }
-  else {   // mode 2: the first step length (descending) whose merit passes the armijo test [upstream ocs2_ddp LineSearchStrategy, recalled]
+  {   // mode 2: the first step length (descending) whose merit passes the armijo test [upstream ocs2_ddp LineSearchStrategy, recalled]
     if (!failed) for (int j = 0; j < n_trials; ++j) { const double c = tb[2 * j], e = tb[2 * j + 1], merit = c + pen * sqrt(e);
         if (merit < merit0 - mdl->ddp_armijo * alpha * fabs(merit0)) { accepted = true; sc = c; se = e; break; } alpha *= mdl->ddp_contraction; }
   }
-  if (mode_ls == 1 || accepted) {
-    const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const double* gb = gains + (size_t)b * nmax * GAIN_DBL; const bool write = mode_ls == 2;
+  if (accepted) {
+    const double* sgb = stage + (size_t)b * nmax * STAGE_DBL; const double* gb = gains + (size_t)b * nmax * GAIN_DBL;
     double xnom[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { xa[i] = p.x0[(size_t)b * NX + i]; xnom[i] = gx[i]; }
-    if (write) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) gx[i] = xa[i]; }
+    for (int i = 0; i < NX; ++i) gx[i] = xa[i];
     for (int k = 0; k < N; ++k) {
       if (ge[k] == 1) {   // event node: identity jump map, no input
-        if (write) { for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = 0.0; }
+        for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = 0.0;
       } else {
         const double* tl = sgb + (size_t)k * STAGE_DBL + ST_TAIL; double dxv[NX], un[NU];
 #pragma unroll
         for (int i = 0; i < NX; ++i) dxv[i] = xa[i] - xnom[i];
         rollout_input(tl, gb + (size_t)k * GAIN_DBL, gu + (size_t)k * NU, dxv, alpha, lfp, un);
-        if (write) { for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = un[i]; }
+        for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = un[i];
         const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; const int fm = flag_mask(mode_at_time(ev, modes, ne, t));
-        if (write) rollout_step<false>(mdl, xa, un, t, dt, fm, ev, modes, ne, tt, ts, nk, cost, eq); else rollout_step<true>(mdl, xa, un, t, dt, fm, ev, modes, ne, tt, ts, nk, cost, eq);
+        rollout_step<false>(mdl, xa, un, t, dt, fm, ev, modes, ne, tt, ts, nk, cost, eq);
       }
       // the nominal state of the next node is read before the new one replaces it (in-place commit)
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { xnom[i] = gx[(size_t)(k + 1) * NX + i]; if (write) gx[(size_t)(k + 1) * NX + i] = xa[i]; }
+      for (int i = 0; i < NX; ++i) { xnom[i] = gx[(size_t)(k + 1) * NX + i]; gx[(size_t)(k + 1) * NX + i] = xa[i]; }
     }
-    if (!write) {   // final cost at x_N
-      const double t = interval_start(gt[N], ge[N]); ne::BaseKin bk; ne::base_eval<false>(mdl, xa, bk); double u0[NU]; for (int i = 0; i < NU; ++i) u0[i] = 0.0;
-      const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4], ee[6]; ne::target_pose(sg, nk, pref, qref); ne::ee_eval<false>(mdl, xa, bk, pref, qref, ee, nullptr);
-      cost += ne::cost_value(mdl, xa, u0, sg, ee, 0, true);
-      tb[2 * tr] = cost; tb[2 * tr + 1] = eq; return; }
   }
   if (!accepted) { alpha = 0.0; sc = base_cost; se = base_eq; }
   // toPrimalSolution [upstream]: input at a pre-event node repeats the previous one; last input repeated
   for (int k = 1; k < n; ++k) { if ((k == n - 1) || (ge[k] == 1)) for (int i = 0; i < NU; ++i) gu[(size_t)k * NU + i] = gu[(size_t)(k - 1) * NU + i]; }
   { int flags = accepted ? 0 : MST_NO_STEP; if (!accepted && iteration + 1 < mdl->sqp_iterations) flags |= MST_CONVERGED; if (flags) atomicOr(&status[b], flags);
     double* si = step_info + (size_t)b * 4; si[0] = alpha; si[1] = sc; si[2] = 0.0; si[3] = se; }
+}
+
+// The trial rollouts of the line search: thread = (robot, step length), the step lengths of a robot on adjacent lanes; cost and equality SSE of every step length go to
+// `trial` [B][RO_MAXTRIALS][2].  The CTA walks the horizon in lock step and stages the feedback gains of its robots' current node in shared memory (one coalesced
+// copy per node instead of 18 x 31 scattered loads per thread: those loads were 45 % of the samples of the unstaged kernel).
+constexpr int RO_RPC_MAX = 16;   // robots per CTA: 16 x 4.9 KB of gains
+__global__ void __launch_bounds__(RO_THREADS, QMB_RO_MINB) mpc_rollout_trials_kernel(const DevModel* __restrict__ mdl, int b0, int B, int nmax, MpcProblemDev p, MpcSolutionDev sol, const double* __restrict__ stage, const double* __restrict__ gains,
+                                                                          double* __restrict__ trial, const double* __restrict__ robot, const int32_t* __restrict__ status, int n_trials, int tr_pitch, int rpc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[]; double* sK = reinterpret_cast<double*>(smem_raw);   // [rpc][GAIN_DBL]
+  __shared__ int s_kmax;
+  const int tid = threadIdx.x, nthr = blockDim.x, r = tid / tr_pitch, tr = tid - r * tr_pitch; const int bfirst = b0 + blockIdx.x * rpc, b = bfirst + r;
+  const bool active = b < B && tr < n_trials && !(status[b] & (MST_CONVERGED | MST_NOT_PD));
+  const int N = active ? sol.n_nodes[b] - 1 : 0;
+  if (tid == 0) s_kmax = 0;
+  __syncthreads();
+  if (active) atomicMax(&s_kmax, N);
+  __syncthreads();
+  const int kmax = s_kmax; if (kmax <= 0) return;   // CTA-uniform
+  const size_t bb = active ? (size_t)b : 0;
+  const double* gt = sol.t + bb * nmax; const int32_t* ge = sol.event + bb * nmax; const double* gx = sol.x + bb * nmax * NX; const double* gu = sol.u + bb * nmax * NU;
+  const int ne = clamp_events(p.n_events[bb]); const double* ev = p.event_times + bb * EMAX; const int32_t* modes = p.modes + bb * (EMAX + 1);
+  const int lfp = pack_leg_foot(mdl);
+  const int nk = clamp_targets(p.n_target[bb]); const double* tt = p.target_times + bb * KMAX; const double* ts = p.target_states + bb * KMAX * TARGET_DIM;
+  const double* sgb = stage + bb * nmax * STAGE_DBL;
+  double alpha = mdl->ddp_max_step; for (int j = 0; j < tr; ++j) alpha *= mdl->ddp_contraction;
+  double xa[NX], xnom[NX], cost = 0.0, eq = 0.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) { xa[i] = p.x0[bb * NX + i]; xnom[i] = gx[i]; }
+  for (int k = 0; k < kmax; ++k) {
+    __syncthreads();                                                   // the readers of node k - 1 are done
+    for (int e = tid; e < rpc * GAIN_DBL; e += nthr) { const int rr = e / GAIN_DBL; const int br = bfirst + rr; sK[e] = (br < B) ? gains[((size_t)br * nmax + k) * GAIN_DBL + (e - rr * GAIN_DBL)] : 0.0; }
+    __syncthreads();
+    if (active && k < N) {
+      if (ge[k] != 1) {   // (event node: identity jump map, no input)
+        const double* tl = sgb + (size_t)k * STAGE_DBL + ST_TAIL; double dxv[NX], un[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dxv[i] = xa[i] - xnom[i];
+        rollout_input(tl, sK + r * GAIN_DBL, gu + (size_t)k * NU, dxv, alpha, lfp, un);
+        const double t = interval_start(gt[k], ge[k]); const double dt = interval_end(gt[k + 1], ge[k + 1]) - t; const int fm = flag_mask(mode_at_time(ev, modes, ne, t));
+        rollout_step<true>(mdl, xa, un, t, dt, fm, ev, modes, ne, tt, ts, nk, cost, eq);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xnom[i] = gx[(size_t)(k + 1) * NX + i];
+    }
+  }
+  if (active) {   // final cost at x_N
+    const double t = interval_start(gt[N], ge[N]); ne::BaseKin bk; ne::base_eval<false>(mdl, xa, bk); double u0[NU]; for (int i = 0; i < NU; ++i) u0[i] = 0.0;
+    const ne::TargetSeg sg = ne::target_segment(tt, ts, nk, t); double pref[3], qref[4], ee[6]; ne::target_pose(sg, nk, pref, qref); ne::ee_eval<false>(mdl, xa, bk, pref, qref, ee, nullptr);
+    cost += ne::cost_value(mdl, xa, u0, sg, ee, 0, true);
+    double* tb = trial + (size_t)b * RO_MAXTRIALS * 2; tb[2 * tr] = cost; tb[2 * tr + 1] = eq; }
 }
 
 __global__ void mpc_fixup_kernel(int B, int nmax, MpcSolutionDev sol) { const int b = blockIdx.x; if (b >= B) return; const int n = sol.n_nodes[b]; if (n >= 2) fixup_inputs(sol, b, nmax, n, threadIdx.x, blockDim.x); }
@@ -1085,6 +1127,7 @@ bool mpc_alloc(MpcBuffers& m, int B, int nmax, std::string& err, std::vector<voi
 int mpc_configure_device() {
   cudaError_t e = cudaFuncSetAttribute(mpc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // 48 B per node and warp: opt-in beyond nmax ~ 250
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_trials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_RPC_MAX * GAIN_DBL * 8);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LqSmem) * LQ_WARPS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem));
   return (int)e;
@@ -1099,7 +1142,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
   const long long nodes = (long long)nb * nmax; const int iters = hm.sqp_iterations < 1 ? 1 : hm.sqp_iterations; int launched = 1;
   const bool ddp = hm.solver == 2; int n_trials = 0, tr_pitch = 1;
   if (ddp) { for (double a = hm.ddp_max_step; a >= hm.ddp_min_step && n_trials < RO_MAXTRIALS; a *= hm.ddp_contraction) ++n_trials; while (tr_pitch < n_trials) tr_pitch *= 2; }   // step lengths of ddp.lineSearch; lanes of a warp: trials of the same robot side by side
-  const int ro_grid = (nb + RO_THREADS - 1) / RO_THREADS, ro_grid_tr = (int)(((long long)nb * tr_pitch + RO_THREADS - 1) / RO_THREADS);
+  const int ro_grid = (nb + RO_THREADS - 1) / RO_THREADS; const int ro_rpc = (RO_THREADS / tr_pitch < RO_RPC_MAX) ? RO_THREADS / tr_pitch : RO_RPC_MAX;   // robots per CTA of the trial kernel
   if (ddp) { mpc_rollout_kernel<<<ro_grid, RO_THREADS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, m.step_info, 0, 1, 1, 0); ++launched; }   // nominal rollout from the measured state
   // SqpSolver::runImpl: for (iter < sqpIteration) { LQ approximation; QP; line search; checkConvergence }.  Robots whose convergence test fired
   // carry MST_CONVERGED and skip the remaining iterations inside the kernels (the per-kernel events time the last iteration's launches).
@@ -1110,7 +1153,7 @@ int mpc_solve_launch(const DevModel* mdl, const DevModel& hm, MpcBuffers& m, con
     if (ev && it == iters - 1) cudaEventRecord(ev[2], stream);
     mpc_riccati_kernel<<<nb, RIC_THREADS, sizeof(RicSmem), stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.dx, m.du, m.robot, m.status);
     if (ev && it == iters - 1) cudaEventRecord(ev[3], stream);
-    if (ddp) { mpc_rollout_kernel<<<ro_grid_tr, RO_THREADS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, m.step_info, 1, n_trials, tr_pitch, it);   // all step lengths side by side
+    if (ddp) { mpc_rollout_trials_kernel<<<(nb + ro_rpc - 1) / ro_rpc, ro_rpc * tr_pitch, (size_t)ro_rpc * GAIN_DBL * 8, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, n_trials, tr_pitch, ro_rpc);   // all step lengths side by side
       mpc_rollout_kernel<<<ro_grid, RO_THREADS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.stage, m.gains, m.ddp_trial, m.robot, m.status, m.step_info, 2, n_trials, tr_pitch, it); ++launched; }   // decision + in-place rollout of the accepted step
     else mpc_linesearch_kernel<<<nb, 32 * LS_WARPS, 0, stream>>>(mdl, b0, b1, nmax, p, next, m.dx, m.du, m.robot, m.status, m.step_info, it);
     launched += 4;
